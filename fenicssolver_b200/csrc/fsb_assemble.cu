@@ -1,0 +1,560 @@
+// K3+K4+K5+K6: P1 element kernels with scatter-add into the block-CSR, facet kernels, Dirichlet rows.
+//
+// One thread per cell: connectivity is read as one vector load, the (L2-resident) vertex coordinates
+// are gathered, the closed-form P1 local matrix is formed in registers (exact for every integrand on
+// the hot path) and its entries are added with fire-and-forget fp64 reductions
+// (RED.E.ADD.F64) at positions taken from the uint8 position map (asm_mode 1) or an in-row binary
+// search (asm_mode 0).
+#include "fsb_internal.cuh"
+
+struct ScalarForm {
+  double kscale;
+  double K[9];      // row-major DxD conductivity tensor
+  double mass;
+  double adv;
+  double vel[3];
+};
+
+template <int D>
+struct Geo {
+  double vol;
+  double G[D + 1][D];
+};
+
+template <int D>
+__device__ __forceinline__ void load_cell(const int32_t* __restrict__ cells, int64_t c, int (&v)[D + 1]) {
+  if constexpr (D == 3) {
+    int4 q = __ldg(reinterpret_cast<const int4*>(cells) + c);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+#pragma unroll
+    for (int a = 0; a <= D; ++a) v[a] = __ldg(cells + c * (D + 1) + a);
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void p1_geometry(const double* __restrict__ xyz, const int (&v)[D + 1], Geo<D>& g) {
+  double X[D + 1][D];
+#pragma unroll
+  for (int a = 0; a <= D; ++a)
+#pragma unroll
+    for (int i = 0; i < D; ++i) X[a][i] = __ldg(xyz + (int64_t)v[a] * D + i);
+  if constexpr (D == 3) {
+    double a[3], b[3], c[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a[i] = X[1][i] - X[0][i]; b[i] = X[2][i] - X[0][i]; c[i] = X[3][i] - X[0][i]; }
+    double bc[3] = {b[1] * c[2] - b[2] * c[1], b[2] * c[0] - b[0] * c[2], b[0] * c[1] - b[1] * c[0]};
+    double ca[3] = {c[1] * a[2] - c[2] * a[1], c[2] * a[0] - c[0] * a[2], c[0] * a[1] - c[1] * a[0]};
+    double ab[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    double det = a[0] * bc[0] + a[1] * bc[1] + a[2] * bc[2];
+    double inv = 1.0 / det;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      g.G[1][i] = bc[i] * inv; g.G[2][i] = ca[i] * inv; g.G[3][i] = ab[i] * inv;
+      g.G[0][i] = -(g.G[1][i] + g.G[2][i] + g.G[3][i]);
+    }
+    g.vol = fabs(det) * (1.0 / 6.0);
+  } else {
+    double a0 = X[1][0] - X[0][0], a1 = X[1][1] - X[0][1], b0 = X[2][0] - X[0][0], b1 = X[2][1] - X[0][1];
+    double det = a0 * b1 - a1 * b0, inv = 1.0 / det;
+    g.G[1][0] = b1 * inv; g.G[1][1] = -b0 * inv;
+    g.G[2][0] = -a1 * inv; g.G[2][1] = a0 * inv;
+    g.G[0][0] = -(g.G[1][0] + g.G[2][0]); g.G[0][1] = -(g.G[1][1] + g.G[2][1]);
+    g.vol = fabs(det) * 0.5;
+  }
+}
+
+// positions of the (D+1)^2 local entries: offset of column v[b] inside row v[a]
+template <int D>
+__device__ __forceinline__ void entry_positions(const uint8_t* __restrict__ posmap, int64_t c, const int (&v)[D + 1],
+                                                const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                                int64_t (&base)[D + 1], int (&pos)[D + 1][D + 1]) {
+  constexpr int NL = D + 1;
+#pragma unroll
+  for (int a = 0; a < NL; ++a) base[a] = __ldg(row_ptr + v[a]);
+  if (posmap) {
+    if constexpr (D == 3) {
+      uint4 q = __ldg(reinterpret_cast<const uint4*>(posmap) + c);
+      unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int a = 0; a < NL; ++a)
+#pragma unroll
+        for (int b = 0; b < NL; ++b) pos[a][b] = (w[a] >> (8 * b)) & 0xff;
+    } else {
+#pragma unroll
+      for (int a = 0; a < NL; ++a)
+#pragma unroll
+        for (int b = 0; b < NL; ++b) pos[a][b] = __ldg(posmap + c * NL * NL + a * NL + b);
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < NL; ++a) {
+      const int len = (int)(__ldg(row_ptr + v[a] + 1) - base[a]);
+      int lo = 0;
+#pragma unroll
+      for (int b = 0; b < NL; ++b) {
+        lo = row_find(col_idx + base[a], lo, len, v[b]);
+        pos[a][b] = lo++;
+      }
+    }
+  }
+}
+
+template <int D, bool ACTION>
+__global__ void __launch_bounds__(128)
+k_scalar_form(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz, ScalarForm f,
+              const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, double* __restrict__ vals,
+              const uint8_t* __restrict__ posmap, const double* __restrict__ x, double* __restrict__ y) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    // KG[b] = K grad phi_b ; vg[b] = vel . grad phi_b
+    double KG[NL][D], vg[NL];
+#pragma unroll
+    for (int b = 0; b < NL; ++b) {
+      vg[b] = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s += f.K[i * D + j] * g.G[b][j];
+        KG[b][i] = s;
+        vg[b] += f.vel[i] * g.G[b][i];
+      }
+    }
+    const double kw = f.kscale * g.vol, mw = f.mass * g.vol / (double)(NL * (NL + 1)), aw = f.adv * g.vol / (double)NL;
+    double Ke[NL][NL];
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int b = 0; b < NL; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) s += g.G[a][i] * KG[b][i];
+        Ke[a][b] = kw * s + mw * (a == b ? 2.0 : 1.0) + aw * vg[b];
+      }
+    if (ACTION) {
+      double xl[NL];
+#pragma unroll
+      for (int b = 0; b < NL; ++b) xl[b] = __ldg(x + v[b]);
+#pragma unroll
+      for (int a = 0; a < NL; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < NL; ++b) s += Ke[a][b] * xl[b];
+        atomicAdd(y + v[a], s);
+      }
+    } else {
+      int64_t base[NL];
+      int pos[NL][NL];
+      entry_positions<D>(posmap, c, v, row_ptr, col_idx, base, pos);
+#pragma unroll
+      for (int a = 0; a < NL; ++a)
+#pragma unroll
+        for (int b = 0; b < NL; ++b) atomicAdd(vals + base[a] + pos[a][b], Ke[a][b]);
+    }
+  }
+}
+
+// K_e[(a,i),(b,j)] = |T| ( mu (G_a.G_b d_ij + G_a[j] G_b[i]) + lambda G_a[i] G_b[j] ), DxD blocks
+template <int D>
+__global__ void __launch_bounds__(128)
+k_elasticity(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz, double mu, double lambda,
+             const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, double* __restrict__ vals,
+             const uint8_t* __restrict__ posmap) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    int64_t base[NL];
+    int pos[NL][NL];
+    entry_positions<D>(posmap, c, v, row_ptr, col_idx, base, pos);
+    const double wmu = mu * g.vol, wl = lambda * g.vol;
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int b = 0; b < NL; ++b) {
+        double gg = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) gg += g.G[a][i] * g.G[b][i];
+        double* blk = vals + (base[a] + pos[a][b]) * (D * D);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            atomicAdd(blk + i * D + j, wmu * ((i == j ? gg : 0.0) + g.G[a][j] * g.G[b][i]) + wl * g.G[a][i] * g.G[b][j]);
+      }
+  }
+}
+
+struct Vec3 { double v[3]; };
+
+template <int D>
+__global__ void k_source_const(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz,
+                               int ncomp, Vec3 S, double scale, const int32_t* __restrict__ tags, int tag,
+                               double* __restrict__ b) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    if (tags && tags[c] != tag) continue;
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    const double w = scale * g.vol / (double)NL;
+    for (int a = 0; a < NL; ++a)
+      for (int k = 0; k < ncomp; ++k) atomicAdd(b + (int64_t)v[a] * ncomp + k, w * S.v[k]);
+  }
+}
+
+template <int D>
+__global__ void k_source_nodal(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz,
+                               int ncomp, const double* __restrict__ S, double scale, double* __restrict__ b) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    const double w = scale * g.vol / (double)(NL * (NL + 1));
+    for (int k = 0; k < ncomp; ++k) {
+      double sl[NL], tot = 0.0;
+      for (int e = 0; e < NL; ++e) { sl[e] = S[(int64_t)v[e] * ncomp + k]; tot += sl[e]; }
+      for (int a = 0; a < NL; ++a) atomicAdd(b + (int64_t)v[a] * ncomp + k, w * (tot + sl[a]));
+    }
+  }
+}
+
+// facet measure (edge length / triangle area) and the un-normalised normal
+template <int D>
+__device__ __forceinline__ double facet_geom(const double* __restrict__ xyz, const int32_t* fv, double (&n)[3], double (&x0)[3]) {
+  if constexpr (D == 3) {
+    double p[3][3];
+    for (int a = 0; a < 3; ++a) for (int i = 0; i < 3; ++i) p[a][i] = xyz[(int64_t)fv[a] * 3 + i];
+    double a[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+    double b[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
+    n[0] = a[1] * b[2] - a[2] * b[1]; n[1] = a[2] * b[0] - a[0] * b[2]; n[2] = a[0] * b[1] - a[1] * b[0];
+    for (int i = 0; i < 3; ++i) x0[i] = p[0][i];
+    return 0.5 * sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  } else {
+    double t0 = xyz[(int64_t)fv[1] * 2] - xyz[(int64_t)fv[0] * 2], t1 = xyz[(int64_t)fv[1] * 2 + 1] - xyz[(int64_t)fv[0] * 2 + 1];
+    n[0] = t1; n[1] = -t0; n[2] = 0.0;
+    x0[0] = xyz[(int64_t)fv[0] * 2]; x0[1] = xyz[(int64_t)fv[0] * 2 + 1]; x0[2] = 0.0;
+    return sqrt(t0 * t0 + t1 * t1);
+  }
+}
+
+template <int D>
+__global__ void k_facet_load(int64_t nf, const int32_t* __restrict__ fverts, const int32_t* __restrict__ opp,
+                             const double* __restrict__ xyz, int ncomp, int mode, Vec3 gval, double scale,
+                             double* __restrict__ b) {
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t* fv = fverts + f * D;
+    double n[3], x0[3];
+    const double meas = facet_geom<D>(xyz, fv, n, x0);
+    double gl[3] = {gval.v[0], gval.v[1], gval.v[2]};
+    if (mode == 1) {
+      double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      double d = 0.0;
+      for (int i = 0; i < D; ++i) d += n[i] * (xyz[(int64_t)opp[f] * D + i] - x0[i]);
+      double sgn = d > 0 ? -1.0 : 1.0;
+      for (int i = 0; i < D; ++i) gl[i] = gval.v[0] * sgn * n[i] / nn;
+    }
+    const double w = scale * meas / (double)D;
+    for (int a = 0; a < D; ++a)
+      for (int k = 0; k < ncomp; ++k) atomicAdd(b + (int64_t)fv[a] * ncomp + k, w * gl[k]);
+  }
+}
+
+template <int D>
+__global__ void k_facet_mass(int64_t nf, const int32_t* __restrict__ fverts, const double* __restrict__ xyz, double h,
+                             const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                             double* __restrict__ vals) {
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t* fv = fverts + f * D;
+    double n[3], x0[3];
+    const double w = h * facet_geom<D>(xyz, fv, n, x0) / (double)(D * (D + 1));
+    for (int a = 0; a < D; ++a) {
+      const int64_t base = row_ptr[fv[a]];
+      const int len = (int)(row_ptr[fv[a] + 1] - base);
+      for (int b = 0; b < D; ++b) {
+        int p = row_find(col_idx + base, 0, len, fv[b]);
+        atomicAdd(vals + base + p, w * (a == b ? 2.0 : 1.0));
+      }
+    }
+  }
+}
+
+template <int D>
+__global__ void k_facet_area(int64_t nf, const int32_t* __restrict__ fverts, const double* __restrict__ xyz,
+                             double* __restrict__ partials) {
+  __shared__ double sm[32];
+  double s = 0.0;
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+    double n[3], x0[3];
+    s += facet_geom<D>(xyz, fverts + f * D, n, x0);
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------ Dirichlet
+__global__ void k_bc_scatter(int64_t nbc, const int64_t* __restrict__ dofs, const double* __restrict__ g,
+                             uint8_t* __restrict__ flag, double* __restrict__ val, double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nbc; i += (int64_t)gridDim.x * blockDim.x) {
+    flag[dofs[i]] = 1;
+    val[dofs[i]] = g[i];
+    if (x) x[dofs[i]] = g[i];
+  }
+}
+
+// one thread per scalar row (R = block row, i = component)
+template <int BS>
+__global__ void k_dirichlet(int64_t nrows, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                            double* __restrict__ vals, const uint8_t* __restrict__ flag, const double* __restrict__ gval,
+                            double* __restrict__ b, int symmetric) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t R = r / BS;
+    const int i = (int)(r % BS);
+    const int64_t k0 = row_ptr[R], k1 = row_ptr[R + 1];
+    if (flag[r]) {
+      for (int64_t k = k0; k < k1; ++k) {
+        const int64_t C = col_idx[k];
+        for (int j = 0; j < BS; ++j) vals[k * BS * BS + i * BS + j] = (C * BS + j == r) ? 1.0 : 0.0;
+      }
+      b[r] = gval[r];
+    } else if (symmetric) {
+      double corr = 0.0;
+      for (int64_t k = k0; k < k1; ++k) {
+        const int64_t C = col_idx[k];
+        for (int j = 0; j < BS; ++j)
+          if (flag[C * BS + j]) {
+            double* p = vals + k * BS * BS + i * BS + j;
+            corr += *p * gval[C * BS + j];
+            *p = 0.0;
+          }
+      }
+      if (corr != 0.0) b[r] -= corr;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ ABI
+static void fill_form(ScalarForm& f, int D, double kscale, const double* ktensor, double mass, double adv, const double* vel) {
+  memset(&f, 0, sizeof(f));
+  f.kscale = kscale; f.mass = mass; f.adv = adv;
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) f.K[i * D + j] = ktensor ? ktensor[i * D + j] : (i == j ? 1.0 : 0.0);
+  if (vel) for (int i = 0; i < D; ++i) f.vel[i] = vel[i];
+}
+
+extern "C" int fsb_assemble_scalar(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor, double mass,
+                                   double adv, const double* vel) {
+  if (!mesh || !A) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (A->bs != 1 || A->nbrows != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "matrix does not belong to a scalar P1 space on this mesh");
+  if (adv != 0.0 && !vel) FSB_FAIL(ctx, FSB_ERR_ARG, "advection needs a velocity");
+  ScalarForm f;
+  fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
+  const uint8_t* pm = (ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3)
+    k_scalar_form<3, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, f, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);
+  else
+    k_scalar_form<2, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, f, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+extern "C" int fsb_apply_scalar(fsb_mesh* mesh, fsb_vec* x, fsb_vec* y, double kscale, const double* ktensor, double mass,
+                                double adv, const double* vel) {
+  if (!mesh || !x || !y) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (x->n != mesh->nverts || y->n != mesh->nverts || x == y) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the mesh");
+  ScalarForm f;
+  fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3)
+    k_scalar_form<3, true><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, f, nullptr, nullptr, nullptr, nullptr, x->d, y->d);
+  else
+    k_scalar_form<2, true><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, f, nullptr, nullptr, nullptr, nullptr, x->d, y->d);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_elasticity(fsb_mesh* mesh, fsb_mat* A, double mu, double lambda) {
+  if (!mesh || !A) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (A->bs != mesh->tdim || A->nbrows != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "elasticity needs a matrix with ncomp == dim on this mesh");
+  const uint8_t* pm = (ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3)
+    k_elasticity<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, mu, lambda, A->row_ptr, A->col_idx, A->vals, pm);
+  else
+    k_elasticity<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, mu, lambda, A->row_ptr, A->col_idx, A->vals, pm);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_source(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, const double* S, double scale,
+                                   const int32_t* cell_tags, int32_t tag) {
+  if (!mesh || !b || !S) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nverts * ncomp) FSB_FAIL(ctx, FSB_ERR_ARG, "rhs size does not match mesh*ncomp");
+  Vec3 s{{0, 0, 0}};
+  for (int k = 0; k < ncomp; ++k) s.v[k] = S[k];
+  int32_t* d_tags = nullptr;
+  if (cell_tags) {
+    int rc = fsb_dmalloc(ctx, &d_tags, (size_t)mesh->ncells);
+    if (rc) return rc;
+    FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tags, cell_tags, sizeof(int32_t) * mesh->ncells, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3)
+    k_source_const<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, ncomp, s, scale, d_tags, tag, b->d);
+  else
+    k_source_const<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, ncomp, s, scale, d_tags, tag, b->d);
+  FSB_LAUNCH_CHECK(ctx);
+  if (d_tags) {
+    FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_tags);
+  }
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_source_nodal(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, fsb_vec* S, double scale) {
+  if (!mesh || !b || !S) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nverts * ncomp || S->n != b->n) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match mesh*ncomp");
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3)
+    k_source_nodal<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, ncomp, S->d, scale, b->d);
+  else
+    k_source_nodal<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, ncomp, S->d, scale, b->d);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+// facets arrive as host arrays; they are small (boundary only) so a temporary upload per call is fine
+struct FacetUpload {
+  int32_t* fverts = nullptr;
+  int32_t* opp = nullptr;
+  ~FacetUpload() { cudaFree(fverts); cudaFree(opp); }
+};
+
+static int upload_facets(fsb_mesh* mesh, int64_t nf, const int32_t* fverts, const int32_t* opp, FacetUpload& up) {
+  fsb_ctx* ctx = mesh->ctx;
+  int rc = fsb_dmalloc(ctx, &up.fverts, (size_t)nf * mesh->tdim);
+  if (rc) return rc;
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(up.fverts, fverts, sizeof(int32_t) * nf * mesh->tdim, cudaMemcpyHostToDevice, ctx->stream));
+  if (opp) {
+    rc = fsb_dmalloc(ctx, &up.opp, (size_t)nf);
+    if (rc) return rc;
+    FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(up.opp, opp, sizeof(int32_t) * nf, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_facet_load(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, int64_t nf, const int32_t* fverts,
+                                       const int32_t* opp, int32_t mode, const double* g, double scale) {
+  if (!mesh || !b || !g || (nf > 0 && !fverts)) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nverts * ncomp) FSB_FAIL(ctx, FSB_ERR_ARG, "rhs size does not match mesh*ncomp");
+  if (mode == 1 && (!opp || ncomp != mesh->tdim)) FSB_FAIL(ctx, FSB_ERR_ARG, "normal loads need opposite vertices and ncomp == dim");
+  if (nf == 0) return FSB_OK;
+  FacetUpload up;
+  int rc = upload_facets(mesh, nf, fverts, opp, up);
+  if (rc) return rc;
+  Vec3 gv{{0, 0, 0}};
+  for (int k = 0; k < (mode == 1 ? 1 : ncomp); ++k) gv.v[k] = g[k];
+  const unsigned grid = fsb_grid(nf, 128, (int64_t)ctx->sm_count * 16);
+  if (mesh->tdim == 3)
+    k_facet_load<3><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, up.opp, mesh->xyz, ncomp, mode, gv, scale, b->d);
+  else
+    k_facet_load<2><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, up.opp, mesh->xyz, ncomp, mode, gv, scale, b->d);
+  FSB_LAUNCH_CHECK(ctx);
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, const int32_t* fverts, double h) {
+  if (!mesh || !A || (nf > 0 && !fverts)) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (A->bs != 1 || A->nbrows != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "facet mass needs the scalar matrix of this mesh");
+  if (nf == 0) return FSB_OK;
+  FacetUpload up;
+  int rc = upload_facets(mesh, nf, fverts, nullptr, up);
+  if (rc) return rc;
+  const unsigned grid = fsb_grid(nf, 128, (int64_t)ctx->sm_count * 16);
+  if (mesh->tdim == 3)
+    k_facet_mass<3><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, h, A->row_ptr, A->col_idx, A->vals);
+  else
+    k_facet_mass<2><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, h, A->row_ptr, A->col_idx, A->vals);
+  FSB_LAUNCH_CHECK(ctx);
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}
+
+extern "C" int fsb_facet_area(fsb_mesh* mesh, int64_t nf, const int32_t* fverts, double* area) {
+  if (!mesh || !area || (nf > 0 && !fverts)) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  *area = 0.0;
+  if (nf == 0) return FSB_OK;
+  FacetUpload up;
+  int rc = upload_facets(mesh, nf, fverts, nullptr, up);
+  if (rc) return rc;
+  const unsigned grid = fsb_grid(nf, 256, 256);
+  if (mesh->tdim == 3)
+    k_facet_area<3><<<grid, 256, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, ctx->d_partials);
+  else
+    k_facet_area<2><<<grid, 256, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, ctx->d_partials);
+  FSB_LAUNCH_CHECK(ctx);
+  std::vector<double> part(grid);
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(part.data(), ctx->d_partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double s = 0.0;
+  for (double p : part) s += p;
+  *area = s;
+  return FSB_OK;
+}
+
+extern "C" int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t nbc, const int64_t* dofs,
+                                   const double* vals, int32_t symmetric) {
+  if (!A || !b || (nbc > 0 && (!dofs || !vals))) return FSB_ERR_ARG;
+  fsb_ctx* ctx = A->ctx;
+  const int64_t n = A->nbrows * A->bs;
+  if (b->n != n || (x && x->n != n)) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the matrix");
+  for (int64_t i = 0; i < nbc; ++i)
+    if (dofs[i] < 0 || dofs[i] >= n) FSB_FAIL(ctx, FSB_ERR_ARG, "Dirichlet dof out of range");
+  if (nbc == 0) return FSB_OK;
+  if (!A->bc_flag) {
+    int rc = fsb_dmalloc(ctx, &A->bc_flag, (size_t)n);
+    if (!rc) rc = fsb_dmalloc(ctx, &A->bc_val, (size_t)n);
+    if (rc) return rc;
+  }
+  FSB_CHECK_CUDA(ctx, cudaMemsetAsync(A->bc_flag, 0, (size_t)n, ctx->stream));
+  int64_t* d_dofs = nullptr;
+  double* d_vals = nullptr;
+  int rc = fsb_dmalloc(ctx, &d_dofs, (size_t)nbc);
+  if (!rc) rc = fsb_dmalloc(ctx, &d_vals, (size_t)nbc);
+  if (rc) { cudaFree(d_dofs); return rc; }
+  cudaMemcpyAsync(d_dofs, dofs, sizeof(int64_t) * nbc, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d_vals, vals, sizeof(double) * nbc, cudaMemcpyHostToDevice, ctx->stream);
+  k_bc_scatter<<<fsb_grid(nbc, 256, 4096), 256, 0, ctx->stream>>>(nbc, d_dofs, d_vals, A->bc_flag, A->bc_val, x ? x->d : nullptr);
+  ctx->launches++;
+  const unsigned grid = fsb_grid(n, 256, (int64_t)ctx->sm_count * 32);
+  if (A->bs == 1) k_dirichlet<1><<<grid, 256, 0, ctx->stream>>>(n, A->row_ptr, A->col_idx, A->vals, A->bc_flag, A->bc_val, b->d, symmetric);
+  else if (A->bs == 2) k_dirichlet<2><<<grid, 256, 0, ctx->stream>>>(n, A->row_ptr, A->col_idx, A->vals, A->bc_flag, A->bc_val, b->d, symmetric);
+  else k_dirichlet<3><<<grid, 256, 0, ctx->stream>>>(n, A->row_ptr, A->col_idx, A->vals, A->bc_flag, A->bc_val, b->d, symmetric);
+  ctx->launches++;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_dofs);
+  cudaFree(d_vals);
+  FSB_CHECK_CUDA(ctx, e);
+  FSB_CHECK_CUDA(ctx, cudaGetLastError());
+  return FSB_OK;
+}

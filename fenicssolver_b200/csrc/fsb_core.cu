@@ -1,0 +1,272 @@
+// Context, vectors and meshes (upload + on-device dolfin-layout box generator).
+#include "fsb_internal.cuh"
+
+// ------------------------------------------------------------------------------------ context
+extern "C" int fsb_init(int device, void* stream, fsb_ctx** out) {
+  if (!out) return FSB_ERR_ARG;
+  *out = nullptr;
+  fsb_ctx* ctx = new fsb_ctx();
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    // no context to carry the message: report on stderr, the Python host raises SolverError
+    fprintf(stderr, "libfsb: cudaSetDevice(%d) failed: %s\n", device, cudaGetErrorString(e));
+    delete ctx;
+    return FSB_ERR_CUDA;
+  }
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return FSB_ERR_CUDA; }
+    ctx->own_stream = true;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaMalloc((void**)&ctx->d_partials, sizeof(double) * kMaxPartials * 4) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->d_scalars, sizeof(double) * 64) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->d_counters, sizeof(unsigned) * 16) == cudaSuccess &&
+            cudaMalloc((void**)&ctx->d_state, sizeof(int) * 8) == cudaSuccess &&
+            cudaMallocHost((void**)&ctx->h_state, sizeof(int) * 16) == cudaSuccess &&
+            cudaMallocHost((void**)&ctx->h_pinned, sizeof(double) * 64) == cudaSuccess;
+  if (!ok) { fsb_destroy(ctx); return FSB_ERR_NOMEM; }
+  cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 16, ctx->stream);
+  cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 64, ctx->stream);
+  cudaMemsetAsync(ctx->d_state, 0, sizeof(int) * 8, ctx->stream);
+  *out = ctx;
+  return FSB_OK;
+}
+
+extern "C" void fsb_destroy(fsb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  fsb_dist_destroy(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_scalars);
+  cudaFree(ctx->d_counters);
+  cudaFree(ctx->d_state);
+  cudaFreeHost(ctx->h_state);
+  cudaFreeHost(ctx->h_pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* fsb_last_error(fsb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int fsb_sync(fsb_ctx* ctx) {
+  if (!ctx) return FSB_ERR_ARG;
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}
+
+extern "C" int fsb_device_info(fsb_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes) {
+  if (!ctx) return FSB_ERR_ARG;
+  size_t f = 0, t = 0;
+  FSB_CHECK_CUDA(ctx, cudaMemGetInfo(&f, &t));
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return FSB_OK;
+}
+
+extern "C" int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return FSB_ERR_ARG;
+  std::string s(name);
+  if (s == "asm_mode") ctx->asm_mode = (int)value;
+  else if (s == "spmv_mode") ctx->spmv_mode = (int)value;
+  else if (s == "profile") ctx->profile = (int)value;
+  else if (s == "graph") ctx->use_graph = (int)value;
+  else if (s == "check_every") ctx->check_every = value < 1 ? 1 : (int)value;
+  else FSB_FAIL(ctx, FSB_ERR_ARG, "unknown option " + s);
+  return FSB_OK;
+}
+
+extern "C" int64_t fsb_launch_count(fsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------ vectors
+__global__ void k_fill(double* __restrict__ p, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_axpy(double* __restrict__ y, double a, const double* __restrict__ x, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+
+extern "C" int fsb_vec_create(fsb_ctx* ctx, int64_t n, fsb_vec** out) {
+  if (!ctx || !out || n < 0) return FSB_ERR_ARG;
+  fsb_vec* v = new fsb_vec{ctx, n, nullptr};
+  int rc = fsb_dmalloc(ctx, &v->d, (size_t)n);
+  if (rc) { delete v; return rc; }
+  FSB_CHECK_CUDA(ctx, cudaMemsetAsync(v->d, 0, sizeof(double) * n + 64, ctx->stream));
+  *out = v;
+  return FSB_OK;
+}
+extern "C" int fsb_vec_fill(fsb_vec* v, double value) {
+  if (!v) return FSB_ERR_ARG;
+  if (v->n == 0) return FSB_OK;
+  k_fill<<<fsb_grid(v->n, 256, 148 * 16), 256, 0, v->ctx->stream>>>(v->d, v->n, value);
+  FSB_LAUNCH_CHECK(v->ctx);
+  return FSB_OK;
+}
+extern "C" int fsb_vec_upload(fsb_vec* v, const double* host, int64_t n) {
+  if (!v || !host || n != v->n) return FSB_ERR_ARG;
+  FSB_CHECK_CUDA(v->ctx, cudaMemcpyAsync(v->d, host, sizeof(double) * n, cudaMemcpyHostToDevice, v->ctx->stream));
+  FSB_CHECK_CUDA(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+  return FSB_OK;
+}
+extern "C" int fsb_vec_download(fsb_vec* v, double* host, int64_t n) {
+  if (!v || !host || n != v->n) return FSB_ERR_ARG;
+  FSB_CHECK_CUDA(v->ctx, cudaMemcpyAsync(host, v->d, sizeof(double) * n, cudaMemcpyDeviceToHost, v->ctx->stream));
+  FSB_CHECK_CUDA(v->ctx, cudaStreamSynchronize(v->ctx->stream));
+  return FSB_OK;
+}
+extern "C" int fsb_vec_copy(fsb_vec* dst, fsb_vec* src) {
+  if (!dst || !src || dst->n != src->n) return FSB_ERR_ARG;
+  FSB_CHECK_CUDA(dst->ctx, cudaMemcpyAsync(dst->d, src->d, sizeof(double) * src->n, cudaMemcpyDeviceToDevice, dst->ctx->stream));
+  return FSB_OK;
+}
+extern "C" int fsb_vec_axpy(fsb_vec* y, double a, fsb_vec* x) {
+  if (!y || !x || y->n != x->n) return FSB_ERR_ARG;
+  if (y->n == 0) return FSB_OK;
+  k_axpy<<<fsb_grid(y->n, 256, 148 * 16), 256, 0, y->ctx->stream>>>(y->d, a, x->d, y->n);
+  FSB_LAUNCH_CHECK(y->ctx);
+  return FSB_OK;
+}
+extern "C" int fsb_vec_size(fsb_vec* v, int64_t* n) {
+  if (!v || !n) return FSB_ERR_ARG;
+  *n = v->n;
+  return FSB_OK;
+}
+extern "C" void* fsb_vec_ptr(fsb_vec* v) { return v ? (void*)v->d : nullptr; }
+extern "C" void fsb_vec_destroy(fsb_vec* v) {
+  if (!v) return;
+  cudaFree(v->d);
+  delete v;
+}
+
+// ------------------------------------------------------------------------------------ meshes
+extern "C" int fsb_mesh_upload(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz,
+                               int64_t ncells, const int32_t* cells, fsb_mesh** out) {
+  if (!ctx || !out || !xyz || !cells) return FSB_ERR_ARG;
+  if (gdim != tdim || (tdim != 2 && tdim != 3)) FSB_FAIL(ctx, FSB_ERR_ARG, "only gdim==tdim in {2,3} is supported");
+  if (nverts <= 0 || ncells <= 0 || nverts > 0x7fffffffll) FSB_FAIL(ctx, FSB_ERR_ARG, "bad mesh sizes");
+  fsb_mesh* m = new fsb_mesh{ctx, gdim, tdim, nverts, ncells};
+  int rc = fsb_dmalloc(ctx, &m->xyz, (size_t)nverts * gdim);
+  if (!rc) rc = fsb_dmalloc(ctx, &m->cells, (size_t)ncells * (tdim + 1));
+  if (rc) { fsb_mesh_destroy(m); return rc; }
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->xyz, xyz, sizeof(double) * nverts * gdim, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->cells, cells, sizeof(int32_t) * ncells * (tdim + 1), cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = m;
+  return FSB_OK;
+}
+
+// vertex id = ix + iy*(nx+1) (+ iz*(nx+1)(ny+1)); x = p0 + ix*(p1-p0)/n evaluated in that operation
+// order without contraction so the coordinates are bit-identical to the numpy oracle.
+template <int D>
+__global__ void k_box_coords(double* __restrict__ xyz, int64_t nverts, int nx, int ny, int nz, int layer0,
+                             double x0, double y0, double z0, double x1, double y1, double z1) {
+  const int64_t px = nx + 1, py = px * (ny + 1);
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nverts; v += (int64_t)gridDim.x * blockDim.x) {
+    if (D == 2) {
+      int64_t iy = v / px + layer0, ix = v % px;
+      xyz[2 * v + 0] = __dadd_rn(x0, __ddiv_rn(__dmul_rn((double)ix, __dsub_rn(x1, x0)), (double)nx));
+      xyz[2 * v + 1] = __dadd_rn(y0, __ddiv_rn(__dmul_rn((double)iy, __dsub_rn(y1, y0)), (double)ny));
+    } else {
+      int64_t iz = v / py + layer0, rem = v % py, iy = rem / px, ix = rem % px;
+      xyz[3 * v + 0] = __dadd_rn(x0, __ddiv_rn(__dmul_rn((double)ix, __dsub_rn(x1, x0)), (double)nx));
+      xyz[3 * v + 1] = __dadd_rn(y0, __ddiv_rn(__dmul_rn((double)iy, __dsub_rn(y1, y0)), (double)ny));
+      xyz[3 * v + 2] = __dadd_rn(z0, __ddiv_rn(__dmul_rn((double)iz, __dsub_rn(z1, z0)), (double)nz));
+    }
+  }
+}
+
+// six tets per hex sharing the v0-v7 diagonal (dolfin BoxMesh), written already sorted:
+// (0,1,3,7) (0,1,5,7) (0,4,5,7) (0,2,3,7) (0,4,6,7) (0,2,6,7) in local hex-corner numbering.
+__global__ void k_box_cells3(int4* __restrict__ cells, int64_t nhex, int nx, int ny) {
+  const int64_t px = nx + 1, py = px * (ny + 1);
+  for (int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; h < nhex; h += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cz = h / ((int64_t)nx * ny), rem = h % ((int64_t)nx * ny), cy = rem / nx, cx = rem % nx;
+    int v0 = (int)(cx + cy * px + cz * py);
+    int c[8] = {v0, v0 + 1, v0 + (int)px, v0 + (int)px + 1, v0 + (int)py, v0 + (int)py + 1, v0 + (int)(py + px), v0 + (int)(py + px) + 1};
+    int4* o = cells + 6 * h;
+    o[0] = make_int4(c[0], c[1], c[3], c[7]);
+    o[1] = make_int4(c[0], c[1], c[5], c[7]);
+    o[2] = make_int4(c[0], c[4], c[5], c[7]);
+    o[3] = make_int4(c[0], c[2], c[3], c[7]);
+    o[4] = make_int4(c[0], c[4], c[6], c[7]);
+    o[5] = make_int4(c[0], c[2], c[6], c[7]);
+  }
+}
+
+// RectangleMesh diagonal "right": (v0,v1,v3), (v0,v2,v3)
+__global__ void k_box_cells2(int32_t* __restrict__ cells, int64_t nquad, int nx) {
+  const int64_t px = nx + 1;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nquad; q += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cy = q / nx, cx = q % nx;
+    int v0 = (int)(cy * px + cx), v1 = v0 + 1, v2 = v0 + (int)px, v3 = v2 + 1;
+    int32_t* o = cells + 6 * q;
+    o[0] = v0; o[1] = v1; o[2] = v3;
+    o[3] = v0; o[4] = v2; o[5] = v3;
+  }
+}
+
+extern "C" int fsb_mesh_box(fsb_ctx* ctx, int32_t tdim, const int32_t* n, const double* p0, const double* p1,
+                            int32_t layer0, int32_t layer1, fsb_mesh** out) {
+  if (!ctx || !out || !n || !p0 || !p1) return FSB_ERR_ARG;
+  if (tdim != 2 && tdim != 3) FSB_FAIL(ctx, FSB_ERR_ARG, "tdim must be 2 or 3");
+  for (int i = 0; i < tdim; ++i)
+    if (n[i] < 1) FSB_FAIL(ctx, FSB_ERR_ARG, "box divisions must be >= 1");
+  const int nlast = n[tdim - 1];
+  if (layer0 < 0 || layer1 > nlast || layer0 >= layer1) FSB_FAIL(ctx, FSB_ERR_ARG, "bad layer range");
+  const int nx = n[0], ny = n[1], nz = tdim == 3 ? n[2] : 1;
+  const int64_t nl = layer1 - layer0;
+  int64_t plane = tdim == 3 ? (int64_t)(nx + 1) * (ny + 1) : (nx + 1);
+  int64_t nverts = plane * (nl + 1);
+  int64_t nbox = tdim == 3 ? (int64_t)nx * ny * nl : (int64_t)nx * nl;
+  int64_t ncells = tdim == 3 ? 6 * nbox : 2 * nbox;
+  if (nverts > 0x7fffffffll) FSB_FAIL(ctx, FSB_ERR_ARG, "mesh too large for int32 vertex ids");
+  fsb_mesh* m = new fsb_mesh{ctx, tdim, tdim, nverts, ncells};
+  int rc = fsb_dmalloc(ctx, &m->xyz, (size_t)nverts * tdim);
+  if (!rc) rc = fsb_dmalloc(ctx, &m->cells, (size_t)ncells * (tdim + 1));
+  if (rc) { fsb_mesh_destroy(m); return rc; }
+  const int cap = ctx->sm_count * 16;
+  if (tdim == 3) {
+    k_box_coords<3><<<fsb_grid(nverts, 256, cap), 256, 0, ctx->stream>>>(m->xyz, nverts, nx, ny, nz, layer0, p0[0], p0[1], p0[2], p1[0], p1[1], p1[2]);
+    FSB_LAUNCH_CHECK(ctx);
+    k_box_cells3<<<fsb_grid(nbox, 256, cap), 256, 0, ctx->stream>>>((int4*)m->cells, nbox, nx, ny);
+    FSB_LAUNCH_CHECK(ctx);
+  } else {
+    k_box_coords<2><<<fsb_grid(nverts, 256, cap), 256, 0, ctx->stream>>>(m->xyz, nverts, nx, ny, 1, layer0, p0[0], p0[1], 0.0, p1[0], p1[1], 0.0);
+    FSB_LAUNCH_CHECK(ctx);
+    k_box_cells2<<<fsb_grid(nbox, 256, cap), 256, 0, ctx->stream>>>(m->cells, nbox, nx);
+    FSB_LAUNCH_CHECK(ctx);
+  }
+  *out = m;
+  return FSB_OK;
+}
+
+extern "C" int fsb_mesh_sizes(fsb_mesh* m, int32_t* gdim, int32_t* tdim, int64_t* nverts, int64_t* ncells) {
+  if (!m) return FSB_ERR_ARG;
+  if (gdim) *gdim = m->gdim;
+  if (tdim) *tdim = m->tdim;
+  if (nverts) *nverts = m->nverts;
+  if (ncells) *ncells = m->ncells;
+  return FSB_OK;
+}
+
+extern "C" int fsb_mesh_download(fsb_mesh* m, double* xyz, int32_t* cells) {
+  if (!m) return FSB_ERR_ARG;
+  fsb_ctx* ctx = m->ctx;
+  if (xyz) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(xyz, m->xyz, sizeof(double) * m->nverts * m->gdim, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cells) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(cells, m->cells, sizeof(int32_t) * m->ncells * (m->tdim + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}
+
+extern "C" void fsb_mesh_destroy(fsb_mesh* m) {
+  if (!m) return;
+  cudaFree(m->xyz);
+  cudaFree(m->cells);
+  delete m;
+}

@@ -1,0 +1,175 @@
+// K8: z-slab distribution — ghost-plane halo exchange and scalar all-reduce over NCCL (NVLink/NVSwitch).
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2": inside a torch process this resolves to the copy
+// torch already loaded) so libfsb.so has no link-time dependency on it; only the handful of entry
+// points used here are declared.  Vectors on a distributed context are laid out in natural plane
+// order [ghost plane below | owned planes | ghost plane above]; the neighbours are rank-1 and rank+1.
+#include "fsb_internal.cuh"
+#include <dlfcn.h>
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[FSB_NCCL_UID_BYTES]; } ncclUniqueId_t;
+enum { kNcclSuccess = 0, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 };
+
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+
+static NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+#define LOAD(field, sym) *(void**)(&api.field) = dlsym(api.handle, sym); if (!api.field) return api
+  LOAD(GetUniqueId, "ncclGetUniqueId");
+  LOAD(CommInitRank, "ncclCommInitRank");
+  LOAD(CommDestroy, "ncclCommDestroy");
+  LOAD(AllReduce, "ncclAllReduce");
+  LOAD(Send, "ncclSend");
+  LOAD(Recv, "ncclRecv");
+  LOAD(GroupStart, "ncclGroupStart");
+  LOAD(GroupEnd, "ncclGroupEnd");
+  LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+  api.ok = true;
+  return api;
+}
+
+struct fsb_dist {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  int ghost_lo = 0, ghost_hi = 0;
+  int64_t owned_planes = 0;
+  bool slab_set = false;
+};
+
+#define FSB_CHECK_NCCL(ctx, call)                                                             \
+  do {                                                                                        \
+    int r__ = (call);                                                                         \
+    if (r__ != kNcclSuccess) {                                                                \
+      (ctx)->err = std::string(#call) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error"); \
+      return FSB_ERR_NCCL;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+extern "C" int fsb_dist_unique_id(void* uid128) {
+  if (!uid128) return FSB_ERR_ARG;
+  if (!nccl().ok) return FSB_ERR_NCCL;
+  ncclUniqueId_t id;
+  if (nccl().GetUniqueId(&id) != kNcclSuccess) return FSB_ERR_NCCL;
+  memcpy(uid128, &id, FSB_NCCL_UID_BYTES);
+  return FSB_OK;
+}
+
+extern "C" int fsb_dist_init(fsb_ctx* ctx, int32_t rank, int32_t nranks, const void* uid128) {
+  if (!ctx || !uid128 || nranks < 1 || rank < 0 || rank >= nranks) return FSB_ERR_ARG;
+  if (!nccl().ok) FSB_FAIL(ctx, FSB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  if (ctx->dist) FSB_FAIL(ctx, FSB_ERR_STATE, "context is already distributed");
+  fsb_dist* d = new fsb_dist();
+  d->rank = rank; d->nranks = nranks;
+  ncclUniqueId_t id;
+  memcpy(&id, uid128, FSB_NCCL_UID_BYTES);
+  FSB_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+  int r = nccl().CommInitRank(&d->comm, nranks, id, rank);
+  if (r != kNcclSuccess) {
+    ctx->err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(r);
+    delete d;
+    return FSB_ERR_NCCL;
+  }
+  ctx->dist = d;
+  return FSB_OK;
+}
+
+void fsb_dist_destroy(fsb_ctx* ctx) {
+  if (!ctx || !ctx->dist) return;
+  if (ctx->dist->comm && nccl().ok) nccl().CommDestroy(ctx->dist->comm);
+  delete ctx->dist;
+  ctx->dist = nullptr;
+}
+
+bool fsb_dist_active(fsb_ctx* ctx) { return ctx && ctx->dist && ctx->dist->nranks > 1; }
+
+extern "C" int fsb_dist_set_slab(fsb_ctx* ctx, int32_t ghost_lo, int32_t ghost_hi, int64_t owned_planes) {
+  if (!ctx) return FSB_ERR_ARG;
+  if (!ctx->dist) FSB_FAIL(ctx, FSB_ERR_STATE, "fsb_dist_init has not been called");
+  if (ghost_lo < 0 || ghost_lo > 1 || ghost_hi < 0 || ghost_hi > 1 || owned_planes < 1) FSB_FAIL(ctx, FSB_ERR_ARG, "bad slab description");
+  fsb_dist* d = ctx->dist;
+  if ((ghost_lo && d->rank == 0) || (ghost_hi && d->rank == d->nranks - 1)) FSB_FAIL(ctx, FSB_ERR_ARG, "ghost plane without a neighbour rank");
+  d->ghost_lo = ghost_lo; d->ghost_hi = ghost_hi; d->owned_planes = owned_planes; d->slab_set = true;
+  return FSB_OK;
+}
+
+void fsb_dist_owned_range(fsb_ctx* ctx, int64_t n, int64_t* o0, int64_t* o1) {
+  *o0 = 0; *o1 = n;
+  if (!fsb_dist_active(ctx) || !ctx->dist->slab_set) return;
+  fsb_dist* d = ctx->dist;
+  const int64_t planes = d->ghost_lo + d->owned_planes + d->ghost_hi;
+  const int64_t plane = n / planes;
+  *o0 = d->ghost_lo * plane;
+  *o1 = *o0 + d->owned_planes * plane;
+}
+
+// v has (ghost_lo + owned + ghost_hi) planes; the plane size follows from n
+static int halo(fsb_ctx* ctx, double* v, int64_t n) {
+  fsb_dist* d = ctx->dist;
+  if (!d->slab_set) FSB_FAIL(ctx, FSB_ERR_STATE, "fsb_dist_set_slab has not been called");
+  const int64_t planes = d->ghost_lo + d->owned_planes + d->ghost_hi;
+  if (n % planes) FSB_FAIL(ctx, FSB_ERR_ARG, "vector length is not a whole number of planes");
+  const size_t plane = (size_t)(n / planes);
+  if (!d->ghost_lo && !d->ghost_hi) return FSB_OK;
+  FSB_CHECK_NCCL(ctx, nccl().GroupStart());
+  if (d->ghost_lo) {
+    FSB_CHECK_NCCL(ctx, nccl().Recv(v, plane, kNcclFloat64, d->rank - 1, d->comm, ctx->stream));
+    FSB_CHECK_NCCL(ctx, nccl().Send(v + plane * d->ghost_lo, plane, kNcclFloat64, d->rank - 1, d->comm, ctx->stream));
+  }
+  if (d->ghost_hi) {
+    FSB_CHECK_NCCL(ctx, nccl().Send(v + plane * (d->ghost_lo + d->owned_planes - 1), plane, kNcclFloat64, d->rank + 1, d->comm, ctx->stream));
+    FSB_CHECK_NCCL(ctx, nccl().Recv(v + plane * (d->ghost_lo + d->owned_planes), plane, kNcclFloat64, d->rank + 1, d->comm, ctx->stream));
+  }
+  FSB_CHECK_NCCL(ctx, nccl().GroupEnd());
+  return FSB_OK;
+}
+
+int fsb_dist_halo_raw(fsb_ctx* ctx, double* v, int64_t n) {
+  if (!fsb_dist_active(ctx)) return FSB_OK;
+  return halo(ctx, v, n);
+}
+
+extern "C" int fsb_dist_halo(fsb_vec* v) {
+  if (!v) return FSB_ERR_ARG;
+  if (!fsb_dist_active(v->ctx)) return FSB_OK;
+  return halo(v->ctx, v->d, v->n);
+}
+
+int fsb_dist_allreduce_sum_dev(fsb_ctx* ctx, double* d_vals, int count) {
+  if (!fsb_dist_active(ctx)) return FSB_OK;
+  FSB_CHECK_NCCL(ctx, nccl().AllReduce(d_vals, d_vals, (size_t)count, kNcclFloat64, kNcclSum, ctx->dist->comm, ctx->stream));
+  return FSB_OK;
+}
+
+extern "C" int fsb_dist_allreduce_max(fsb_ctx* ctx, double* value) {
+  if (!ctx || !value) return FSB_ERR_ARG;
+  if (!fsb_dist_active(ctx)) return FSB_OK;
+  double* d = ctx->d_scalars + 40;
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d, value, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_NCCL(ctx, nccl().AllReduce(d, d, 1, kNcclFloat64, kNcclMax, ctx->dist->comm, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(value, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}

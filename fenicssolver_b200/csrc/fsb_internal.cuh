@@ -1,0 +1,159 @@
+// Internal definitions shared by the libfsb translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fsb.h"
+
+struct fsb_dist;   // fsb_dist.cu
+
+struct fsb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string err;
+  int64_t launches = 0;
+  // options
+  int asm_mode = 1;      // 0 search+atomics, 1 position map + atomics
+  int spmv_mode = 0;     // 0 TMA-staged tiles, 1 plain row-per-thread
+  int profile = 0;
+  int use_graph = 1;
+  int check_every = 32;
+  // scratch for reductions: per-CTA partials + a few scalars, and a pinned host mirror
+  double* d_partials = nullptr;   // [kMaxPartials * 4]
+  double* d_scalars = nullptr;    // [64]
+  unsigned* d_counters = nullptr; // [16] last-block counters (self-resetting)
+  int* d_state = nullptr;         // [8] Krylov state: done, iterations, outcome
+  double* h_pinned = nullptr;     // [64]
+  int* h_state = nullptr;         // [16] pinned mirror of d_state (two polling slots)
+  fsb_dist* dist = nullptr;
+};
+
+static constexpr int kMaxPartials = 4096;
+
+struct fsb_mesh {
+  fsb_ctx* ctx;
+  int gdim, tdim;
+  int64_t nverts, ncells;
+  double* xyz = nullptr;     // [nverts][gdim]
+  int32_t* cells = nullptr;  // [ncells][tdim+1] sorted per cell
+};
+
+struct fsb_vec {
+  fsb_ctx* ctx;
+  int64_t n;
+  double* d = nullptr;
+};
+
+struct fsb_mat {
+  fsb_ctx* ctx;
+  fsb_mesh* mesh = nullptr;    // pattern source (may be null for from_csr)
+  int bs = 1;                  // block size (ncomp)
+  int64_t nbrows = 0;          // block rows
+  int64_t nnzb = 0;            // blocks
+  int64_t* row_ptr = nullptr;  // [nbrows+1]
+  int32_t* col_idx = nullptr;  // [nnzb] (+pad)
+  double* vals = nullptr;      // [nnzb][bs][bs] (+pad)
+  uint8_t* posmap = nullptr;   // [ncells][(tdim+1)^2] in-row offsets, or null
+  int max_row_len = 0;
+  int64_t own0 = 0, own1 = 0;  // owned block rows
+  // SpMV tiling (TMA-staged): tiles of ~tile_nnz blocks snapped to row boundaries
+  int tile_nnz = 0;
+  int64_t ntiles = 0;
+  int64_t* tile_row = nullptr; // [ntiles+1] first block row of each tile (within owned range)
+  int tile_cap = 0;            // smem capacity in blocks per stage
+  // dirichlet scratch
+  uint8_t* bc_flag = nullptr;  // [nbrows*bs]
+  double* bc_val = nullptr;
+};
+
+#define FSB_CHECK_CUDA(ctx, call)                                                         \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                   ":" + std::to_string(__LINE__) + ")";                                  \
+      return e__ == cudaErrorMemoryAllocation ? FSB_ERR_NOMEM : FSB_ERR_CUDA;             \
+    }                                                                                     \
+  } while (0)
+
+#define FSB_FAIL(ctx, code, msg) \
+  do {                           \
+    (ctx)->err = (msg);          \
+    return (code);               \
+  } while (0)
+
+#define FSB_LAUNCH_CHECK(ctx)                   \
+  do {                                          \
+    (ctx)->launches++;                          \
+    FSB_CHECK_CUDA(ctx, cudaGetLastError());    \
+  } while (0)
+
+template <typename T>
+static inline int fsb_dmalloc(fsb_ctx* ctx, T** p, size_t count, size_t pad_bytes = 512) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + pad_bytes);   // pad: TMA tiles may over-read a few entries
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) + " bytes: " + cudaGetErrorString(e);
+    *p = nullptr;
+    cudaGetLastError();
+    return FSB_ERR_NOMEM;
+  }
+  *p = (T*)q;
+  return FSB_OK;
+}
+
+static inline unsigned fsb_grid(int64_t n, int block, int64_t cap = (1ll << 31) - 1) {
+  int64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (unsigned)g;
+}
+
+// device-wide exclusive scan int32 -> int64 (out has n+1 entries, out[n] = total)   [fsb_pattern.cu]
+int fsb_exclusive_scan(fsb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
+// SpMV tiling setup after row_ptr / owned range are known   [fsb_solve.cu]
+int fsb_mat_setup_tiles(fsb_mat* A);
+// distributed hooks [fsb_dist.cu]
+bool fsb_dist_active(fsb_ctx* ctx);
+int fsb_dist_halo_raw(fsb_ctx* ctx, double* v, int64_t n);
+int fsb_dist_allreduce_sum_dev(fsb_ctx* ctx, double* d_vals, int count);
+void fsb_dist_owned_range(fsb_ctx* ctx, int64_t n, int64_t* o0, int64_t* o1);
+void fsb_dist_destroy(fsb_ctx* ctx);
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum, result valid in thread 0 (deterministic order). smem: >= 32 doubles
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  return v;
+}
+
+// in-row search: position of `col` in the sorted list cols[0..len), starting the search at lo
+__device__ __forceinline__ int row_find(const int32_t* __restrict__ cols, int lo, int len, int32_t col) {
+  int hi = len;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(cols + mid) < col) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+#endif

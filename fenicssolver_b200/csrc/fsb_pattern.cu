@@ -1,0 +1,397 @@
+// K2: DofMap + sparsity pattern on the device (dolfin SparsityPatternBuilder equivalent).
+//
+// vertex->cell adjacency (count, scan, fill) then one warp per row: the candidate columns are the
+// vertices of the incident cells; duplicates are removed and the survivors ranked inside the warp, so
+// row_ptr/col_idx come out sorted without any global sort.  A per-cell position map (uint8 offset of
+// each local (a,b) entry inside row a) is emitted for the numeric phase.
+#include "fsb_internal.cuh"
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------ scan
+static constexpr int kScanThreads = 512;
+static constexpr int kScanItems = 8;   // per thread
+static constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void k_scan_block_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ bsum) {
+  __shared__ long long smi[32];
+  int64_t base = (int64_t)blockIdx.x * kScanTile;
+  long long s = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + (int64_t)k * kScanThreads + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) smi[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    long long t = threadIdx.x < (kScanThreads >> 5) ? smi[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of the block sums in place
+__global__ void k_scan_spine(int64_t* __restrict__ bsum, int64_t nb) {
+  __shared__ long long smi[32];
+  __shared__ long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nb; base += blockDim.x) {
+    int64_t i = base + threadIdx.x;
+    long long v = i < nb ? bsum[i] : 0, incl = v;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) smi[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      long long t = lane < (int)(blockDim.x >> 5) ? smi[lane] : 0, ti = t;
+      for (int o = 1; o < 32; o <<= 1) {
+        long long u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
+      }
+      smi[lane] = ti - t;   // exclusive warp offsets
+    }
+    __syncthreads();
+    long long carry = carry_s;
+    if (i < nb) bsum[i] = carry + smi[w] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = carry + smi[w] + incl;
+    __syncthreads();
+  }
+}
+
+__global__ void k_scan_apply(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ bsum,
+                             int64_t* __restrict__ out) {
+  // items are laid out thread-major inside the tile so that each thread scans kScanItems consecutive values
+  __shared__ long long smi[32];
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  long long v[kScanItems], s = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    v[k] = i < n ? in[i] : 0;
+    s += v[k];
+  }
+  long long incl = s;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) smi[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    long long t = lane < (kScanThreads >> 5) ? smi[lane] : 0, ti = t;
+    for (int o = 1; o < 32; o <<= 1) {
+      long long u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    smi[lane] = ti - t;
+  }
+  __syncthreads();
+  long long run = bsum[blockIdx.x] + smi[w] + incl - s;
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    if (i < n) out[i] = run;
+    run += v[k];
+    if (i == n - 1) out[n] = run;
+  }
+}
+
+int fsb_exclusive_scan(fsb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n) {
+  if (n <= 0) {
+    int64_t z = 0;
+    FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(out, &z, sizeof(z), cudaMemcpyHostToDevice, ctx->stream));
+    FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FSB_OK;
+  }
+  int64_t nb = (n + kScanTile - 1) / kScanTile;
+  int64_t* bsum = nullptr;
+  int rc = fsb_dmalloc(ctx, &bsum, (size_t)nb);
+  if (rc) return rc;
+  // block sums use a strided read, the apply pass a thread-major read; both cover the same tile
+  k_scan_block_sums<<<(unsigned)nb, kScanThreads, 0, ctx->stream>>>(in, n, bsum);
+  FSB_LAUNCH_CHECK(ctx);
+  k_scan_spine<<<1, 1024, 0, ctx->stream>>>(bsum, nb);
+  FSB_LAUNCH_CHECK(ctx);
+  k_scan_apply<<<(unsigned)nb, kScanThreads, 0, ctx->stream>>>(in, n, bsum, out);
+  FSB_LAUNCH_CHECK(ctx);
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(bsum);
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------ vertex -> cell adjacency
+__global__ void k_v2c_count(const int32_t* __restrict__ cells, int64_t nent, int32_t* __restrict__ deg) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nent; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(deg + cells[i], 1);
+}
+__global__ void k_v2c_fill(const int32_t* __restrict__ cells, int64_t ncells, int nl, const int64_t* __restrict__ vptr,
+                           int32_t* __restrict__ cursor, int32_t* __restrict__ v2c) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x)
+    for (int a = 0; a < nl; ++a) {
+      int v = cells[c * nl + a];
+      int slot = atomicAdd(cursor + v, 1);
+      v2c[vptr[v] + slot] = (int32_t)c;
+    }
+}
+
+// ------------------------------------------------------------------------------------ rows
+// One warp per row.  Candidates L[i] = cells[v2c[p0 + i/nl]][i%nl], i < m = deg*nl.  They are cached in
+// shared memory when m <= kRowCap, otherwise re-read from global (L1) on every access.
+static constexpr int kRowCap = 384;
+static constexpr int kRowWarps = 8;
+
+template <bool FILL>
+__global__ void __launch_bounds__(kRowWarps * 32)
+k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vptr, const int32_t* __restrict__ v2c,
+       int64_t nrows, int32_t* __restrict__ row_len, const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx) {
+  __shared__ int32_t s_cand[kRowWarps][kRowCap];
+  __shared__ uint8_t s_first[kRowWarps][kRowCap];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * kRowWarps + w; r < nrows; r += (int64_t)gridDim.x * kRowWarps) {
+    const int64_t p0 = vptr[r];
+    const int m = (int)(vptr[r + 1] - p0) * nl;
+    const bool cached = m <= kRowCap;
+    auto cand = [&](int i) -> int32_t {
+      return cached ? s_cand[w][i] : cells[(int64_t)v2c[p0 + i / nl] * nl + i % nl];
+    };
+    if (cached)
+      for (int i = lane; i < m; i += 32) s_cand[w][i] = cells[(int64_t)v2c[p0 + i / nl] * nl + i % nl];
+    __syncwarp();
+    // pass 1: first occurrences
+    int nfirst = 0;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+      int i = i0 + lane;
+      bool first = i < m;
+      int32_t v = first ? cand(i) : 0;
+      for (int j = 0; j < i0 + 32 && j < m; ++j) {
+        int32_t u = cand(j);
+        if (j < i && u == v) first = false;
+      }
+      if (cached && i < m) s_first[w][i] = first;
+      nfirst += __popc(__ballot_sync(0xffffffffu, first));
+      if (FILL && !cached) {
+        // uncached rows: rank directly (first flags recomputed on the fly below)
+        if (first) {
+          int pos = 0;
+          for (int j = 0; j < m; ++j) {
+            int32_t u = cand(j);
+            if (u < v) {
+              bool jf = true;
+              for (int k = 0; k < j; ++k) if (cand(k) == u) { jf = false; break; }
+              pos += jf;
+            }
+          }
+          col_idx[row_ptr[r] + pos] = v;
+        }
+      }
+    }
+    __syncwarp();
+    if (!FILL) {
+      if (lane == 0) row_len[r] = nfirst;
+    } else if (cached) {
+      // pass 2: rank of each first occurrence among the first occurrences
+      for (int i = lane; i < m; i += 32) {
+        if (!s_first[w][i]) continue;
+        int32_t v = s_cand[w][i];
+        int pos = 0;
+        for (int j = 0; j < m; ++j) pos += (s_first[w][j] && s_cand[w][j] < v);
+        col_idx[row_ptr[r] + pos] = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// position map: for cell c and local pair (a,b): offset of column cells[c][b] inside row cells[c][a]
+__global__ void k_posmap(const int32_t* __restrict__ cells, int64_t ncells, int nl, const int64_t* __restrict__ row_ptr,
+                         const int32_t* __restrict__ col_idx, uint8_t* __restrict__ posmap) {
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[4];
+    for (int a = 0; a < nl; ++a) v[a] = cells[c * nl + a];
+    for (int a = 0; a < nl; ++a) {
+      const int64_t base = row_ptr[v[a]];
+      const int len = (int)(row_ptr[v[a] + 1] - base);
+      int lo = 0;
+      for (int b = 0; b < nl; ++b) {
+        lo = row_find(col_idx + base, lo, len, v[b]);
+        posmap[c * nl * nl + a * nl + b] = (uint8_t)lo;
+        ++lo;
+      }
+    }
+  }
+}
+
+__global__ void k_max_i32(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+  int m = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, in[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// ------------------------------------------------------------------------------------ matrix objects
+extern "C" void fsb_mat_destroy(fsb_mat* A) {
+  if (!A) return;
+  cudaFree(A->row_ptr);
+  cudaFree(A->col_idx);
+  cudaFree(A->vals);
+  cudaFree(A->posmap);
+  cudaFree(A->tile_row);
+  cudaFree(A->bc_flag);
+  cudaFree(A->bc_val);
+  delete A;
+}
+
+extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
+  if (!mesh || !out) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (ncomp < 1 || ncomp > 3) FSB_FAIL(ctx, FSB_ERR_ARG, "ncomp must be 1..3");
+  const int nl = mesh->tdim + 1;
+  const int64_t nv = mesh->nverts, nc = mesh->ncells;
+  const int cap = ctx->sm_count * 16;
+  fsb_mat* A = new fsb_mat();
+  A->ctx = ctx; A->mesh = mesh; A->bs = ncomp; A->nbrows = nv; A->own0 = 0; A->own1 = nv;
+  int32_t *deg = nullptr, *v2c = nullptr, *d_max = nullptr;
+  int64_t* vptr = nullptr;
+  int rc = FSB_OK;
+  auto cleanup = [&]() { cudaFree(deg); cudaFree(v2c); cudaFree(vptr); cudaFree(d_max); };
+#define TRY(x) do { rc = (x); if (rc) { cleanup(); fsb_mat_destroy(A); return rc; } } while (0)
+#define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); fsb_mat_destroy(A); return FSB_ERR_CUDA; } } while (0)
+  TRY(fsb_dmalloc(ctx, &deg, (size_t)nv + 1));
+  TRY(fsb_dmalloc(ctx, &vptr, (size_t)nv + 1));
+  TRY(fsb_dmalloc(ctx, &v2c, (size_t)nc * nl));
+  TRY(fsb_dmalloc(ctx, &d_max, 1));
+  TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+  k_v2c_count<<<fsb_grid(nc * nl, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc * nl, deg);
+  ctx->launches++; TRYCUDA(cudaGetLastError());
+  TRY(fsb_exclusive_scan(ctx, deg, vptr, nv));
+  TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+  k_v2c_fill<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, nl, vptr, deg, v2c);
+  ctx->launches++; TRYCUDA(cudaGetLastError());
+  // row lengths -> row_ptr
+  TRY(fsb_dmalloc(ctx, &A->row_ptr, (size_t)nv + 1));
+  k_rows<false><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cells, nl, vptr, v2c, nv, deg, nullptr, nullptr);
+  ctx->launches++; TRYCUDA(cudaGetLastError());
+  TRYCUDA(cudaMemsetAsync(d_max, 0, sizeof(int32_t), ctx->stream));
+  k_max_i32<<<fsb_grid(nv, 256, cap), 256, 0, ctx->stream>>>(deg, nv, d_max);
+  ctx->launches++; TRYCUDA(cudaGetLastError());
+  TRY(fsb_exclusive_scan(ctx, deg, A->row_ptr, nv));
+  int64_t nnzb = 0;
+  int32_t maxlen = 0;
+  TRYCUDA(cudaMemcpyAsync(&nnzb, A->row_ptr + nv, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  TRYCUDA(cudaMemcpyAsync(&maxlen, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  TRYCUDA(cudaStreamSynchronize(ctx->stream));
+  A->nnzb = nnzb;
+  A->max_row_len = maxlen;
+  TRY(fsb_dmalloc(ctx, &A->col_idx, (size_t)nnzb));
+  k_rows<true><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cells, nl, vptr, v2c, nv, nullptr, A->row_ptr, A->col_idx);
+  ctx->launches++; TRYCUDA(cudaGetLastError());
+  TRYCUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(v2c); v2c = nullptr;
+  cudaFree(vptr); vptr = nullptr;
+  TRY(fsb_dmalloc(ctx, &A->vals, (size_t)nnzb * ncomp * ncomp));
+  TRYCUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * nnzb * ncomp * ncomp + 512, ctx->stream));
+  if (maxlen <= 256) {
+    TRY(fsb_dmalloc(ctx, &A->posmap, (size_t)nc * nl * nl));
+    k_posmap<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, nl, A->row_ptr, A->col_idx, A->posmap);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+  }
+  TRY(fsb_mat_setup_tiles(A));
+  TRYCUDA(cudaStreamSynchronize(ctx->stream));
+  cleanup();
+#undef TRY
+#undef TRYCUDA
+  *out = A;
+  return FSB_OK;
+}
+
+extern "C" int fsb_mat_from_csr(fsb_ctx* ctx, int64_t nrows, const int64_t* row_ptr, const int32_t* col_idx,
+                                const double* vals, fsb_mat** out) {
+  if (!ctx || !out || !row_ptr || !col_idx || !vals || nrows <= 0) return FSB_ERR_ARG;
+  fsb_mat* A = new fsb_mat();
+  A->ctx = ctx; A->bs = 1; A->nbrows = nrows; A->own0 = 0; A->own1 = nrows;
+  A->nnzb = row_ptr[nrows];
+  int maxlen = 0;
+  for (int64_t r = 0; r < nrows; ++r) maxlen = std::max<int64_t>(maxlen, row_ptr[r + 1] - row_ptr[r]);
+  A->max_row_len = maxlen;
+  int rc = fsb_dmalloc(ctx, &A->row_ptr, (size_t)nrows + 1);
+  if (!rc) rc = fsb_dmalloc(ctx, &A->col_idx, (size_t)A->nnzb);
+  if (!rc) rc = fsb_dmalloc(ctx, &A->vals, (size_t)A->nnzb);
+  if (rc) { fsb_mat_destroy(A); return rc; }
+  cudaMemsetAsync(A->col_idx + A->nnzb, 0, 512, ctx->stream);
+  cudaMemsetAsync(A->vals + A->nnzb, 0, 512, ctx->stream);
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(A->row_ptr, row_ptr, sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(A->col_idx, col_idx, sizeof(int32_t) * A->nnzb, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(A->vals, vals, sizeof(double) * A->nnzb, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  rc = fsb_mat_setup_tiles(A);
+  if (rc) { fsb_mat_destroy(A); return rc; }
+  *out = A;
+  return FSB_OK;
+}
+
+extern "C" int fsb_mat_sizes(fsb_mat* A, int64_t* nrows, int64_t* nnz, int32_t* bs, int64_t* nnzb) {
+  if (!A) return FSB_ERR_ARG;
+  if (nrows) *nrows = A->nbrows * A->bs;
+  if (nnz) *nnz = A->nnzb * A->bs * A->bs;
+  if (bs) *bs = A->bs;
+  if (nnzb) *nnzb = A->nnzb;
+  return FSB_OK;
+}
+
+extern "C" int fsb_mat_zero(fsb_mat* A) {
+  if (!A) return FSB_ERR_ARG;
+  FSB_CHECK_CUDA(A->ctx, cudaMemsetAsync(A->vals, 0, sizeof(double) * A->nnzb * A->bs * A->bs, A->ctx->stream));
+  return FSB_OK;
+}
+
+extern "C" int fsb_mat_set_owned_rows(fsb_mat* A, int64_t row0, int64_t row1) {
+  if (!A) return FSB_ERR_ARG;
+  if (row0 < 0 || row1 > A->nbrows || row0 > row1) FSB_FAIL(A->ctx, FSB_ERR_ARG, "bad owned row range");
+  A->own0 = row0; A->own1 = row1;
+  return fsb_mat_setup_tiles(A);
+}
+
+// scalar CSR view of the block matrix: scalar row bs*R+i holds, for each block (R,C) in order, the
+// columns bs*C+0..bs-1, so columns stay sorted.
+extern "C" int fsb_mat_download_csr(fsb_mat* A, int64_t* row_ptr, int32_t* col_idx, double* vals) {
+  if (!A) return FSB_ERR_ARG;
+  fsb_ctx* ctx = A->ctx;
+  const int bs = A->bs;
+  std::vector<int64_t> rp((size_t)A->nbrows + 1);
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(rp.data(), A->row_ptr, sizeof(int64_t) * (A->nbrows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (bs == 1) {
+    if (row_ptr) memcpy(row_ptr, rp.data(), sizeof(int64_t) * (A->nbrows + 1));
+    if (col_idx) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(col_idx, A->col_idx, sizeof(int32_t) * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vals) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(vals, A->vals, sizeof(double) * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+    FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FSB_OK;
+  }
+  std::vector<int32_t> ci((size_t)A->nnzb);
+  std::vector<double> bv;
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(ci.data(), A->col_idx, sizeof(int32_t) * A->nnzb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (vals) {
+    bv.resize((size_t)A->nnzb * bs * bs);
+    FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(bv.data(), A->vals, sizeof(double) * bv.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t R = 0; R < A->nbrows; ++R) {
+    const int64_t len = rp[R + 1] - rp[R];
+    for (int i = 0; i < bs; ++i) {
+      const int64_t srow = R * bs + i;
+      const int64_t sbase = rp[R] * bs * bs + (int64_t)i * len * bs;
+      if (row_ptr) row_ptr[srow] = sbase;
+      for (int64_t k = 0; k < len; ++k)
+        for (int j = 0; j < bs; ++j) {
+          if (col_idx) col_idx[sbase + k * bs + j] = ci[rp[R] + k] * bs + j;
+          if (vals) vals[sbase + k * bs + j] = bv[(rp[R] + k) * bs * bs + i * bs + j];
+        }
+    }
+  }
+  if (row_ptr) row_ptr[A->nbrows * bs] = A->nnzb * bs * bs;
+  return FSB_OK;
+}

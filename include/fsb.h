@@ -1,0 +1,171 @@
+/* fsb.h — C-ABI of the B200-native FEM assemble-and-solve library (libfsb.so).
+ *
+ * This is the drop-in boundary for the FenicsSolver hot path.  The reference has no FFI of its
+ * own: its seam is the Python layer above dolfin, so each entry point below names the dolfin call
+ * it replaces and the reference line that makes that call (paths relative to
+ * /root/reference/FenicsSolver/).  The Python host (fenicssolver_b200/_lib.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a FenicsSolver maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative fsb_status on failure; nothing throws
+ *     across the ABI; fsb_last_error(ctx) returns the message of the last failure on that ctx.
+ *   - handles are opaque; the caller owns all host memory (copied before return), the library owns
+ *     all device memory until the matching *_destroy.
+ *   - one context per GPU, calls on one context are serialised by the caller; kernels run on the
+ *     context's stream; a call blocks only where it returns host-visible data.
+ *   - DoF numbering is vertex order: scalar dof = v, vector dof = ncomp*v + c.  Matrices are
+ *     block-CSR (block size = ncomp) with int64 row_ptr, int32 col_idx sorted ascending,
+ *     structural zeros kept; fsb_mat_download_csr returns the equivalent scalar CSR.
+ *   - distributed runs (fsb_dist_*): each rank holds a z-slab of a box mesh in natural plane order
+ *     [ghost plane | owned planes | ghost plane]; vectors have local length, reductions and SpMV
+ *     run over the owned rows, ghosts are refreshed by the halo exchange inside the solvers.
+ */
+#ifndef FSB_H
+#define FSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsb_ctx fsb_ctx;
+typedef struct fsb_mesh fsb_mesh;
+typedef struct fsb_mat fsb_mat;
+typedef struct fsb_vec fsb_vec;
+
+typedef enum {
+  FSB_OK = 0,
+  FSB_ERR_CUDA = -1,     /* a CUDA runtime call failed */
+  FSB_ERR_ARG = -2,      /* bad argument */
+  FSB_ERR_NOMEM = -3,    /* device allocation failed */
+  FSB_ERR_BREAKDOWN = -4,/* Krylov breakdown (zero/NaN pivot scalar) */
+  FSB_ERR_NCCL = -5,     /* NCCL missing or a collective failed */
+  FSB_ERR_STATE = -6     /* object used in the wrong state */
+} fsb_status;
+
+/* result of a Krylov solve (PETScKrylovSolver.solve return + monitor, SolverBase.py:663-670) */
+typedef struct {
+  int32_t iterations;
+  int32_t converged;     /* 1 converged, 0 hit maxit, -1 breakdown */
+  double rnorm;          /* final ||r||_2 (recurrence residual) */
+  double bnorm;          /* ||b||_2 */
+  double solve_ms;       /* device time of the iteration loop (CUDA events on the ctx stream) */
+  double spmv_ms;        /* accumulated device time of the SpMV launches when profiling is on, else 0 */
+} fsb_solve_info;
+
+/* ---- context --------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t the caller owns (e.g. torch.cuda.Stream().cuda_stream) or NULL for a
+ * library-owned non-blocking stream. */
+int fsb_init(int device, void* stream, fsb_ctx** ctx);
+void fsb_destroy(fsb_ctx* ctx);
+const char* fsb_last_error(fsb_ctx* ctx);
+int fsb_sync(fsb_ctx* ctx);
+int fsb_device_info(fsb_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes);
+/* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 position-map+atomics),
+ * "spmv_mode" (0 TMA-staged tiles, 1 plain row-per-thread), "profile" (0/1), "graph" (0/1),
+ * "check_every" (iterations between host convergence polls). */
+int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value);
+int64_t fsb_launch_count(fsb_ctx* ctx);   /* kernels launched by this library on ctx so far */
+
+/* ---- mesh: dolfin Mesh / UnitCubeMesh / BoxMesh / RectangleMesh ------------------------------- */
+/* Mesh(filename) (SolverBase.py:224): host arrays; cells[ncells][tdim+1] sorted ascending per cell. */
+int fsb_mesh_upload(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz,
+                    int64_t ncells, const int32_t* cells, fsb_mesh** mesh);
+/* UnitSquareMesh/RectangleMesh (tdim 2, diagonal "right") and UnitCubeMesh/BoxMesh (tdim 3)
+ * generated on the device in dolfin's layout (examples/test_heat_transfer.py:34,
+ * examples/test_linear_elasticity.py:42).  layer0/layer1 select the cell layers [layer0,layer1)
+ * along the last axis (a z-slab; pass 0,n[tdim-1] for the whole mesh); vertex ids are local to the
+ * slab: global id - layer0*plane_size. */
+int fsb_mesh_box(fsb_ctx* ctx, int32_t tdim, const int32_t* n, const double* p0, const double* p1,
+                 int32_t layer0, int32_t layer1, fsb_mesh** mesh);
+int fsb_mesh_sizes(fsb_mesh* mesh, int32_t* gdim, int32_t* tdim, int64_t* nverts, int64_t* ncells);
+int fsb_mesh_download(fsb_mesh* mesh, double* xyz, int32_t* cells);
+void fsb_mesh_destroy(fsb_mesh* mesh);
+
+/* ---- vectors: dolfin GenericVector ----------------------------------------------------------- */
+int fsb_vec_create(fsb_ctx* ctx, int64_t n, fsb_vec** v);
+int fsb_vec_fill(fsb_vec* v, double value);
+int fsb_vec_upload(fsb_vec* v, const double* host, int64_t n);
+int fsb_vec_download(fsb_vec* v, double* host, int64_t n);
+int fsb_vec_copy(fsb_vec* dst, fsb_vec* src);
+int fsb_vec_axpy(fsb_vec* y, double a, fsb_vec* x);            /* y += a x */
+int fsb_vec_size(fsb_vec* v, int64_t* n);
+void* fsb_vec_ptr(fsb_vec* v);                                 /* device pointer (for interop) */
+void fsb_vec_destroy(fsb_vec* v);
+
+/* ---- matrix: DofMap + SparsityPatternBuilder + GenericMatrix ---------------------------------- */
+/* builds the topology-based pattern of a P1 space with ncomp components on `mesh` (what dolfin does
+ * inside assemble()/LinearVariationalSolver, SolverBase.py:595,608-612,644); values are zero. */
+int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** A);
+/* arbitrary scalar CSR from the host (for SpMV / Krylov use without a mesh). */
+int fsb_mat_from_csr(fsb_ctx* ctx, int64_t nrows, const int64_t* row_ptr, const int32_t* col_idx,
+                     const double* vals, fsb_mat** A);
+int fsb_mat_sizes(fsb_mat* A, int64_t* nrows, int64_t* nnz, int32_t* bs, int64_t* nnzb);
+int fsb_mat_download_csr(fsb_mat* A, int64_t* row_ptr, int32_t* col_idx, double* vals);
+int fsb_mat_zero(fsb_mat* A);
+int fsb_mat_set_owned_rows(fsb_mat* A, int64_t row0, int64_t row1);  /* block rows [row0,row1) this rank owns */
+void fsb_mat_destroy(fsb_mat* A);
+
+/* ---- assembly: FFC tabulate_tensor + MatSetValues/VecSetValues ADD_VALUES --------------------- */
+/* A += kscale * int (K grad u).grad v  +  mass * int u v  +  adv * int (vel.grad u) v     (P1 scalar)
+ * ktensor: gdim*gdim row-major conductivity tensor or NULL for identity; vel: gdim or NULL.
+ * Restates ScalarTransportSolver.py:284-285 (F_static), :292 (transient mass), :311 (convection). */
+int fsb_assemble_scalar(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor,
+                        double mass, double adv, const double* vel);
+/* y += (kscale*K + mass*M + adv*C(vel)) x   cell by cell without forming the matrix: the
+ * Crank-Nicolson right-hand side (1/dt) c M T_prev - (1-theta) K T_prev, ScalarTransportSolver.py:292-293 */
+int fsb_apply_scalar(fsb_mesh* mesh, fsb_vec* x, fsb_vec* y, double kscale, const double* ktensor,
+                     double mass, double adv, const double* vel);
+/* A += int sigma(u):grad(v), sigma = 2 mu sym(grad u) + lambda div(u) I   (LinearElasticitySolver.py:62-69,215) */
+int fsb_assemble_elasticity(fsb_mesh* mesh, fsb_mat* A, double mu, double lambda);
+/* b += scale * int S.v dx, S constant[ncomp]  (ScalarTransportSolver.py:213-226; LinearElasticitySolver.py:227-228);
+ * cell_tags/tag (host int32[ncells] or NULL): restrict to dx(tag). */
+int fsb_assemble_source(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, const double* S, double scale,
+                        const int32_t* cell_tags, int32_t tag);
+/* b += scale * int S_h v dx with S_h the P1 interpolant of the nodal vector S (same layout as b). */
+int fsb_assemble_source_nodal(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, fsb_vec* S, double scale);
+/* exterior-facet terms over nf facets given by host vertex lists fverts[nf][tdim] (+ opposite vertex
+ * opp[nf] when the outward normal is needed):
+ *   mode 0: b += scale * int g.v ds            g constant[ncomp]              (ScalarTransportSolver.py:179-208)
+ *   mode 1: b += scale * int (g[0] n).v ds     pressure / normal force        (LinearElasticitySolver.py:176-189)  */
+int fsb_assemble_facet_load(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, int64_t nf, const int32_t* fverts,
+                            const int32_t* opp, int32_t mode, const double* g, double scale);
+/* A += h * int u v ds over the facets: the HTC/Robin matrix term (ScalarTransportSolver.py:201-208). */
+int fsb_assemble_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, const int32_t* fverts, double h);
+/* assemble(Constant(1)*ds(id))  (LinearElasticitySolver.py:171) */
+int fsb_facet_area(fsb_mesh* mesh, int64_t nf, const int32_t* fverts, double* area);
+
+/* ---- DirichletBC.apply / assemble_system ------------------------------------------------------ */
+/* symmetric=0: zero row, unit diagonal, b=g (bc.apply(A,b), SolverBase.py:598-602, 608);
+ * symmetric=1: additionally b -= A[:,bc] g and zero the column (assemble_system, SolverBase.py:644).
+ * x (optional) gets x[dof]=g so a Krylov start vector satisfies the BCs.  dofs/vals are host arrays. */
+int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t nbc, const int64_t* dofs,
+                        const double* vals, int32_t symmetric);
+
+/* ---- Krylov: PETSc KSPCG / KSPBCGS + PCJacobi -------------------------------------------------- */
+int fsb_spmv(fsb_mat* A, fsb_vec* x, fsb_vec* y);               /* y = A x over the owned rows */
+int fsb_dot(fsb_vec* x, fsb_vec* y, double* result);            /* owned range, allreduced when distributed */
+/* precond: 0 none, 1 Jacobi.  Convergence: ||r||_2 <= max(rtol*||b||_2, atol).  x holds the start
+ * vector on entry and the solution on exit.  (SolverBase.py:603-612, 663-670) */
+int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit,
+                 int32_t precond, fsb_solve_info* info);
+int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit,
+                       int32_t precond, fsb_solve_info* info);
+
+/* ---- distributed: mesh partition + PETSc VecScatter/MPI_Allreduce (SolverBase.py:102-118, 634) -- */
+#define FSB_NCCL_UID_BYTES 128
+int fsb_dist_unique_id(void* uid128);                           /* rank 0 creates, host broadcasts */
+int fsb_dist_init(fsb_ctx* ctx, int32_t rank, int32_t nranks, const void* uid128);
+/* declare the slab layout of vectors on this ctx: ghost planes below/above (0 or 1) and the number
+ * of owned vertex planes; the plane size follows from each vector's length; neighbours are
+ * rank-1 / rank+1. */
+int fsb_dist_set_slab(fsb_ctx* ctx, int32_t ghost_lo, int32_t ghost_hi, int64_t owned_planes);
+int fsb_dist_halo(fsb_vec* v);                                  /* refresh ghost planes of v */
+int fsb_dist_allreduce_max(fsb_ctx* ctx, double* value);        /* host scalar, for timing */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB_H */

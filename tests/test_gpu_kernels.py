@@ -1,0 +1,510 @@
+"""GPU parity tests, kernel level: every libfsb entry point against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): integer work (connectivity, CSR row_ptr/col_idx) bit-exact; assembled
+values to 1e-13 of the row scale (atomic summation order differs from the oracle's); solution vectors
+within 1e-10 relative L2 of the oracle's direct solve.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+from oracle import fem_oracle as fo  # noqa: E402  (checker only)
+from fenicssolver_b200 import _lib  # noqa: E402
+
+VAL_TOL = 1e-13
+SOL_TOL = 1e-10
+
+
+def csr_from_device(A):
+    rp, ci, va = A.download_csr()
+    n = rp.size - 1
+    return sp.csr_matrix((va, ci.astype(np.int64), rp), shape=(n, n)), rp, ci
+
+
+def assert_vals_close(dev, ref, tol=VAL_TOL):
+    assert dev.shape == ref.shape
+    scale = np.abs(ref).max()
+    err = np.abs(dev - ref).max()
+    assert err <= tol * scale, "max abs err %.3e vs scale %.3e" % (err, scale)
+
+
+def jitter(coords, n, seed=0, amp=0.2):
+    rng = np.random.default_rng(seed)
+    return coords + amp / n * (rng.random(coords.shape) * 2 - 1)
+
+
+# ----------------------------------------------------------------------------------- meshes
+@pytest.mark.parametrize("n", [(3, 2), (5, 7), (4, 3, 2), (6, 5, 7)])
+def test_box_mesh_bit_exact(ctx, n):
+    if len(n) == 2:
+        p0, p1 = (0.25, -1.0), (2.0, 0.5)
+        c, t = fo.rectangle_mesh(p0[0], p0[1], p1[0], p1[1], *n)
+    else:
+        p0, p1 = (0.0, -1.0, 0.5), (10.0, 1.0, 1.75)
+        c, t = fo.box_mesh(p0, p1, *n)
+    m = _lib.DeviceMesh.box(ctx, n, p0, p1)
+    xyz, cells = m.download()
+    assert np.array_equal(cells, t)
+    assert np.array_equal(xyz, c)          # bit-exact coordinates
+
+
+def test_box_mesh_slab_matches_global(ctx):
+    n = (4, 3, 6)
+    c, t = fo.unit_cube_mesh(*n)
+    plane = (n[0] + 1) * (n[1] + 1)
+    m = _lib.DeviceMesh.box(ctx, n, (0, 0, 0), (1, 1, 1), 2, 5)
+    xyz, cells = m.download()
+    assert np.array_equal(xyz, c[2 * plane:6 * plane])
+    ncl = 6 * n[0] * n[1]
+    assert np.array_equal(cells + 2 * plane, t[2 * ncl:5 * ncl])
+
+
+# ----------------------------------------------------------------------------------- pattern
+@pytest.mark.parametrize("n", [(4, 4), (9, 5), (2, 2, 2), (8, 8, 8), (5, 3, 4)])
+def test_pattern_exact_box(ctx, n):
+    c, t = (fo.rectangle_mesh(0, 0, 1, 1, *n) if len(n) == 2 else fo.unit_cube_mesh(*n))
+    m = _lib.DeviceMesh.box(ctx, n, (0,) * len(n), (1,) * len(n))
+    A = _lib.DeviceMatrix.create(m, 1)
+    rp, ci, _ = A.download_csr(values=False)
+    rp0, ci0 = fo.csr_pattern(t, c.shape[0])
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+    if len(n) == 3 and n[0] == n[1] == n[2]:
+        N = n[0]
+        assert ci.size == (N + 1) ** 3 + 2 * (3 * N * (N + 1) ** 2 + 3 * N * N * (N + 1) + N ** 3)
+
+
+def test_pattern_exact_fixture_golden(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "fixture_mesh.npz"))
+    e = np.load(os.path.join(golden_dir, "fixture_expected.npz"))
+    m = _lib.DeviceMesh.upload(ctx, g["coords"], g["cells"])
+    A = _lib.DeviceMatrix.create(m, 1)
+    rp, ci, _ = A.download_csr(values=False)
+    assert np.array_equal(rp, e["row_ptr"]) and np.array_equal(ci, e["col_idx"])
+    assert ci.size == 13315
+
+
+@pytest.mark.parametrize("ncomp,n", [(2, (4, 3)), (3, (3, 2, 4))])
+def test_pattern_exact_vector(ctx, ncomp, n):
+    c, t = (fo.rectangle_mesh(0, 0, 1, 1, *n) if len(n) == 2 else fo.unit_cube_mesh(*n))
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, ncomp)
+    rp, ci, _ = A.download_csr(values=False)
+    rp0, ci0 = fo.csr_pattern(t, c.shape[0], ncomp)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+
+
+def test_pattern_high_valence_vertex(ctx):
+    """A fan of triangles around one vertex: valence above the shared-memory row cache (uncached path)."""
+    k = 200
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    coords = np.vstack([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], 1)])
+    cells = np.sort(np.stack([np.zeros(k, int), 1 + np.arange(k), 1 + (np.arange(k) + 1) % k], 1), axis=1).astype(np.int32)
+    m = _lib.DeviceMesh.upload(ctx, coords, cells)
+    A = _lib.DeviceMatrix.create(m, 1)
+    rp, ci, _ = A.download_csr(values=False)
+    rp0, ci0 = fo.csr_pattern(cells, coords.shape[0])
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+    assert (rp[1] - rp[0]) == k + 1
+
+
+# ----------------------------------------------------------------------------------- assembly
+@pytest.mark.parametrize("asm_mode", [0, 1])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_assemble_scalar_terms(ctx, dim, asm_mode):
+    n = (7, 5) if dim == 2 else (5, 4, 6)
+    c, t = (fo.rectangle_mesh(0, 0, 2, 1, *n) if dim == 2 else fo.box_mesh((0, 0, 0), (2, 1, 3), *n))
+    c = jitter(c, max(n), seed=1)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    ctx.set_option("asm_mode", asm_mode)
+    try:
+        rng = np.random.default_rng(2)
+        kt = rng.random((dim, dim)) + dim * np.eye(dim)
+        vel = rng.random(dim) - 0.5
+        cases = [
+            dict(kscale=20.0),
+            dict(kscale=0.0, mass=3.5),
+            dict(kscale=0.0, adv=2.0, vel=vel),
+            dict(kscale=0.7, ktensor=kt, mass=1.25, adv=4.0, vel=vel),
+        ]
+        rp0, ci0 = fo.csr_pattern(t, nv)
+        for kw in cases:
+            A = _lib.DeviceMatrix.create(m, 1)
+            A.assemble_scalar(**kw)
+            dev, rp, ci = csr_from_device(A)
+            Ke = kw.get("kscale", 1.0) * fo.local_laplace(c, t, kw.get("ktensor", 1.0))
+            if kw.get("mass"):
+                Ke = Ke + fo.local_mass(c, t, kw["mass"])
+            if kw.get("adv"):
+                Ke = Ke + fo.local_advection(c, t, kw["vel"], kw["adv"])
+            ref = fo.conform(fo.assemble_matrix(t, Ke, nv), rp0, ci0)
+            assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+            assert_vals_close(dev.data, ref.data)
+    finally:
+        ctx.set_option("asm_mode", 1)
+
+
+def test_assemble_accumulates_and_zero(ctx):
+    c, t = fo.unit_cube_mesh(3, 3, 3)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=1.0)
+    A.assemble_scalar(kscale=2.0)
+    dev, _, _ = csr_from_device(A)
+    ref = fo.assemble_matrix(t, 3.0 * fo.local_laplace(c, t), c.shape[0])
+    assert_vals_close(dev.toarray(), ref.toarray())
+    A.zero()
+    assert np.all(csr_from_device(A)[0].data == 0.0)
+
+
+def test_cube_stencil_invariants(ctx):
+    """SURVEY 8c KAT 3: 15 structural / 7 numerical non-zeros per interior row, 7-point stencil k*h*(6,-1..)."""
+    N, k = 8, 20.0
+    m = _lib.DeviceMesh.box(ctx, (N, N, N), (0, 0, 0), (1, 1, 1))
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=k)
+    M, rp, ci = csr_from_device(A)
+    p = N + 1
+    r = 4 + 4 * p + 4 * p * p
+    row = M.getrow(r)
+    assert row.nnz == 15
+    h = 1.0 / N
+    dense = np.zeros(M.shape[0]); dense[row.indices] = row.data
+    assert abs(dense[r] - 6 * k * h) < 1e-12
+    for off in (1, p, p * p):
+        assert abs(dense[r + off] + k * h) < 1e-12 and abs(dense[r - off] + k * h) < 1e-12
+    assert (np.abs(row.data) > 1e-12).sum() == 7
+    assert np.abs(M @ np.ones(M.shape[0])).max() < 1e-11
+    assert abs(M - M.T).max() < 1e-12
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_apply_scalar_matches_matrix_action(ctx, dim):
+    n = (6, 5) if dim == 2 else (4, 5, 3)
+    c, t = (fo.rectangle_mesh(0, 0, 1, 1, *n) if dim == 2 else fo.unit_cube_mesh(*n))
+    c = jitter(c, max(n), seed=3)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    rng = np.random.default_rng(4)
+    xh = rng.random(nv)
+    x = _lib.DeviceVector.from_numpy(ctx, xh)
+    y = _lib.DeviceVector(ctx, nv)
+    y.fill(1.0)
+    _lib.apply_scalar(m, x, y, kscale=-0.5 * 0.6, mass=4.2e3)
+    ref = 1.0 + fo.assemble_matrix(t, -0.3 * fo.local_laplace(c, t) + fo.local_mass(c, t, 4.2e3), nv) @ xh
+    assert_vals_close(y.numpy(), ref)
+
+
+@pytest.mark.parametrize("asm_mode", [0, 1])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_assemble_elasticity(ctx, dim, asm_mode):
+    n = (5, 4) if dim == 2 else (3, 4, 3)
+    c, t = (fo.rectangle_mesh(0, 0, 2, 1, *n) if dim == 2 else fo.box_mesh((0, 0, 0), (4, 1, 1), *n))
+    c = jitter(c, max(n), seed=5)
+    nv = c.shape[0]
+    mu, lam = fo.lame(2e11, 0.27)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    ctx.set_option("asm_mode", asm_mode)
+    try:
+        A = _lib.DeviceMatrix.create(m, dim)
+        A.assemble_elasticity(mu, lam)
+    finally:
+        ctx.set_option("asm_mode", 1)
+    dev, rp, ci = csr_from_device(A)
+    rp0, ci0 = fo.csr_pattern(t, nv, dim)
+    ref = fo.conform(fo.assemble_matrix(t, fo.local_elasticity(c, t, mu, lam), nv, dim), rp0, ci0)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+    assert_vals_close(dev.data, ref.data)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_rhs_terms(ctx, dim):
+    n = (6, 4) if dim == 2 else (4, 3, 5)
+    c, t = (fo.rectangle_mesh(0, 0, 1, 2, *n) if dim == 2 else fo.box_mesh((0, 0, 0), (1, 2, 1), *n))
+    c = jitter(c, max(n), seed=6)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    fverts, opp, _ = fo.exterior_facets(t)
+    rng = np.random.default_rng(7)
+    # constant scalar source, restricted to tagged cells
+    tags = (rng.random(t.shape[0]) < 0.5).astype(np.int32) + 1
+    b = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_source(m, b, 1000.0)
+    _lib.assemble_source(m, b, 3.0, scale=-2.0, cell_tags=tags, tag=2)
+    ref = fo.assemble_source(c, t, 1000.0) - 2.0 * fo.assemble_source(c, t, 3.0, cell_mask=(tags == 2))
+    assert_vals_close(b.numpy(), ref)
+    # nodal source and vector constant source
+    Sn = rng.random(nv * dim)
+    bv = _lib.DeviceVector(ctx, nv * dim)
+    S = _lib.DeviceVector.from_numpy(ctx, Sn)
+    _lib.assemble_source_nodal(m, bv, S, ncomp=dim, scale=1.5)
+    gvec = rng.random(dim)
+    _lib.assemble_source(m, bv, gvec, ncomp=dim)
+    ref = 1.5 * fo.assemble_source(c, t, Sn.reshape(nv, dim), ncomp=dim) + fo.assemble_source(c, t, gvec, ncomp=dim)
+    assert_vals_close(bv.numpy(), ref)
+    # facet loads: scalar flux, vector traction, pressure along the outward normal
+    sel = rng.random(fverts.shape[0]) < 0.6
+    b2 = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_facet_load(m, b2, fverts[sel], 36.0)
+    assert_vals_close(b2.numpy(), fo.assemble_facet_load(c, fverts[sel], 36.0, nv))
+    b3 = _lib.DeviceVector(ctx, nv * dim)
+    _lib.assemble_facet_load(m, b3, fverts[sel], gvec, ncomp=dim, scale=-1.0)
+    _lib.assemble_facet_load(m, b3, fverts[sel], 1e6, ncomp=dim, opp=opp[sel], normal=True)
+    meas, nrm = fo.facet_measure(c, fverts[sel], opp[sel])
+    ref = -fo.assemble_facet_load(c, fverts[sel], gvec, nv, dim) + fo.assemble_facet_load(c, fverts[sel], 1e6 * nrm, nv, dim)
+    assert_vals_close(b3.numpy(), ref)
+    # boundary area functional and the Robin boundary matrix
+    assert abs(_lib.facet_area(m, fverts[sel]) - fo.boundary_area(c, fverts[sel])) < 1e-12 * fo.boundary_area(c, fverts[sel])
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_facet_mass(fverts[sel], 100.0)
+    dev, rp, ci = csr_from_device(A)
+    ref = fo.conform(fo._scatter(fverts[sel], fo.local_facet_mass(c, fverts[sel], 100.0), nv), rp, ci)
+    assert_vals_close(dev.data, ref.data)
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+@pytest.mark.parametrize("ncomp", [1, 3])
+def test_apply_dirichlet(ctx, ncomp, symmetric):
+    c, t = fo.unit_cube_mesh(4, 3, 3)
+    c = jitter(c, 4, seed=8)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, ncomp)
+    if ncomp == 1:
+        A.assemble_scalar(kscale=2.0, mass=0.3)
+        ref = fo.assemble_matrix(t, 2.0 * fo.local_laplace(c, t) + fo.local_mass(c, t, 0.3), nv)
+    else:
+        A.assemble_elasticity(3.0, 5.0)
+        ref = fo.assemble_matrix(t, fo.local_elasticity(c, t, 3.0, 5.0), nv, 3)
+    rng = np.random.default_rng(9)
+    n = nv * ncomp
+    bh = rng.random(n)
+    dofs = np.sort(rng.choice(n, size=n // 5, replace=False))
+    vals = rng.random(dofs.size) * 10
+    b = _lib.DeviceVector.from_numpy(ctx, bh)
+    x = _lib.DeviceVector(ctx, n)
+    A.apply_dirichlet(b, dofs, vals, symmetric=symmetric, x=x)
+    dev, rp, ci = csr_from_device(A)
+    Aref, bref = fo.apply_dirichlet(fo.conform(ref, rp, ci), bh, dofs, vals, symmetric)
+    assert_vals_close(dev.data, Aref.data)
+    assert_vals_close(b.numpy(), bref)
+    xh = x.numpy()
+    assert np.array_equal(xh[dofs], vals) and np.count_nonzero(xh) <= dofs.size
+
+
+# ----------------------------------------------------------------------------------- SpMV / Krylov
+def random_csr(n, avg, seed, empty_rows=False, long_row=0):
+    rng = np.random.default_rng(seed)
+    M = sp.random(n, n, density=avg / n, format="lil", random_state=seed, data_rvs=lambda k: rng.random(k) - 0.5)
+    if not empty_rows:
+        M.setdiag(rng.random(n) + 1.0)
+    if long_row:
+        M[n // 2, :long_row] = rng.random(long_row)
+    M = M.tocsr()
+    M.sort_indices()
+    return M
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", ["fem", "random", "ragged_empty_rows", "long_row", "tiny"])
+def test_spmv_matches_scipy(ctx, case, mode):
+    if case == "fem":
+        c, t = fo.unit_cube_mesh(12, 11, 10)
+        M = fo.assemble_matrix(t, fo.local_laplace(c, t, 3.0) + fo.local_mass(c, t), c.shape[0])
+    elif case == "random":
+        M = random_csr(20011, 9, 1)
+    elif case == "ragged_empty_rows":
+        M = random_csr(5003, 2, 2, empty_rows=True)
+    elif case == "long_row":
+        M = random_csr(3001, 5, 3, long_row=2500)
+    else:
+        M = random_csr(3, 2, 4)
+    ctx.set_option("spmv_mode", mode)
+    try:
+        A = _lib.DeviceMatrix.from_csr(ctx, M.indptr, M.indices, M.data)
+        xh = np.random.default_rng(5).random(M.shape[0]) - 0.5
+        x = _lib.DeviceVector.from_numpy(ctx, xh)
+        y = _lib.DeviceVector(ctx, M.shape[0])
+        y.fill(7.0)
+        A.spmv(x, y)
+        yh = y.numpy()
+    finally:
+        ctx.set_option("spmv_mode", 0)
+    ref = M @ xh
+    assert np.abs(yh - ref).max() <= 1e-14 * max(1.0, np.abs(M).dot(np.abs(xh)).max())
+
+
+def test_spmv_block3_matches_scalar_csr(ctx):
+    c, t = fo.box_mesh((0, 0, 0), (4, 1, 1), 8, 5, 4)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 3)
+    A.assemble_elasticity(1.0, 2.0)
+    M, _, _ = csr_from_device(A)
+    xh = np.random.default_rng(6).random(3 * nv) - 0.5
+    for mode in (0, 1):
+        ctx.set_option("spmv_mode", mode)
+        x = _lib.DeviceVector.from_numpy(ctx, xh)
+        y = _lib.DeviceVector(ctx, 3 * nv)
+        A.spmv(x, y)
+        assert np.abs(y.numpy() - M @ xh).max() <= 1e-13 * np.abs(M @ xh).max()
+    ctx.set_option("spmv_mode", 0)
+
+
+def test_dot_is_reproducible(ctx):
+    rng = np.random.default_rng(10)
+    a, b = rng.random(1_000_003), rng.random(1_000_003)
+    x, y = _lib.DeviceVector.from_numpy(ctx, a), _lib.DeviceVector.from_numpy(ctx, b)
+    d1, d2 = x.dot(y), x.dot(y)
+    assert d1 == d2
+    assert abs(d1 - a @ b) <= 1e-12 * abs(a @ b)
+
+
+def heat_problem(N, jit=False):
+    c, t = fo.unit_cube_mesh(N, N, N)
+    z0 = np.nonzero(c[:, 2] == 0)[0]
+    z1 = np.nonzero(c[:, 2] == 1)[0]
+    if jit:
+        keep = c.copy()
+        c = jitter(c, N, seed=11)
+        bnd = (keep == 0) | (keep == 1)
+        c[bnd] = keep[bnd]
+    return c, t, z0, z1
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_cg_heat_matches_oracle_direct_and_iteration_count(ctx, symmetric):
+    """SURVEY 8c KAT 4 + iteration-for-iteration agreement with the oracle's PCG."""
+    N = 16
+    c, t, z0, z1 = heat_problem(N)
+    nv = c.shape[0]
+    Ao, bo = fo.heat_system(c, t, 20.0, [(z0, 350.0), (z1, 300.0)], source=1000.0, symmetric=symmetric)
+    xd = fo.solve_direct(Ao, bo)
+    m = _lib.DeviceMesh.box(ctx, (N, N, N), (0, 0, 0), (1, 1, 1))
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=20.0)
+    b = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_source(m, b, 1000.0)
+    x = _lib.DeviceVector(ctx, nv)
+    dofs = np.concatenate([z0, z1])
+    vals = np.concatenate([np.full(z0.size, 350.0), np.full(z1.size, 300.0)])
+    A.apply_dirichlet(b, dofs, vals, symmetric=symmetric, x=x)
+    info = A.solve(b, x, "cg" if symmetric else "bicgstab", rtol=1e-12)
+    xh = x.numpy()
+    assert info["converged"] == 1
+    assert fo.relative_l2(xh, xd) < SOL_TOL
+    z = c[:, 2]
+    assert fo.relative_l2(xh, 350 - 50 * z + 1000 * z * (1 - z) / 40) < SOL_TOL   # nodally exact profile
+    x0 = np.zeros(nv); x0[dofs] = vals
+    if symmetric:
+        _, it, _ = fo.pcg_jacobi(Ao, bo, x0=x0, rtol=1e-12)
+    else:
+        _, it, _ = fo.bicgstab_jacobi(Ao, bo, x0=x0, rtol=1e-12)
+    assert abs(info["iterations"] - it) <= max(2, it // 20)
+    assert info["rnorm"] <= 1e-12 * info["bnorm"]
+
+
+def test_cg_is_bitwise_reproducible(ctx):
+    N = 12
+    c, t, z0, z1 = heat_problem(N, jit=True)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    dofs = np.concatenate([z0, z1])
+    vals = np.concatenate([np.full(z0.size, 1.0), np.full(z1.size, 0.0)])
+    sols = []
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=1.0)
+    b = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_source(m, b, 1.0)
+    x0 = _lib.DeviceVector(ctx, nv)
+    A.apply_dirichlet(b, dofs, vals, symmetric=True, x=x0)
+    for _ in range(2):
+        x = _lib.DeviceVector(ctx, nv)
+        x.copy_from(x0)
+        info = A.solve(b, x, "cg", rtol=1e-10)
+        sols.append((x.numpy(), info["iterations"]))
+    assert sols[0][1] == sols[1][1]
+    assert np.array_equal(sols[0][0], sols[1][0])
+
+
+def test_cg_maxit_and_zero_rhs(ctx):
+    N = 8
+    c, t, z0, z1 = heat_problem(N)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=1.0, mass=1.0)
+    b = _lib.DeviceVector(ctx, nv)
+    x = _lib.DeviceVector(ctx, nv)
+    info = A.solve(b, x, "cg", rtol=1e-12)          # b = 0: converged at iteration 0
+    assert info["iterations"] == 0 and info["converged"] == 1
+    _lib.assemble_source(m, b, 1.0)
+    info = A.solve(b, x, "cg", rtol=1e-14, maxit=5)
+    assert info["iterations"] == 5 and info["converged"] == 0
+
+
+def test_fixture_kat_on_device(ctx, golden_dir):
+    """data/TestHeatTransfer.json on data/mesh.xml: exact discrete answer T = 350 - 2.5 z (golden fixture)."""
+    g = np.load(os.path.join(golden_dir, "fixture_mesh.npz"))
+    e = np.load(os.path.join(golden_dir, "fixture_expected.npz"))
+    c, t = g["coords"], g["cells"]
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=20.0)
+    b = _lib.DeviceVector(ctx, nv)
+    x = _lib.DeviceVector(ctx, nv)
+    x.fill(293.0)
+    dofs = np.concatenate([e["dofs_tag1"], e["dofs_tag2"]])
+    vals = np.concatenate([np.full(e["dofs_tag1"].size, 350.0), np.full(e["dofs_tag2"].size, 300.0)])
+    A.apply_dirichlet(b, dofs, vals, symmetric=True, x=x)
+    info = A.solve(b, x, "cg", rtol=1e-13)
+    assert info["converged"] == 1
+    assert fo.relative_l2(x.numpy(), e["analytic"]) < SOL_TOL
+    assert fo.relative_l2(x.numpy(), e["solution"]) < SOL_TOL
+
+
+def test_elasticity_patch_and_cg(ctx):
+    """Linear displacement field is reproduced exactly (constant strain patch test); CG on the 3x3-block matrix."""
+    n = (6, 3, 3)
+    c, t = fo.box_mesh((0, 0, 0), (4, 1, 1), *n)
+    c0 = c.copy()
+    c = jitter(c, 6, seed=12)
+    bnd = np.zeros(c.shape[0], bool)
+    for d, (lo, hi) in enumerate([(0, 4), (0, 1), (0, 1)]):
+        bnd |= (c0[:, d] == lo) | (c0[:, d] == hi)
+    c[bnd] = c0[bnd]
+    nv = c.shape[0]
+    mu, lam = fo.lame(10.0, 0.3)
+    G = np.array([[0.01, 0.02, -0.01], [0.0, -0.02, 0.03], [0.015, 0.0, 0.01]])
+    uex = (c @ G.T + np.array([0.1, -0.2, 0.3])).reshape(-1)
+    bv = np.nonzero(bnd)[0]
+    dofs = (bv[:, None] * 3 + np.arange(3)).reshape(-1)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 3)
+    A.assemble_elasticity(mu, lam)
+    b = _lib.DeviceVector(ctx, 3 * nv)
+    x = _lib.DeviceVector(ctx, 3 * nv)
+    A.apply_dirichlet(b, dofs, uex[dofs], symmetric=True, x=x)
+    info = A.solve(b, x, "cg", rtol=1e-13)
+    assert info["converged"] == 1
+    assert fo.relative_l2(x.numpy(), uex) < SOL_TOL
+
+
+def test_errors_are_reported(ctx):
+    c, t = fo.unit_cube_mesh(2, 2, 2)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    bad = _lib.DeviceVector(ctx, 5)
+    with pytest.raises(_lib.SolverError):
+        A.spmv(bad, bad)
+    with pytest.raises(_lib.SolverError):
+        A.assemble_elasticity(1.0, 1.0)
+    with pytest.raises(_lib.SolverError):
+        _lib.DeviceMesh.box(ctx, (0, 2, 2), (0, 0, 0), (1, 1, 1))
+    with pytest.raises(_lib.SolverError):
+        ctx.set_option("no_such_option", 1)
