@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: Mdof/s for assemble + Jacobi-CG solve, 3D steady heat, P1 on an
+N^3 UnitCubeMesh (BASELINE.json configs[1]: N = 256, ~17 M DoF), on 1/2/4/8 B200s.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1         # CPU restatement of the reference path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path on the resident mesh: zero A, assemble K and the load vector,
+symmetric Dirichlet elimination, Jacobi-CG to rtol 1e-12 (the tolerance that lands within 1e-10 of the
+reference's direct solve).  `value` is timed with CUDA events on the library's stream with the mesh and
+the sparsity pattern already in HBM; `e2e` goes through the public API (ScalarTransportSolver(settings)
+.solve() -> vector().get_local()) with the mesh arriving as pinned host arrays, so it contains the H2D
+copy of the mesh, the symbolic phase, the solve and the D2H copy of the solution.
+Inputs are larger than L2 (CSR 3 GB, vectors 136 MB each at 256^3), so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RTOL = 1e-12
+# Jacobi-PCG iterations to rtol 1e-12 on this exact problem (measured on the device path; the CPU
+# restatement runs the same recurrences and agrees at every size the tests compare, e.g. N=16: 91 = 91)
+KNOWN_ITERS = {64: 0, 128: 544, 256: 996}
+
+
+def case_settings(N, mesh=None, distributed=False):
+    """Config C2: material from data/TestHeatTransfer.json, Dirichlet 350 on z=0, 300 on z=1,
+    natural elsewhere, body source 1000, initial 293."""
+    from fenicssolver_b200.dolfin_compat import near
+    return {
+        'solver_name': 'ScalarTransportSolver', 'scalar_name': 'temperature',
+        'mesh': mesh if mesh is not None else {'type': 'UnitCubeMesh', 'n': [N, N, N]},
+        'fe_degree': 1, 'fe_family': 'CG',
+        'material': {'name': 'oil', 'density': 1000, 'specific_heat_capacity': 500, 'thermal_conductivity': 20},
+        'boundary_conditions': {
+            'inlet': {'boundary': lambda x: near(x[2], 0.0), 'boundary_id': 1, 'type': 'Dirichlet', 'value': 350},
+            'outlet': {'boundary': lambda x: near(x[2], 1.0), 'boundary_id': 2, 'type': 'Dirichlet', 'value': 300}},
+        'body_source': 1000, 'initial_values': {'temperature': 293},
+        'solver_settings': {
+            'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.01, 'ending_time': 0.03},
+            'reference_values': {'temperature': 293},
+            'solver_parameters': {'relative_tolerance': RTOL, 'maximum_iterations': 100000},
+            'distributed': distributed, 'gather_result': False},
+        'report_settings': {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0,
+                            'plotting_interactive': False},
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic_bytes():
+    """dram bytes per SpMV launch from the committed ncu capture (profiles/spmv_traffic.json), else None."""
+    p = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except ValueError:
+            return None
+    return None
+
+
+def cpu_heat(N, iters_full, sample_iters, steps=1, warmup=0):
+    """CPU restatement (oracle/fem_oracle_c.c, OpenMP on every host core) of the same step on a bounded
+    sample: the whole assembly + Dirichlet, then `sample_iters` CG iterations; the solve time is scaled to
+    the `iters_full` iterations the full solve needs (same recurrence => same count)."""
+    from oracle import c_oracle as co
+    cores = co.num_threads()
+    h = co.HeatCube(N)
+    times = []
+    for s in range(warmup + steps):
+        r = h.step(rtol=RTOL, maxit=sample_iters)
+        t = r["t_assemble"] + r["t_solve"] / max(r["iterations"], 1) * iters_full
+        if s >= warmup:
+            times.append((t, r))
+    t_step = float(np.mean([t for t, _ in times]))
+    r = times[-1][1]
+    ndof = (N + 1) ** 3
+    return {"value": ndof / t_step / 1e6, "unit": "Mdof/s", "cores": cores, "kind": "port",
+            "sample": "N=%d: full assembly + Dirichlet (%.2f s) + first %d of %d Jacobi-CG iterations (%.3f s/iter), "
+                      "solve time scaled to %d iterations; OpenMP C restatement, not dolfin/PETSc"
+                      % (N, r["t_assemble"], r["iterations"], iters_full, r["t_solve"] / max(r["iterations"], 1), iters_full),
+            "ms_per_step": t_step * 1e3, "setup_s": h.t_setup}
+
+
+def iters_needed(N):
+    return KNOWN_ITERS.get(N) or int(round(3.9 * N))
+
+
+def run_reference(args):
+    """--impl reference: the reference path's CPU restatement on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    N = args.size
+    res = cpu_heat(N, iters_needed(N), args.cpu_sample_iters, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "Mdof/s assemble+CG-solve, 3D heat P1 on N^3 cube", "value": res["value"], "unit": "Mdof/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D steady heat, UnitCubeMesh %d^3 P1 tets, %d DoF, Jacobi-CG rtol %g" % (N, (N + 1) ** 3, RTOL)},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "Mdof/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=int(os.environ.get("FSB_BENCH_N", "256")))
+    ap.add_argument("--cpu-sample-iters", type=int, default=25)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from fenicssolver_b200 import ScalarTransportSolver, backend
+    from fenicssolver_b200.SolverBase import collect_dirichlet
+    from fenicssolver_b200.dolfin_compat import UnitCubeMesh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    ctx = backend.get_context(local_rank, stream=stream.cuda_stream)
+    ctx.set_option("profile", 1)          # event pairs around every SpMV launch -> per-kernel time inside the timed region
+    N = args.size
+    ndof = (N + 1) ** 3
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: `value`
+    solver = ScalarTransportSolver.ScalarTransportSolver(case_settings(N, distributed=world > 1))
+    solver.init_solver()
+    solver.current_step = 0
+    F, bcs = solver.generate_form(0, None, None, solver.w_current, solver.w_prev)
+    dofs, vals = collect_dirichlet(bcs, solver.mesh)
+    space = solver.device_space()                       # mesh generation + symbolic phase, once
+    x = space.vector()
+    infos = []
+
+    def step():
+        x.fill(293.0)
+        b, symmetric = F.assemble(space)
+        space.apply_dirichlet(b, dofs, vals, symmetric=True, x=x)
+        infos.append(space.solve(b, x, method="cg", rtol=RTOL, maxit=100000))
+
+    for _ in range(args.warmup):
+        step()
+    infos.clear()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = ndof / (ms_per_step * 1e-3) / 1e6
+    info = infos[-1]
+    iters = info["iterations"]
+    xs = space.owned_values(x)
+    zc = (np.arange(space.v_off + space.own_v0, space.v_off + space.own_v1) // ((N + 1) ** 2)) / N
+    exact = 350 - 50 * zc + 1000 * zc * (1 - zc) / 40          # nodally exact 1-D profile (SURVEY 8c KAT 4)
+    err2 = np.array([np.sum((xs - exact) ** 2), np.sum(exact ** 2)])
+    if world > 1:
+        t = torch.tensor(err2, device="cuda")
+        dist.all_reduce(t)
+        err2 = t.cpu().numpy()
+    rel_err = float(np.sqrt(err2[0] / err2[1]))
+
+    # roofline of the dominant kernel (CSR SpMV inside CG), this rank's share
+    s = space.A.sizes()
+    rows_local = (space.own_v1 - space.own_v0)
+    nnz_local = s["nnz"] if world == 1 else int(round(s["nnz"] * rows_local / max(space.nv_local, 1)))
+    spmv_bytes = 12 * nnz_local + 24 * rows_local
+    spmv_ms = float(np.mean([i["spmv_ms"] / max(i["iterations"], 1) for i in infos]))
+    peak, peak_src = measured_peak_gbs()
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    solve_ms = float(np.mean([i["solve_ms"] for i in infos]))
+    roofline = {"bound": "hbm", "kernel": "k_spmv_tma<1,256> (CSR SpMV + fused p.q dot)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
+                "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_ms, "launches_per_step": iters,
+                "share_of_step": spmv_ms * iters / ms_per_step,
+                "cg_iteration": {"ms": solve_ms / max(iters, 1), "bytes": spmv_bytes + 88 * rows_local,
+                                 "GBps": (spmv_bytes + 88 * rows_local) / (solve_ms / max(iters, 1) * 1e-3) / 1e9}}
+
+    # ---------------- end-to-end arm: public API, host mesh in pinned memory -> device -> solution on host
+    e2e = None
+    if not args.no_e2e:
+        hmesh = UnitCubeMesh(N, N, N)
+        c, t = hmesh.coordinates(), hmesh.cells()
+        pc = torch.empty(c.shape, dtype=torch.float64, pin_memory=True)
+        pt = torch.empty(t.shape, dtype=torch.int32, pin_memory=True)
+        pc.numpy()[:] = c
+        pt.numpy()[:] = t
+        hmesh._coords, hmesh._cells = pc.numpy(), pt.numpy()
+        hmesh.force_upload = True
+        hmesh.exterior_facets()
+        del c, t
+        h2d = d2h = 0
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            sv = ScalarTransportSolver.ScalarTransportSolver(case_settings(N, mesh=hmesh, distributed=world > 1))
+            T = sv.solve()
+            out = sv.local_result() if world > 1 else T.vector().get_local()
+            sp = sv.device_space()
+            h2d = sp.nv_local * 24 + sp.nc_local * 16 + sp.nv_local * 8 + dofs.size * 16
+            d2h = out.nbytes
+            return out
+
+        n_e2e = max(1, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": ndof / dt / 1e6, "unit": "Mdof/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "what": "ScalarTransportSolver(settings with a pinned host Mesh).solve() + vector().get_local(): mesh H2D, symbolic, assemble, CG, solution D2H"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_heat(N, iters, args.cpu_sample_iters)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:          # the baseline is a reported extra, never a reason to lose the bench line
+            cpu = {"value": None, "unit": "Mdof/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {"metric": "Mdof/s assemble+CG-solve, 3D heat P1 on N^3 cube", "value": value, "unit": "Mdof/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "3D steady heat (ScalarTransportSolver), UnitCubeMesh %d^3 P1 tets, %d DoF, k=20, S=1000, "
+                                       "Dirichlet 350/300 on z faces, Jacobi-CG rtol %g" % (N, ndof, RTOL),
+                           "partition": "z-slabs x%d" % world if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2 (CSR %.2f GB), no flush needed" % (12 * s["nnz"] / 1e9),
+                           "timed": "A.zero + assemble K,b + symmetric Dirichlet + Jacobi-PCG; symbolic phase (%.0f ms) reused across steps"
+                                    % (solver.timings.get("symbolic", 0) * 1e3)},
+                "iterations": iters, "converged": info["converged"], "rel_l2_vs_exact": rel_err,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,255 @@
+"""ScalarTransportSolver — heat / species / electrostatics: diffusion (+ advection) with Dirichlet,
+flux, Neumann, HTC/Robin boundaries, steady or Crank-Nicolson transient.
+
+Mirrors /root/reference/FenicsSolver/ScalarTransportSolver.py: material look-ups :73-129, boundary
+types :142-211, body source :213-226, weak form :228-311, linear solve :378-383.  The UFL form is
+replaced by a ScalarForm record that libfsb assembles:
+
+  steady     A = K(k) + c C(v) + sum_i h_i M_F(i)
+             b = sum_i int g_i q ds(i) + sum_i h_i Ta_i int q ds(i) + int S q dx
+  transient  A = (c/dt) M + theta K(k) + c C(v) + sum h M_F        theta = 0.5 (Crank-Nicolson)
+             b = (c/dt) M T_prev - (1-theta) K(k) T_prev + loads
+(convection and the boundary/source loads are fully implicit, exactly as the reference writes them,
+:297-311).  Out of scope on the device path: radiation, nonlinear material, SUPG/IP stabilisation,
+point sources -> SolverError.
+"""
+from __future__ import annotations
+
+import numbers
+
+import numpy as np
+
+from . import _lib
+from .SolverBase import SolverBase, SolverError
+from .dolfin_compat import Constant, DirichletBC, Function
+
+supported_scalars = {'temperature', 'electric_potential', 'species_concentration'}
+electric_permittivity_in_vacumm = 8.854187817e-12
+
+
+class ScalarForm:
+    """Plain-data description of the linear scalar transport form; assemble() runs it on the device."""
+
+    def __init__(self, solver):
+        self.solver = solver
+        self.conductivity = 1.0          # number or dim x dim tensor
+        self.capacity = 1.0
+        self.transient = False
+        self.dt = None
+        self.theta = 0.5
+        self.velocity = None             # constant vector
+        self.neumann = []                # (marker id, constant g)
+        self.robin = []                  # (marker id, h, T_ambient)
+        self.sources = []                # (value (number | nodal array), subdomain id | None)
+        self.T_prev = None
+
+    def _k(self):
+        k = self.conductivity
+        if isinstance(k, np.ndarray) and k.ndim == 2:
+            return 1.0, k
+        return float(k), None
+
+    def assemble(self, space):
+        """-> (rhs DeviceVector, matrix_is_symmetric).  A is assembled into space.A."""
+        s = self.solver
+        A = space.A
+        A.zero()
+        kscale, ktensor = self._k()
+        c = float(self.capacity)
+        vel = None if self.velocity is None else np.asarray(self.velocity, dtype=np.float64)
+        adv = c if vel is not None else 0.0
+        b = space.vector()
+        if self.transient:
+            A.assemble_scalar(kscale=self.theta * kscale, ktensor=ktensor, mass=c / self.dt, adv=adv, vel=vel)
+            tp = self.T_prev.device_vector()
+            if tp is None or tp.n != space.ndof_local:
+                tp = space.vector_from_global(self.T_prev.array())
+            elif space.comm.nranks > 1:
+                tp.halo()
+            _lib.apply_scalar(space.dmesh, tp, b, kscale=-(1.0 - self.theta) * kscale, ktensor=ktensor, mass=c / self.dt)
+        else:
+            A.assemble_scalar(kscale=kscale, ktensor=ktensor, adv=adv, vel=vel)
+        for marker, g in self.neumann:
+            fv, _ = space.local_facets(*s.boundary_facets.facets(marker))
+            _lib.assemble_facet_load(space.dmesh, b, fv, g)
+        for marker, h, Ta in self.robin:
+            fv, _ = space.local_facets(*s.boundary_facets.facets(marker))
+            A.assemble_facet_mass(fv, h)
+            _lib.assemble_facet_load(space.dmesh, b, fv, h * Ta)
+        for value, sub_id in self.sources:
+            if isinstance(value, np.ndarray):
+                if sub_id is not None:
+                    raise SolverError('nodal body source restricted to a subdomain is not implemented')
+                _lib.assemble_source_nodal(space.dmesh, b, space.vector_from_global(value))
+            else:
+                tags = None
+                if sub_id is not None:
+                    if s.subdomains is None:
+                        raise SolverError('body_source per subdomain needs cell markers (mesh_physical_region.xml)')
+                    tags = s.subdomains.array()
+                _lib.assemble_source(space.dmesh, b, float(value), cell_tags=tags, tag=sub_id or 0)
+        symmetric = vel is None and (ktensor is None or np.allclose(ktensor, ktensor.T, rtol=0, atol=0))
+        return b, symmetric
+
+
+class ScalarTransportSolver(SolverBase):
+    """general scalar transport (diffusion and advection) solver, exampled by heat transfer"""
+
+    def __init__(self, s):
+        SolverBase.__init__(self, s)
+        if 'scalar_name' in self.settings:
+            self.scalar_name = self.settings['scalar_name'].lower()
+        else:
+            self.scalar_name = "temperature"
+        self.using_diffusion_form = False
+        self.nonlinear = False
+        self.nonlinear_material = False
+        for v in self.material.values():
+            if callable(v) and not isinstance(v, Constant):
+                self.nonlinear = True
+
+    def _material_number(self, c, T):
+        from inspect import isfunction
+        if isfunction(c):
+            self.nonlinear_material = True
+            return c(T)
+        return self.get_material_value(c)
+
+    def capacity(self, T=None):
+        if 'capacity' in self.material:
+            c = self.material['capacity']
+        elif self.scalar_name == "temperature":
+            c = self.material['density'] * self.material['specific_heat_capacity']
+        elif self.scalar_name == "electric_potential":
+            c = electric_permittivity_in_vacumm
+        elif self.scalar_name == "spicies_concentration":      # sic: the reference's spelling (:83)
+            c = 1
+        else:
+            raise SolverError('material capacity property is not found for {}'.format(self.scalar_name))
+        return self._material_number(c, T)
+
+    def diffusivity(self, T=None):
+        if 'diffusivity' in self.material:
+            c = self.material['diffusivity']
+        elif self.scalar_name == "temperature":
+            c = self.material['thermal_conductivity'] / self.capacity()
+        elif self.scalar_name == "electric_potential":
+            c = self.material['relative_electric_permittivity']
+        else:
+            raise SolverError('conductivity material property is not found for {}'.format(self.scalar_name))
+        return self._material_number(c, T)
+
+    def conductivity(self, T=None):
+        if 'conductivity' in self.material:
+            c = self.material['conductivity']
+        elif self.scalar_name == "temperature":
+            c = self.material['thermal_conductivity']
+        elif self.scalar_name == "electric_potential":
+            c = self.material['relative_electric_permittivity'] * electric_permittivity_in_vacumm
+        elif self.scalar_name == "spicies_concentration":
+            c = self.material['diffusivity']
+        else:
+            c = self.diffusivity() * self.capacity()
+        return self._material_number(c, T)
+
+    def _constant(self, value, what):
+        v = self.translate_value(value)
+        if isinstance(v, numbers.Number):
+            return float(v)
+        raise SolverError('{} must be a constant on the device path (got {})'.format(what, type(value)))
+
+    def update_boundary_conditions(self, time_iter_, T, Tq, ds):
+        """-> (DirichletBC list, ScalarForm with the boundary integrals filled in); `ds` is the form."""
+        F = ds
+        capacity = self.capacity(T)
+        bcs = []
+        if 'point_source' in self.settings and self.settings['point_source']:
+            raise SolverError('point_source is not implemented on the device path')
+        if 'surface_source' in self.settings and self.settings['surface_source']:
+            raise SolverError('surface_source is broken in the reference scalar solver (undefined get_flux) and not implemented')
+
+        for name, bc_settings in self.boundary_conditions.items():
+            i = bc_settings['boundary_id']
+            bc = self.get_boundary_variable(bc_settings)
+            btype = bc['type']
+            if btype == 'Dirichlet' or btype == 'fixedValue':
+                if not isinstance(bc['value'], DirichletBC):
+                    T_bc = self.translate_value(bc['value'])
+                    bcs.append(DirichletBC(self.function_space, T_bc, self.boundary_facets, i))
+                else:
+                    bcs.append(bc['value'])
+            elif btype == 'Neumann' or btype == 'fixedGradient':
+                g = self._constant(bc['value'], 'Neumann gradient')
+                F.neumann.append((i, g if self.using_diffusion_form else capacity * g))     # :181 as written
+            elif btype == 'symmetry':
+                pass
+            elif btype == 'mixed' or btype == 'Robin':
+                T_bc = self.translate_value(bc['value'])
+                g = self._constant(bc['gradient'], 'Robin gradient')
+                F.neumann.append((i, g if self.using_diffusion_form else capacity * g))
+                bcs.append(DirichletBC(self.function_space, T_bc, self.boundary_facets, i))
+            elif btype.lower().find('flux') >= 0 or btype == 'electric_current':
+                g = self._constant(bc['value'], 'flux')
+                F.neumann.append((i, g / capacity if self.using_diffusion_form else g))
+            elif btype == 'HTC':
+                Ta = self._constant(bc['ambient'], 'HTC ambient')
+                htc = self._constant(bc['value'], 'HTC coefficient')
+                if self.using_diffusion_form:
+                    htc = htc / capacity
+                F.robin.append((i, htc, Ta))
+            else:
+                raise SolverError('boundary type`{}` is not supported'.format(btype))
+        return bcs, F
+
+    def get_body_source_items(self, time_iter_, T, Tq, dx):
+        bs = self.get_body_source()
+        if bs is not None and isinstance(bs, dict):
+            return [(v['value'], v['subdomain_id']) for k, v in bs.items()]
+        elif bs is not None:
+            return [(bs, None)]
+        return None
+
+    def generate_form(self, time_iter_, T, T_test, T_current, T_prev):
+        F = ScalarForm(self)
+        conductivity = self.conductivity(T)
+        capacity = self.capacity(T)
+        if self.nonlinear or self.nonlinear_material:
+            raise SolverError('nonlinear material is outside the device hot path')
+        if isinstance(conductivity, (Function,)) or callable(conductivity):
+            raise SolverError('conductivity must be a number or a constant tensor on the device path')
+        F.conductivity, F.capacity = conductivity, capacity
+
+        if not hasattr(self, 'convective_velocity'):
+            if 'convective_velocity' in self.settings and self.settings['convective_velocity'] is not None:
+                self.convective_velocity = self.settings['convective_velocity']
+            else:
+                self.convective_velocity = None
+        if self.convective_velocity is not None:
+            ads = self.settings.get('advection_settings') or {'stabilization_method': None}
+            if ads.get('stabilization_method'):
+                raise SolverError('advection stabilisation (SPUG/IP) is not implemented on the device path')
+            vel = self.translate_value(self.convective_velocity)
+            if not (isinstance(vel, np.ndarray) and vel.shape == (self.dimension,)):
+                raise SolverError('convective_velocity must be a constant vector on the device path')
+            F.velocity = vel
+
+        if self.transient_settings['transient']:
+            F.transient = True
+            F.dt = self.get_time_step(time_iter_)
+            F.theta = 0.5
+            F.T_prev = T_prev
+
+        bcs, F = self.update_boundary_conditions(time_iter_, T, T_test, F)
+        bs_items = self.get_body_source_items(time_iter_, T, T_test, None)
+        if bs_items:
+            F.sources.extend(bs_items)
+
+        if self.scalar_name == "temperature":
+            if self.settings.get('radiation_settings') or getattr(self, 'radiation_settings', None):
+                raise SolverError('radiation is nonlinear and outside the device hot path')
+        return F, bcs
+
+    def solve_form(self, F, T_current, bcs):
+        if self.nonlinear:
+            raise SolverError('nonlinear solve is outside the device hot path')
+        return self.solve_linear_problem(F, T_current, bcs)

@@ -1,0 +1,194 @@
+"""Device side of a P1 space: mesh upload/generation, pattern, assembly calls, Dirichlet, Krylov.
+
+This is the layer SolverBase.solve_linear_problem / solve_amg delegate to instead of dolfin's
+assemble / assemble_system / LinearVariationalSolver / PETScKrylovSolver
+(/root/reference/FenicsSolver/SolverBase.py:592-672).  It only sequences libfsb calls; there is no
+numerical fallback on the host.
+
+Distributed runs (one process per GPU): a box mesh is cut into z-slabs of vertex planes, each rank
+generates its slab plus one ghost plane per neighbour on its own device, assembles without
+communication (owner computes) and solves with halo exchange + all-reduced dot products.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import SolverError
+
+_contexts = {}
+
+
+def get_context(device=None, stream=None):
+    """One libfsb context per device and process (LOCAL_RANK selects the device by default).
+    `stream`: a cudaStream_t handle (e.g. torch.cuda.Stream().cuda_stream) for the first creation."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = _contexts.get(device)
+    if ctx is None or ctx.h is None:
+        ctx = _lib.Context(device, stream=stream)
+        _contexts[device] = ctx
+    return ctx
+
+
+class Comm:
+    """Process group description for the z-slab decomposition.  `bootstrap` broadcasts the NCCL
+    unique id (torch.distributed is used only for that and for host-side gathers)."""
+
+    def __init__(self, rank=0, nranks=1, bootstrap=None):
+        self.rank, self.nranks, self.bootstrap = rank, nranks, bootstrap
+
+    @classmethod
+    def from_torch(cls):
+        import torch.distributed as dist
+        if not dist.is_available() or not dist.is_initialized():
+            return cls()
+
+        def bcast(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        return cls(dist.get_rank(), dist.get_world_size(), bcast)
+
+
+def slab_partition(nplanes, nranks):
+    """Contiguous blocks of vertex planes, as even as possible: [(p0, p1), ...] per rank."""
+    base, rem = divmod(nplanes, nranks)
+    out, p = [], 0
+    for r in range(nranks):
+        k = base + (1 if r < rem else 0)
+        out.append((p, p + k))
+        p += k
+    return out
+
+
+class DeviceSpace:
+    """P1 space with `ncomp` components on a mesh, resident on one GPU (or one slab of it)."""
+
+    def __init__(self, mesh, ncomp=1, ctx=None, comm=None):
+        self.mesh, self.ncomp = mesh, ncomp
+        self.ctx = ctx or get_context()
+        self.comm = comm or Comm()
+        self.timings = {}
+        t0 = time.perf_counter()
+        self.v_off = 0                                  # global vertex id of local vertex 0
+        self.ghost_lo = self.ghost_hi = 0
+        nv_global = mesh.num_vertices()
+        if self.comm.nranks > 1:
+            if not mesh.box:
+                raise SolverError("distributed runs need a generated box mesh (z-slab partition); "
+                                  "unstructured partitioning is not implemented")
+            n = mesh.box["n"]
+            nlast = n[-1]
+            if nlast + 1 < self.comm.nranks:
+                raise SolverError("more ranks than vertex planes")
+            self.plane = int(np.prod([k + 1 for k in n[:-1]]))
+            zp0, zp1 = slab_partition(nlast + 1, self.comm.nranks)[self.comm.rank]
+            layer0, layer1 = max(zp0 - 1, 0), min(zp1, nlast)
+            self.ghost_lo, self.ghost_hi = int(zp0 > 0), int(zp1 <= nlast)
+            self.owned_planes = zp1 - zp0
+            self.v_off = layer0 * self.plane
+            if getattr(mesh, "force_upload", False):
+                # host mesh arrays (e.g. pinned): upload this rank's slab, renumbered to local vertex ids
+                per_layer = mesh.num_cells() // nlast
+                nvl = (layer1 - layer0 + 1) * self.plane
+                self.dmesh = _lib.DeviceMesh.upload(self.ctx, mesh.coordinates()[self.v_off:self.v_off + nvl],
+                                                    mesh.cells()[per_layer * layer0:per_layer * layer1] - self.v_off)
+            else:
+                self.dmesh = _lib.DeviceMesh.box(self.ctx, n, mesh.box["p0"], mesh.box["p1"], layer0, layer1)
+            if self.ctx.nranks == 1:
+                uid = self.ctx.dist_unique_id() if self.comm.rank == 0 else None
+                uid = self.comm.bootstrap(uid)
+                self.ctx.dist_init(self.comm.rank, self.comm.nranks, uid)
+            self.ctx.dist_set_slab(self.ghost_lo, self.ghost_hi, self.owned_planes)
+        elif mesh.box and not getattr(mesh, "force_upload", False):
+            self.dmesh = _lib.DeviceMesh.box(self.ctx, mesh.box["n"], mesh.box["p0"], mesh.box["p1"])
+        else:
+            self.dmesh = _lib.DeviceMesh.upload(self.ctx, mesh.coordinates(), mesh.cells())
+        _, _, self.nv_local, self.nc_local = self.dmesh.sizes()
+        self.own_v0 = self.ghost_lo * getattr(self, "plane", 0)
+        self.own_v1 = self.own_v0 + (self.owned_planes * self.plane if self.comm.nranks > 1 else self.nv_local)
+        self.nv_global = nv_global
+        self.ctx.sync()
+        self.timings["mesh"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self.A = _lib.DeviceMatrix.create(self.dmesh, ncomp)          # symbolic phase (K2)
+        if self.comm.nranks > 1:
+            self.A.set_owned_rows(self.own_v0, self.own_v1)
+        self.ctx.sync()
+        self.timings["symbolic"] = time.perf_counter() - t0
+
+    # ---- index helpers ----------------------------------------------------------------------------
+    @property
+    def ndof_local(self):
+        return self.nv_local * self.ncomp
+
+    @property
+    def ndof_global(self):
+        return self.nv_global * self.ncomp
+
+    def local_vertices(self, gverts):
+        """Global vertex ids -> local ids, dropping those outside this rank's planes."""
+        g = np.asarray(gverts, dtype=np.int64)
+        l = g - self.v_off
+        return l[(l >= 0) & (l < self.nv_local)]
+
+    def local_facets(self, fverts, opp=None):
+        fv = np.asarray(fverts, dtype=np.int64) - self.v_off
+        keep = np.all((fv >= 0) & (fv < self.nv_local), axis=1) if fv.size else np.zeros(0, bool)
+        if opp is None:
+            return fv[keep].astype(np.int32), None
+        op = np.asarray(opp, dtype=np.int64) - self.v_off
+        keep &= (op >= 0) & (op < self.nv_local)
+        return fv[keep].astype(np.int32), op[keep].astype(np.int32)
+
+    def local_dofs(self, gdofs, gvals):
+        """Global dof ids/values -> local, dropping those outside this rank's planes."""
+        g = np.asarray(gdofs, dtype=np.int64)
+        v = np.broadcast_to(np.asarray(gvals, dtype=np.float64), g.shape)
+        l = g - self.v_off * self.ncomp
+        keep = (l >= 0) & (l < self.ndof_local)
+        return l[keep], v[keep]
+
+    def local_coordinates(self):
+        if self.comm.nranks == 1:
+            return self.mesh.coordinates()
+        return self.mesh.coordinates()[self.v_off:self.v_off + self.nv_local]
+
+    # ---- vectors ----------------------------------------------------------------------------------
+    def vector(self, fill=None):
+        v = _lib.DeviceVector(self.ctx, self.ndof_local)
+        if fill is not None and fill != 0.0:
+            v.fill(fill)
+        return v
+
+    def vector_from_global(self, values):
+        a = np.asarray(values, dtype=np.float64).ravel()
+        lo = self.v_off * self.ncomp
+        return _lib.DeviceVector.from_numpy(self.ctx, a[lo:lo + self.ndof_local])
+
+    def owned_values(self, dvec):
+        a = dvec.numpy()
+        return a[self.own_v0 * self.ncomp:self.own_v1 * self.ncomp]
+
+    def gather_global(self, dvec):
+        """Solution in global vertex order on every rank (host).  Single GPU: one D2H copy."""
+        mine = self.owned_values(dvec)
+        if self.comm.nranks == 1:
+            return mine
+        import torch.distributed as dist
+        parts = [None] * self.comm.nranks
+        dist.all_gather_object(parts, mine)
+        return np.concatenate(parts)
+
+    # ---- Dirichlet + solve ------------------------------------------------------------------------
+    def apply_dirichlet(self, b, gdofs, gvals, symmetric, x=None):
+        d, v = self.local_dofs(gdofs, gvals)
+        self.A.apply_dirichlet(b, d, v, symmetric=symmetric, x=x)
+
+    def solve(self, b, x, method="cg", rtol=1e-12, atol=0.0, maxit=100000, precond="jacobi"):
+        info = self.A.solve(b, x, method=method, rtol=rtol, atol=atol, maxit=maxit, precond=precond)
+        return info

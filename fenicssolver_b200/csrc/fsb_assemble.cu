@@ -3,7 +3,7 @@
 // One thread per cell: connectivity is read as one vector load, the (L2-resident) vertex coordinates
 // are gathered, the closed-form P1 local matrix is formed in registers (exact for every integrand on
 // the hot path) and its entries are added with fire-and-forget fp64 reductions
-// (RED.E.ADD.F64) at positions taken from the uint8 position map (asm_mode 1) or an in-row binary
+// (REDG.E.ADD.F64) at positions taken from the uint8 position map (asm_mode 1) or an in-row binary
 // search (asm_mode 0).
 #include "fsb_internal.cuh"
 

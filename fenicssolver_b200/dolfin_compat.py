@@ -1,0 +1,579 @@
+"""Plain-data stand-ins for the dolfin objects FenicsSolver user code passes in.
+
+Reference scripts do `from dolfin import *` and hand Mesh / FunctionSpace / Constant / SubDomain
+objects to the solvers (e.g. /root/reference/examples/test_heat_transfer.py:34-45,59-89).  The same
+scripts run against this package with `from fenicssolver_b200.dolfin_compat import *`: the classes
+below carry only data (numpy arrays, numbers, predicates); all arithmetic happens in libfsb.
+
+Host-side integer work that dolfin does at mesh construction lives here too (K1 in SURVEY 2.2):
+facet numbering (global facet id = lexicographic rank of the sorted vertex tuple), exterior-facet
+detection, SubDomain.mark.
+"""
+from __future__ import annotations
+
+import math
+import numbers
+import os
+import re
+
+import numpy as np
+
+from ._lib import SolverError
+
+DOLFIN_EPS = 3.0e-16
+__all__ = ["DOLFIN_EPS", "near", "Point", "Constant", "Expression", "Mesh", "UnitSquareMesh", "RectangleMesh",
+           "UnitCubeMesh", "BoxMesh", "SubDomain", "AutoSubDomain", "MeshFunction", "FacetMarkers", "FunctionSpace",
+           "VectorFunctionSpace", "Function", "DirichletBC", "SolverError"]
+
+
+def near(a, b, eps=DOLFIN_EPS):
+    """dolfin.near: |a-b| <= eps (absolute).  Vectorised over numpy arrays."""
+    return np.abs(np.asarray(a) - b) <= eps
+
+
+class Point:
+    def __init__(self, *xyz):
+        self.x = np.array(xyz, dtype=np.float64)
+
+    def __getitem__(self, i):
+        return self.x[i]
+
+    def __len__(self):
+        return self.x.size
+
+
+class Constant:
+    """dolfin.Constant: a number or a tuple of numbers."""
+
+    def __init__(self, value):
+        self._v = np.array(value, dtype=np.float64)
+
+    def values(self):
+        return np.atleast_1d(self._v).copy()
+
+    @property
+    def ufl_shape(self):
+        return self._v.shape
+
+    def __float__(self):
+        return float(self._v)
+
+    def __repr__(self):
+        return "Constant(%s)" % (self._v.tolist(),)
+
+
+_EXPR_NAMES = {k: getattr(np, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt", "fabs", "floor", "ceil", "arctan2")}
+_EXPR_NAMES.update({"pow": np.power, "abs": np.abs, "pi": math.pi, "atan2": np.arctan2, "DOLFIN_PI": math.pi})
+
+
+class Expression:
+    """dolfin.Expression for C++-style strings in x[0..2] (and keyword parameters), evaluated at the
+    vertices, i.e. interpolated into P1 as SolverBase.py:310-314,364,387 do."""
+
+    def __init__(self, code, degree=1, **params):
+        self.code = code
+        self.degree = degree
+        self.params = params
+
+    def _eval_one(self, src, x):
+        env = dict(_EXPR_NAMES)
+        env.update(self.params)
+        env["x"] = x
+        if not re.fullmatch(r"[\w\s\.\+\-\*/\(\)\[\],<>=!&|?:]*", src):
+            raise SolverError("unsupported characters in Expression %r" % src)
+        val = eval(src.replace("&&", " and ").replace("||", " or "), {"__builtins__": {}}, env)  # noqa: S307
+        return np.broadcast_to(np.asarray(val, dtype=np.float64), x[0].shape).copy()
+
+    def __call__(self, coords):
+        """coords [n, gdim] -> values [n] (scalar expression) or [n, k]."""
+        x = [coords[:, i] for i in range(coords.shape[1])]
+        if isinstance(self.code, (tuple, list)):
+            return np.stack([self._eval_one(str(c), x) for c in self.code], axis=1)
+        return self._eval_one(str(self.code), x)
+
+
+# ------------------------------------------------------------------------------------------ meshes
+_HEX_TETS = np.array([(0, 1, 3, 7), (0, 1, 5, 7), (0, 4, 5, 7), (0, 2, 3, 7), (0, 4, 6, 7), (0, 2, 6, 7)])
+
+
+class Mesh:
+    """A simplex mesh.  Either host arrays (file / user supplied) or a dolfin-layout box description
+    that is generated directly on the device (UnitCubeMesh(256,256,256) never crosses PCIe)."""
+
+    def __init__(self, coordinates=None, cells=None, box=None):
+        if isinstance(coordinates, str):
+            c, t = read_dolfin_xml_mesh(coordinates)
+            coordinates, cells = c, t
+        self.box = box                      # dict(n=(..), p0=(..), p1=(..)) or None
+        self._coords = None if coordinates is None else np.ascontiguousarray(coordinates, dtype=np.float64)
+        self._cells = None if cells is None else np.sort(np.ascontiguousarray(cells, dtype=np.int32), axis=1)
+        if box is None and (self._coords is None or self._cells is None):
+            raise SolverError("Mesh needs coordinates and cells, or a box description")
+        self._exterior = None
+        self._facet_table = None
+
+    # geometry()/topology() give the two numbers the reference reads (SolverBase.py:153-154)
+    class _Dim:
+        def __init__(self, d):
+            self._d = d
+
+        def dim(self):
+            return self._d
+
+    def geometry(self):
+        return Mesh._Dim(self.gdim)
+
+    def topology(self):
+        return Mesh._Dim(self.tdim)
+
+    @property
+    def gdim(self):
+        return len(self.box["n"]) if self.box else self._coords.shape[1]
+
+    @property
+    def tdim(self):
+        return len(self.box["n"]) if self.box else self._cells.shape[1] - 1
+
+    def num_vertices(self):
+        if self.box:
+            return int(np.prod([k + 1 for k in self.box["n"]]))
+        return self._coords.shape[0]
+
+    def num_cells(self):
+        if self.box:
+            return int(np.prod(self.box["n"])) * (6 if self.tdim == 3 else 2)
+        return self._cells.shape[0]
+
+    def coordinates(self):
+        if self._coords is None:
+            n, p0, p1 = self.box["n"], self.box["p0"], self.box["p1"]
+            axes = [p0[i] + np.arange(n[i] + 1) * (p1[i] - p0[i]) / n[i] for i in range(len(n))]
+            grids = np.meshgrid(*axes[::-1], indexing="ij")          # last axis slowest, x fastest
+            self._coords = np.stack([g.ravel() for g in grids[::-1]], axis=1)
+        return self._coords
+
+    def cells(self):
+        if self._cells is None:
+            self._cells = box_cells(self.box["n"])
+        return self._cells
+
+    # ---- facets -------------------------------------------------------------------------------
+    def exterior_facets(self):
+        """(fverts[nbf, tdim], opposite_vertex[nbf]) of the exterior facets."""
+        if self._exterior is None:
+            if self.box:
+                self._exterior = box_exterior_facets(self.box["n"])
+            else:
+                facets, cf, count = self.facet_table()
+                ci, li = np.nonzero(count[cf] == 1)
+                fid = cf[ci, li]
+                order = np.argsort(fid, kind="stable")
+                self._exterior = (facets[fid[order]].astype(np.int32), self._cells[ci[order], li[order]].astype(np.int32), fid[order])
+        return self._exterior[0], self._exterior[1]
+
+    def exterior_facet_ids(self):
+        """dolfin facet indices of the exterior facets (file meshes only)."""
+        self.exterior_facets()
+        if len(self._exterior) < 3:
+            raise SolverError("global facet numbering is not materialised for generated box meshes")
+        return self._exterior[2]
+
+    def facet_table(self):
+        """All facets in dolfin numbering: local facet i is opposite local vertex i of the sorted cell;
+        global facet id = lexicographic rank of the sorted facet vertex tuple (verified against
+        data/mesh_facet_region.xml).  Returns (facets, cell_facets, count)."""
+        if self._facet_table is None:
+            cells = self.cells()
+            nc, nl = cells.shape
+            allf = np.stack([np.delete(cells, i, axis=1) for i in range(nl)], axis=1).reshape(-1, nl - 1)
+            facets, inv, count = np.unique(allf, axis=0, return_inverse=True, return_counts=True)
+            self._facet_table = (facets, inv.reshape(nc, nl), count)
+        return self._facet_table
+
+
+def box_cells(n):
+    """Cells of the dolfin box layout, sorted per cell (BoxMesh: six tets per hex on the v0-v7
+    diagonal; RectangleMesh 'right': (v0,v1,v3),(v0,v2,v3))."""
+    if len(n) == 2:
+        nx, ny = n
+        cx, cy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+        v0 = (cy * (nx + 1) + cx).ravel()
+        v1, v2, v3 = v0 + 1, v0 + nx + 1, v0 + nx + 2
+        cells = np.stack([np.stack([v0, v1, v3], 1), np.stack([v0, v2, v3], 1)], axis=1).reshape(-1, 3)
+        return cells.astype(np.int32)
+    nx, ny, nz = n
+    px, py = nx + 1, (nx + 1) * (ny + 1)
+    cz, cy, cx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    v0 = (cx + cy * px + cz * py).ravel()
+    hv = np.stack([v0, v0 + 1, v0 + px, v0 + px + 1, v0 + py, v0 + py + 1, v0 + py + px, v0 + py + px + 1], axis=1)
+    return hv[:, _HEX_TETS].reshape(-1, 4).astype(np.int32)
+
+
+def box_exterior_facets(n):
+    """Exterior facets of the box layout without touching the interior: O(surface) work.
+    For every boundary plane take the layer of boxes touching it, form their simplices and keep the
+    facets whose vertices all lie in the plane."""
+    d = len(n)
+    strides = np.cumprod([1] + [k + 1 for k in n[:-1]])
+    fv_all, opp_all = [], []
+
+    def layer_cells(axis, idx):
+        rng = [np.arange(k) for k in n]
+        rng[axis] = np.array([idx])
+        grids = np.meshgrid(*rng[::-1], indexing="ij")
+        c = [g.ravel() for g in grids[::-1]]
+        v0 = sum(ci * s for ci, s in zip(c, strides))
+        if d == 2:
+            px = strides[1]
+            v1, v2, v3 = v0 + 1, v0 + px, v0 + px + 1
+            return np.stack([np.stack([v0, v1, v3], 1), np.stack([v0, v2, v3], 1)], axis=1).reshape(-1, 3)
+        px, py = strides[1], strides[2]
+        hv = np.stack([v0, v0 + 1, v0 + px, v0 + px + 1, v0 + py, v0 + py + 1, v0 + py + px, v0 + py + px + 1], axis=1)
+        return hv[:, _HEX_TETS].reshape(-1, 4)
+
+    for axis in range(d):
+        for idx, plane in ((0, 0), (n[axis] - 1, n[axis])):
+            cells = layer_cells(axis, idx)
+            nl = cells.shape[1]
+            for i in range(nl):
+                f = np.delete(cells, i, axis=1)
+                coord = (f // strides[axis]) % (n[axis] + 1)
+                keep = np.all(coord == plane, axis=1)
+                fv_all.append(f[keep])
+                opp_all.append(cells[keep, i])
+    fv = np.concatenate(fv_all).astype(np.int32)
+    opp = np.concatenate(opp_all).astype(np.int32)
+    order = np.lexsort(fv.T[::-1])
+    return fv[order], opp[order]
+
+
+def UnitSquareMesh(nx, ny, diagonal="right"):
+    if diagonal != "right":
+        raise SolverError("only the default 'right' diagonal is implemented")
+    return Mesh(box=dict(n=(int(nx), int(ny)), p0=(0.0, 0.0), p1=(1.0, 1.0)))
+
+
+def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
+    if diagonal != "right":
+        raise SolverError("only the default 'right' diagonal is implemented")
+    return Mesh(box=dict(n=(int(nx), int(ny)), p0=(float(p0[0]), float(p0[1])), p1=(float(p1[0]), float(p1[1]))))
+
+
+def UnitCubeMesh(nx, ny, nz):
+    return Mesh(box=dict(n=(int(nx), int(ny), int(nz)), p0=(0.0, 0.0, 0.0), p1=(1.0, 1.0, 1.0)))
+
+
+def BoxMesh(p0, p1, nx, ny, nz):
+    return Mesh(box=dict(n=(int(nx), int(ny), int(nz)), p0=tuple(float(p0[i]) for i in range(3)), p1=tuple(float(p1[i]) for i in range(3))))
+
+
+def read_dolfin_xml_mesh(path):
+    """dolfin-XML mesh (Mesh(filename), SolverBase.py:224).  Cells are sorted per cell as mesh.order() does."""
+    txt = open(path, "r").read()
+    m = re.search(r'<mesh[^>]*celltype="(\w+)"[^>]*dim="(\d+)"', txt)
+    if not m:
+        raise SolverError("%s is not a dolfin-XML mesh" % path)
+    celltype, dim = m.group(1), int(m.group(2))
+    if celltype not in ("tetrahedron", "triangle"):
+        raise SolverError("cell type %s is not supported" % celltype)
+    nv = int(re.search(r'<vertices size="(\d+)"', txt).group(1))
+    nc = int(re.search(r'<cells size="(\d+)"', txt).group(1))
+    names = ["x", "y", "z"][:dim]
+    vre = re.compile(r'<vertex index="(\d+)"' + "".join(r'\s+%s="([^"]+)"' % k for k in names))
+    varr = np.array([[float(g) for g in mm.groups()] for mm in vre.finditer(txt)])
+    coords = np.zeros((nv, dim))
+    coords[varr[:, 0].astype(np.int64)] = varr[:, 1:]
+    nl = 4 if celltype == "tetrahedron" else 3
+    cre = re.compile(r'<%s index="(\d+)"' % celltype + "".join(r'\s+v%d="(\d+)"' % k for k in range(nl)))
+    carr = np.array([[int(g) for g in mm.groups()] for mm in cre.finditer(txt)], dtype=np.int64)
+    cells = np.zeros((nc, nl), dtype=np.int32)
+    cells[carr[:, 0]] = carr[:, 1:]
+    return coords, np.sort(cells, axis=1)
+
+
+def read_mesh_function_xml(path):
+    """dolfin-XML MeshFunction (SolverBase.py:229,236) -> (dim, int values[size])."""
+    txt = open(path, "r").read()
+    m = re.search(r'<mesh_function type="\w+" dim="(\d+)" size="(\d+)"', txt)
+    if not m:
+        raise SolverError("%s is not a dolfin-XML mesh function" % path)
+    dim, size = int(m.group(1)), int(m.group(2))
+    arr = np.array([[int(a), int(b)] for a, b in re.findall(r'<entity index="(\d+)" value="(-?\d+)"', txt)], dtype=np.int64)
+    vals = np.zeros(size, dtype=np.int64)
+    if arr.size:
+        vals[arr[:, 0]] = arr[:, 1]
+    return dim, vals
+
+
+# ------------------------------------------------------------------------------------------ subdomains / markers
+class SubDomain:
+    """dolfin.SubDomain: override inside(x, on_boundary)."""
+
+    def inside(self, x, on_boundary):
+        raise NotImplementedError
+
+    def _call(self, x, on_boundary):
+        return self.inside(x, on_boundary)
+
+    def mark(self, markers, value):
+        markers.mark_subdomain(self, value)
+
+
+class AutoSubDomain(SubDomain):
+    """dolfin.AutoSubDomain(lambda x: ...) or (lambda x, on_boundary: ...)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+        try:
+            import inspect
+            self.nargs = len(inspect.signature(fn).parameters)
+        except (TypeError, ValueError):
+            self.nargs = 1
+
+    def inside(self, x, on_boundary):
+        return self.fn(x) if self.nargs == 1 else self.fn(x, on_boundary)
+
+
+def _evaluate_predicate(sub, pts):
+    """inside() over points [n, gdim]: vectorised call with x[i] = coordinate arrays, falling back to a
+    per-point loop when the predicate is not array-friendly."""
+    if not isinstance(sub, SubDomain):
+        if callable(sub):
+            sub = AutoSubDomain(sub)
+        else:
+            raise SolverError("a boundary must be a SubDomain or a predicate, got %r" % type(sub))
+    n = pts.shape[0]
+    try:
+        r = sub._call([pts[:, i] for i in range(pts.shape[1])], True)
+        r = np.asarray(r)
+        if r.shape == (n,):
+            return r.astype(bool)
+        if r.shape == ():
+            return np.full(n, bool(r))
+    except (ValueError, TypeError):
+        pass
+    return np.array([bool(sub._call(pts[i], True)) for i in range(n)], dtype=bool)
+
+
+class FacetMarkers:
+    """MeshFunction('size_t', mesh, tdim-1) restricted to the exterior facets (deviation from dolfin:
+    interior facets are never marked; every boundary in the reference's cases lies on the surface)."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.fverts, self.opp = mesh.exterior_facets()
+        self.values = np.zeros(self.fverts.shape[0], dtype=np.int64)
+
+    def set_all(self, v):
+        self.values[:] = v
+
+    def mark_subdomain(self, sub, value):
+        """SubDomain.mark: a facet is marked iff all its vertices and its midpoint are inside
+        (dolfin's default check_midpoint=True; SolverBase.py:281-282)."""
+        X = self.mesh.coordinates()[self.fverts]              # [nf, d, gdim]
+        nf, d, g = X.shape
+        ok = _evaluate_predicate(sub, X.mean(axis=1))
+        for a in range(d):
+            ok &= _evaluate_predicate(sub, X[:, a, :])
+        self.values[ok] = value
+
+    def facets(self, marker):
+        sel = self.values == marker
+        return self.fverts[sel], self.opp[sel]
+
+    def vertices(self, marker):
+        return np.unique(self.fverts[self.values == marker])
+
+    def array(self):
+        return self.values
+
+
+class MeshFunction:
+    """Cell markers (MeshFunction('size_t', mesh, tdim)); facet markers are FacetMarkers."""
+
+    def __new__(cls, kind, mesh, dim_or_file, value=0):
+        if isinstance(dim_or_file, str):
+            dim, vals = read_mesh_function_xml(dim_or_file)
+        else:
+            dim, vals = int(dim_or_file), None
+        if dim == mesh.tdim - 1:
+            fm = FacetMarkers(mesh)
+            if vals is not None:
+                fm.values = vals[mesh.exterior_facet_ids()]
+            return fm
+        obj = super().__new__(cls)
+        obj.mesh, obj.dim = mesh, dim
+        obj.values = vals if vals is not None else np.full(mesh.num_cells() if dim == mesh.tdim else mesh.num_vertices(), value, dtype=np.int64)
+        return obj
+
+    def set_all(self, v):
+        self.values[:] = v
+
+    def array(self):
+        return self.values
+
+
+# ------------------------------------------------------------------------------------------ spaces / functions
+class _UflElement:
+    def __init__(self, degree):
+        self._degree = degree
+
+    def degree(self):
+        return self._degree
+
+
+class FunctionSpace:
+    """P1 Lagrange on a mesh; ncomp = 1 (scalar) or dim (vector).  DoF numbering is vertex order."""
+
+    def __init__(self, mesh, family="CG", degree=1, ncomp=1, constrained_domain=None):
+        if family not in ("CG", "Lagrange", "P"):
+            raise SolverError("element family %r is not supported (CG/Lagrange only)" % family)
+        if degree != 1:
+            raise SolverError("fe_degree %r is not implemented yet: only P1 runs on the device path" % degree)
+        if constrained_domain is not None:
+            raise SolverError("periodic boundaries are not implemented")
+        self._mesh, self.ncomp = mesh, ncomp
+        self._ufl_element = _UflElement(degree)
+
+    def mesh(self):
+        return self._mesh
+
+    def dim(self):
+        return self._mesh.num_vertices() * self.ncomp
+
+
+def VectorFunctionSpace(mesh, family="CG", degree=1, dim=None, constrained_domain=None):
+    return FunctionSpace(mesh, family, degree, ncomp=dim or mesh.gdim, constrained_domain=constrained_domain)
+
+
+class _Vector:
+    def __init__(self, fn):
+        self._fn = fn
+
+    def get_local(self):
+        return self._fn.array().copy()
+
+    def array(self):
+        return self._fn.array()
+
+    def __getitem__(self, i):
+        return self._fn.array()[i]
+
+    def __setitem__(self, i, v):
+        a = self._fn.array()
+        a[i] = v
+        self._fn.assign_array(a)
+
+    def size(self):
+        return self._fn.function_space.dim()
+
+    def norm(self, kind="l2"):
+        return float(np.linalg.norm(self._fn.array()))
+
+
+class Function:
+    """Nodal P1 field.  Values live on the device after a solve and are downloaded lazily."""
+
+    def __init__(self, V, values=None):
+        self.function_space = V
+        self._host = None if values is None else np.ascontiguousarray(values, dtype=np.float64).ravel().copy()
+        self._dev = None          # _lib.DeviceVector holding the same values (None: host only)
+        self._host_valid = True
+        if self._host is None:
+            self._host = np.zeros(V.dim())
+        self._name = "f"
+
+    def array(self):
+        if not self._host_valid:
+            self._host = self._dev.numpy()       # the one D2H copy of a solve result, on demand
+            self._host_valid = True
+        return self._host
+
+    def assign_array(self, a):
+        self._host = np.ascontiguousarray(a, dtype=np.float64).ravel().copy()
+        self._host_valid = True
+        self._dev = None
+
+    def set_device(self, dev):
+        """Adopt a device vector as the current value (host copy becomes stale)."""
+        self._dev = dev
+        self._host_valid = False
+
+    def device_vector(self):
+        return self._dev
+
+    def assign(self, other):
+        if isinstance(other, Function):
+            if other._dev is not None and not other._host_valid:
+                # device-resident value: copy on the device, no PCIe round trip per time step
+                from ._lib import DeviceVector
+                if self._dev is None or self._dev is other._dev or self._dev.n != other._dev.n:
+                    self._dev = DeviceVector(other._dev.ctx, other._dev.n)
+                self._dev.copy_from(other._dev)
+                self._host_valid = False
+            else:
+                self.assign_array(other.array())
+        else:
+            raise SolverError("Function.assign needs another Function")
+
+    def vector(self):
+        return _Vector(self)
+
+    def compute_vertex_values(self, mesh=None):
+        a = self.array()
+        nc = self.function_space.ncomp
+        return a if nc == 1 else a.reshape(-1, nc).T.reshape(-1)     # dolfin returns component-major
+
+    @property
+    def values(self):
+        a = self.array()
+        nc = self.function_space.ncomp
+        return a if nc == 1 else a.reshape(-1, nc)
+
+    def copy(self, deepcopy=True):
+        return Function(self.function_space, self.array())
+
+    def rename(self, name, label=""):
+        self._name = name
+
+    def __call__(self, *x):
+        raise SolverError("point evaluation is not implemented; use .values (vertex order)")
+
+
+class DirichletBC:
+    """DirichletBC(V, value, markers, id) (topological): the dofs of every facet carrying the marker.
+    `component` restricts a vector space to V.sub(component)."""
+
+    def __init__(self, V, value, markers, marker_id, component=None):
+        self.V, self.value, self.markers, self.marker_id, self.component = V, value, markers, marker_id, component
+
+    def dofs_and_values(self, coords):
+        verts = self.markers.vertices(self.marker_id)
+        nc = self.V.ncomp
+        comps = range(nc) if self.component is None else [self.component]
+        comps = list(comps)
+        val = self.value
+        if isinstance(val, Constant):
+            val = val.values()
+            val = val[0] if val.size == 1 else val
+        if isinstance(val, Expression):
+            val = val(coords)                       # nodal values over the whole mesh
+        elif isinstance(val, Function):
+            val = val.values
+        val = np.asarray(val, dtype=np.float64)
+        nv = coords.shape[0]
+        dofs, vals = [], []
+        for k, c in enumerate(comps):
+            dofs.append(verts.astype(np.int64) * nc + c)
+            if val.ndim == 0:                                        # one constant
+                v = np.full(verts.size, float(val))
+            elif val.ndim == 1 and len(comps) > 1 and val.size == len(comps):   # constant vector
+                v = np.full(verts.size, val[k])
+            elif val.ndim == 1 and val.size == nv:                   # nodal scalar field
+                v = val[verts]
+            elif val.ndim == 2 and val.shape[0] == nv:               # nodal vector field
+                v = val[verts, c if self.component is None else 0]
+            else:
+                raise SolverError("cannot interpret a Dirichlet value of shape %r" % (val.shape,))
+            vals.append(v)
+        return np.concatenate(dofs), np.concatenate(vals)

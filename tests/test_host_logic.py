@@ -1,0 +1,275 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/fsb.h declares,
+settings parsing / boundary marking / value translation mirror the reference, the product path fails
+loudly without a GPU, and the z-slab partition logic is consistent across a world_size-2 gloo group."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from fenicssolver_b200 import LinearElasticitySolver, ScalarTransportSolver, SolverBase, _lib, backend
+from fenicssolver_b200.dolfin_compat import (AutoSubDomain, BoxMesh, Constant, Expression, FacetMarkers, FunctionSpace, Mesh, MeshFunction,
+                                             Point, SubDomain, UnitCubeMesh, UnitSquareMesh, VectorFunctionSpace, near)
+from fenicssolver_b200.main import load_settings, main
+from oracle import fem_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from fenicssolver_b200 import build
+    lib_path = build.build()
+    header = open(os.path.join(ROOT, "include", "fsb.h")).read()
+    declared = set(re.findall(r"\b(fsb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"fsb_status"}
+    assert len(declared) >= 40
+    lib = _lib.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libfsb.so does not export %s" % name
+        assert name in _lib.SIGNATURES, "no ctypes prototype for %s" % name
+    assert set(_lib.SIGNATURES) == declared
+    # the shared object is self-contained sm_100a code with TMA bulk copies in the SpMV kernel
+    if os.environ.get("FSB_CHECK_SASS", "1") == "1":
+        out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True)
+        if out.returncode == 0:
+            assert "sm_100a" in out.stdout and "UBLKCP" in out.stdout and "REDG.E.ADD.F64" in out.stdout
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is visible")
+    except ImportError:
+        pass
+    with pytest.raises(_lib.SolverError):
+        _lib.Context(0)
+    mesh = UnitSquareMesh(4, 4)
+    s = heat_settings(mesh)
+    solver = ScalarTransportSolver.ScalarTransportSolver(s)
+    with pytest.raises(_lib.SolverError):
+        solver.solve()
+    # nothing in the product package imports the oracle
+    for fn in os.listdir(os.path.join(ROOT, "fenicssolver_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "fenicssolver_b200", fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def heat_settings(mesh, bcs=None):
+    top = AutoSubDomain(lambda x: near(x[1], 1))
+    bottom = AutoSubDomain(lambda x: near(x[1], 0))
+    bcs = bcs or {"hot": {'boundary': top, 'boundary_id': 1, 'type': 'Dirichlet', 'value': Constant(360)},
+                  "cold": {'boundary': bottom, 'boundary_id': 2, 'values': {'temperature': {'variable': 'temperature', 'type': 'HTC', 'value': Constant(100), 'ambient': Constant(300)}}}}
+    return {'solver_name': 'ScalarEquationSolver', 'mesh': None, 'function_space': FunctionSpace(mesh, "CG", 1),
+            'periodic_boundary': None, 'fe_degree': 1, 'boundary_conditions': bcs, 'body_source': None,
+            'initial_values': {'temperature': 300},
+            'material': {'density': 1000, 'specific_heat_capacity': 4200, 'thermal_conductivity': 0.1},
+            'solver_settings': {'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.1, 'ending_time': 1},
+                                'reference_values': {'temperature': 300},
+                                'solver_parameters': {"relative_tolerance": 1e-9, "maximum_iterations": 500, "monitor_convergence": True}},
+            'scalar_name': 'temperature'}
+
+
+def test_box_meshes_match_dolfin_layout():
+    for n in [(5, 3), (4, 3, 2)]:
+        if len(n) == 2:
+            m, (c, t) = UnitSquareMesh(*n), fo.unit_square_mesh(*n)
+        else:
+            m, (c, t) = BoxMesh(Point(0, 0, 0), Point(10, 1, 1), *n), fo.box_mesh((0, 0, 0), (10, 1, 1), *n)
+        assert np.array_equal(m.coordinates(), c) and np.array_equal(m.cells(), t)
+        fv, opp = m.exterior_facets()
+        f2, o2, _ = fo.exterior_facets(t)
+        assert set(map(tuple, np.hstack([fv, opp[:, None]]))) == set(map(tuple, np.hstack([f2, o2[:, None]])))
+        assert m.num_vertices() == c.shape[0] and m.num_cells() == t.shape[0] and m.geometry().dim() == len(n)
+
+
+def test_subdomain_marking_semantics():
+    m = UnitCubeMesh(4, 4, 4)
+    fm = FacetMarkers(m)
+    fm.set_all(0)
+    fm.mark_subdomain(AutoSubDomain(lambda x: near(x[2], 1.0)), 2)
+    assert (fm.values == 2).sum() == 32
+    fm.mark_subdomain(AutoSubDomain(lambda x, on_boundary: on_boundary and near(x[0], 0.0)), 3)
+    assert (fm.values == 3).sum() == 32 and (fm.values == 2).sum() == 32      # disjoint facets: nothing overwritten
+
+    class Corner(SubDomain):           # python `and` on arrays -> falls back to the per-point loop
+        def inside(self, x, on_boundary):
+            return bool(near(x[0], 0)) and bool(near(x[1], 0))
+    fm.mark_subdomain(Corner(), 5)
+    assert (fm.values == 5).sum() == 0                                        # an edge holds no whole facet
+    fm.mark_subdomain(lambda x: x[2] > 0.5 - 1e-12, 7)                        # later ids overwrite earlier ones
+    assert (fm.values == 2).sum() == 0 and (fm.values == 7).sum() >= 32
+    assert np.array_equal(fm.vertices(3), np.unique(fm.facets(3)[0]))
+
+
+def test_xml_readers_and_marker_files(tmp_path, golden_dir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_solvers import write_dolfin_xml
+    g = np.load(os.path.join(golden_dir, "fixture_mesh.npz"))
+    path = write_dolfin_xml(str(tmp_path), g)
+    mesh = Mesh(path)
+    assert np.array_equal(mesh.coordinates(), g["coords"]) and np.array_equal(mesh.cells(), g["cells"])
+    fm = MeshFunction("size_t", mesh, path[:-4] + "_facet_region.xml")
+    assert (fm.values == 1).sum() == 100 and (fm.values == 2).sum() == 100 and fm.values.size == 1400
+    assert np.all(mesh.coordinates()[fm.vertices(1), 2] == 0.0) and np.all(mesh.coordinates()[fm.vertices(2), 2] == 20.0)
+    cm = MeshFunction("size_t", mesh, path[:-4] + "_physical_region.xml")
+    assert np.all(cm.array() == 3) and cm.array().size == 4355
+    settings = json.load(open(os.path.join(golden_dir, "TestHeatTransfer.json")))
+    settings["mesh"] = path
+    solver = ScalarTransportSolver.ScalarTransportSolver(load_settings(settings))
+    assert solver.dimension == 3 and solver.function_space.dim() == 1069
+    assert solver.conductivity() == 20 and solver.capacity() == 1000 * 500
+    kp = solver.krylov_parameters()
+    assert kp["rtol"] == 1e-12 and kp["maxit"] >= 100000                       # parity mode tightens the JSON's 1e-7 / 500
+    solver.solver_settings['solver_parameters']['parity_mode'] = False
+    kp = solver.krylov_parameters()
+    assert kp["rtol"] == 1e-7 and kp["maxit"] == 500
+
+
+def test_settings_errors_mirror_reference():
+    with pytest.raises(SolverBase.SolverError):
+        ScalarTransportSolver.ScalarTransportSolver("case.json")                # must be a dict (SolverBase.py:96-101)
+    with pytest.raises(SolverBase.SolverError):
+        ScalarTransportSolver.ScalarTransportSolver({'boundary_conditions': {}, 'solver_settings': {}})   # no mesh / space
+    with pytest.raises(TypeError):
+        load_settings(["not", "a", "path"])                                     # main.py:74-75
+    with pytest.raises(NameError):
+        main({'solver_name': 'NoSuchSolver'})                                   # main.py:92-93
+    with pytest.raises(SolverBase.SolverError):
+        FunctionSpace(UnitSquareMesh(2, 2), "CG", 2)                            # P2 is next-tier: loud, not silent P1
+    m = UnitSquareMesh(2, 2)
+    s = heat_settings(m)
+    s['mesh'] = "/no/such/mesh.xml"
+    with pytest.raises(SolverBase.SolverError):
+        ScalarTransportSolver.ScalarTransportSolver(s)
+
+
+def test_form_generation_matches_reference_rules():
+    mesh = UnitSquareMesh(6, 6)
+    solver = ScalarTransportSolver.ScalarTransportSolver(heat_settings(mesh))
+    solver.init_solver()
+    solver.current_step = 0
+    F, bcs = solver.generate_form(0, None, None, solver.w_current, solver.w_prev)
+    assert F.conductivity == 0.1 and F.capacity == 4200000 and F.robin == [(2, 100.0, 300.0)] and F.neumann == []
+    d, v = SolverBase.collect_dirichlet(bcs, mesh)
+    assert d.size == 7 and np.all(v == 360) and np.all(mesh.coordinates()[d, 1] == 1)
+    # Neumann gradient is scaled by the capacity, flux is not (ScalarTransportSolver.py:176-200)
+    left = AutoSubDomain(lambda x: near(x[0], 0))
+    bc2 = {"a": {'boundary': left, 'boundary_id': 3, 'type': 'Neumann', 'value': 2.0},
+           "b": {'boundary': AutoSubDomain(lambda x: near(x[0], 1)), 'boundary_id': 4, 'type': 'heatFlux', 'value': Constant(5.0)},
+           "c": {'boundary': AutoSubDomain(lambda x: near(x[1], 1)), 'boundary_id': 1, 'type': 'Dirichlet', 'value': "300 + x[0]"}}
+    s = heat_settings(mesh, bc2)
+    s['convective_velocity'] = Constant((0.5, -0.5))
+    solver = ScalarTransportSolver.ScalarTransportSolver(s)
+    solver.init_solver()
+    solver.current_step = 0
+    F, bcs = solver.generate_form(0, None, None, solver.w_current, solver.w_prev)
+    assert F.neumann == [(3, 2.0 * 4200000), (4, 5.0)] and np.array_equal(F.velocity, [0.5, -0.5])
+    d, v = SolverBase.collect_dirichlet(bcs, mesh)
+    assert np.allclose(v, 300 + mesh.coordinates()[d, 0])                       # string Expression interpolated at the vertices
+    # initial values and translate_value
+    assert np.all(solver.w_current.array() == 300)
+    assert solver.translate_value((1, 2)).tolist() == [1.0, 2.0] and solver.translate_value(Constant(3)) == 3.0
+    assert solver.get_variable_name() == 'temperature'
+    with pytest.raises(TypeError):
+        solver.translate_value(None)
+
+
+def test_elasticity_form_and_per_component_dirichlet():
+    mesh = BoxMesh(Point(0, 0, 0), Point(10, 1, 1), 6, 2, 2)
+
+    class Left(SubDomain):
+        def inside(self, x, on_boundary):
+            return near(x[0], 0.0)
+
+    class Right(SubDomain):
+        def inside(self, x, on_boundary):
+            return near(x[0], 10.0)
+    import copy
+    s = copy.deepcopy(SolverBase.default_case_settings)
+    s['material'] = {'elastic_modulus': 2e11, 'poisson_ratio': 0.27, 'density': 7800}
+    s['function_space'] = VectorFunctionSpace(mesh, "Lagrange", 1)
+    s['boundary_conditions'] = {"fixed": {'boundary': Left(), 'boundary_id': 1, 'type': 'Dirichlet', 'value': (Constant(0), None, None)},
+                                "displ": {'boundary': Right(), 'boundary_id': 2, 'type': 'Dirichlet', 'value': Constant((0, 0, 1e-3))}}
+    s['body_source'] = (0.0, 0.0, -7800 * 9.8)
+    solver = LinearElasticitySolver.LinearElasticitySolver(s)
+    assert solver.settings['vector_name'] == 'displacement' and solver.function_space.ncomp == 3
+    mu, lam = solver.lame_parameters()
+    assert np.allclose((mu, lam), fo.lame(2e11, 0.27))
+    solver.init_solver()
+    solver.current_step = 0
+    F, bcs = solver.generate_form(0, None, None, solver.w_current, solver.w_prev)
+    assert F.load_sign == -1.0 and len(bcs) == 2 and bcs[0].component == 0 and bcs[1].component is None
+    d, v = SolverBase.collect_dirichlet(bcs, mesh)
+    nside = 9
+    assert d.size == nside + 3 * nside
+    c = mesh.coordinates()
+    right = d[c[d // 3, 0] == 10]
+    assert np.allclose(v[c[d // 3, 0] == 10][right % 3 == 2], 1e-3)
+    assert np.all(d[c[d // 3, 0] == 0] % 3 == 0)
+
+
+def test_expression_evaluation():
+    c = np.array([[0.0, 0.5], [1.0, 2.0]])
+    assert np.allclose(Expression("sin(x[0]) + pow(x[1], 2)", degree=1)(c), np.sin(c[:, 0]) + c[:, 1] ** 2)
+    assert Expression(("10*rho", "0", "0.0"), rho=7800, degree=2)(np.zeros((3, 3))).shape == (3, 3)
+    with pytest.raises(SolverBase.SolverError):
+        Expression("__import__('os')")(c)
+
+
+def test_slab_partition_and_index_maps():
+    parts = backend.slab_partition(257, 8)
+    assert parts[0][0] == 0 and parts[-1][1] == 257 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    assert max(p1 - p0 for p0, p1 in parts) - min(p1 - p0 for p0, p1 in parts) <= 1
+    assert backend.slab_partition(5, 2) == [(0, 3), (3, 5)]
+
+
+GLOO_SCRIPT = r"""
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+from fenicssolver_b200 import backend
+from fenicssolver_b200.dolfin_compat import UnitCubeMesh
+comm = backend.Comm.from_torch()
+assert comm.nranks == 2 and comm.rank == dist.get_rank()
+uid = comm.bootstrap(b"x" * 128 if comm.rank == 0 else None)      # the NCCL-id broadcast path
+assert uid == b"x" * 128
+N = 6
+mesh = UnitCubeMesh(N, N, N)
+plane = (N + 1) ** 2
+zp0, zp1 = backend.slab_partition(N + 1, comm.nranks)[comm.rank]
+layer0, layer1 = max(zp0 - 1, 0), min(zp1, N)
+v_off = layer0 * plane
+nv_local = (layer1 - layer0 + 1) * plane
+# every rank's local cells, renumbered, are exactly the global cells of its layers
+per_layer = mesh.num_cells() // N
+local_cells = mesh.cells()[per_layer * layer0:per_layer * layer1] - v_off
+assert local_cells.min() >= 0 and local_cells.max() < nv_local
+# owned rows of all ranks tile the global vertex range exactly once
+owned = np.arange(zp0 * plane, zp1 * plane)
+parts = [None, None]
+dist.all_gather_object(parts, owned)
+allv = np.concatenate(parts)
+assert np.array_equal(allv, np.arange(mesh.num_vertices()))
+# every neighbour column of an owned row is inside the local planes (one ghost plane suffices)
+cells = mesh.cells()
+touch = np.isin(cells, owned).any(axis=1)
+assert cells[touch].min() >= v_off and cells[touch].max() < v_off + nv_local
+dist.destroy_process_group()
+print("rank", comm.rank, "ok")
+"""
+
+
+def test_world_size_two_gloo_partition(tmp_path):
+    script = os.path.join(str(tmp_path), "gloo_part.py")
+    open(script, "w").write(GLOO_SCRIPT % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", script], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
