@@ -63,7 +63,7 @@ class ScalarForm:
             A.assemble_scalar(kscale=self.theta * kscale, ktensor=ktensor, mass=c / self.dt, adv=adv, vel=vel)
             tp = self.T_prev.device_vector()
             if tp is None or tp.n != space.ndof_local:
-                tp = space.vector_from_global(self.T_prev.array())
+                tp = space.vector_from_function(self.T_prev)
             elif space.comm.nranks > 1:
                 tp.halo()
             _lib.apply_scalar(space.dmesh, tp, b, kscale=-(1.0 - self.theta) * kscale, ktensor=ktensor, mass=c / self.dt)

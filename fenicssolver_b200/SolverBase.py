@@ -222,7 +222,7 @@ class SolverBase():
                 vals = Expression(tuple(str(v) for v in v0), degree=self.settings['fe_degree'])(self.mesh.coordinates()).reshape(-1)
             u0 = Function(self.function_space, vals)
         elif 'scalar_name' in self.settings and isinstance(v0, numbers.Number):
-            u0 = Function(self.function_space, np.full(nv, float(v0)))
+            u0 = Function(self.function_space, fill=float(v0))        # stays symbolic: filled on the device
         elif 'scalar_name' in self.settings and isinstance(v0, str) and not os.path.exists(v0):
             u0 = Function(self.function_space, Expression(v0, degree=self.settings['fe_degree'])(self.mesh.coordinates()))
         elif isinstance(v0, Function):
@@ -439,7 +439,7 @@ class SolverBase():
         method = kp['method'] or ('cg' if symmetric_form else 'bicgstab')
         x = u.device_vector()
         if x is None or x.n != space.ndof_local:
-            x = space.vector_from_global(u.array())
+            x = space.vector_from_function(u)
         dofs, vals = collect_dirichlet(Dirichlet_bcs, self.mesh)
         # symmetric elimination (assemble_system) keeps A SPD for CG; plain bc.apply for BiCGStab
         space.apply_dirichlet(b, dofs, vals, symmetric=(method == 'cg'), x=x)

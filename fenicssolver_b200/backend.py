@@ -170,6 +170,13 @@ class DeviceSpace:
         lo = self.v_off * self.ncomp
         return _lib.DeviceVector.from_numpy(self.ctx, a[lo:lo + self.ndof_local])
 
+    def vector_from_function(self, fn):
+        """Device copy of a Function: a known-uniform field is filled on the device (no H2D copy)."""
+        u = fn.uniform_value()
+        if u is not None:
+            return self.vector(fill=u)
+        return self.vector_from_global(fn.array())
+
     def owned_values(self, dvec):
         a = dvec.numpy()
         return a[self.own_v0 * self.ncomp:self.own_v1 * self.ncomp]

@@ -20,7 +20,8 @@ struct fsb_ctx {
   int64_t launches = 0;
   // options
   int asm_mode = 1;      // 0 search+atomics, 1 position map + atomics
-  int spmv_mode = 0;     // 0 TMA-staged tiles, 1 plain row-per-thread
+  int spmv_mode = 0;     // 0 TMA-staged tiles v2, 1 plain row-per-thread, 2 TMA-staged v1 (one thread per row)
+  int spmv_lpr = 2;      // lanes per row in the v2 kernel (1, 2 or 4)
   int profile = 0;
   int use_graph = 1;
   int check_every = 32;

@@ -158,6 +158,122 @@ __global__ void __launch_bounds__(THREADS) k_spmv_tma(SpmvArgs a) {
   }
 }
 
+// v2 of the staged kernel: LPR lanes share one scalar row (halving the dependent gather chain and doubling
+// the warps per SM), the tile's slice of row_ptr arrives by TMA with the values/columns, and the tile
+// bounds are published through shared memory by the issuing thread, so the compute phase starts with no
+// global-memory dependency other than the x gathers, which are issued UNR at a time.
+template <int BS, int LPR>
+struct SpmvV2 {
+  static constexpr int ROWS = (BS == 3 ? 192 : 256);   // scalar rows per pass
+  static constexpr int THREADS = ROWS * LPR;
+  static constexpr int RCAP = 2 * (ROWS / BS) + 8;     // block rows whose row_ptr slice fits the stage
+  static constexpr int UNR = BS == 1 ? 8 : (BS == 2 ? 4 : 3);   // gathers in flight per lane (x BS)
+};
+
+template <int BS, int LPR>
+__global__ void __launch_bounds__(SpmvV2<BS, LPR>::THREADS) k_spmv_tma2(SpmvArgs a) {
+  using Cfg = SpmvV2<BS, LPR>;
+  constexpr int THREADS = Cfg::THREADS, RCAP = Cfg::RCAP, UNR = Cfg::UNR;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int64_t s_info[2][4];      // per stage: r0, r1, aligned first nnz, aligned first row (or -1: row_ptr not staged)
+  __shared__ double red[32];
+  if (a.done && *a.done) return;
+  constexpr int VB = 8 * BS * BS;
+  const size_t rp_bytes = (size_t)(RCAP + 4) * 8;
+  const size_t stage_bytes = (size_t)a.cap * (VB + 4) + rp_bytes;
+  auto vals_s = [&](int s) { return reinterpret_cast<const double*>(smem + s * stage_bytes); };
+  auto cols_s = [&](int s) { return reinterpret_cast<const int32_t*>(smem + s * stage_bytes + (size_t)a.cap * VB); };
+  auto rptr_s = [&](int s) { return reinterpret_cast<const int64_t*>(smem + s * stage_bytes + (size_t)a.cap * (VB + 4)); };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int s) {
+    const int64_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
+    s_info[s][0] = r0; s_info[s][1] = r1;
+    if (r1 <= r0) { mbar_arrive(&bar[s]); return; }
+    const int64_t k0 = a.row_ptr[r0], k1 = a.row_ptr[r1];
+    const int64_t al0 = k0 & ~3ll;
+    const uint32_t cnt = (uint32_t)(((k1 - al0) + 3) & ~3ll);
+    const int64_t ra0 = r0 & ~1ll;
+    const bool stage_rp = (r1 - ra0 + 1) <= RCAP;
+    const uint32_t nrp = stage_rp ? (uint32_t)(((r1 - ra0 + 1) + 1) & ~1ll) : 0u;
+    s_info[s][2] = al0; s_info[s][3] = stage_rp ? ra0 : -1;
+    mbar_expect_tx(&bar[s], cnt * (VB + 4) + nrp * 8);
+    bulk_g2s((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &bar[s]);
+    bulk_g2s((void*)cols_s(s), a.col_idx + al0, cnt * 4, &bar[s]);
+    if (stage_rp) bulk_g2s((void*)rptr_s(s), a.row_ptr + ra0, nrp * 8, &bar[s]);
+  };
+
+  const int sub = threadIdx.x % LPR;
+  double d0 = 0.0, d1 = 0.0;
+  int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < a.ntiles) issue(tile, 0);
+  for (int it = 0; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < a.ntiles) issue(next, s ^ 1);
+    mbar_wait(&bar[s], (it >> 1) & 1);
+    const int64_t r0 = s_info[s][0], r1 = s_info[s][1];
+    if (r1 > r0) {
+      const int64_t al0 = s_info[s][2], ra0 = s_info[s][3];
+      const double* __restrict__ vs = vals_s(s);
+      const int32_t* __restrict__ cs = cols_s(s);
+      const int64_t* __restrict__ rp = rptr_s(s);
+      const int nscalar = (int)(r1 - r0) * BS;
+      for (int base = 0; base < nscalar; base += THREADS / LPR) {       // warp-uniform trip count
+        const int lr = base + threadIdx.x / LPR;
+        const bool live = lr < nscalar;
+        const int64_t R = r0 + (live ? lr / BS : 0);
+        const int i = live ? lr % BS : 0;
+        int ks, ke;
+        if (ra0 >= 0) { ks = (int)(rp[R - ra0] - al0); ke = (int)(rp[R + 1 - ra0] - al0); }
+        else { ks = (int)(a.row_ptr[R] - al0); ke = (int)(a.row_ptr[R + 1] - al0); }
+        if (!live) ke = ks;
+        double acc = 0.0;
+        for (int k = ks + sub; k < ke; k += LPR * UNR) {
+          double v[UNR][BS], xg[UNR][BS];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int kk = k + u * LPR;
+            const bool ok = kk < ke;
+            const int64_t c = ok ? cs[kk] : 0;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+              v[u][j] = ok ? vs[(kk * BS + i) * BS + j] : 0.0;
+              xg[u][j] = ok ? __ldg(a.x + c * BS + j) : 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) acc += v[u][j] * xg[u][j];
+        }
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (live && sub == 0) {
+          const int64_t row = R * BS + i;
+          a.y[row] = acc;
+          if (a.w) d0 += acc * a.w[row];
+          if (a.want_yy) d1 += acc * acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (a.out) {
+    double mine[2];
+    mine[0] = block_sum(d0, red);
+    mine[1] = block_sum(d1, red);
+    finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+  }
+}
+
 // plain fallback: one thread per scalar row straight from global memory
 template <int BS>
 __global__ void __launch_bounds__(256) k_spmv_plain(SpmvArgs a) {
@@ -224,7 +340,7 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
   T = (T + 15) & ~15ll;
   int64_t cap = T + A->max_row_len + 8;
   cap = (cap + 3) & ~3ll;
-  const size_t stage = (size_t)cap * (8 * bs * bs + 4);
+  const size_t stage = (size_t)cap * (8 * bs * bs + 4) + (size_t)(2 * rows_target + 12) * 8;
   if (2 * stage > kSmemBudget) return FSB_OK;   // not tileable (very long rows): plain kernel is used
   A->tile_nnz = (int)T;
   A->tile_cap = (int)cap;
@@ -246,8 +362,28 @@ static int launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, 
   a.x = x; a.y = y; a.w = w; a.want_yy = want_yy;
   a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
   if (A->own1 <= A->own0) return FSB_OK;
-  const bool tiled = ctx->spmv_mode == 0 && A->ntiles > 0;
-  if (tiled) {
+  const bool tiled = ctx->spmv_mode != 1 && A->ntiles > 0;
+  if (tiled && ctx->spmv_mode == 0) {
+    // v2: LPR lanes per row, row_ptr slice staged with the tile
+    const int lpr = ctx->spmv_lpr;
+#define FSB_SPMV2_LAUNCH(BS, LPR)                                                                                      \
+  do {                                                                                                                 \
+    using Cfg = SpmvV2<BS, LPR>;                                                                                       \
+    const size_t smem = 2 * ((size_t)A->tile_cap * (8 * BS * BS + 4) + (size_t)(Cfg::RCAP + 4) * 8);                   \
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / Cfg::THREADS, (224 * 1024) / (smem + 1024)));        \
+    const unsigned grid = (unsigned)std::min<int64_t>(A->ntiles, (int64_t)ctx->sm_count * per_sm);                     \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_spmv_tma2<BS, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    k_spmv_tma2<BS, LPR><<<grid, Cfg::THREADS, smem, ctx->stream>>>(a);                                                \
+  } while (0)
+    if (A->bs == 1) { if (lpr == 1) FSB_SPMV2_LAUNCH(1, 1); else if (lpr == 4) FSB_SPMV2_LAUNCH(1, 4); else FSB_SPMV2_LAUNCH(1, 2); }
+    else if (A->bs == 2) { if (lpr == 1) FSB_SPMV2_LAUNCH(2, 1); else FSB_SPMV2_LAUNCH(2, 2); }
+    else { if (lpr == 1) FSB_SPMV2_LAUNCH(3, 1); else if (lpr == 4) FSB_SPMV2_LAUNCH(3, 4); else FSB_SPMV2_LAUNCH(3, 2); }
+#undef FSB_SPMV2_LAUNCH
+  } else if (tiled) {
     const size_t smem = 2 * (size_t)A->tile_cap * (8 * A->bs * A->bs + 4);
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
     const unsigned grid = (unsigned)std::min<int64_t>(A->ntiles, (int64_t)ctx->sm_count * per_sm);

@@ -370,11 +370,14 @@ class FacetMarkers:
     def mark_subdomain(self, sub, value):
         """SubDomain.mark: a facet is marked iff all its vertices and its midpoint are inside
         (dolfin's default check_midpoint=True; SolverBase.py:281-282)."""
-        X = self.mesh.coordinates()[self.fverts]              # [nf, d, gdim]
-        nf, d, g = X.shape
-        ok = _evaluate_predicate(sub, X.mean(axis=1))
-        for a in range(d):
-            ok &= _evaluate_predicate(sub, X[:, a, :])
+        geom = getattr(self.mesh, "_boundary_geometry", None)
+        if geom is None:      # unique boundary vertices, their coordinates and the facet midpoints: once per mesh
+            uv, inv = np.unique(self.fverts, return_inverse=True)
+            inv = inv.reshape(self.fverts.shape)
+            pts = self.mesh.coordinates()[uv]
+            geom = self.mesh._boundary_geometry = (inv, pts, pts[inv].mean(axis=1))
+        inv, pts, mid = geom
+        ok = _evaluate_predicate(sub, mid) & _evaluate_predicate(sub, pts)[inv].all(axis=1)
         self.values[ok] = value
 
     def facets(self, marker):
@@ -474,19 +477,28 @@ class _Vector:
 class Function:
     """Nodal P1 field.  Values live on the device after a solve and are downloaded lazily."""
 
-    def __init__(self, V, values=None):
+    def __init__(self, V, values=None, fill=None):
+        """`fill`: a uniform value (scalar space) kept symbolic until someone asks for the array, so a
+        constant initial field costs neither host memory traffic nor an H2D copy."""
         self.function_space = V
         self._host = None if values is None else np.ascontiguousarray(values, dtype=np.float64).ravel().copy()
         self._dev = None          # _lib.DeviceVector holding the same values (None: host only)
         self._host_valid = True
+        self._fill = None
         if self._host is None:
-            self._host = np.zeros(V.dim())
+            self._fill = 0.0 if fill is None else float(fill)
         self._name = "f"
+
+    def uniform_value(self):
+        """The value if the field is a known constant (and nothing else has been stored), else None."""
+        return self._fill if (self._host is None and self._dev is None) else None
 
     def array(self):
         if not self._host_valid:
             self._host = self._dev.numpy()       # the one D2H copy of a solve result, on demand
             self._host_valid = True
+        elif self._host is None:
+            self._host = np.full(self.function_space.dim(), self._fill)
         return self._host
 
     def assign_array(self, a):
@@ -498,13 +510,16 @@ class Function:
         """Adopt a device vector as the current value (host copy becomes stale)."""
         self._dev = dev
         self._host_valid = False
+        self._host = None
 
     def device_vector(self):
         return self._dev
 
     def assign(self, other):
         if isinstance(other, Function):
-            if other._dev is not None and not other._host_valid:
+            if other.uniform_value() is not None:
+                self._host, self._dev, self._host_valid, self._fill = None, None, True, other._fill
+            elif other._dev is not None and not other._host_valid:
                 # device-resident value: copy on the device, no PCIe round trip per time step
                 from ._lib import DeviceVector
                 if self._dev is None or self._dev is other._dev or self._dev.n != other._dev.n:
@@ -531,6 +546,8 @@ class Function:
         return a if nc == 1 else a.reshape(-1, nc)
 
     def copy(self, deepcopy=True):
+        if self.uniform_value() is not None:
+            return Function(self.function_space, fill=self._fill)
         return Function(self.function_space, self.array())
 
     def rename(self, name, label=""):

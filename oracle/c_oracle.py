@@ -86,9 +86,9 @@ class HeatCube:
     """Config C2 at size N on the CPU: setup (mesh + pattern, untimed like the GPU arm's symbolic phase)
     then step() = assemble + Dirichlet + Jacobi-PCG, the timed unit."""
 
-    def __init__(self, N, k=20.0, S=1000.0, T0=350.0, T1=300.0):
+    def __init__(self, N, k=20.0, S=1000.0, T0=350.0, T1=300.0, T_init=293.0):
         self.lib = load()
-        self.N, self.k, self.S = N, k, S
+        self.N, self.k, self.S, self.T_init = N, k, S, T_init
         t = time.perf_counter()
         self.coords, self.cells = box_mesh((N, N, N))
         self.nv = self.coords.shape[0]
@@ -113,7 +113,7 @@ class HeatCube:
         lib.fo_assemble_heat(self.cells.shape[0], _p(self.cells), _p(self.coords), self.k, self.S, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b))
         lib.fo_apply_dirichlet_sym(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.flag), _p(self.g))
         t1 = time.perf_counter()
-        self.x[:] = self.g * self.flag
+        self.x[:] = np.where(self.flag, self.g, self.T_init)      # initial field, Dirichlet values imposed
         rel = C.c_double()
         it = lib.fo_pcg_jacobi(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.x), rtol, 0.0, maxit, C.byref(rel))
         t2 = time.perf_counter()

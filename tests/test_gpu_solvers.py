@@ -135,13 +135,13 @@ def test_heat_transfer_htc_and_convection():
         "cold": {'boundary': bottom, 'boundary_id': 2, 'values': {'temperature': {'variable': 'temperature', 'type': 'HTC', 'value': Constant(htc), 'ambient': Constant(Ta)}}},
     }
     settings, mesh = heat_settings(bcs, 24, 24)
-    settings['convective_velocity'] = Constant((0.005e-3, -0.005e-3))     # cell Peclet ~ O(1) for k = 0.6, c = 4.2e6
+    settings['convective_velocity'] = Constant((0.4e-6, -0.4e-6))      # global Peclet c|v|L/k ~ 4: well-posed with a flux inflow
     solver = ScalarTransportSolver.ScalarTransportSolver(settings)
     solver.material['conductivity'] = k
     T = solver.solve()
     c, t, fv, sel = square_sets(24, 24)
     A, b = fo.heat_system(c, t, k, [], neumann=[(fv[sel["top"]], heat_flux)], robin=[(fv[sel["bottom"]], htc, Ta)],
-                          velocity=np.array([0.005e-3, -0.005e-3]), capacity=1000 * 4200.0, symmetric=False)
+                          velocity=np.array([0.4e-6, -0.4e-6]), capacity=1000 * 4200.0, symmetric=False)
     assert fo.relative_l2(T.vector().get_local(), fo.solve_direct(A, b)) < TOL
     assert solver.solve_info["converged"] == 1
 

@@ -186,7 +186,7 @@ def test_c_oracle_matches_numpy_oracle():
     A, b = fo.heat_system(c, t, 20.0, [(z0, 350.0), (z1, 300.0)], source=1000.0)
     assert np.abs(h.vals - A.data).max() <= 1e-13 * np.abs(A.data).max()
     assert np.abs(h.b - b).max() <= 1e-13 * np.abs(b).max()
-    x0 = np.zeros(c.shape[0]); x0[z0] = 350; x0[z1] = 300
+    x0 = np.full(c.shape[0], 293.0); x0[z0] = 350; x0[z1] = 300      # HeatCube's start: initial field with the BCs imposed
     x, it, _ = fo.pcg_jacobi(A, b, x0=x0, rtol=1e-12)
     assert abs(r["iterations"] - it) <= 1
     assert fo.relative_l2(h.x, fo.solve_direct(A, b)) < 1e-10

@@ -35,14 +35,25 @@ def main():
     timed("dirichlet (symmetric)", lambda: A.apply_dirichlet(b, dofs, vals, True, x))
     y = _lib.DeviceVector(ctx, nv)
     b_spmv = 12 * nnz + 24 * nv
-    for mode in (0, 1, 0):
-        ctx.set_option("spmv_mode", mode)
-        A.spmv(x, y)
-        def rep():
+    def time_spmv(A, x, y, bytes_, label):
+        for mode, lpr in ((2, 0), (1, 0), (0, 1), (0, 2), (0, 4), (0, 2)):
+            ctx.set_option("spmv_mode", mode)
+            if lpr:
+                ctx.set_option("spmv_lpr", lpr)
+            A.spmv(x, y)
+            ctx.sync(); t = time.perf_counter()
             for _ in range(20): A.spmv(x, y)
-        ctx.sync(); t = time.perf_counter(); rep(); ctx.sync(); dt = (time.perf_counter() - t) / 20
-        print("spmv mode %d                  %9.3f ms  %.1f GB/s" % (mode, dt * 1e3, b_spmv / dt / 1e9), flush=True)
-    ctx.set_option("spmv_mode", 0)
+            ctx.sync(); dt = (time.perf_counter() - t) / 20
+            print("%s spmv mode %d lpr %d        %9.3f ms  %.1f GB/s" % (label, mode, lpr, dt * 1e3, bytes_ / dt / 1e9), flush=True)
+        ctx.set_option("spmv_mode", 0); ctx.set_option("spmv_lpr", 2)
+    time_spmv(A, x, y, b_spmv, "csr ")
+    if os.environ.get("PROBE_ELASTICITY", "1") == "1" and N <= 160:
+        A3 = timed("mat_create bs=3", lambda: _lib.DeviceMatrix.create(m, 3))
+        s3 = A3.sizes()
+        timed("assemble elasticity", lambda: A3.assemble_elasticity(7.9e10, 9.2e10), 16 * nc + 24 * nv + 8 * s3["nnz"])
+        x3 = _lib.DeviceVector(ctx, 3 * nv); y3 = _lib.DeviceVector(ctx, 3 * nv); x3.fill(1.0)
+        time_spmv(A3, x3, y3, s3["nnzb"] * 76 + nv * (8 + 24 + 24), "bsr3")
+        del A3, x3, y3
     for prof in (0, 1):
         ctx.set_option("profile", prof)
         x.fill(0.0); A.apply_dirichlet(b, dofs, vals, True, x)
