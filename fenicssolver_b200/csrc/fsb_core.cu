@@ -76,6 +76,8 @@ extern "C" int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value) {
   if (s == "asm_mode") ctx->asm_mode = (int)value;
   else if (s == "spmv_mode") ctx->spmv_mode = (int)value;
   else if (s == "spmv_lpr") ctx->spmv_lpr = (int)value;
+  else if (s == "spmv_rows") ctx->spmv_rows = (int)value;
+  else if (s == "spmv_stages") ctx->spmv_stages = (int)value;
   else if (s == "profile") ctx->profile = (int)value;
   else if (s == "graph") ctx->use_graph = (int)value;
   else if (s == "check_every") ctx->check_every = value < 1 ? 1 : (int)value;

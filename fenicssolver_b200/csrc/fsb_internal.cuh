@@ -21,7 +21,9 @@ struct fsb_ctx {
   // options
   int asm_mode = 1;      // 0 search+atomics, 1 position map + atomics
   int spmv_mode = 0;     // 0 TMA-staged tiles v2, 1 plain row-per-thread, 2 TMA-staged v1 (one thread per row)
-  int spmv_lpr = 2;      // lanes per row in the v2 kernel (1, 2 or 4)
+  int spmv_lpr = 2;      // lanes per row in the v2 kernel (2 or 4)
+  int spmv_rows = 256;   // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks)
+  int spmv_stages = 2;   // TMA pipeline depth of the v2 kernel (2..4)
   int profile = 0;
   int use_graph = 1;
   int check_every = 32;
@@ -68,6 +70,8 @@ struct fsb_mat {
   int64_t ntiles = 0;
   int64_t* tile_row = nullptr; // [ntiles+1] first block row of each tile (within owned range)
   int tile_cap = 0;            // smem capacity in blocks per stage
+  int tile_rows = 0;           // scalar rows per tile this tiling was built for
+  size_t stage_bytes = 0;      // shared memory per pipeline stage (values + columns + row_ptr slice)
   // dirichlet scratch
   uint8_t* bc_flag = nullptr;  // [nbrows*bs]
   double* bc_val = nullptr;

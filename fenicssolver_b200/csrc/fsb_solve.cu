@@ -158,25 +158,25 @@ __global__ void __launch_bounds__(THREADS) k_spmv_tma(SpmvArgs a) {
   }
 }
 
-// v2 of the staged kernel: LPR lanes share one scalar row (halving the dependent gather chain and doubling
-// the warps per SM), the tile's slice of row_ptr arrives by TMA with the values/columns, and the tile
-// bounds are published through shared memory by the issuing thread, so the compute phase starts with no
-// global-memory dependency other than the x gathers, which are issued UNR at a time.
-template <int BS, int LPR>
+// v2 of the staged kernel.  LPR lanes share one scalar row (shorter dependent gather chain, more warps
+// per SM); the tile's slice of row_ptr arrives by TMA with the values/columns and the tile bounds are
+// published through shared memory by the issuing thread, so the compute phase has no global-memory
+// dependency other than the x gathers (issued UNR at a time); NST stages keep NST-1 tiles in flight per
+// CTA, which is what covers the loaded HBM latency (ncu: long-scoreboard + barrier stalls, r1 profile).
+template <int BS, int ROWS, int LPR>
 struct SpmvV2 {
-  static constexpr int ROWS = (BS == 3 ? 192 : 256);   // scalar rows per pass
-  static constexpr int THREADS = ROWS * LPR;
+  static constexpr int THREADS = ROWS * LPR;           // ROWS scalar rows per pass
   static constexpr int RCAP = 2 * (ROWS / BS) + 8;     // block rows whose row_ptr slice fits the stage
   static constexpr int UNR = BS == 1 ? 8 : (BS == 2 ? 4 : 3);   // gathers in flight per lane (x BS)
 };
 
-template <int BS, int LPR>
-__global__ void __launch_bounds__(SpmvV2<BS, LPR>::THREADS) k_spmv_tma2(SpmvArgs a) {
-  using Cfg = SpmvV2<BS, LPR>;
+template <int BS, int ROWS, int LPR, int NST>
+__global__ void __launch_bounds__(SpmvV2<BS, ROWS, LPR>::THREADS) k_spmv_tma2(SpmvArgs a) {
+  using Cfg = SpmvV2<BS, ROWS, LPR>;
   constexpr int THREADS = Cfg::THREADS, RCAP = Cfg::RCAP, UNR = Cfg::UNR;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ int64_t s_info[2][4];      // per stage: r0, r1, aligned first nnz, aligned first row (or -1: row_ptr not staged)
+  __shared__ __align__(8) uint64_t bar[NST];
+  __shared__ int64_t s_info[NST][4];    // per stage: r0, r1, aligned first nnz, aligned first row (or -1: row_ptr not staged)
   __shared__ double red[32];
   if (a.done && *a.done) return;
   constexpr int VB = 8 * BS * BS;
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(SpmvV2<BS, LPR>::THREADS) k_spmv_tma2(SpmvArgs
   auto rptr_s = [&](int s) { return reinterpret_cast<const int64_t*>(smem + s * stage_bytes + (size_t)a.cap * (VB + 4)); };
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+#pragma unroll
+    for (int s = 0; s < NST; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -213,12 +213,17 @@ __global__ void __launch_bounds__(SpmvV2<BS, LPR>::THREADS) k_spmv_tma2(SpmvArgs
   const int sub = threadIdx.x % LPR;
   double d0 = 0.0, d1 = 0.0;
   int64_t tile = blockIdx.x;
-  if (threadIdx.x == 0 && tile < a.ntiles) issue(tile, 0);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int d = 0; d < NST - 1; ++d)
+      if (tile + (int64_t)d * gridDim.x < a.ntiles) issue(tile + (int64_t)d * gridDim.x, d);
+  }
   for (int it = 0; tile < a.ntiles; tile += gridDim.x, ++it) {
-    const int s = it & 1;
-    const int64_t next = tile + gridDim.x;
-    if (threadIdx.x == 0 && next < a.ntiles) issue(next, s ^ 1);
-    mbar_wait(&bar[s], (it >> 1) & 1);
+    const int s = it % NST;
+    const int64_t ahead = tile + (int64_t)(NST - 1) * gridDim.x;
+    // stage (it+NST-1)%NST was consumed in iteration it-1, which ended with __syncthreads
+    if (threadIdx.x == 0 && ahead < a.ntiles) issue(ahead, (it + NST - 1) % NST);
+    mbar_wait(&bar[s], (it / NST) & 1);
     const int64_t r0 = s_info[s][0], r1 = s_info[s][1];
     if (r1 > r0) {
       const int64_t al0 = s_info[s][2], ra0 = s_info[s][3];
@@ -317,7 +322,8 @@ __global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, i
   }
 }
 
-static int spmv_threads(int bs) { return bs == 3 ? 192 : 256; }
+// scalar rows per tile: 256 (192 for 3x3 blocks) or half of that (ctx option spmv_rows)
+static int spmv_rows(fsb_ctx* ctx, int bs) { const int big = bs == 3 ? 192 : 256; return ctx->spmv_rows == 128 ? big / 2 : big; }
 static constexpr size_t kSmemBudget = 200 * 1024;
 
 int fsb_mat_setup_tiles(fsb_mat* A) {
@@ -334,7 +340,8 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
   const int64_t nnz = k01[1] - k01[0];
   if (nnz <= 0) return FSB_OK;
   const int bs = A->bs;
-  const int rows_target = spmv_threads(bs) / bs;
+  const int rows_target = spmv_rows(ctx, bs) / bs;
+  A->tile_rows = spmv_rows(ctx, bs);
   const double avg = (double)nnz / (double)nrows;
   int64_t T = (int64_t)std::ceil(avg * rows_target);
   T = (T + 15) & ~15ll;
@@ -342,6 +349,7 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
   cap = (cap + 3) & ~3ll;
   const size_t stage = (size_t)cap * (8 * bs * bs + 4) + (size_t)(2 * rows_target + 12) * 8;
   if (2 * stage > kSmemBudget) return FSB_OK;   // not tileable (very long rows): plain kernel is used
+  A->stage_bytes = stage;
   A->tile_nnz = (int)T;
   A->tile_cap = (int)cap;
   A->ntiles = (nnz + T - 1) / T;
@@ -362,27 +370,39 @@ static int launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, 
   a.x = x; a.y = y; a.w = w; a.want_yy = want_yy;
   a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
   if (A->own1 <= A->own0) return FSB_OK;
+  if (ctx->spmv_mode != 1 && A->tile_rows != spmv_rows(ctx, A->bs)) {
+    int rc = fsb_mat_setup_tiles(A);      // the tile size option changed since the matrix was set up
+    if (rc) return rc;
+    a.tile_row = A->tile_row; a.ntiles = A->ntiles; a.cap = A->tile_cap;
+  }
   const bool tiled = ctx->spmv_mode != 1 && A->ntiles > 0;
   if (tiled && ctx->spmv_mode == 0) {
-    // v2: LPR lanes per row, row_ptr slice staged with the tile
+    // v2: ROWS x LPR threads, NST stages (clamped to what fits in shared memory)
     const int lpr = ctx->spmv_lpr;
-#define FSB_SPMV2_LAUNCH(BS, LPR)                                                                                      \
-  do {                                                                                                                 \
-    using Cfg = SpmvV2<BS, LPR>;                                                                                       \
-    const size_t smem = 2 * ((size_t)A->tile_cap * (8 * BS * BS + 4) + (size_t)(Cfg::RCAP + 4) * 8);                   \
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / Cfg::THREADS, (224 * 1024) / (smem + 1024)));        \
+    const int rows = A->tile_rows;
+    int nst = std::max(2, std::min(ctx->spmv_stages, (int)((224 * 1024) / A->stage_bytes)));
+    const size_t smem = (size_t)nst * A->stage_bytes;
+    bool launched = false;
+#define FSB_SPMV2_CASE(BS, ROWS, LPR, NST)                                                                             \
+  if (!launched && A->bs == BS && rows == ROWS && lpr == LPR && nst == NST) {                                          \
+    using Cfg = SpmvV2<BS, ROWS, LPR>;                                                                                 \
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / Cfg::THREADS, (227 * 1024) / (smem + 1024)));        \
     const unsigned grid = (unsigned)std::min<int64_t>(A->ntiles, (int64_t)ctx->sm_count * per_sm);                     \
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
-      FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_spmv_tma2<BS, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); \
+      FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_spmv_tma2<BS, ROWS, LPR, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
-    k_spmv_tma2<BS, LPR><<<grid, Cfg::THREADS, smem, ctx->stream>>>(a);                                                \
-  } while (0)
-    if (A->bs == 1) { if (lpr == 1) FSB_SPMV2_LAUNCH(1, 1); else if (lpr == 4) FSB_SPMV2_LAUNCH(1, 4); else FSB_SPMV2_LAUNCH(1, 2); }
-    else if (A->bs == 2) { if (lpr == 1) FSB_SPMV2_LAUNCH(2, 1); else FSB_SPMV2_LAUNCH(2, 2); }
-    else { if (lpr == 1) FSB_SPMV2_LAUNCH(3, 1); else if (lpr == 4) FSB_SPMV2_LAUNCH(3, 4); else FSB_SPMV2_LAUNCH(3, 2); }
-#undef FSB_SPMV2_LAUNCH
+    k_spmv_tma2<BS, ROWS, LPR, NST><<<grid, Cfg::THREADS, smem, ctx->stream>>>(a);                                     \
+    launched = true;                                                                                                   \
+  }
+#define FSB_SPMV2_NST(BS, ROWS, LPR) FSB_SPMV2_CASE(BS, ROWS, LPR, 2) FSB_SPMV2_CASE(BS, ROWS, LPR, 3) FSB_SPMV2_CASE(BS, ROWS, LPR, 4)
+    FSB_SPMV2_NST(1, 256, 2) FSB_SPMV2_NST(1, 256, 4) FSB_SPMV2_NST(1, 128, 2) FSB_SPMV2_NST(1, 128, 4)
+    FSB_SPMV2_NST(2, 256, 2) FSB_SPMV2_NST(2, 128, 2)
+    FSB_SPMV2_NST(3, 192, 2) FSB_SPMV2_NST(3, 192, 4) FSB_SPMV2_NST(3, 96, 2) FSB_SPMV2_NST(3, 96, 4)
+#undef FSB_SPMV2_NST
+#undef FSB_SPMV2_CASE
+    if (!launched) FSB_FAIL(ctx, FSB_ERR_ARG, "unsupported spmv_rows/spmv_lpr/spmv_stages combination");
   } else if (tiled) {
     const size_t smem = 2 * (size_t)A->tile_cap * (8 * A->bs * A->bs + 4);
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
@@ -457,7 +477,8 @@ enum { S_PQ0 = 0, S_PQ1 = 1, S_RZ0 = 2, S_RR0 = 3, S_BB = 4, S_RZ1 = 5, S_RR1 = 
        S_RHO0 = 8, S_RRB0 = 9, S_BBB = 10, S_RHO1 = 11, S_RRB1 = 12, S_RV = 13, S_TS = 14, S_TT = 15, S_SPARE = 16 };
 // state ints in ctx->d_state: [0] done, [1] iterations, [2] outcome (1 converged, 0 maxit, -1 breakdown)
 
-// r = b - q ; p = z = dinv r ; sums rz, rr, bb -> out[0..3)
+// r = b - q ; p = z = dinv r ; sums r.z, z.z, (dinv b).(dinv b) -> out[0..3)
+// (convergence is tested on the preconditioned residual ||M^-1 r||, PETSc's KSP default norm)
 __global__ void __launch_bounds__(kVecThreads)
 k_cg_init(int64_t n0, int64_t n1, const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
           double* __restrict__ r, double* __restrict__ p, double* partials, double* out, unsigned* counter) {
@@ -466,7 +487,8 @@ k_cg_init(int64_t n0, int64_t n1, const double* __restrict__ b, const double* __
   for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
     const double bi = b[i], ri = bi - q[i], zi = dinv[i] * ri;
     r[i] = ri; p[i] = zi;
-    s0 += ri * zi; s1 += ri * ri; s2 += bi * bi;
+    const double zb = dinv[i] * bi;
+    s0 += ri * zi; s1 += zi * zi; s2 += zb * zb;
   }
   double mine[3] = {block_sum(s0, red), block_sum(s1, red), block_sum(s2, red)};
   finish_partials<3>(mine, partials, kMaxPartials, out, counter, red);
@@ -496,8 +518,9 @@ k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot
     x[i] += alpha * p[i];
     const double ri = r[i] - alpha * q[i];
     r[i] = ri;
-    s0 += ri * (dinv[i] * ri);
-    s1 += ri * ri;
+    const double zi = dinv[i] * ri;
+    s0 += ri * zi;
+    s1 += zi * zi;
   }
   double mine[2] = {block_sum(s0, red), block_sum(s1, red)};
   finish_partials<2>(mine, partials, kMaxPartials, out, counter, red);
@@ -673,19 +696,19 @@ extern "C" int fsb_dot(fsb_vec* x, fsb_vec* y, double* result) {
 }
 
 // ------------------------------------------------------------------------------------ BiCGStab
-// r = b - q ; rhat = r ; sums rho=rhat.r, rr, bb -> out[0..3)
+// r = b - q ; rhat = r ; sums rho=rhat.r, |dinv r|^2, |dinv b|^2 -> out[0..3)
 __global__ void __launch_bounds__(kVecThreads)
-k_bcg_init(int64_t n0, int64_t n1, const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ r,
-           double* __restrict__ rhat, double* partials, double* out, unsigned* counter) {
+k_bcg_init(int64_t n0, int64_t n1, const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
+           double* __restrict__ r, double* __restrict__ rhat, double* partials, double* out, unsigned* counter) {
   __shared__ double red[32];
-  double s0 = 0, s2 = 0;
+  double s0 = 0, s1 = 0, s2 = 0;
   for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
     const double bi = b[i], ri = bi - q[i];
     r[i] = ri; rhat[i] = ri;
-    s0 += ri * ri; s2 += bi * bi;
+    const double zi = dinv[i] * ri, zb = dinv[i] * bi;
+    s0 += ri * ri; s1 += zi * zi; s2 += zb * zb;
   }
-  double mine[3] = {block_sum(s0, red), 0.0, block_sum(s2, red)};
-  mine[1] = mine[0];
+  double mine[3] = {block_sum(s0, red), block_sum(s1, red), block_sum(s2, red)};
   finish_partials<3>(mine, partials, kMaxPartials, out, counter, red);
 }
 
@@ -724,8 +747,8 @@ k_bcg_s(int64_t n0, int64_t n1, const double* __restrict__ scal, int rho_cur, co
 // omega = (t.s)/(t.t) ; x += alpha ph + omega sh ; r = s - omega t ; sums rho'=rhat.r, rr -> out[0..2)
 __global__ void __launch_bounds__(kVecThreads)
 k_bcg_x(int64_t n0, int64_t n1, const double* __restrict__ scal, int rho_cur, const double* __restrict__ ph,
-        const double* __restrict__ sh, const double* __restrict__ t, const double* __restrict__ rhat, double* __restrict__ x,
-        double* __restrict__ r, double* partials, double* out, unsigned* counter, const int* done) {
+        const double* __restrict__ sh, const double* __restrict__ t, const double* __restrict__ rhat,
+        const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, double* partials, double* out, unsigned* counter, const int* done) {
   __shared__ double red[32];
   if (*done) return;
   const double alpha = scal[rho_cur] / scal[S_RV];
@@ -735,8 +758,9 @@ k_bcg_x(int64_t n0, int64_t n1, const double* __restrict__ scal, int rho_cur, co
     x[i] += alpha * ph[i] + omega * sh[i];
     const double ri = r[i] - omega * t[i];
     r[i] = ri;
+    const double zi = dinv[i] * ri;
     s0 += rhat[i] * ri;
-    s1 += ri * ri;
+    s1 += zi * zi;
   }
   double mine[2] = {block_sum(s0, red), block_sum(s1, red)};
   finish_partials<2>(mine, partials, kMaxPartials, out, counter, red);
@@ -784,7 +808,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   FSB_LAUNCH_CHECK(ctx);
   if (dist && (rc = fsb_dist_halo_raw(ctx, x->d, n))) return rc;
   if ((rc = launch_spmv(A, x->d, v, nullptr, 0, nullptr, nullptr))) return rc;
-  k_bcg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, v, r, rhat, ctx->d_partials, scal + S_RHO0, ctx->d_counters + 1);
+  k_bcg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, v, dinv, r, rhat, ctx->d_partials, scal + S_RHO0, ctx->d_counters + 1);
   FSB_LAUNCH_CHECK(ctx);
   if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RHO0, 3))) return rc;
   k_check0<<<1, 1, 0, ctx->stream>>>(scal, S_RRB0, S_BBB, rtol, atol, maxit, state, scal + S_FINAL_RR);
@@ -807,7 +831,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
       if (dist && (rc = fsb_dist_halo_raw(ctx, sh, n))) return rc;
       if ((rc = launch_spmv(A, sh, t, r, 1, scal + S_TS, state))) return rc;
       if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_TS, 2))) return rc;
-      k_bcg_x<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, ph, sh, t, rhat, x->d, r, ctx->d_partials, scal + rhon, ctx->d_counters + 2, state);
+      k_bcg_x<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, ph, sh, t, rhat, dinv, x->d, r, ctx->d_partials, scal + rhon, ctx->d_counters + 2, state);
       FSB_LAUNCH_CHECK(ctx);
       if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + rhon, 2))) return rc;
       k_bcg_check<<<1, 1, 0, ctx->stream>>>(scal, rhon, rrn, rtol, atol, maxit, state);

@@ -49,8 +49,8 @@ typedef enum {
 typedef struct {
   int32_t iterations;
   int32_t converged;     /* 1 converged, 0 hit maxit, -1 breakdown */
-  double rnorm;          /* final ||r||_2 (recurrence residual) */
-  double bnorm;          /* ||b||_2 */
+  double rnorm;          /* final ||M^-1 r||_2 (recurrence residual, preconditioned norm) */
+  double bnorm;          /* ||M^-1 b||_2 */
   double solve_ms;       /* device time of the iteration loop (CUDA events on the ctx stream) */
   double spmv_ms;        /* accumulated device time of the SpMV launches when profiling is on, else 0 */
 } fsb_solve_info;
@@ -147,8 +147,9 @@ int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t nbc, const i
 /* ---- Krylov: PETSc KSPCG / KSPBCGS + PCJacobi -------------------------------------------------- */
 int fsb_spmv(fsb_mat* A, fsb_vec* x, fsb_vec* y);               /* y = A x over the owned rows */
 int fsb_dot(fsb_vec* x, fsb_vec* y, double* result);            /* owned range, allreduced when distributed */
-/* precond: 0 none, 1 Jacobi.  Convergence: ||r||_2 <= max(rtol*||b||_2, atol).  x holds the start
- * vector on entry and the solution on exit.  (SolverBase.py:603-612, 663-670) */
+/* precond: 0 none, 1 Jacobi (M = diag A).  Convergence is tested on the preconditioned residual, as PETSc's
+ * KSP does by default: ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol).  x holds the start vector on entry and
+ * the solution on exit.  (SolverBase.py:603-612, 663-670) */
 int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit,
                  int32_t precond, fsb_solve_info* info);
 int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit,

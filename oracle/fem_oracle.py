@@ -340,19 +340,19 @@ def solve_direct(A, b):
 
 
 def pcg_jacobi(A, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000):
-    """Jacobi-preconditioned CG, the exact recurrence the CUDA path runs (textbook PCG, convergence
-    on the true-residual recurrence norm ||r||_2 <= max(rtol*||b||_2, atol)).
-    Returns (x, iterations, relres)."""
+    """Jacobi-preconditioned CG, the exact recurrence the CUDA path runs (textbook PCG; convergence on
+    the preconditioned recurrence residual ||M^-1 r||_2 <= max(rtol*||M^-1 b||_2, atol), PETSc's default
+    KSP norm, which is insensitive to row scaling).  Returns (x, iterations, relres)."""
     A = A.tocsr()
     dinv = 1.0 / A.diagonal()
     x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
     r = b - A @ x
-    bnorm = np.linalg.norm(b)
+    bnorm = np.linalg.norm(dinv * b)
     tol = max(rtol * bnorm, atol)
     z = dinv * r
     p = z.copy()
     rz = r @ z
-    rn = np.linalg.norm(r)
+    rn = np.linalg.norm(z)
     it = 0
     while rn > tol and it < maxit:
         q = A @ p
@@ -361,7 +361,7 @@ def pcg_jacobi(A, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000):
         r -= alpha * q
         z = dinv * r
         rz_new = r @ z
-        rn = np.linalg.norm(r)
+        rn = np.linalg.norm(z)
         p = z + (rz_new / rz) * p
         rz = rz_new
         it += 1
@@ -369,18 +369,19 @@ def pcg_jacobi(A, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000):
 
 
 def bicgstab_jacobi(A, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000):
-    """Right-Jacobi-preconditioned BiCGStab (van der Vorst), r0_hat = r0.  Returns (x, it, relres)."""
+    """Right-Jacobi-preconditioned BiCGStab (van der Vorst), r0_hat = r0; convergence on ||M^-1 r||_2 as in
+    pcg_jacobi.  Returns (x, it, relres)."""
     A = A.tocsr()
     dinv = 1.0 / A.diagonal()
     x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
     r = b - A @ x
     rhat = r.copy()
-    bnorm = np.linalg.norm(b)
+    bnorm = np.linalg.norm(dinv * b)
     tol = max(rtol * bnorm, atol)
     rho = alpha = omega = 1.0
     v = np.zeros_like(b)
     p = np.zeros_like(b)
-    rn = np.linalg.norm(r)
+    rn = np.linalg.norm(dinv * r)
     it = 0
     while rn > tol and it < maxit:
         rho_new = rhat @ r
@@ -396,7 +397,7 @@ def bicgstab_jacobi(A, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000):
         x += alpha * ph + omega * sh
         r = s - omega * t
         rho = rho_new
-        rn = np.linalg.norm(r)
+        rn = np.linalg.norm(dinv * r)
         it += 1
     return x, it, rn / bnorm if bnorm > 0 else rn
 

@@ -180,7 +180,7 @@ static void spmv(int64_t n, const int64_t* rp, const int32_t* ci, const double* 
 void fo_spmv(int64_t n, const int64_t* rp, const int32_t* ci, const double* va, const double* x, double* y) { spmv(n, rp, ci, va, x, y); }
 
 /* Jacobi-PCG; x holds the start vector.  Returns the iteration count; *relres = ||r||/||b||.
- * stops at ||r|| <= max(rtol*||b||, atol) or after maxit iterations. */
+ * stops at ||M^-1 r|| <= max(rtol*||M^-1 b||, atol) (preconditioned norm, PETSc's KSP default) or after maxit. */
 int fo_pcg_jacobi(int64_t n, const int64_t* rp, const int32_t* ci, const double* va, const double* b, double* x,
                   double rtol, double atol, int maxit, double* relres) {
   double* r = (double*)malloc(sizeof(double) * n);
@@ -198,7 +198,7 @@ int fo_pcg_jacobi(int64_t n, const int64_t* rp, const int32_t* ci, const double*
     r[i] = b[i] - q[i];
     const double z = dinv[i] * r[i];
     p[i] = z;
-    rz += r[i] * z; rr += r[i] * r[i]; bbn += b[i] * b[i];
+    rz += r[i] * z; rr += z * z; bbn += (dinv[i] * b[i]) * (dinv[i] * b[i]);   /* preconditioned norms */
   }
   const double tol2 = fmax(rtol * rtol * bbn, atol * atol);
   int it = 0;
@@ -215,8 +215,9 @@ int fo_pcg_jacobi(int64_t n, const int64_t* rp, const int32_t* ci, const double*
       x[i] += alpha * p[i];
       const double ri = r[i] - alpha * q[i];
       r[i] = ri;
-      rzn += ri * (dinv[i] * ri);
-      rr += ri * ri;
+      const double zi = dinv[i] * ri;
+      rzn += ri * zi;
+      rr += zi * zi;
     }
     const double beta = rzn / rz;
 #pragma omp parallel for schedule(static)

@@ -36,16 +36,16 @@ def main():
     y = _lib.DeviceVector(ctx, nv)
     b_spmv = 12 * nnz + 24 * nv
     def time_spmv(A, x, y, bytes_, label):
-        for mode, lpr in ((2, 0), (1, 0), (0, 1), (0, 2), (0, 4), (0, 2)):
-            ctx.set_option("spmv_mode", mode)
-            if lpr:
-                ctx.set_option("spmv_lpr", lpr)
+        combos = [(2, 256, 2, 2), (1, 256, 2, 2)] + [(0, r, l, s) for r in (256, 128) for l in (2, 4) for s in (2, 3, 4)]
+        for mode, rows, lpr, nst in combos:
+            ctx.set_option("spmv_mode", mode); ctx.set_option("spmv_rows", rows)
+            ctx.set_option("spmv_lpr", lpr); ctx.set_option("spmv_stages", nst)
             A.spmv(x, y)
             ctx.sync(); t = time.perf_counter()
             for _ in range(20): A.spmv(x, y)
             ctx.sync(); dt = (time.perf_counter() - t) / 20
-            print("%s spmv mode %d lpr %d        %9.3f ms  %.1f GB/s" % (label, mode, lpr, dt * 1e3, bytes_ / dt / 1e9), flush=True)
-        ctx.set_option("spmv_mode", 0); ctx.set_option("spmv_lpr", 2)
+            print("%s spmv mode %d rows %3d lpr %d stages %d   %9.3f ms  %.1f GB/s" % (label, mode, rows, lpr, nst, dt * 1e3, bytes_ / dt / 1e9), flush=True)
+        ctx.set_option("spmv_mode", 0); ctx.set_option("spmv_rows", 256); ctx.set_option("spmv_lpr", 2); ctx.set_option("spmv_stages", 2)
     time_spmv(A, x, y, b_spmv, "csr ")
     if os.environ.get("PROBE_ELASTICITY", "1") == "1" and N <= 160:
         A3 = timed("mat_create bs=3", lambda: _lib.DeviceMatrix.create(m, 3))
