@@ -68,7 +68,7 @@ struct fsb_mat {
   // SpMV tiling (TMA-staged): tiles of ~tile_nnz blocks snapped to row boundaries
   int tile_nnz = 0;
   int64_t ntiles = 0;
-  int64_t* tile_row = nullptr; // [ntiles+1] first block row of each tile (within owned range)
+  int64_t* tile_row = nullptr; // [2*(ntiles+1)]: first block row of each tile, then row_ptr at that row
   int tile_cap = 0;            // smem capacity in blocks per stage
   int tile_rows = 0;           // scalar rows per tile this tiling was built for
   size_t stage_bytes = 0;      // shared memory per pipeline stage (values + columns + row_ptr slice)
@@ -122,8 +122,10 @@ static inline unsigned fsb_grid(int64_t n, int block, int64_t cap = (1ll << 31) 
 
 // device-wide exclusive scan int32 -> int64 (out has n+1 entries, out[n] = total)   [fsb_pattern.cu]
 int fsb_exclusive_scan(fsb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
-// SpMV tiling setup after row_ptr / owned range are known   [fsb_solve.cu]
+// SpMV tiling setup after row_ptr / owned range are known, and y = A x (+ fused dots d0 = y.w, d1 = y.y
+// written to out[0..2)) on the ctx stream; `done` is an optional device early-exit flag   [fsb_spmv.cu]
 int fsb_mat_setup_tiles(fsb_mat* A);
+int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done);
 // distributed hooks [fsb_dist.cu]
 bool fsb_dist_active(fsb_ctx* ctx);
 int fsb_dist_halo_raw(fsb_ctx* ctx, double* v, int64_t n);

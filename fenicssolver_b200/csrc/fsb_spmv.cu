@@ -1,0 +1,407 @@
+// K7a: block-CSR SpMV  y = A x  (+ fused dot products) for the Krylov kernel chains.
+//
+// Design (HBM-bound: 12 B per non-zero + 24 B per row of algorithmic traffic):
+//   * the non-zero stream is cut into tiles of ~T blocks snapped to row boundaries (equal bytes per tile;
+//     per-tile first row and first non-zero are precomputed once per matrix);
+//   * persistent CTAs, one producer warp + consumer warps.  The producer streams each tile's values,
+//     column indices and row_ptr slice into shared memory with 1-D TMA bulk copies (cp.async.bulk ->
+//     SASS UBLKCP) signalling a `full` mbarrier; consumers release the stage through an `empty`
+//     mbarrier, so tile issue (two dependent index loads) is off the consumers' critical path and NST-1
+//     tiles stay in flight per CTA;
+//   * LPR lanes share one scalar row; each lane gathers up to UNR x-entries at once through L1/L2
+//     (x is read once from HBM: neighbouring rows reuse it from L2), partial sums are combined by
+//     warp shuffles, rows are written once;
+//   * fused reductions (y.w, y.y) leave per-CTA partials that the last CTA combines in a fixed order.
+// Modes kept for A/B measurements: 2 = first version (one thread per row, no specialisation),
+// 1 = plain row-per-thread kernel without staging (also the fallback for untileable matrices).
+#include "fsb_device.cuh"
+#include <algorithm>
+#include <cmath>
+
+struct SpmvArgs {
+  const int64_t* row_ptr;
+  const int32_t* col_idx;
+  const double* vals;
+  const int64_t* tile_row;  // [ntiles+1] first block row per tile
+  const int64_t* tile_k;    // [ntiles+1] row_ptr[tile_row[t]]
+  int64_t ntiles;
+  int64_t own0, own1;       // owned block rows
+  int cap;                  // stage capacity in blocks
+  const double* x;
+  double* y;
+  const double* w;          // optional: d0 = sum y.w
+  int want_yy;              // d1 = sum y.y
+  double* partials;
+  double* out;              // out[0]=d0, out[1]=d1
+  unsigned* counter;
+  const int* done;          // optional early-exit flag
+};
+
+// ------------------------------------------------------------------------------------ mode 2: first version
+template <int BS, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_spmv_tma(SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ double red[32];
+  if (a.done && *a.done) return;
+  constexpr int VB = 8 * BS * BS;   // bytes of values per block
+  const size_t stage_bytes = (size_t)a.cap * (VB + 4);
+  auto vals_s = [&](int s) { return reinterpret_cast<const double*>(smem + s * stage_bytes); };
+  auto cols_s = [&](int s) { return reinterpret_cast<const int32_t*>(smem + s * stage_bytes + (size_t)a.cap * VB); };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int s) {
+    const int64_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
+    if (r1 <= r0) { mbar_arrive(&bar[s]); return; }
+    const int64_t k0 = a.row_ptr[r0], k1 = a.row_ptr[r1];
+    const int64_t al0 = k0 & ~3ll;
+    const uint32_t cnt = (uint32_t)(((k1 - al0) + 3) & ~3ll);
+    mbar_expect_tx(&bar[s], cnt * (VB + 4));
+    bulk_g2s((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &bar[s]);
+    bulk_g2s((void*)cols_s(s), a.col_idx + al0, cnt * 4, &bar[s]);
+  };
+
+  double d0 = 0.0, d1 = 0.0;
+  int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < a.ntiles) issue(tile, 0);
+  for (int it = 0; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < a.ntiles) issue(next, s ^ 1);
+    const int64_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
+    mbar_wait(&bar[s], (it >> 1) & 1);
+    if (r1 > r0) {
+      const int64_t al0 = a.row_ptr[r0] & ~3ll;
+      const double* __restrict__ vs = vals_s(s);
+      const int32_t* __restrict__ cs = cols_s(s);
+      const int nscalar = (int)(r1 - r0) * BS;
+      for (int lr = threadIdx.x; lr < nscalar; lr += THREADS) {
+        const int64_t R = r0 + lr / BS;
+        const int i = lr % BS;
+        const int ks = (int)(a.row_ptr[R] - al0), ke = (int)(a.row_ptr[R + 1] - al0);
+        double acc = 0.0;
+#pragma unroll 4
+        for (int k = ks; k < ke; ++k) {
+          const int64_t c = cs[k];
+#pragma unroll
+          for (int j = 0; j < BS; ++j) acc += vs[(k * BS + i) * BS + j] * __ldg(a.x + c * BS + j);
+        }
+        const int64_t row = R * BS + i;
+        a.y[row] = acc;
+        if (a.w) d0 += acc * a.w[row];
+        if (a.want_yy) d1 += acc * acc;
+      }
+    }
+    __syncthreads();   // stage s is free for the prefetch issued at the top of the next iteration
+  }
+  if (a.out) {
+    double mine[2];
+    mine[0] = block_sum(d0, red);
+    mine[1] = block_sum(d1, red);
+    finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+  }
+}
+
+// ------------------------------------------------------------------------------------ mode 0: producer/consumer
+template <int BS, int ROWS, int LPR>
+struct SpmvCfg {
+  static constexpr int CONSUMERS = ROWS * LPR;         // ROWS scalar rows per pass
+  static constexpr int THREADS = CONSUMERS + 32;       // + one producer warp
+  static constexpr int RCAP = 2 * (ROWS / BS) + 8;     // block rows whose row_ptr slice fits the stage
+  static constexpr int UNR = BS == 1 ? 8 : (BS == 2 ? 4 : 3);   // gathers in flight per lane (x BS)
+};
+
+template <int BS, int ROWS, int LPR, int NST>
+__global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(SpmvArgs a) {
+  using Cfg = SpmvCfg<BS, ROWS, LPR>;
+  constexpr int CONSUMERS = Cfg::CONSUMERS, RCAP = Cfg::RCAP, UNR = Cfg::UNR;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full[NST], empty[NST];
+  __shared__ int64_t s_info[NST][4];    // per stage: r0, r1, aligned first nnz, aligned first row (or -1: row_ptr not staged)
+  __shared__ double red[32];
+  if (a.done && *a.done) return;
+  constexpr int VB = 8 * BS * BS;
+  const size_t rp_bytes = (size_t)(RCAP + 4) * 8;
+  const size_t stage_bytes = (size_t)a.cap * (VB + 4) + rp_bytes;
+  auto vals_s = [&](int s) { return reinterpret_cast<const double*>(smem + s * stage_bytes); };
+  auto cols_s = [&](int s) { return reinterpret_cast<const int32_t*>(smem + s * stage_bytes + (size_t)a.cap * VB); };
+  auto rptr_s = [&](int s) { return reinterpret_cast<const int64_t*>(smem + s * stage_bytes + (size_t)a.cap * (VB + 4)); };
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CONSUMERS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double d0 = 0.0, d1 = 0.0;
+  if (threadIdx.x >= CONSUMERS) {
+    // ===== producer warp: lane 0 walks the tiles and issues the bulk copies (the warp stays converged) =====
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % NST;
+      if (threadIdx.x == CONSUMERS) {
+        if (it >= NST) mbar_wait(&empty[s], ((it / NST) - 1) & 1);      // consumers have drained this stage
+        const int64_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
+        const int64_t k0 = a.tile_k[tile], k1 = a.tile_k[tile + 1];
+        s_info[s][0] = r0; s_info[s][1] = r1;
+        if (r1 <= r0) {
+          mbar_arrive(&full[s]);
+        } else {
+          const int64_t al0 = k0 & ~3ll;
+          const uint32_t cnt = (uint32_t)(((k1 - al0) + 3) & ~3ll);
+          const int64_t ra0 = r0 & ~1ll;
+          const bool stage_rp = (r1 - ra0 + 1) <= RCAP;
+          const uint32_t nrp = stage_rp ? (uint32_t)(((r1 - ra0 + 1) + 1) & ~1ll) : 0u;
+          s_info[s][2] = al0; s_info[s][3] = stage_rp ? ra0 : -1;
+          mbar_expect_tx(&full[s], cnt * (VB + 4) + nrp * 8);
+          bulk_g2s((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &full[s]);
+          bulk_g2s((void*)cols_s(s), a.col_idx + al0, cnt * 4, &full[s]);
+          if (stage_rp) bulk_g2s((void*)rptr_s(s), a.row_ptr + ra0, nrp * 8, &full[s]);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== consumer warps =====
+    const int sub = threadIdx.x % LPR;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % NST;
+      mbar_wait(&full[s], (it / NST) & 1);
+      const int64_t r0 = s_info[s][0], r1 = s_info[s][1];
+      if (r1 > r0) {
+        const int64_t al0 = s_info[s][2], ra0 = s_info[s][3];
+        const double* __restrict__ vs = vals_s(s);
+        const int32_t* __restrict__ cs = cols_s(s);
+        const int64_t* __restrict__ rp = rptr_s(s);
+        const int nscalar = (int)(r1 - r0) * BS;
+        for (int base = 0; base < nscalar; base += ROWS) {       // warp-uniform trip count
+          const int lr = base + threadIdx.x / LPR;
+          const bool live = lr < nscalar;
+          const int64_t R = r0 + (live ? lr / BS : 0);
+          const int i = live ? lr % BS : 0;
+          const int64_t row = R * BS + i;
+          int ks, ke;
+          if (ra0 >= 0) { ks = (int)(rp[R - ra0] - al0); ke = (int)(rp[R + 1 - ra0] - al0); }
+          else { ks = (int)(a.row_ptr[R] - al0); ke = (int)(a.row_ptr[R + 1] - al0); }
+          if (!live) ke = ks;
+          const double wv = (a.w && live && sub == 0) ? __ldg(a.w + row) : 0.0;   // issued with the gathers
+          double acc = 0.0;
+          for (int k = ks + sub; k < ke; k += LPR * UNR) {
+            double v[UNR][BS], xg[UNR][BS];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const int kk = k + u * LPR;
+              const bool ok = kk < ke;
+              const int64_t c = ok ? cs[kk] : 0;
+#pragma unroll
+              for (int j = 0; j < BS; ++j) {
+                v[u][j] = ok ? vs[(kk * BS + i) * BS + j] : 0.0;
+                xg[u][j] = ok ? __ldg(a.x + c * BS + j) : 0.0;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+              for (int j = 0; j < BS; ++j) acc += v[u][j] * xg[u][j];
+          }
+#pragma unroll
+          for (int o = LPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (live && sub == 0) {
+            a.y[row] = acc;
+            d0 += acc * wv;
+            if (a.want_yy) d1 += acc * acc;
+          }
+        }
+      }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);      // this warp is done with stage s
+    }
+  }
+  if (a.out) {
+    double mine[2];
+    mine[0] = block_sum(d0, red);
+    mine[1] = block_sum(d1, red);
+    finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+  }
+}
+
+// ------------------------------------------------------------------------------------ mode 1: plain
+template <int BS>
+__global__ void __launch_bounds__(256) k_spmv_plain(SpmvArgs a) {
+  __shared__ double red[32];
+  if (a.done && *a.done) return;
+  double d0 = 0.0, d1 = 0.0;
+  const int64_t n0 = a.own0 * BS, n1 = a.own1 * BS;
+  for (int64_t row = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n1; row += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t R = row / BS;
+    const int i = (int)(row % BS);
+    double acc = 0.0;
+    for (int64_t k = a.row_ptr[R]; k < a.row_ptr[R + 1]; ++k) {
+      const int64_t c = a.col_idx[k];
+#pragma unroll
+      for (int j = 0; j < BS; ++j) acc += a.vals[(k * BS + i) * BS + j] * __ldg(a.x + c * BS + j);
+    }
+    a.y[row] = acc;
+    if (a.w) d0 += acc * a.w[row];
+    if (a.want_yy) d1 += acc * acc;
+  }
+  if (a.out) {
+    double mine[2];
+    mine[0] = block_sum(d0, red);
+    mine[1] = block_sum(d1, red);
+    finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+  }
+}
+
+// ------------------------------------------------------------------------------------ tiling
+// tile t covers block rows [tile_row[t], tile_row[t+1]): the first row whose row_ptr reaches the t-th
+// multiple of tile_nnz past the owned range's first non-zero; tile_k[t] = row_ptr[tile_row[t]].
+__global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, int64_t own1, int64_t tile_nnz,
+                            int64_t ntiles, int64_t* __restrict__ tile_row, int64_t* __restrict__ tile_k) {
+  const int64_t base = row_ptr[own0];
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t <= ntiles; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = own0, hi = own1;          // first row r in [own0, own1] with row_ptr[r] >= target
+    if (t == ntiles) lo = own1;
+    else {
+      const int64_t target = base + t * tile_nnz;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] < target) lo = mid + 1; else hi = mid;
+      }
+    }
+    tile_row[t] = lo;
+    tile_k[t] = row_ptr[lo];
+  }
+}
+
+// scalar rows per tile: 256 (192 for 3x3 blocks) or half of that (ctx option spmv_rows)
+static int spmv_rows(fsb_ctx* ctx, int bs) {
+  const int big = bs == 3 ? 192 : 256;
+  return ctx->spmv_rows == 128 ? big / 2 : big;
+}
+static constexpr size_t kSmemBudget = 200 * 1024;
+
+int fsb_mat_setup_tiles(fsb_mat* A) {
+  fsb_ctx* ctx = A->ctx;
+  cudaFree(A->tile_row);
+  A->tile_row = nullptr;
+  A->ntiles = 0; A->tile_nnz = 0; A->tile_cap = 0; A->stage_bytes = 0;
+  A->tile_rows = spmv_rows(ctx, A->bs);
+  const int64_t nrows = A->own1 - A->own0;
+  if (nrows <= 0) return FSB_OK;
+  int64_t k01[2];
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(&k01[0], A->row_ptr + A->own0, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(&k01[1], A->row_ptr + A->own1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t nnz = k01[1] - k01[0];
+  if (nnz <= 0) return FSB_OK;
+  const int bs = A->bs;
+  const int rows_target = A->tile_rows / bs;
+  const double avg = (double)nnz / (double)nrows;
+  int64_t T = (int64_t)std::ceil(avg * rows_target);
+  T = (T + 15) & ~15ll;
+  int64_t cap = T + A->max_row_len + 8;
+  cap = (cap + 3) & ~3ll;
+  const size_t stage = (size_t)cap * (8 * bs * bs + 4) + (size_t)(2 * rows_target + 12) * 8;
+  if (2 * stage > kSmemBudget) return FSB_OK;   // not tileable (very long rows): plain kernel is used
+  A->stage_bytes = stage;
+  A->tile_nnz = (int)T;
+  A->tile_cap = (int)cap;
+  A->ntiles = (nnz + T - 1) / T;
+  int rc = fsb_dmalloc(ctx, &A->tile_row, 2 * ((size_t)A->ntiles + 1));
+  if (rc) return rc;
+  k_tile_rows<<<fsb_grid(A->ntiles + 1, 256, 4096), 256, 0, ctx->stream>>>(A->row_ptr, A->own0, A->own1, T, A->ntiles, A->tile_row,
+                                                                           A->tile_row + A->ntiles + 1);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------------------------ launch
+int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done) {
+  fsb_ctx* ctx = A->ctx;
+  if (A->own1 <= A->own0) return FSB_OK;
+  if (ctx->spmv_mode != 1 && A->tile_rows != spmv_rows(ctx, A->bs)) {
+    int rc = fsb_mat_setup_tiles(A);      // the tile size option changed since the matrix was set up
+    if (rc) return rc;
+  }
+  SpmvArgs a;
+  a.row_ptr = A->row_ptr; a.col_idx = A->col_idx; a.vals = A->vals;
+  a.tile_row = A->tile_row; a.tile_k = A->tile_row ? A->tile_row + A->ntiles + 1 : nullptr;
+  a.ntiles = A->ntiles; a.own0 = A->own0; a.own1 = A->own1; a.cap = A->tile_cap;
+  a.x = x; a.y = y; a.w = w; a.want_yy = want_yy;
+  a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
+  const bool tiled = ctx->spmv_mode != 1 && A->ntiles > 0;
+  if (tiled && ctx->spmv_mode == 0) {
+    const int lpr = ctx->spmv_lpr;
+    const int rows = A->tile_rows;
+    const int nst = std::max(2, std::min(ctx->spmv_stages, (int)((224 * 1024) / A->stage_bytes)));
+    const size_t smem = (size_t)nst * A->stage_bytes;
+    bool launched = false;
+#define FSB_SPMV_CASE(BS, ROWS, LPR, NST)                                                                              \
+  if (!launched && A->bs == BS && rows == ROWS && lpr == LPR && nst == NST) {                                          \
+    using Cfg = SpmvCfg<BS, ROWS, LPR>;                                                                                \
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / Cfg::THREADS, (227 * 1024) / (smem + 1024)));  \
+    const unsigned grid = (unsigned)std::min<int64_t>(A->ntiles, (int64_t)ctx->sm_count * per_sm);                     \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_spmv_ws<BS, ROWS, LPR, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    k_spmv_ws<BS, ROWS, LPR, NST><<<grid, Cfg::THREADS, smem, ctx->stream>>>(a);                                       \
+    launched = true;                                                                                                   \
+  }
+#define FSB_SPMV_NST(BS, ROWS, LPR) FSB_SPMV_CASE(BS, ROWS, LPR, 2) FSB_SPMV_CASE(BS, ROWS, LPR, 3) FSB_SPMV_CASE(BS, ROWS, LPR, 4)
+    FSB_SPMV_NST(1, 256, 1) FSB_SPMV_NST(1, 256, 2) FSB_SPMV_NST(1, 128, 1) FSB_SPMV_NST(1, 128, 2) FSB_SPMV_NST(1, 128, 4)
+    FSB_SPMV_NST(2, 256, 2) FSB_SPMV_NST(2, 128, 2)
+    FSB_SPMV_NST(3, 192, 2) FSB_SPMV_NST(3, 192, 4) FSB_SPMV_NST(3, 96, 2) FSB_SPMV_NST(3, 96, 4)
+#undef FSB_SPMV_NST
+#undef FSB_SPMV_CASE
+    if (!launched) FSB_FAIL(ctx, FSB_ERR_ARG, "unsupported spmv_rows/spmv_lpr/spmv_stages combination");
+  } else if (tiled) {
+    const size_t smem = 2 * (size_t)A->tile_cap * (8 * A->bs * A->bs + 4);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
+    const unsigned grid = (unsigned)std::min<int64_t>(A->ntiles, (int64_t)ctx->sm_count * per_sm);
+    static bool attr_set[4] = {false, false, false, false};
+#define FSB_SPMV1_LAUNCH(BS, TH)                                                                                      \
+  do {                                                                                                                \
+    if (!attr_set[BS]) {                                                                                              \
+      FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_spmv_tma<BS, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+      attr_set[BS] = true;                                                                                            \
+    }                                                                                                                 \
+    k_spmv_tma<BS, TH><<<grid, TH, smem, ctx->stream>>>(a);                                                           \
+  } while (0)
+    if (A->bs == 1) FSB_SPMV1_LAUNCH(1, 256);
+    else if (A->bs == 2) FSB_SPMV1_LAUNCH(2, 256);
+    else FSB_SPMV1_LAUNCH(3, 192);
+#undef FSB_SPMV1_LAUNCH
+  } else {
+    const unsigned grid = fsb_grid((A->own1 - A->own0) * A->bs, 256, (int64_t)ctx->sm_count * 8);
+    if (A->bs == 1) k_spmv_plain<1><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (A->bs == 2) k_spmv_plain<2><<<grid, 256, 0, ctx->stream>>>(a);
+    else k_spmv_plain<3><<<grid, 256, 0, ctx->stream>>>(a);
+  }
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+extern "C" int fsb_spmv(fsb_mat* A, fsb_vec* x, fsb_vec* y) {
+  if (!A || !x || !y) return FSB_ERR_ARG;
+  const int64_t n = A->nbrows * A->bs;
+  if (x->n != n || y->n != n || x == y) FSB_FAIL(A->ctx, FSB_ERR_ARG, "vector sizes do not match the matrix");
+  if (fsb_dist_active(A->ctx)) {
+    int rc = fsb_dist_halo_raw(A->ctx, x->d, x->n);
+    if (rc) return rc;
+  }
+  return fsb_launch_spmv(A, x->d, y->d, nullptr, 0, nullptr, nullptr);
+}
