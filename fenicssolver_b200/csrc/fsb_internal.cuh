@@ -21,9 +21,9 @@ struct fsb_ctx {
   // options
   int asm_mode = 1;      // 0 search+atomics, 1 position map + atomics
   int spmv_mode = 0;     // 0 TMA-staged tiles v2, 1 plain row-per-thread, 2 TMA-staged v1 (one thread per row)
-  int spmv_lpr = 2;      // lanes per row in the v2 kernel (2 or 4)
-  int spmv_rows = 256;   // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks)
-  int spmv_stages = 2;   // TMA pipeline depth of the v2 kernel (2..4)
+  int spmv_lpr = 0;      // lanes per row in the staged kernel (1, 2 or 4; 0 = best per block size)
+  int spmv_rows = 0;     // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks; 0 = best per block size)
+  int spmv_stages = 0;   // TMA pipeline depth (2..4; 0 = 2)
   int profile = 0;
   int use_graph = 1;
   int check_every = 32;

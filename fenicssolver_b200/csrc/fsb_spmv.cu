@@ -285,11 +285,15 @@ __global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, i
   }
 }
 
-// scalar rows per tile: 256 (192 for 3x3 blocks) or half of that (ctx option spmv_rows)
+// Scalar rows per tile: 256 (192 for 3x3 blocks) or half of that.  Option value 0 = measured best per
+// block size on B200 (profiles/spmv_sweep_r1.txt): CSR 256 rows x 2 lanes, 3x3 blocks 96 rows x 4 lanes,
+// two stages each (two CTAs per SM beat a deeper pipeline with one).
 static int spmv_rows(fsb_ctx* ctx, int bs) {
   const int big = bs == 3 ? 192 : 256;
-  return ctx->spmv_rows == 128 ? big / 2 : big;
+  const int opt = ctx->spmv_rows ? ctx->spmv_rows : (bs == 3 ? 128 : 256);
+  return opt == 128 ? big / 2 : big;
 }
+static int spmv_lpr(fsb_ctx* ctx, int bs) { return ctx->spmv_lpr ? ctx->spmv_lpr : (bs == 3 ? 4 : 2); }
 static constexpr size_t kSmemBudget = 200 * 1024;
 
 int fsb_mat_setup_tiles(fsb_mat* A) {
@@ -343,9 +347,9 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
   a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
   const bool tiled = ctx->spmv_mode != 1 && A->ntiles > 0;
   if (tiled && ctx->spmv_mode == 0) {
-    const int lpr = ctx->spmv_lpr;
+    const int lpr = spmv_lpr(ctx, A->bs);
     const int rows = A->tile_rows;
-    const int nst = std::max(2, std::min(ctx->spmv_stages, (int)((224 * 1024) / A->stage_bytes)));
+    const int nst = std::max(2, std::min(ctx->spmv_stages ? ctx->spmv_stages : 2, (int)((224 * 1024) / A->stage_bytes)));
     const size_t smem = (size_t)nst * A->stage_bytes;
     bool launched = false;
 #define FSB_SPMV_CASE(BS, ROWS, LPR, NST)                                                                              \

@@ -48,7 +48,7 @@ def main():
             for _ in range(20): A.spmv(x, y)
             ctx.sync(); dt = (time.perf_counter() - t) / 20
             print("%s spmv mode %d rows %3d lpr %d stages %d   %9.3f ms  %.1f GB/s" % (label, mode, rows, lpr, nst, dt * 1e3, bytes_ / dt / 1e9), flush=True)
-        ctx.set_option("spmv_mode", 0); ctx.set_option("spmv_rows", 256); ctx.set_option("spmv_lpr", 2); ctx.set_option("spmv_stages", 2)
+        ctx.set_option("spmv_mode", 0); ctx.set_option("spmv_rows", 0); ctx.set_option("spmv_lpr", 0); ctx.set_option("spmv_stages", 0)
     time_spmv(A, x, y, b_spmv, "csr ")
     if os.environ.get("PROBE_ELASTICITY", "1") == "1" and N <= 160:
         A3 = timed("mat_create bs=3", lambda: _lib.DeviceMatrix.create(m, 3))
