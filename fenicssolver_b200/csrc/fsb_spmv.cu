@@ -114,7 +114,7 @@ struct SpmvCfg {
   static constexpr int CONSUMERS = ROWS * LPR;         // ROWS scalar rows per pass
   static constexpr int THREADS = CONSUMERS + 32;       // + one producer warp
   static constexpr int RCAP = 2 * (ROWS / BS) + 8;     // block rows whose row_ptr slice fits the stage
-  static constexpr int UNR = BS == 1 ? 8 : (BS == 2 ? 4 : 3);   // gathers in flight per lane (x BS)
+  static constexpr int UNR = BS == 1 ? 8 : 4;          // blocks in flight per lane (x BS gathers each)
 };
 
 template <int BS, int ROWS, int LPR, int NST>
@@ -368,7 +368,7 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
 #define FSB_SPMV_NST(BS, ROWS, LPR) FSB_SPMV_CASE(BS, ROWS, LPR, 2) FSB_SPMV_CASE(BS, ROWS, LPR, 3) FSB_SPMV_CASE(BS, ROWS, LPR, 4)
     FSB_SPMV_NST(1, 256, 1) FSB_SPMV_NST(1, 256, 2) FSB_SPMV_NST(1, 128, 1) FSB_SPMV_NST(1, 128, 2) FSB_SPMV_NST(1, 128, 4)
     FSB_SPMV_NST(2, 256, 2) FSB_SPMV_NST(2, 128, 2)
-    FSB_SPMV_NST(3, 192, 2) FSB_SPMV_NST(3, 192, 4) FSB_SPMV_NST(3, 96, 2) FSB_SPMV_NST(3, 96, 4)
+    FSB_SPMV_NST(3, 192, 2) FSB_SPMV_NST(3, 192, 4) FSB_SPMV_NST(3, 96, 2) FSB_SPMV_NST(3, 96, 4) FSB_SPMV_NST(3, 96, 8)
 #undef FSB_SPMV_NST
 #undef FSB_SPMV_CASE
     if (!launched) FSB_FAIL(ctx, FSB_ERR_ARG, "unsupported spmv_rows/spmv_lpr/spmv_stages combination");

@@ -36,7 +36,7 @@ def main():
     y = _lib.DeviceVector(ctx, nv)
     b_spmv = 12 * nnz + 24 * nv
     def time_spmv(A, x, y, bytes_, label):
-        combos = [(2, 256, 2, 2), (1, 256, 2, 2)] + [(0, r, l, s) for r in (256, 128) for l in (1, 2, 4) for s in (2, 3, 4)]
+        combos = [(2, 256, 2, 2), (1, 256, 2, 2)] + [(0, r, l, s) for r in (256, 128) for l in (1, 2, 4, 8) for s in (2, 3)]
         for mode, rows, lpr, nst in combos:
             ctx.set_option("spmv_mode", mode); ctx.set_option("spmv_rows", rows)
             ctx.set_option("spmv_lpr", lpr); ctx.set_option("spmv_stages", nst)
