@@ -537,13 +537,19 @@ extern "C" int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t n
     if (rc) return rc;
   }
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(A->bc_flag, 0, (size_t)n, ctx->stream));
-  int64_t* d_dofs = nullptr;
-  double* d_vals = nullptr;
-  int rc = fsb_dmalloc(ctx, &d_dofs, (size_t)nbc);
-  if (!rc) rc = fsb_dmalloc(ctx, &d_vals, (size_t)nbc);
-  if (rc) { cudaFree(d_dofs); return rc; }
-  cudaMemcpyAsync(d_dofs, dofs, sizeof(int64_t) * nbc, cudaMemcpyHostToDevice, ctx->stream);
-  cudaMemcpyAsync(d_vals, vals, sizeof(double) * nbc, cudaMemcpyHostToDevice, ctx->stream);
+  if (nbc > A->bc_cap) {      // staging buffers are kept on the matrix: a transient run applies the BCs every step
+    cudaFree(A->bc_dofs); cudaFree(A->bc_vals);
+    A->bc_dofs = nullptr; A->bc_vals = nullptr; A->bc_cap = 0;
+    int rc = fsb_dmalloc(ctx, &A->bc_dofs, (size_t)nbc);
+    if (!rc) rc = fsb_dmalloc(ctx, &A->bc_vals, (size_t)nbc);
+    if (rc) return rc;
+    A->bc_cap = nbc;
+  }
+  int64_t* d_dofs = A->bc_dofs;
+  double* d_vals = A->bc_vals;
+  // the host arrays are pageable and caller-owned: the copies below complete before this call returns
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dofs, dofs, sizeof(int64_t) * nbc, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_vals, vals, sizeof(double) * nbc, cudaMemcpyHostToDevice, ctx->stream));
   k_bc_scatter<<<fsb_grid(nbc, 256, 4096), 256, 0, ctx->stream>>>(nbc, d_dofs, d_vals, A->bc_flag, A->bc_val, x ? x->d : nullptr);
   ctx->launches++;
   const unsigned grid = fsb_grid(n, 256, (int64_t)ctx->sm_count * 32);
@@ -551,10 +557,6 @@ extern "C" int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t n
   else if (A->bs == 2) k_dirichlet<2><<<grid, 256, 0, ctx->stream>>>(n, A->row_ptr, A->col_idx, A->vals, A->bc_flag, A->bc_val, b->d, symmetric);
   else k_dirichlet<3><<<grid, 256, 0, ctx->stream>>>(n, A->row_ptr, A->col_idx, A->vals, A->bc_flag, A->bc_val, b->d, symmetric);
   ctx->launches++;
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_dofs);
-  cudaFree(d_vals);
-  FSB_CHECK_CUDA(ctx, e);
   FSB_CHECK_CUDA(ctx, cudaGetLastError());
   return FSB_OK;
 }

@@ -75,6 +75,12 @@ struct fsb_mat {
   // dirichlet scratch
   uint8_t* bc_flag = nullptr;  // [nbrows*bs]
   double* bc_val = nullptr;
+  int64_t* bc_dofs = nullptr;  // staging for the uploaded Dirichlet list (capacity bc_cap)
+  double* bc_vals = nullptr;
+  int64_t bc_cap = 0;
+  // Krylov work vectors, kept across solves (transient runs re-solve every step)
+  double* work[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int work_count = 0;
 };
 
 #define FSB_CHECK_CUDA(ctx, call)                                                         \

@@ -242,6 +242,9 @@ extern "C" void fsb_mat_destroy(fsb_mat* A) {
   cudaFree(A->tile_row);
   cudaFree(A->bc_flag);
   cudaFree(A->bc_val);
+  cudaFree(A->bc_dofs);
+  cudaFree(A->bc_vals);
+  for (double* w : A->work) cudaFree(w);
   delete A;
 }
 

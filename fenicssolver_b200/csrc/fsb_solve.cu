@@ -86,13 +86,31 @@ k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot
   if (*done) return;
   const double alpha = scal[rz_slot] / scal[pq_slot];
   double s0 = 0, s1 = 0;
-  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
+  auto one = [&](int64_t i) {
     x[i] += alpha * p[i];
     const double ri = r[i] - alpha * q[i];
     r[i] = ri;
     const double zi = dinv[i] * ri;
     s0 += ri * zi;
     s1 += zi * zi;
+  };
+  // 16-byte accesses over the even-aligned body (two rows per thread and trip: twice the bytes in flight)
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t a0 = min((n0 + 1) & ~1ll, n1), npair = (n1 - a0) >> 1;
+  if (tid == 0 && a0 > n0) one(n0);
+  if (tid == 1 && a0 + 2 * npair < n1) one(n1 - 1);
+  for (int64_t j = tid; j < npair; j += nth) {
+    const int64_t i = a0 + 2 * j;
+    const double2 pv = *reinterpret_cast<const double2*>(p + i), qv = *reinterpret_cast<const double2*>(q + i);
+    const double2 dv = *reinterpret_cast<const double2*>(dinv + i);
+    double2 xv = *reinterpret_cast<double2*>(x + i), rv = *reinterpret_cast<double2*>(r + i);
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
+    *reinterpret_cast<double2*>(x + i) = xv;
+    *reinterpret_cast<double2*>(r + i) = rv;
+    const double z0 = dv.x * rv.x, z1 = dv.y * rv.y;
+    s0 += rv.x * z0 + rv.y * z1;
+    s1 += z0 * z0 + z1 * z1;
   }
   double mine[2] = {block_sum(s0, red), block_sum(s1, red)};
   finish_partials<2>(mine, partials, kMaxPartials, out, counter, red);
@@ -106,8 +124,18 @@ k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int 
   if (state[0]) return;
   const double rzn = scal[rz_new], rzo = scal[rz_old];
   const double beta = rzn / rzo;
-  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = dinv[i] * r[i] + beta * p[i];
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t a0 = min((n0 + 1) & ~1ll, n1), npair = (n1 - a0) >> 1;
+  if (tid == 0 && a0 > n0) p[n0] = dinv[n0] * r[n0] + beta * p[n0];
+  if (tid == 1 && a0 + 2 * npair < n1) p[n1 - 1] = dinv[n1 - 1] * r[n1 - 1] + beta * p[n1 - 1];
+  for (int64_t j = tid; j < npair; j += nth) {
+    const int64_t i = a0 + 2 * j;
+    const double2 dv = *reinterpret_cast<const double2*>(dinv + i), rv = *reinterpret_cast<const double2*>(r + i);
+    double2 pv = *reinterpret_cast<double2*>(p + i);
+    pv.x = dv.x * rv.x + beta * pv.x;
+    pv.y = dv.y * rv.y + beta * pv.y;
+    *reinterpret_cast<double2*>(p + i) = pv;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double rr = scal[rr_new], bb = scal[S_BB], pq = scal[pq_slot];
     const double tol2 = fmax(rtol * rtol * bb, atol * atol);
@@ -121,15 +149,24 @@ k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int 
 }
 
 // ------------------------------------------------------------------------------------ Krylov drivers
+// Work vectors live on the matrix and are reused by later solves (cudaMalloc/cudaFree synchronise the
+// device; a transient run solves every step).  Every vector is zeroed at hand-out: ghost entries of a
+// distributed solve are read by the SpMV gathers before the first halo exchange touches them.
 struct Workspace {
-  fsb_ctx* ctx;
-  std::vector<double*> bufs;
+  fsb_mat* A;
+  int next = 0;
   int alloc(double** p, int64_t n) {
-    int rc = fsb_dmalloc(ctx, p, (size_t)n);
-    if (!rc) { bufs.push_back(*p); cudaMemsetAsync(*p, 0, sizeof(double) * n, ctx->stream); }
-    return rc;
+    fsb_ctx* ctx = A->ctx;
+    if (next >= 8) FSB_FAIL(ctx, FSB_ERR_STATE, "Krylov workspace exhausted");
+    if (next >= A->work_count) {
+      int rc = fsb_dmalloc(ctx, &A->work[next], (size_t)n);
+      if (rc) return rc;
+      A->work_count = next + 1;
+    }
+    *p = A->work[next++];
+    FSB_CHECK_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(double) * n, ctx->stream));
+    return FSB_OK;
   }
-  ~Workspace() { for (double* b : bufs) cudaFree(b); }
 };
 
 struct SpmvTimer {
@@ -172,7 +209,7 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   memset(info, 0, sizeof(*info));
   const int64_t n0 = A->own0 * A->bs, n1 = A->own1 * A->bs;
   const bool dist = fsb_dist_active(ctx);
-  Workspace ws{ctx};
+  Workspace ws{A};
   double *r, *p, *q, *dinv;
   int rc;
   if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&p, n)) || (rc = ws.alloc(&q, n)) || (rc = ws.alloc(&dinv, n))) return rc;
@@ -359,7 +396,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   memset(info, 0, sizeof(*info));
   const int64_t n0 = A->own0 * A->bs, n1 = A->own1 * A->bs;
   const bool dist = fsb_dist_active(ctx);
-  Workspace ws{ctx};
+  Workspace ws{A};
   double *r, *rhat, *p, *ph, *v, *sh, *t, *dinv;
   int rc;
   if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&rhat, n)) || (rc = ws.alloc(&p, n)) || (rc = ws.alloc(&ph, n)) ||

@@ -286,14 +286,16 @@ __global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, i
 }
 
 // Scalar rows per tile: 256 (192 for 3x3 blocks) or half of that.  Option value 0 = measured best per
-// block size on B200 (profiles/spmv_sweep_r1.txt): CSR 256 rows x 2 lanes, 3x3 blocks 96 rows x 4 lanes,
-// two stages each (two CTAs per SM beat a deeper pipeline with one).
+// block size on B200 (profiles/spmv_sweep_r1.txt): CSR 256 rows x 2 lanes x 2 stages (two CTAs per SM beat
+// a deeper pipeline with one); 3x3 blocks 192 rows x 2 lanes x 3 stages (one CTA per SM either way, so
+// the third stage is free and keeps two 73 KB tiles in flight).
 static int spmv_rows(fsb_ctx* ctx, int bs) {
   const int big = bs == 3 ? 192 : 256;
-  const int opt = ctx->spmv_rows ? ctx->spmv_rows : (bs == 3 ? 128 : 256);
+  const int opt = ctx->spmv_rows ? ctx->spmv_rows : 256;
   return opt == 128 ? big / 2 : big;
 }
-static int spmv_lpr(fsb_ctx* ctx, int bs) { return ctx->spmv_lpr ? ctx->spmv_lpr : (bs == 3 ? 4 : 2); }
+static int spmv_lpr(fsb_ctx* ctx, int bs) { return ctx->spmv_lpr ? ctx->spmv_lpr : 2; }
+static int spmv_stages(fsb_ctx* ctx, int bs) { return ctx->spmv_stages ? ctx->spmv_stages : (bs == 3 ? 3 : 2); }
 static constexpr size_t kSmemBudget = 200 * 1024;
 
 int fsb_mat_setup_tiles(fsb_mat* A) {
@@ -349,7 +351,7 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
   if (tiled && ctx->spmv_mode == 0) {
     const int lpr = spmv_lpr(ctx, A->bs);
     const int rows = A->tile_rows;
-    const int nst = std::max(2, std::min(ctx->spmv_stages ? ctx->spmv_stages : 2, (int)((224 * 1024) / A->stage_bytes)));
+    const int nst = std::max(2, std::min(spmv_stages(ctx, A->bs), (int)((224 * 1024) / A->stage_bytes)));
     const size_t smem = (size_t)nst * A->stage_bytes;
     bool launched = false;
 #define FSB_SPMV_CASE(BS, ROWS, LPR, NST)                                                                              \

@@ -55,7 +55,7 @@ def test_c3_elasticity_128_patch_test():
     N = 128
     G = np.array([[0.010, 0.020, -0.010], [0.000, -0.020, 0.030], [0.015, 0.000, 0.010]]) * 1e-3
     t0 = np.array([1e-4, -2e-4, 3e-4])
-    exprs = tuple("%r*x[0] + %r*x[1] + %r*x[2] + %r" % (G[i, 0], G[i, 1], G[i, 2], t0[i]) for i in range(3))
+    exprs = tuple("%r*x[0] + %r*x[1] + %r*x[2] + %r" % (float(G[i, 0]), float(G[i, 1]), float(G[i, 2]), float(t0[i])) for i in range(3))
     s = {'solver_name': 'LinearElasticitySolver', 'mesh': {'type': 'UnitCubeMesh', 'n': [N, N, N]},
          'material': {'name': 'steel', 'elastic_modulus': 2e11, 'poisson_ratio': 0.27, 'density': 7800},
          'boundary_conditions': {'all': {'boundary': lambda x, on_boundary: on_boundary, 'boundary_id': 1, 'type': 'Dirichlet', 'value': exprs}},
