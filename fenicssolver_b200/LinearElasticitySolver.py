@@ -36,7 +36,7 @@ class ElasticityForm:
         A = space.A
         A.zero()
         A.assemble_elasticity(self.mu, self.lmbda)
-        b = space.vector()
+        b = space.scratch_vector('rhs')
         dim = s.dimension
         for marker, t in self.tractions:
             fv, _ = space.local_facets(*s.boundary_facets.facets(marker))

@@ -58,7 +58,7 @@ class ScalarForm:
         c = float(self.capacity)
         vel = None if self.velocity is None else np.asarray(self.velocity, dtype=np.float64)
         adv = c if vel is not None else 0.0
-        b = space.vector()
+        b = space.scratch_vector('rhs')
         if self.transient:
             A.assemble_scalar(kscale=self.theta * kscale, ktensor=ktensor, mass=c / self.dt, adv=adv, vel=vel)
             tp = self.T_prev.device_vector()

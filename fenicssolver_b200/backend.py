@@ -170,6 +170,17 @@ class DeviceSpace:
         lo = self.v_off * self.ncomp
         return _lib.DeviceVector.from_numpy(self.ctx, a[lo:lo + self.ndof_local])
 
+    def scratch_vector(self, key):
+        """A zeroed device vector owned by the space and reused between calls (the right-hand side of every
+        time step): cudaMalloc/cudaFree synchronise the device and are kept out of the step."""
+        cache = self.__dict__.setdefault("_scratch", {})
+        v = cache.get(key)
+        if v is None:
+            v = cache[key] = _lib.DeviceVector(self.ctx, self.ndof_local)
+        else:
+            v.fill(0.0)
+        return v
+
     def vector_from_function(self, fn):
         """Device copy of a Function: a known-uniform field is filled on the device (no H2D copy)."""
         u = fn.uniform_value()

@@ -547,7 +547,7 @@ extern "C" int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t n
   }
   int64_t* d_dofs = A->bc_dofs;
   double* d_vals = A->bc_vals;
-  // the host arrays are pageable and caller-owned: the copies below complete before this call returns
+  // the host arrays are pageable and caller-owned: cudaMemcpyAsync stages pageable sources before it returns
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_dofs, dofs, sizeof(int64_t) * nbc, cudaMemcpyHostToDevice, ctx->stream));
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_vals, vals, sizeof(double) * nbc, cudaMemcpyHostToDevice, ctx->stream));
   k_bc_scatter<<<fsb_grid(nbc, 256, 4096), 256, 0, ctx->stream>>>(nbc, d_dofs, d_vals, A->bc_flag, A->bc_val, x ? x->d : nullptr);

@@ -96,7 +96,8 @@ k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot
   };
   // 16-byte accesses over the even-aligned body (two rows per thread and trip: twice the bytes in flight)
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  const int64_t a0 = min((n0 + 1) & ~1ll, n1), npair = (n1 - a0) >> 1;
+  const int64_t a_up = (n0 + 1) & ~(int64_t)1;
+  const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
   if (tid == 0 && a0 > n0) one(n0);
   if (tid == 1 && a0 + 2 * npair < n1) one(n1 - 1);
   for (int64_t j = tid; j < npair; j += nth) {
@@ -125,7 +126,8 @@ k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int 
   const double rzn = scal[rz_new], rzo = scal[rz_old];
   const double beta = rzn / rzo;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  const int64_t a0 = min((n0 + 1) & ~1ll, n1), npair = (n1 - a0) >> 1;
+  const int64_t a_up = (n0 + 1) & ~(int64_t)1;
+  const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
   if (tid == 0 && a0 > n0) p[n0] = dinv[n0] * r[n0] + beta * p[n0];
   if (tid == 1 && a0 + 2 * npair < n1) p[n1 - 1] = dinv[n1 - 1] * r[n1 - 1] + beta * p[n1 - 1];
   for (int64_t j = tid; j < npair; j += nth) {
