@@ -421,7 +421,7 @@ extern "C" int fsb_assemble_source(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, co
   FSB_LAUNCH_CHECK(ctx);
   if (d_tags) {
     FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_tags);
+    fsb_dfree(ctx, d_tags);
   }
   return FSB_OK;
 }
@@ -441,9 +441,11 @@ extern "C" int fsb_assemble_source_nodal(fsb_mesh* mesh, fsb_vec* b, int32_t nco
 
 // facets arrive as host arrays; they are small (boundary only) so a temporary upload per call is fine
 struct FacetUpload {
+  fsb_ctx* ctx;
   int32_t* fverts = nullptr;
   int32_t* opp = nullptr;
-  ~FacetUpload() { cudaFree(fverts); cudaFree(opp); }
+  explicit FacetUpload(fsb_ctx* c) : ctx(c) {}
+  ~FacetUpload() { fsb_dfree(ctx, fverts); fsb_dfree(ctx, opp); }
 };
 
 static int upload_facets(fsb_mesh* mesh, int64_t nf, const int32_t* fverts, const int32_t* opp, FacetUpload& up) {
@@ -466,7 +468,7 @@ extern "C" int fsb_assemble_facet_load(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp
   if (ncomp < 1 || ncomp > 3 || b->n != mesh->nverts * ncomp) FSB_FAIL(ctx, FSB_ERR_ARG, "rhs size does not match mesh*ncomp");
   if (mode == 1 && (!opp || ncomp != mesh->tdim)) FSB_FAIL(ctx, FSB_ERR_ARG, "normal loads need opposite vertices and ncomp == dim");
   if (nf == 0) return FSB_OK;
-  FacetUpload up;
+  FacetUpload up(ctx);
   int rc = upload_facets(mesh, nf, fverts, opp, up);
   if (rc) return rc;
   Vec3 gv{{0, 0, 0}};
@@ -486,7 +488,7 @@ extern "C" int fsb_assemble_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, c
   fsb_ctx* ctx = mesh->ctx;
   if (A->bs != 1 || A->nbrows != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "facet mass needs the scalar matrix of this mesh");
   if (nf == 0) return FSB_OK;
-  FacetUpload up;
+  FacetUpload up(ctx);
   int rc = upload_facets(mesh, nf, fverts, nullptr, up);
   if (rc) return rc;
   const unsigned grid = fsb_grid(nf, 128, (int64_t)ctx->sm_count * 16);
@@ -504,7 +506,7 @@ extern "C" int fsb_facet_area(fsb_mesh* mesh, int64_t nf, const int32_t* fverts,
   fsb_ctx* ctx = mesh->ctx;
   *area = 0.0;
   if (nf == 0) return FSB_OK;
-  FacetUpload up;
+  FacetUpload up(ctx);
   int rc = upload_facets(mesh, nf, fverts, nullptr, up);
   if (rc) return rc;
   const unsigned grid = fsb_grid(nf, 256, 256);
@@ -538,7 +540,7 @@ extern "C" int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t n
   }
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(A->bc_flag, 0, (size_t)n, ctx->stream));
   if (nbc > A->bc_cap) {      // staging buffers are kept on the matrix: a transient run applies the BCs every step
-    cudaFree(A->bc_dofs); cudaFree(A->bc_vals);
+    fsb_dfree(A->ctx, A->bc_dofs); fsb_dfree(A->ctx, A->bc_vals);
     A->bc_dofs = nullptr; A->bc_vals = nullptr; A->bc_cap = 0;
     int rc = fsb_dmalloc(ctx, &A->bc_dofs, (size_t)nbc);
     if (!rc) rc = fsb_dmalloc(ctx, &A->bc_vals, (size_t)nbc);

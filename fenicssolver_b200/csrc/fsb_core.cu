@@ -23,6 +23,13 @@ extern "C" int fsb_init(int device, void* stream, fsb_ctx** out) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  // device buffers come from the default stream-ordered pool; keep freed blocks instead of returning them
+  // to the OS, so building a second solver on the same GPU reuses the first one's memory at no cost
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   bool ok = cudaMalloc((void**)&ctx->d_partials, sizeof(double) * kMaxPartials * 4) == cudaSuccess &&
             cudaMalloc((void**)&ctx->d_scalars, sizeof(double) * 64) == cudaSuccess &&
             cudaMalloc((void**)&ctx->d_counters, sizeof(unsigned) * 16) == cudaSuccess &&
@@ -143,7 +150,7 @@ extern "C" int fsb_vec_size(fsb_vec* v, int64_t* n) {
 extern "C" void* fsb_vec_ptr(fsb_vec* v) { return v ? (void*)v->d : nullptr; }
 extern "C" void fsb_vec_destroy(fsb_vec* v) {
   if (!v) return;
-  cudaFree(v->d);
+  fsb_dfree(v->ctx, v->d);
   delete v;
 }
 
@@ -269,7 +276,7 @@ extern "C" int fsb_mesh_download(fsb_mesh* m, double* xyz, int32_t* cells) {
 
 extern "C" void fsb_mesh_destroy(fsb_mesh* m) {
   if (!m) return;
-  cudaFree(m->xyz);
-  cudaFree(m->cells);
+  fsb_dfree(m->ctx, m->xyz);
+  fsb_dfree(m->ctx, m->cells);
   delete m;
 }

@@ -108,7 +108,9 @@ struct fsb_mat {
 template <typename T>
 static inline int fsb_dmalloc(fsb_ctx* ctx, T** p, size_t count, size_t pad_bytes = 512) {
   void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + pad_bytes);   // pad: TMA tiles may over-read a few entries
+  // stream-ordered pool allocation (the pool keeps freed blocks: repeated solver construction does not pay
+  // cudaMalloc/cudaFree device synchronisations); pad: TMA tiles may over-read a few entries
+  cudaError_t e = cudaMallocAsync(&q, count * sizeof(T) + pad_bytes, ctx->stream);
   if (e != cudaSuccess) {
     ctx->err = std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) + " bytes: " + cudaGetErrorString(e);
     *p = nullptr;
@@ -117,6 +119,10 @@ static inline int fsb_dmalloc(fsb_ctx* ctx, T** p, size_t count, size_t pad_byte
   }
   *p = (T*)q;
   return FSB_OK;
+}
+
+static inline void fsb_dfree(fsb_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
 }
 
 static inline unsigned fsb_grid(int64_t n, int block, int64_t cap = (1ll << 31) - 1) {

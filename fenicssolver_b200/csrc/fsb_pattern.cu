@@ -119,7 +119,7 @@ int fsb_exclusive_scan(fsb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n)
   k_scan_apply<<<(unsigned)nb, kScanThreads, 0, ctx->stream>>>(in, n, bsum, out);
   FSB_LAUNCH_CHECK(ctx);
   FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaFree(bsum);
+  fsb_dfree(ctx, bsum);
   return FSB_OK;
 }
 
@@ -235,16 +235,16 @@ __global__ void k_max_i32(const int32_t* __restrict__ in, int64_t n, int32_t* __
 // ------------------------------------------------------------------------------------ matrix objects
 extern "C" void fsb_mat_destroy(fsb_mat* A) {
   if (!A) return;
-  cudaFree(A->row_ptr);
-  cudaFree(A->col_idx);
-  cudaFree(A->vals);
-  cudaFree(A->posmap);
-  cudaFree(A->tile_row);
-  cudaFree(A->bc_flag);
-  cudaFree(A->bc_val);
-  cudaFree(A->bc_dofs);
-  cudaFree(A->bc_vals);
-  for (double* w : A->work) cudaFree(w);
+  fsb_dfree(A->ctx, A->row_ptr);
+  fsb_dfree(A->ctx, A->col_idx);
+  fsb_dfree(A->ctx, A->vals);
+  fsb_dfree(A->ctx, A->posmap);
+  fsb_dfree(A->ctx, A->tile_row);
+  fsb_dfree(A->ctx, A->bc_flag);
+  fsb_dfree(A->ctx, A->bc_val);
+  fsb_dfree(A->ctx, A->bc_dofs);
+  fsb_dfree(A->ctx, A->bc_vals);
+  for (double* w : A->work) fsb_dfree(A->ctx, w);
   delete A;
 }
 
@@ -260,7 +260,7 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   int32_t *deg = nullptr, *v2c = nullptr, *d_max = nullptr;
   int64_t* vptr = nullptr;
   int rc = FSB_OK;
-  auto cleanup = [&]() { cudaFree(deg); cudaFree(v2c); cudaFree(vptr); cudaFree(d_max); };
+  auto cleanup = [&]() { fsb_dfree(ctx, deg); fsb_dfree(ctx, v2c); fsb_dfree(ctx, vptr); fsb_dfree(ctx, d_max); };
 #define TRY(x) do { rc = (x); if (rc) { cleanup(); fsb_mat_destroy(A); return rc; } } while (0)
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); fsb_mat_destroy(A); return FSB_ERR_CUDA; } } while (0)
   TRY(fsb_dmalloc(ctx, &deg, (size_t)nv + 1));
@@ -293,8 +293,8 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   k_rows<true><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cells, nl, vptr, v2c, nv, nullptr, A->row_ptr, A->col_idx);
   ctx->launches++; TRYCUDA(cudaGetLastError());
   TRYCUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(v2c); v2c = nullptr;
-  cudaFree(vptr); vptr = nullptr;
+  fsb_dfree(ctx, v2c); v2c = nullptr;
+  fsb_dfree(ctx, vptr); vptr = nullptr;
   TRY(fsb_dmalloc(ctx, &A->vals, (size_t)nnzb * ncomp * ncomp));
   TRYCUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * nnzb * ncomp * ncomp + 512, ctx->stream));
   if (maxlen <= 256) {

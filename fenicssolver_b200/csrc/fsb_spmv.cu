@@ -300,7 +300,7 @@ static constexpr size_t kSmemBudget = 200 * 1024;
 
 int fsb_mat_setup_tiles(fsb_mat* A) {
   fsb_ctx* ctx = A->ctx;
-  cudaFree(A->tile_row);
+  fsb_dfree(A->ctx, A->tile_row);
   A->tile_row = nullptr;
   A->ntiles = 0; A->tile_nnz = 0; A->tile_cap = 0; A->stage_bytes = 0;
   A->tile_rows = spmv_rows(ctx, A->bs);
