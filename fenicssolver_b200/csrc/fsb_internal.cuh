@@ -34,6 +34,8 @@ struct fsb_ctx {
   int* d_state = nullptr;         // [8] Krylov state: done, iterations, outcome
   double* h_pinned = nullptr;     // [64]
   int* h_state = nullptr;         // [16] pinned mirror of d_state (two polling slots)
+  void* h_stage[2] = {nullptr, nullptr};   // pinned staging chunks for large downloads into pageable memory
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
   fsb_dist* dist = nullptr;
 };
 

@@ -139,9 +139,9 @@ __global__ void k_v2c_fill(const int32_t* __restrict__ cells, int64_t ncells, in
 }
 
 // ------------------------------------------------------------------------------------ rows
-// One warp per row.  Candidates L[i] = cells[v2c[p0 + i/nl]][i%nl], i < m = deg*nl.  They are cached in
-// shared memory when m <= kRowCap, otherwise re-read from global (L1) on every access.
-static constexpr int kRowCap = 384;
+// One warp per row.  Candidates L[i] = cells[v2c[p0 + i/nl]][i%nl], i < m = deg*nl.  They are sorted in
+// shared memory when m <= kRowCap, otherwise scanned from global memory (L1).
+static constexpr int kRowCap = 512;      // power of two
 static constexpr int kRowWarps = 8;
 
 template <bool FILL>
@@ -149,18 +149,44 @@ __global__ void __launch_bounds__(kRowWarps * 32)
 k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vptr, const int32_t* __restrict__ v2c,
        int64_t nrows, int32_t* __restrict__ row_len, const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx) {
   __shared__ int32_t s_cand[kRowWarps][kRowCap];
-  __shared__ uint8_t s_first[kRowWarps][kRowCap];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int64_t r = (int64_t)blockIdx.x * kRowWarps + w; r < nrows; r += (int64_t)gridDim.x * kRowWarps) {
     const int64_t p0 = vptr[r];
     const int m = (int)(vptr[r + 1] - p0) * nl;
     const bool cached = m <= kRowCap;
-    auto cand = [&](int i) -> int32_t {
-      return cached ? s_cand[w][i] : cells[(int64_t)v2c[p0 + i / nl] * nl + i % nl];
-    };
-    if (cached)
-      for (int i = lane; i < m; i += 32) s_cand[w][i] = cells[(int64_t)v2c[p0 + i / nl] * nl + i % nl];
-    __syncwarp();
+    if (cached) {
+      // common case: bitonic-sort the candidates in shared memory (padded with INT_MAX to a power of
+      // two), then the first element of each run of equal values is a column; ranks come from ballots
+      int P = 32;
+      while (P < m) P <<= 1;
+      for (int i = lane; i < P; i += 32)
+        s_cand[w][i] = i < m ? cells[(int64_t)v2c[p0 + i / nl] * nl + i % nl] : 0x7fffffff;
+      __syncwarp();
+      for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = lane; t < (P >> 1); t += 32) {
+            const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;     // t-th compare-exchange pair
+            const int32_t a = s_cand[w][lo], b = s_cand[w][hi];
+            const bool up = (lo & k) == 0;
+            if ((a > b) == up) { s_cand[w][lo] = b; s_cand[w][hi] = a; }
+          }
+          __syncwarp();
+        }
+      int count = 0;
+      for (int i0 = 0; i0 < m; i0 += 32) {
+        const int i = i0 + lane;
+        const int32_t v = i < m ? s_cand[w][i] : 0x7fffffff;
+        const bool first = i < m && (i == 0 || s_cand[w][i - 1] != v);
+        const unsigned mask = __ballot_sync(0xffffffffu, first);
+        if (FILL && first) col_idx[row_ptr[r] + count + __popc(mask & ((1u << lane) - 1))] = v;
+        count += __popc(mask);
+      }
+      if (!FILL && lane == 0) row_len[r] = count;
+      __syncwarp();
+      continue;
+    }
+    // rare case (valence above the shared-memory cache): quadratic scan straight from global memory
+    auto cand = [&](int i) -> int32_t { return cells[(int64_t)v2c[p0 + i / nl] * nl + i % nl]; };
     // pass 1: first occurrences
     int nfirst = 0;
     for (int i0 = 0; i0 < m; i0 += 32) {
@@ -171,10 +197,9 @@ k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vp
         int32_t u = cand(j);
         if (j < i && u == v) first = false;
       }
-      if (cached && i < m) s_first[w][i] = first;
       nfirst += __popc(__ballot_sync(0xffffffffu, first));
-      if (FILL && !cached) {
-        // uncached rows: rank directly (first flags recomputed on the fly below)
+      if (FILL) {
+        // rank directly (first flags recomputed on the fly below)
         if (first) {
           int pos = 0;
           for (int j = 0; j < m; ++j) {
@@ -190,18 +215,7 @@ k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vp
       }
     }
     __syncwarp();
-    if (!FILL) {
-      if (lane == 0) row_len[r] = nfirst;
-    } else if (cached) {
-      // pass 2: rank of each first occurrence among the first occurrences
-      for (int i = lane; i < m; i += 32) {
-        if (!s_first[w][i]) continue;
-        int32_t v = s_cand[w][i];
-        int pos = 0;
-        for (int j = 0; j < m; ++j) pos += (s_first[w][j] && s_cand[w][j] < v);
-        col_idx[row_ptr[r] + pos] = v;
-      }
-    }
+    if (!FILL && lane == 0) row_len[r] = nfirst;
     __syncwarp();
   }
 }
