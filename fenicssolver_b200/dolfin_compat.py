@@ -454,7 +454,12 @@ class _Vector:
         self._fn = fn
 
     def get_local(self):
-        return self._fn.array().copy()
+        """A copy of the values (dolfin semantics).  A device-resident result is downloaded straight into the
+        returned array: one D2H copy, no second host copy."""
+        fn = self._fn
+        if not fn._host_valid and fn._dev is not None:
+            return fn._dev.numpy()
+        return fn.array().copy()
 
     def array(self):
         return self._fn.array()
