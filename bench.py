@@ -149,6 +149,15 @@ def cpu_heat(N, iters_full, sample_iters, steps=1, warmup=0):
             "ms_per_step": t_step * 1e3, "setup_s": h.t_setup}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def iters_needed(N):
     return KNOWN_ITERS.get(N) or int(round(3.9 * N))
 
@@ -165,7 +174,7 @@ def run_reference(args):
             "config": {"workload": "3D steady heat, UnitCubeMesh %d^3 P1 tets, %d DoF, Jacobi-CG rtol %g" % (N, (N + 1) ** 3, RTOL)},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "Mdof/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -180,6 +189,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # exactly ONE line on stdout (the JSON): library chatter such as "NCCL version ..." goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -200,6 +214,8 @@ def main():
     stream = torch.cuda.Stream()
     ctx = backend.get_context(local_rank, stream=stream.cuda_stream)
     ctx.set_option("profile", 1)          # event pairs around every SpMV launch -> per-kernel time inside the timed region
+    if os.environ.get("FSB_DIST_P2P") == "0":
+        ctx.set_option("dist_p2p", 0)     # A/B: NCCL send/recv + all-reduce instead of the peer-memory mailboxes/halo
     N = args.size
     ndof = (N + 1) ** 3
 
@@ -346,7 +362,7 @@ def main():
                                     % (solver.timings.get("symbolic", 0) * 1e3)},
                 "iterations": iters, "converged": info["converged"], "rel_l2_vs_exact": rel_err,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -61,3 +61,104 @@ __device__ __forceinline__ void finish_partials(const double (&mine)[NV], double
   if (threadIdx.x == 0) *counter = 0;
 }
 
+
+// ------------------------------------------------------------------------------------ peer memory (one node)
+// Distributed CG without collective launches.  Every rank owns a small CommBuf that all ranks map through
+// CUDA IPC (NVLink / NVSwitch peer memory):
+//   * reductions: the last CTA of the producing kernel stores this rank's partial sums into the mailbox
+//     of every rank (peer stores), fenced and tagged with a sequence number; the consuming kernel waits for
+//     all ranks' entries in its own mailbox and adds them in rank order, so every rank gets bitwise the same
+//     value and takes the same convergence decision;
+//   * halo: the p-update kernel writes its boundary planes straight into the neighbours' ghost planes and
+//     the last CTA raises a flag in the neighbour's CommBuf; the next SpMV waits for that flag.
+// Slots are reused every second iteration; a rank can only overwrite a slot after it has consumed a value
+// its peers produce after their own reads of that slot, so two parities are enough.
+static constexpr int kMaxRanks = 8;
+static constexpr int kMailSlots = 4;      // {p.q, (r.z, z.z)} x iteration parity
+enum { MAIL_PQ = 0, MAIL_RZ = 2 };
+struct MailEntry { double v[3]; unsigned long long seq; };
+struct CommBuf {
+  MailEntry mail[kMailSlots][kMaxRanks];
+  unsigned long long halo_flag[2];        // [0] raised by rank-1, [1] raised by rank+1
+};
+struct PeerComm {
+  int rank, nranks;                       // nranks <= 1: single GPU, scalars stay in ctx->d_scalars
+  CommBuf* buf[kMaxRanks];                // buf[r]: rank r's CommBuf (peer mapping); buf[rank] is local
+  double* lo_dst;                         // rank-1's upper ghost plane inside its p vector (or null)
+  double* hi_dst;                         // rank+1's lower ghost plane inside its p vector (or null)
+  long long plane;                        // dofs per vertex plane
+};
+
+// what one SpMV launch of the distributed CG waits for and posts
+struct fsb_spmv_dist {
+  PeerComm pc;
+  unsigned long long halo_seq;
+  int mail_slot;
+  unsigned long long mail_seq;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// last-CTA reduction as finish_partials, but the totals go to every rank's mailbox slot instead of `out`
+template <int NV>
+__device__ __forceinline__ void finish_partials_mail(const double (&mine)[NV], double* __restrict__ partials, int stride,
+                                                     unsigned* counter, double* sm, const PeerComm& pc, int slot,
+                                                     unsigned long long seq) {
+  __shared__ bool is_last_m;
+  __shared__ double tot[3];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[k * stride + blockIdx.x] = mine[k];
+    __threadfence();
+    unsigned t = atomicAdd(counter, 1u);
+    is_last_m = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last_m) return;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partials + k * stride + i);
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) tot[k] = s;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < pc.nranks) {
+    MailEntry* e = &pc.buf[threadIdx.x]->mail[slot][pc.rank];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) e->v[k] = tot[k];
+    __threadfence_system();
+    st_release_sys(&e->seq, seq);
+  }
+  if (threadIdx.x == 0) *counter = 0;
+}
+
+// wait for all ranks' entries of `slot` (sequence >= seq) and add them in rank order; every thread gets v[]
+template <int NV>
+__device__ __forceinline__ void mail_sum(const PeerComm& pc, int slot, unsigned long long seq, double (&v)[NV], double* sm4) {
+  if (threadIdx.x == 0) {
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (int r = 0; r < pc.nranks; ++r) {
+      const MailEntry* e = &pc.buf[pc.rank]->mail[slot][r];
+      while (ld_acquire_sys(&e->seq) < seq) { }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc[k] += *reinterpret_cast<const volatile double*>(&e->v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sm4[k] = acc[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = sm4[k];
+  __syncthreads();
+}

@@ -4,7 +4,7 @@
 // torch already loaded) so libfsb.so has no link-time dependency on it; only the handful of entry
 // points used here are declared.  Vectors on a distributed context are laid out in natural plane
 // order [ghost plane below | owned planes | ghost plane above]; the neighbours are rank-1 and rank+1.
-#include "fsb_internal.cuh"
+#include "fsb_device.cuh"
 #include <dlfcn.h>
 
 typedef struct ncclComm* ncclComm_t;
@@ -17,6 +17,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -41,6 +42,7 @@ static NcclApi& nccl() {
   LOAD(CommInitRank, "ncclCommInitRank");
   LOAD(CommDestroy, "ncclCommDestroy");
   LOAD(AllReduce, "ncclAllReduce");
+  LOAD(AllGather, "ncclAllGather");
   LOAD(Send, "ncclSend");
   LOAD(Recv, "ncclRecv");
   LOAD(GroupStart, "ncclGroupStart");
@@ -57,6 +59,11 @@ struct fsb_dist {
   int ghost_lo = 0, ghost_hi = 0;
   int64_t owned_planes = 0;
   bool slab_set = false;
+  // peer memory (CUDA IPC): this rank's CommBuf and every rank's mapping of it
+  CommBuf* comm_local = nullptr;
+  CommBuf* comm_of[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool p2p = false;
+  unsigned long long seq = 1;     // next unused sequence number; advances identically on every rank
 };
 
 #define FSB_CHECK_NCCL(ctx, call)                                                             \
@@ -67,6 +74,8 @@ struct fsb_dist {
       return FSB_ERR_NCCL;                                                                    \
     }                                                                                         \
   } while (0)
+
+static int fsb_dist_map_mailboxes(fsb_ctx* ctx);
 
 extern "C" int fsb_dist_unique_id(void* uid128) {
   if (!uid128) return FSB_ERR_ARG;
@@ -93,17 +102,129 @@ extern "C" int fsb_dist_init(fsb_ctx* ctx, int32_t rank, int32_t nranks, const v
     return FSB_ERR_NCCL;
   }
   ctx->dist = d;
+  // peer-memory mailboxes (best effort: without them the solvers fall back to NCCL collectives)
+  if (nranks > 1 && nranks <= kMaxRanks && ctx->dist_p2p) {
+    int rc = fsb_dist_map_mailboxes(ctx);
+    if (rc) { d->p2p = false; ctx->err.clear(); }
+  }
   return FSB_OK;
 }
 
 void fsb_dist_destroy(fsb_ctx* ctx) {
   if (!ctx || !ctx->dist) return;
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (ctx->dist->comm_of[r] && r != ctx->dist->rank) cudaIpcCloseMemHandle(ctx->dist->comm_of[r]);
+  cudaFree(ctx->dist->comm_local);
   if (ctx->dist->comm && nccl().ok) nccl().CommDestroy(ctx->dist->comm);
   delete ctx->dist;
   ctx->dist = nullptr;
 }
 
 bool fsb_dist_active(fsb_ctx* ctx) { return ctx && ctx->dist && ctx->dist->nranks > 1; }
+
+// ------------------------------------------------------------------------------------ peer memory set-up
+// Records are exchanged with ncclAllGather (bytes), so no host-side rendezvous beyond NCCL's is needed.
+struct ShareRec {
+  cudaIpcMemHandle_t handle;    // 64 bytes
+  long long ghost_lo, owned, n, plane;
+  char pad[128 - 64 - 32];
+};
+static_assert(sizeof(ShareRec) == 128, "ShareRec must be 128 bytes");
+
+static int allgather_records(fsb_ctx* ctx, const ShareRec& mine, std::vector<ShareRec>& all) {
+  fsb_dist* d = ctx->dist;
+  char* dbuf = nullptr;
+  FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&dbuf, sizeof(ShareRec) * (d->nranks + 1)));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(dbuf, &mine, sizeof(ShareRec), cudaMemcpyHostToDevice, ctx->stream));
+  int r = nccl().AllGather(dbuf, dbuf + sizeof(ShareRec), sizeof(ShareRec), 0 /* ncclInt8 */, d->comm, ctx->stream);
+  if (r != kNcclSuccess) { cudaFree(dbuf); FSB_FAIL(ctx, FSB_ERR_NCCL, std::string("ncclAllGather: ") + nccl().GetErrorString(r)); }
+  all.resize(d->nranks);
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(all.data(), dbuf + sizeof(ShareRec), sizeof(ShareRec) * d->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(dbuf);
+  return FSB_OK;
+}
+
+static int fsb_dist_map_mailboxes(fsb_ctx* ctx) {
+  fsb_dist* d = ctx->dist;
+  FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&d->comm_local, sizeof(CommBuf)));
+  FSB_CHECK_CUDA(ctx, cudaMemset(d->comm_local, 0, sizeof(CommBuf)));
+  ShareRec mine;
+  memset(&mine, 0, sizeof(mine));
+  FSB_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&mine.handle, d->comm_local));
+  std::vector<ShareRec> all;
+  int rc = allgather_records(ctx, mine, all);
+  if (rc) return rc;
+  for (int r = 0; r < d->nranks; ++r) {
+    if (r == d->rank) { d->comm_of[r] = d->comm_local; continue; }
+    void* q = nullptr;
+    FSB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&q, all[r].handle, cudaIpcMemLazyEnablePeerAccess));
+    d->comm_of[r] = (CommBuf*)q;
+  }
+  d->p2p = true;
+  return FSB_OK;
+}
+
+bool fsb_dist_p2p_ready(fsb_ctx* ctx) { return fsb_dist_active(ctx) && ctx->dist->p2p && ctx->dist->slab_set && ctx->dist_p2p; }
+
+unsigned long long fsb_dist_seq_reserve(fsb_ctx* ctx, unsigned long long count) {
+  unsigned long long base = ctx->dist->seq;
+  ctx->dist->seq += count;
+  return base;
+}
+
+// Collective: (re)allocate the IPC-exportable search-direction vector of A and map the neighbours' copies.
+int fsb_dist_share_p(fsb_mat* A, int64_t n) {
+  fsb_ctx* ctx = A->ctx;
+  fsb_dist* d = ctx->dist;
+  if (A->p_dist && A->p_dist_n == n) return FSB_OK;
+  fsb_dist_release_mat(A);
+  FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&A->p_dist, sizeof(double) * n + 512));
+  FSB_CHECK_CUDA(ctx, cudaMemset(A->p_dist, 0, sizeof(double) * n + 512));
+  A->p_dist_n = n;
+  const long long planes = d->ghost_lo + d->owned_planes + d->ghost_hi;
+  ShareRec mine;
+  memset(&mine, 0, sizeof(mine));
+  FSB_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&mine.handle, A->p_dist));
+  mine.ghost_lo = d->ghost_lo; mine.owned = d->owned_planes; mine.n = n; mine.plane = n / planes;
+  std::vector<ShareRec> all;
+  int rc = allgather_records(ctx, mine, all);
+  if (rc) return rc;
+  if (d->ghost_lo) {
+    void* q = nullptr;
+    FSB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&q, all[d->rank - 1].handle, cudaIpcMemLazyEnablePeerAccess));
+    A->p_lo_remote = (double*)q;
+    A->lo_ghost_offset = (all[d->rank - 1].ghost_lo + all[d->rank - 1].owned) * all[d->rank - 1].plane;
+  }
+  if (d->ghost_hi) {
+    void* q = nullptr;
+    FSB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&q, all[d->rank + 1].handle, cudaIpcMemLazyEnablePeerAccess));
+    A->p_hi_remote = (double*)q;
+  }
+  return FSB_OK;
+}
+
+void fsb_dist_release_mat(fsb_mat* A) {
+  if (A->p_lo_remote) cudaIpcCloseMemHandle(A->p_lo_remote);
+  if (A->p_hi_remote) cudaIpcCloseMemHandle(A->p_hi_remote);
+  if (A->p_dist) cudaFree(A->p_dist);
+  A->p_lo_remote = A->p_hi_remote = A->p_dist = nullptr;
+  A->p_dist_n = 0;
+}
+
+int fsb_dist_peer_comm(fsb_mat* A, PeerComm* pc) {
+  fsb_ctx* ctx = A->ctx;
+  fsb_dist* d = ctx->dist;
+  memset(pc, 0, sizeof(*pc));
+  pc->rank = d->rank; pc->nranks = d->nranks;
+  for (int r = 0; r < d->nranks; ++r) pc->buf[r] = d->comm_of[r];
+  const long long planes = d->ghost_lo + d->owned_planes + d->ghost_hi;
+  pc->plane = A->p_dist_n / planes;
+  pc->lo_dst = A->p_lo_remote ? A->p_lo_remote + A->lo_ghost_offset : nullptr;
+  pc->hi_dst = A->p_hi_remote ? A->p_hi_remote : nullptr;     // rank+1's lower ghost plane is its plane 0
+  return FSB_OK;
+}
+
 
 extern "C" int fsb_dist_set_slab(fsb_ctx* ctx, int32_t ghost_lo, int32_t ghost_hi, int64_t owned_planes) {
   if (!ctx) return FSB_ERR_ARG;

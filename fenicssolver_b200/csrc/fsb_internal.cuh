@@ -24,6 +24,7 @@ struct fsb_ctx {
   int spmv_lpr = 0;      // lanes per row in the staged kernel (1, 2 or 4; 0 = best per block size)
   int spmv_rows = 0;     // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks; 0 = best per block size)
   int spmv_stages = 0;   // TMA pipeline depth (2..4; 0 = 2)
+  int dist_p2p = 1;      // distributed CG through peer-memory mailboxes/halo (1) or NCCL collectives (0)
   int profile = 0;
   int use_graph = 1;
   int check_every = 32;
@@ -80,6 +81,13 @@ struct fsb_mat {
   int64_t* bc_dofs = nullptr;  // staging for the uploaded Dirichlet list (capacity bc_cap)
   double* bc_vals = nullptr;
   int64_t bc_cap = 0;
+  // distributed CG over peer memory: the search direction lives in a cudaMalloc'ed (IPC-exportable) vector
+  // whose ghost planes the neighbours write directly   [fsb_dist.cu]
+  double* p_dist = nullptr;
+  int64_t p_dist_n = 0;
+  double* p_lo_remote = nullptr;   // rank-1's p vector (peer mapping) or null
+  double* p_hi_remote = nullptr;   // rank+1's p vector
+  int64_t lo_ghost_offset = 0;     // index of rank-1's upper ghost plane inside its p vector
   // Krylov work vectors, kept across solves (transient runs re-solve every step)
   double* work[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int work_count = 0;
@@ -139,13 +147,24 @@ int fsb_exclusive_scan(fsb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n)
 // SpMV tiling setup after row_ptr / owned range are known, and y = A x (+ fused dots d0 = y.w, d1 = y.y
 // written to out[0..2)) on the ctx stream; `done` is an optional device early-exit flag   [fsb_spmv.cu]
 int fsb_mat_setup_tiles(fsb_mat* A);
-int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done);
+struct fsb_spmv_dist;   // fsb_device.cuh: peer-memory wait/post instructions for one launch
+int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done,
+                    const fsb_spmv_dist* dd = nullptr);
+bool fsb_spmv_supports_p2p(fsb_mat* A);
 // distributed hooks [fsb_dist.cu]
 bool fsb_dist_active(fsb_ctx* ctx);
 int fsb_dist_halo_raw(fsb_ctx* ctx, double* v, int64_t n);
 int fsb_dist_allreduce_sum_dev(fsb_ctx* ctx, double* d_vals, int count);
 void fsb_dist_owned_range(fsb_ctx* ctx, int64_t n, int64_t* o0, int64_t* o1);
 void fsb_dist_destroy(fsb_ctx* ctx);
+// peer-memory CG support [fsb_dist.cu]: is the IPC mailbox mapped on every rank; collective set-up of the
+// shared search-direction vector of a matrix; release; sequence numbers (identical on every rank)
+struct PeerComm;
+bool fsb_dist_p2p_ready(fsb_ctx* ctx);
+int fsb_dist_share_p(fsb_mat* A, int64_t n);
+void fsb_dist_release_mat(fsb_mat* A);
+int fsb_dist_peer_comm(fsb_mat* A, PeerComm* pc);
+unsigned long long fsb_dist_seq_reserve(fsb_ctx* ctx, unsigned long long count);
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

@@ -259,6 +259,7 @@ extern "C" void fsb_mat_destroy(fsb_mat* A) {
   fsb_dfree(A->ctx, A->bc_dofs);
   fsb_dfree(A->ctx, A->bc_vals);
   for (double* w : A->work) fsb_dfree(A->ctx, w);
+  fsb_dist_release_mat(A);
   delete A;
 }
 

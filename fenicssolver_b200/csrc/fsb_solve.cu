@@ -77,14 +77,43 @@ __global__ void k_check0(const double* __restrict__ scal, int rr_slot, int bb_sl
   else { state[0] = 0; state[2] = 0; }
 }
 
-// alpha = rz/pq ; x += alpha p ; r -= alpha q ; z = dinv r ; sums rz', rr' -> out[0..2)
+// Distributed CG over peer memory: which mailbox entries iteration `it` (seq = base + it, parity par) uses:
+//   r.z at its start   MAIL_RZ + par      seq          (seeded after the start-up all-reduce, then posted by k_cg_update)
+//   p.q                MAIL_PQ + par      seq + 1      (posted by the SpMV)
+//   r.z, z.z after it  MAIL_RZ + (par^1)  seq + 1      (posted by k_cg_update)
+//   halo flags raised by k_cg_pupdate to seq + 1, awaited by the next SpMV
+struct CgPeer {
+  PeerComm pc;              // pc.nranks <= 1: single GPU (or NCCL path): scalars come from ctx->d_scalars
+  unsigned long long seq;
+};
+
+__global__ void k_mail_seed(PeerComm pc, int slot, unsigned long long seq, const double* __restrict__ scal, int s0, int s1) {
+  if (threadIdx.x < pc.nranks) {      // the all-reduced start values enter the local mailbox as rank 0's contribution
+    MailEntry* e = &pc.buf[pc.rank]->mail[slot][threadIdx.x];
+    e->v[0] = threadIdx.x == 0 ? scal[s0] : 0.0;
+    e->v[1] = threadIdx.x == 0 ? scal[s1] : 0.0;
+    e->v[2] = 0.0;
+    __threadfence();
+    e->seq = seq;
+  }
+}
+
+// alpha = rz/pq ; x += alpha p ; r -= alpha q ; z = dinv r ; sums rz', rr' -> out[0..2) (or the mailboxes)
 __global__ void __launch_bounds__(kVecThreads)
 k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot, int pq_slot, const double* __restrict__ p,
             const double* __restrict__ q, const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-            double* partials, double* out, unsigned* counter, const int* done) {
+            double* partials, double* out, unsigned* counter, const int* done, CgPeer cp, int par) {
   __shared__ double red[32];
   if (*done) return;
-  const double alpha = scal[rz_slot] / scal[pq_slot];
+  double alpha;
+  if (cp.pc.nranks > 1) {
+    double a[2], b[2];
+    mail_sum<2>(cp.pc, MAIL_RZ + par, cp.seq, a, red);
+    mail_sum<2>(cp.pc, MAIL_PQ + par, cp.seq + 1, b, red);
+    alpha = a[0] / b[0];
+  } else {
+    alpha = scal[rz_slot] / scal[pq_slot];
+  }
   double s0 = 0, s1 = 0;
   auto one = [&](int64_t i) {
     x[i] += alpha * p[i];
@@ -114,22 +143,41 @@ k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot
     s1 += z0 * z0 + z1 * z1;
   }
   double mine[2] = {block_sum(s0, red), block_sum(s1, red)};
-  finish_partials<2>(mine, partials, kMaxPartials, out, counter, red);
+  if (cp.pc.nranks > 1) finish_partials_mail<2>(mine, partials, kMaxPartials, counter, red, cp.pc, MAIL_RZ + (par ^ 1), cp.seq + 1);
+  else finish_partials<2>(mine, partials, kMaxPartials, out, counter, red);
 }
 
-// beta = rz'/rz ; p = dinv r + beta p ; block 0 / thread 0 advances the iteration state
+// beta = rz'/rz ; p = dinv r + beta p ; block 0 / thread 0 advances the iteration state.  Distributed: the
+// boundary planes of the new p are also stored into the neighbours' ghost planes (peer memory) and the
+// last CTA raises the neighbours' halo flags.
 __global__ void __launch_bounds__(kVecThreads)
 k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int rz_new, int rr_new, int pq_slot,
              const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ p, double rtol, double atol,
-             int maxit, int* state) {
+             int maxit, int* state, CgPeer cp, int par, unsigned* counter) {
+  __shared__ double red[8];
   if (state[0]) return;
-  const double rzn = scal[rz_new], rzo = scal[rz_old];
+  const bool peer = cp.pc.nranks > 1;
+  double rzn, rzo, rr_v, pq_v;
+  if (peer) {
+    double a[2], b[2], c[2];
+    mail_sum<2>(cp.pc, MAIL_RZ + (par ^ 1), cp.seq + 1, a, red);
+    mail_sum<2>(cp.pc, MAIL_RZ + par, cp.seq, b, red);
+    mail_sum<2>(cp.pc, MAIL_PQ + par, cp.seq + 1, c, red);
+    rzn = a[0]; rr_v = a[1]; rzo = b[0]; pq_v = c[0];
+  } else {
+    rzn = scal[rz_new]; rzo = scal[rz_old]; rr_v = scal[rr_new]; pq_v = scal[pq_slot];
+  }
   const double beta = rzn / rzo;
+  const int64_t plane = cp.pc.plane;
+  auto push = [&](int64_t i, double v) {       // owned boundary planes -> neighbours' ghost planes
+    if (cp.pc.lo_dst && i < n0 + plane) cp.pc.lo_dst[i - n0] = v;
+    if (cp.pc.hi_dst && i >= n1 - plane) cp.pc.hi_dst[i - (n1 - plane)] = v;
+  };
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   const int64_t a_up = (n0 + 1) & ~(int64_t)1;
   const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
-  if (tid == 0 && a0 > n0) p[n0] = dinv[n0] * r[n0] + beta * p[n0];
-  if (tid == 1 && a0 + 2 * npair < n1) p[n1 - 1] = dinv[n1 - 1] * r[n1 - 1] + beta * p[n1 - 1];
+  if (tid == 0 && a0 > n0) { const double v = dinv[n0] * r[n0] + beta * p[n0]; p[n0] = v; if (peer) push(n0, v); }
+  if (tid == 1 && a0 + 2 * npair < n1) { const double v = dinv[n1 - 1] * r[n1 - 1] + beta * p[n1 - 1]; p[n1 - 1] = v; if (peer) push(n1 - 1, v); }
   for (int64_t j = tid; j < npair; j += nth) {
     const int64_t i = a0 + 2 * j;
     const double2 dv = *reinterpret_cast<const double2*>(dinv + i), rv = *reinterpret_cast<const double2*>(r + i);
@@ -137,9 +185,23 @@ k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int 
     pv.x = dv.x * rv.x + beta * pv.x;
     pv.y = dv.y * rv.y + beta * pv.y;
     *reinterpret_cast<double2*>(p + i) = pv;
+    if (peer) { push(i, pv.x); push(i + 1, pv.y); }
+  }
+  if (peer) {
+    __threadfence_system();           // this CTA's peer stores are visible system-wide before it counts itself done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(counter, 1u);
+      if (t == gridDim.x - 1) {
+        *counter = 0;
+        __threadfence_system();
+        if (cp.pc.rank > 0) st_release_sys(&cp.pc.buf[cp.pc.rank - 1]->halo_flag[1], cp.seq + 1);
+        if (cp.pc.rank < cp.pc.nranks - 1) st_release_sys(&cp.pc.buf[cp.pc.rank + 1]->halo_flag[0], cp.seq + 1);
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const double rr = scal[rr_new], bb = scal[S_BB], pq = scal[pq_slot];
+    const double rr = rr_v, bb = scal[S_BB], pq = pq_v;
     const double tol2 = fmax(rtol * rtol * bb, atol * atol);
     const int it = state[1] + 1;
     state[1] = it;
@@ -211,10 +273,25 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   memset(info, 0, sizeof(*info));
   const int64_t n0 = A->own0 * A->bs, n1 = A->own1 * A->bs;
   const bool dist = fsb_dist_active(ctx);
+  // peer-memory path: mailboxes mapped on every rank, staged SpMV kernel; the decision is the same on every rank
+  const bool p2p = dist && fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(A);
   Workspace ws{A};
   double *r, *p, *q, *dinv;
   int rc;
-  if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&p, n)) || (rc = ws.alloc(&q, n)) || (rc = ws.alloc(&dinv, n))) return rc;
+  if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&q, n)) || (rc = ws.alloc(&dinv, n))) return rc;
+  CgPeer cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.pc.nranks = 1;
+  unsigned long long seq_base = 0;
+  if (p2p) {
+    if ((rc = fsb_dist_share_p(A, n))) return rc;          // collective; the neighbours write p's ghost planes directly
+    p = A->p_dist;
+    FSB_CHECK_CUDA(ctx, cudaMemsetAsync(p, 0, sizeof(double) * n, ctx->stream));
+    if ((rc = fsb_dist_peer_comm(A, &cp.pc))) return rc;
+    seq_base = fsb_dist_seq_reserve(ctx, 0);
+  } else if ((rc = ws.alloc(&p, n))) {
+    return rc;
+  }
   double* scal = ctx->d_scalars;
   int* state = ctx->d_state;
   const unsigned vg = vec_grid(ctx, n1 - n0);
@@ -226,6 +303,8 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   FSB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
 
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(state, 0, sizeof(int) * 8, ctx->stream));
+  // last-CTA counters: a kernel that observes `done` half-way may leave one partially counted
+  FSB_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 16, ctx->stream));
 #define DINV_LAUNCH(BS) k_extract_dinv<BS><<<fsb_grid(n1 - n0, 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(n0, n1, A->row_ptr, A->col_idx, A->vals, dinv, precond == 1)
   if (A->bs == 1) DINV_LAUNCH(1); else if (A->bs == 2) DINV_LAUNCH(2); else DINV_LAUNCH(3);
 #undef DINV_LAUNCH
@@ -238,6 +317,10 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RZ0, 3))) return rc;
   k_check0<<<1, 1, 0, ctx->stream>>>(scal, S_RR0, S_BB, rtol, atol, maxit, state, scal + S_FINAL_RR);
   FSB_LAUNCH_CHECK(ctx);
+  if (p2p) {
+    k_mail_seed<<<1, 32, 0, ctx->stream>>>(cp.pc, MAIL_RZ + 0, seq_base, scal, S_RZ0, S_RR0);
+    FSB_LAUNCH_CHECK(ctx);
+  }
 
   // iteration batches; the host polls the state one batch behind the launches
   const int batch = std::max(2, ctx->check_every & ~1);
@@ -252,17 +335,24 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
     const bool more = launched < maxit;
     if (more) {
       for (int k = 0; k < batch; ++k) {
-        const int par = (launched + k) & 1;
+        const int it = launched + k, par = it & 1;
         const int pq = par ? S_PQ1 : S_PQ0, rz = par ? S_RZ1 : S_RZ0, rzn = par ? S_RZ0 : S_RZ1, rrn = par ? S_RR0 : S_RR1;
-        if (dist && (rc = fsb_dist_halo_raw(ctx, p, n))) return rc;
+        cp.seq = seq_base + (unsigned long long)it;
+        // ghost planes of p: NCCL send/recv, or (peer path) already written by the neighbours' k_cg_pupdate
+        if (dist && (!p2p || it == 0) && (rc = fsb_dist_halo_raw(ctx, p, n))) return rc;
         if (ctx->profile) cudaEventRecord(timer.next(slot), ctx->stream);
-        if ((rc = fsb_launch_spmv(A, p, q, p, 0, scal + pq, state))) return rc;
+        if (p2p) {
+          fsb_spmv_dist dd{cp.pc, it > 0 ? cp.seq : 0ull, MAIL_PQ + par, cp.seq + 1};
+          if ((rc = fsb_launch_spmv(A, p, q, p, 0, nullptr, state, &dd))) return rc;
+        } else if ((rc = fsb_launch_spmv(A, p, q, p, 0, scal + pq, state))) {
+          return rc;
+        }
         if (ctx->profile) cudaEventRecord(timer.next(slot), ctx->stream);
-        if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + pq, 1))) return rc;
-        k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, pq, p, q, dinv, x->d, r, ctx->d_partials, scal + rzn, ctx->d_counters + 2, state);
+        if (dist && !p2p && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + pq, 1))) return rc;
+        k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, pq, p, q, dinv, x->d, r, ctx->d_partials, scal + rzn, ctx->d_counters + 2, state, cp, par);
         FSB_LAUNCH_CHECK(ctx);
-        if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + rzn, 2))) return rc;
-        k_cg_pupdate<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, rzn, rrn, pq, r, dinv, p, rtol, atol, maxit, state);
+        if (dist && !p2p && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + rzn, 2))) return rc;
+        k_cg_pupdate<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, rzn, rrn, pq, r, dinv, p, rtol, atol, maxit, state, cp, par, ctx->d_counters + 4);
         FSB_LAUNCH_CHECK(ctx);
       }
       launched += batch;
@@ -282,6 +372,7 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   FSB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
   rc = read_outcome(ctx, S_FINAL_RR, S_BB, info);
   if (rc) return rc;
+  if (p2p) fsb_dist_seq_reserve(ctx, (unsigned long long)info->iterations + 2);   // identical on every rank
   if (ctx->profile) { timer.collect(0); timer.collect(1); info->spmv_ms = timer.total_ms; }
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
@@ -413,6 +504,8 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{e0, e1};
   FSB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(state, 0, sizeof(int) * 8, ctx->stream));
+  // last-CTA counters: a kernel that observes `done` half-way may leave one partially counted
+  FSB_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 16, ctx->stream));
 #define DINV_LAUNCH(BS) k_extract_dinv<BS><<<fsb_grid(n1 - n0, 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(n0, n1, A->row_ptr, A->col_idx, A->vals, dinv, precond == 1)
   if (A->bs == 1) DINV_LAUNCH(1); else if (A->bs == 2) DINV_LAUNCH(2); else DINV_LAUNCH(3);
 #undef DINV_LAUNCH

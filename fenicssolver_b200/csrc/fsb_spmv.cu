@@ -35,6 +35,11 @@ struct SpmvArgs {
   double* out;              // out[0]=d0, out[1]=d1
   unsigned* counter;
   const int* done;          // optional early-exit flag
+  // distributed CG over peer memory (pc.nranks <= 1: off)
+  PeerComm pc;
+  unsigned long long halo_seq;   // != 0: wait until the neighbours have delivered their planes of x (flag >= halo_seq)
+  int mail_slot;                 // >= 0: post (d0, d1) to every rank's mailbox with mail_seq instead of `out`
+  unsigned long long mail_seq;
 };
 
 // ------------------------------------------------------------------------------------ mode 2: first version
@@ -140,6 +145,11 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
       mbar_init(&empty[s], CONSUMERS / 32);
     }
     mbar_fence_init();
+    if (a.halo_seq) {     // ghost planes of x are written by the neighbours' p-update kernels (peer stores)
+      const CommBuf* mine = a.pc.buf[a.pc.rank];
+      if (a.pc.rank > 0) while (ld_acquire_sys(&mine->halo_flag[0]) < a.halo_seq) { }
+      if (a.pc.rank < a.pc.nranks - 1) while (ld_acquire_sys(&mine->halo_flag[1]) < a.halo_seq) { }
+    }
   }
   __syncthreads();
 
@@ -228,7 +238,12 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
       if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);      // this warp is done with stage s
     }
   }
-  if (a.out) {
+  if (a.mail_slot >= 0) {
+    double mine[2];
+    mine[0] = block_sum(d0, red);
+    mine[1] = block_sum(d1, red);
+    finish_partials_mail<2>(mine, a.partials, kMaxPartials, a.counter, red, a.pc, a.mail_slot, a.mail_seq);
+  } else if (a.out) {
     double mine[2];
     mine[0] = block_sum(d0, red);
     mine[1] = block_sum(d1, red);
@@ -334,7 +349,10 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
 }
 
 // ------------------------------------------------------------------------------------ launch
-int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done) {
+bool fsb_spmv_supports_p2p(fsb_mat* A) { return A->ctx->spmv_mode == 0 && A->ntiles > 0; }
+
+int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done,
+                    const fsb_spmv_dist* dd) {
   fsb_ctx* ctx = A->ctx;
   if (A->own1 <= A->own0) return FSB_OK;
   if (ctx->spmv_mode != 1 && A->tile_rows != spmv_rows(ctx, A->bs)) {
@@ -347,6 +365,12 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
   a.ntiles = A->ntiles; a.own0 = A->own0; a.own1 = A->own1; a.cap = A->tile_cap;
   a.x = x; a.y = y; a.w = w; a.want_yy = want_yy;
   a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
+  memset(&a.pc, 0, sizeof(a.pc));
+  a.halo_seq = 0; a.mail_slot = -1; a.mail_seq = 0;
+  if (dd) {
+    if (!fsb_spmv_supports_p2p(A)) FSB_FAIL(ctx, FSB_ERR_STATE, "peer-memory SpMV needs the staged kernel (spmv_mode 0)");
+    a.pc = dd->pc; a.halo_seq = dd->halo_seq; a.mail_slot = dd->mail_slot; a.mail_seq = dd->mail_seq;
+  }
   const bool tiled = ctx->spmv_mode != 1 && A->ntiles > 0;
   if (tiled && ctx->spmv_mode == 0) {
     const int lpr = spmv_lpr(ctx, A->bs);
@@ -409,5 +433,5 @@ extern "C" int fsb_spmv(fsb_mat* A, fsb_vec* x, fsb_vec* y) {
     int rc = fsb_dist_halo_raw(A->ctx, x->d, x->n);
     if (rc) return rc;
   }
-  return fsb_launch_spmv(A, x->d, y->d, nullptr, 0, nullptr, nullptr);
+  return fsb_launch_spmv(A, x->d, y->d, nullptr, 0, nullptr, nullptr, nullptr);
 }
