@@ -214,17 +214,17 @@ class SolverBase():
             else:
                 raise SolverError('only vector and scalar function can run this method')
 
-        nv = self.mesh.num_vertices()
+        nv = self.function_space.num_nodes()
         if 'vector_name' in self.settings and isinstance(v0, (tuple, list)) and isinstance(v0[0], (str, numbers.Number)):
             if all(isinstance(v, numbers.Number) for v in v0):
                 vals = np.tile(np.asarray(v0, dtype=np.float64), nv)
             else:
-                vals = Expression(tuple(str(v) for v in v0), degree=self.settings['fe_degree'])(self.mesh.coordinates()).reshape(-1)
+                vals = Expression(tuple(str(v) for v in v0), degree=self.settings['fe_degree'])(self.function_space.node_coordinates()).reshape(-1)
             u0 = Function(self.function_space, vals)
         elif 'scalar_name' in self.settings and isinstance(v0, numbers.Number):
             u0 = Function(self.function_space, fill=float(v0))        # stays symbolic: filled on the device
         elif 'scalar_name' in self.settings and isinstance(v0, str) and not os.path.exists(v0):
-            u0 = Function(self.function_space, Expression(v0, degree=self.settings['fe_degree'])(self.mesh.coordinates()))
+            u0 = Function(self.function_space, Expression(v0, degree=self.settings['fe_degree'])(self.function_space.node_coordinates()))
         elif isinstance(v0, Function):
             u0 = v0.copy()
         elif isinstance(v0, np.ndarray) and v0.size == self.function_space.dim():
@@ -253,7 +253,7 @@ class SolverBase():
             if len(value) == self.dimension and all(isinstance(v, numbers.Number) for v in value):
                 values_0 = np.asarray(value, dtype=np.float64)
             elif len(value) == self.dimension and all(isinstance(v, str) for v in value):
-                values_0 = Expression(tuple(value), degree=self.settings['fe_degree'])(self.mesh.coordinates())
+                values_0 = Expression(tuple(value), degree=self.settings['fe_degree'])(self.function_space.node_coordinates())
             elif self.transient_settings['transient'] and len(value) > self.dimension:
                 values_0 = self.translate_value(value[self.current_step])
             else:
@@ -266,14 +266,14 @@ class SolverBase():
         elif isinstance(value, Function):
             values_0 = value.values
         elif isinstance(value, Expression):
-            values_0 = value(self.mesh.coordinates())
+            values_0 = value(self.function_space.node_coordinates())
         elif callable(value) and self.transient_settings['transient']:
             values_0 = self.translate_value(value(self.get_current_time()))
         elif isinstance(value, str):
             if os.path.exists(value):
                 values_0 = np.load(value)
             else:
-                values_0 = Expression(value, degree=self.settings['fe_degree'])(self.mesh.coordinates())
+                values_0 = Expression(value, degree=self.settings['fe_degree'])(self.function_space.node_coordinates())
         elif value is None:
             raise TypeError('None type is supplied as value to be translated')
         else:
@@ -396,7 +396,7 @@ class SolverBase():
             return
         if self.dimension == 2 and self.function_space.ncomp == 1:
             c = self.mesh.coordinates()
-            plt.tricontourf(mtri.Triangulation(c[:, 0], c[:, 1], self.mesh.cells()), self.result.array(), 32)
+            plt.tricontourf(mtri.Triangulation(c[:, 0], c[:, 1], self.mesh.cells()), self.result.compute_vertex_values(), 32)
             plt.colorbar()
             plt.show()
 
@@ -414,7 +414,7 @@ class SolverBase():
     def device_space(self):
         """The device-resident space (mesh + pattern), created on first use and reused by every step."""
         if self._space is None:
-            self._space = DeviceSpace(self.mesh, self.function_space.ncomp, comm=self.comm)
+            self._space = DeviceSpace(self.mesh, self.function_space.ncomp, comm=self.comm, space=self.function_space)
             self.timings.update({'mesh_upload': self._space.timings['mesh'], 'symbolic': self._space.timings['symbolic']})
         return self._space
 
@@ -440,7 +440,7 @@ class SolverBase():
         x = u.device_vector()
         if x is None or x.n != space.ndof_local:
             x = space.vector_from_function(u)
-        dofs, vals = collect_dirichlet(Dirichlet_bcs, self.mesh)
+        dofs, vals = collect_dirichlet(Dirichlet_bcs, self.function_space)
         # symmetric elimination (assemble_system) keeps A SPD for CG; plain bc.apply for BiCGStab
         space.apply_dirichlet(b, dofs, vals, symmetric=(method == 'cg'), x=x)
         space.ctx.sync()
@@ -472,12 +472,12 @@ class SolverBase():
         raise SolverError('nonlinear problems (Newton) are outside the device hot path')
 
 
-def collect_dirichlet(bcs, mesh):
+def collect_dirichlet(bcs, space):
     """DirichletBC list -> (global dofs, values); later conditions win on shared dofs, as repeated
-    bc.apply calls do."""
+    bc.apply calls do.  `space`: the FunctionSpace (a Mesh is accepted for P1)."""
     if not bcs:
         return np.zeros(0, dtype=np.int64), np.zeros(0)
-    coords = mesh.coordinates()
+    coords = space.node_coordinates() if hasattr(space, "node_coordinates") else space.coordinates()
     merged = {}
     dofs_all, vals_all = [], []
     for bc in bcs:
@@ -526,7 +526,7 @@ def write_vtk(path, mesh, values, name):
         f.write("CELL_TYPES %d\n" % t.shape[0])
         np.savetxt(f, np.full(t.shape[0], 10 if nl == 4 else 5), fmt="%d")
         f.write("POINT_DATA %d\n" % nv)
-        vals = np.asarray(values)
+        vals = np.asarray(values)[:nv]                  # degree 2: the vertex nodes come first
         if vals.ndim == 1:
             f.write("SCALARS %s double 1\nLOOKUP_TABLE default\n" % name)
             np.savetxt(f, vals, fmt="%.16g")

@@ -38,6 +38,7 @@ SIGNATURES = {
     "fsb_launch_count": (c_i64, [c_vp]),
     "fsb_mesh_upload": (C.c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, P(c_vp)]),
     "fsb_mesh_box": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, P(c_vp)]),
+    "fsb_mesh_upload_p2": (C.c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_i64, P(c_vp)]),
     "fsb_mesh_sizes": (C.c_int, [c_vp, P(c_i32), P(c_i32), P(c_i64), P(c_i64)]),
     "fsb_mesh_download": (C.c_int, [c_vp, c_vp, c_vp]),
     "fsb_mesh_destroy": (None, [c_vp]),
@@ -199,6 +200,17 @@ class DeviceMesh(_Handle):
         h = c_vp()
         gdim, tdim = coords.shape[1], cells.shape[1] - 1
         ctx.check(ctx.lib.fsb_mesh_upload(ctx.h, gdim, tdim, coords.shape[0], _ptr(coords), cells.shape[0], _ptr(cells), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def upload_p2(cls, ctx, coords, cell_nodes, nnodes):
+        """Degree-2 node layout: cell_nodes[nc][6|10] = sorted vertices then edge nodes (UFC order)."""
+        coords = _np(coords, np.float64)
+        cell_nodes = _np(cell_nodes, np.int32)
+        gdim = coords.shape[1]
+        h = c_vp()
+        ctx.check(ctx.lib.fsb_mesh_upload_p2(ctx.h, gdim, gdim, coords.shape[0], _ptr(coords), cell_nodes.shape[0], _ptr(cell_nodes),
+                                             int(nnodes), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

@@ -68,16 +68,23 @@ def slab_partition(nplanes, nranks):
 class DeviceSpace:
     """P1 space with `ncomp` components on a mesh, resident on one GPU (or one slab of it)."""
 
-    def __init__(self, mesh, ncomp=1, ctx=None, comm=None):
+    def __init__(self, mesh, ncomp=1, ctx=None, comm=None, space=None):
         self.mesh, self.ncomp = mesh, ncomp
+        self.fs = space                                 # FunctionSpace (None: P1 on the mesh)
+        self.degree = getattr(space, "degree", 1)
         self.ctx = ctx or get_context()
         self.comm = comm or Comm()
         self.timings = {}
         t0 = time.perf_counter()
         self.v_off = 0                                  # global vertex id of local vertex 0
         self.ghost_lo = self.ghost_hi = 0
-        nv_global = mesh.num_vertices()
-        if self.comm.nranks > 1:
+        nv_global = mesh.num_vertices() if self.degree == 1 else space.num_nodes()
+        if self.degree == 2:
+            if self.comm.nranks > 1:
+                raise SolverError("distributed P2 spaces are not implemented")
+            # degree-2 node layout: host integer work (edge numbering), then one upload
+            self.dmesh = _lib.DeviceMesh.upload_p2(self.ctx, mesh.coordinates(), space.cell_nodes(), space.num_nodes())
+        elif self.comm.nranks > 1:
             if not mesh.box:
                 raise SolverError("distributed runs need a generated box mesh (z-slab partition); "
                                   "unstructured partitioning is not implemented")
@@ -109,6 +116,8 @@ class DeviceSpace:
         else:
             self.dmesh = _lib.DeviceMesh.upload(self.ctx, mesh.coordinates(), mesh.cells())
         _, _, self.nv_local, self.nc_local = self.dmesh.sizes()
+        if self.degree == 2:
+            self.nv_local = space.num_nodes()           # rows are P2 nodes (vertices + edges)
         self.own_v0 = self.ghost_lo * getattr(self, "plane", 0)
         self.own_v1 = self.own_v0 + (self.owned_planes * self.plane if self.comm.nranks > 1 else self.nv_local)
         self.nv_global = nv_global
@@ -137,6 +146,11 @@ class DeviceSpace:
         return l[(l >= 0) & (l < self.nv_local)]
 
     def local_facets(self, fverts, opp=None):
+        """Facets (global vertex lists) -> what the facet kernels take: local vertex lists (P1) or the facets'
+        P2 node lists (vertices then edges), plus the opposite vertices when given."""
+        if self.degree == 2:
+            fn = self.fs.facet_nodes(fverts)
+            return fn, (None if opp is None else np.asarray(opp, dtype=np.int32))
         fv = np.asarray(fverts, dtype=np.int64) - self.v_off
         keep = np.all((fv >= 0) & (fv < self.nv_local), axis=1) if fv.size else np.zeros(0, bool)
         if opp is None:

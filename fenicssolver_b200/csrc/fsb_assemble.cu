@@ -290,13 +290,13 @@ __global__ void k_facet_mass(int64_t nf, const int32_t* __restrict__ fverts, con
 }
 
 template <int D>
-__global__ void k_facet_area(int64_t nf, const int32_t* __restrict__ fverts, const double* __restrict__ xyz,
+__global__ void k_facet_area(int64_t nf, const int32_t* __restrict__ fverts, int stride, const double* __restrict__ xyz,
                              double* __restrict__ partials) {
   __shared__ double sm[32];
   double s = 0.0;
   for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
     double n[3], x0[3];
-    s += facet_geom<D>(xyz, fverts + f * D, n, x0);
+    s += facet_geom<D>(xyz, fverts + f * stride, n, x0);     // the facet's vertices come first in its node list
   }
   s = block_sum(s, sm);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
@@ -356,8 +356,9 @@ extern "C" int fsb_assemble_scalar(fsb_mesh* mesh, fsb_mat* A, double kscale, co
                                    double adv, const double* vel) {
   if (!mesh || !A) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
-  if (A->bs != 1 || A->nbrows != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "matrix does not belong to a scalar P1 space on this mesh");
+  if (A->bs != 1 || A->nbrows != mesh->nnodes) FSB_FAIL(ctx, FSB_ERR_ARG, "matrix does not belong to a scalar P1 space on this mesh");
   if (adv != 0.0 && !vel) FSB_FAIL(ctx, FSB_ERR_ARG, "advection needs a velocity");
+  if (mesh->degree == 2) return fsb_p2_scalar(mesh, A, nullptr, nullptr, kscale, ktensor, mass, adv, vel);
   ScalarForm f;
   fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
   const uint8_t* pm = (ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
@@ -374,7 +375,8 @@ extern "C" int fsb_apply_scalar(fsb_mesh* mesh, fsb_vec* x, fsb_vec* y, double k
                                 double adv, const double* vel) {
   if (!mesh || !x || !y) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
-  if (x->n != mesh->nverts || y->n != mesh->nverts || x == y) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the mesh");
+  if (x->n != mesh->nnodes || y->n != mesh->nnodes || x == y) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the mesh");
+  if (mesh->degree == 2) return fsb_p2_scalar(mesh, nullptr, x, y, kscale, ktensor, mass, adv, vel);
   ScalarForm f;
   fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
@@ -389,7 +391,8 @@ extern "C" int fsb_apply_scalar(fsb_mesh* mesh, fsb_vec* x, fsb_vec* y, double k
 extern "C" int fsb_assemble_elasticity(fsb_mesh* mesh, fsb_mat* A, double mu, double lambda) {
   if (!mesh || !A) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
-  if (A->bs != mesh->tdim || A->nbrows != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "elasticity needs a matrix with ncomp == dim on this mesh");
+  if (A->bs != mesh->tdim || A->nbrows != mesh->nnodes) FSB_FAIL(ctx, FSB_ERR_ARG, "elasticity needs a matrix with ncomp == dim on this mesh");
+  if (mesh->degree == 2) return fsb_p2_elasticity(mesh, A, mu, lambda);
   const uint8_t* pm = (ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3)
@@ -404,7 +407,7 @@ extern "C" int fsb_assemble_source(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, co
                                    const int32_t* cell_tags, int32_t tag) {
   if (!mesh || !b || !S) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
-  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nverts * ncomp) FSB_FAIL(ctx, FSB_ERR_ARG, "rhs size does not match mesh*ncomp");
+  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nnodes * ncomp) FSB_FAIL(ctx, FSB_ERR_ARG, "rhs size does not match mesh*ncomp");
   Vec3 s{{0, 0, 0}};
   for (int k = 0; k < ncomp; ++k) s.v[k] = S[k];
   int32_t* d_tags = nullptr;
@@ -414,7 +417,10 @@ extern "C" int fsb_assemble_source(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, co
     FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tags, cell_tags, sizeof(int32_t) * mesh->ncells, cudaMemcpyHostToDevice, ctx->stream));
   }
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
-  if (mesh->tdim == 3)
+  if (mesh->degree == 2) {
+    int rc = fsb_p2_source(mesh, b->d, ncomp, s.v, nullptr, scale, d_tags, tag);
+    if (rc) { fsb_dfree(ctx, d_tags); return rc; }
+  } else if (mesh->tdim == 3)
     k_source_const<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, ncomp, s, scale, d_tags, tag, b->d);
   else
     k_source_const<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, ncomp, s, scale, d_tags, tag, b->d);
@@ -429,7 +435,8 @@ extern "C" int fsb_assemble_source(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, co
 extern "C" int fsb_assemble_source_nodal(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, fsb_vec* S, double scale) {
   if (!mesh || !b || !S) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
-  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nverts * ncomp || S->n != b->n) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match mesh*ncomp");
+  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nnodes * ncomp || S->n != b->n) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match mesh*ncomp");
+  if (mesh->degree == 2) return fsb_p2_source(mesh, b->d, ncomp, nullptr, S->d, scale, nullptr, 0);
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3)
     k_source_nodal<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, ncomp, S->d, scale, b->d);
@@ -450,9 +457,11 @@ struct FacetUpload {
 
 static int upload_facets(fsb_mesh* mesh, int64_t nf, const int32_t* fverts, const int32_t* opp, FacetUpload& up) {
   fsb_ctx* ctx = mesh->ctx;
-  int rc = fsb_dmalloc(ctx, &up.fverts, (size_t)nf * mesh->tdim);
+  // nodes per facet: tdim vertices (degree 1) or the facet's P2 nodes, vertices then edges (degree 2)
+  const int nfn = mesh->degree == 2 ? mesh->tdim * (mesh->tdim + 1) / 2 : mesh->tdim;
+  int rc = fsb_dmalloc(ctx, &up.fverts, (size_t)nf * nfn);
   if (rc) return rc;
-  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(up.fverts, fverts, sizeof(int32_t) * nf * mesh->tdim, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(up.fverts, fverts, sizeof(int32_t) * nf * nfn, cudaMemcpyHostToDevice, ctx->stream));
   if (opp) {
     rc = fsb_dmalloc(ctx, &up.opp, (size_t)nf);
     if (rc) return rc;
@@ -465,7 +474,7 @@ extern "C" int fsb_assemble_facet_load(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp
                                        const int32_t* opp, int32_t mode, const double* g, double scale) {
   if (!mesh || !b || !g || (nf > 0 && !fverts)) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
-  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nverts * ncomp) FSB_FAIL(ctx, FSB_ERR_ARG, "rhs size does not match mesh*ncomp");
+  if (ncomp < 1 || ncomp > 3 || b->n != mesh->nnodes * ncomp) FSB_FAIL(ctx, FSB_ERR_ARG, "rhs size does not match mesh*ncomp");
   if (mode == 1 && (!opp || ncomp != mesh->tdim)) FSB_FAIL(ctx, FSB_ERR_ARG, "normal loads need opposite vertices and ncomp == dim");
   if (nf == 0) return FSB_OK;
   FacetUpload up(ctx);
@@ -474,7 +483,10 @@ extern "C" int fsb_assemble_facet_load(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp
   Vec3 gv{{0, 0, 0}};
   for (int k = 0; k < (mode == 1 ? 1 : ncomp); ++k) gv.v[k] = g[k];
   const unsigned grid = fsb_grid(nf, 128, (int64_t)ctx->sm_count * 16);
-  if (mesh->tdim == 3)
+  if (mesh->degree == 2) {
+    rc = fsb_p2_facet_load(mesh, b->d, ncomp, nf, up.fverts, up.opp, mode, g, scale);
+    if (rc) return rc;
+  } else if (mesh->tdim == 3)
     k_facet_load<3><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, up.opp, mesh->xyz, ncomp, mode, gv, scale, b->d);
   else
     k_facet_load<2><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, up.opp, mesh->xyz, ncomp, mode, gv, scale, b->d);
@@ -486,13 +498,16 @@ extern "C" int fsb_assemble_facet_load(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp
 extern "C" int fsb_assemble_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, const int32_t* fverts, double h) {
   if (!mesh || !A || (nf > 0 && !fverts)) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
-  if (A->bs != 1 || A->nbrows != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "facet mass needs the scalar matrix of this mesh");
+  if (A->bs != 1 || A->nbrows != mesh->nnodes) FSB_FAIL(ctx, FSB_ERR_ARG, "facet mass needs the scalar matrix of this mesh");
   if (nf == 0) return FSB_OK;
   FacetUpload up(ctx);
   int rc = upload_facets(mesh, nf, fverts, nullptr, up);
   if (rc) return rc;
   const unsigned grid = fsb_grid(nf, 128, (int64_t)ctx->sm_count * 16);
-  if (mesh->tdim == 3)
+  if (mesh->degree == 2) {
+    rc = fsb_p2_facet_mass(mesh, A, nf, up.fverts, h);
+    if (rc) return rc;
+  } else if (mesh->tdim == 3)
     k_facet_mass<3><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, h, A->row_ptr, A->col_idx, A->vals);
   else
     k_facet_mass<2><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, h, A->row_ptr, A->col_idx, A->vals);
@@ -510,10 +525,11 @@ extern "C" int fsb_facet_area(fsb_mesh* mesh, int64_t nf, const int32_t* fverts,
   int rc = upload_facets(mesh, nf, fverts, nullptr, up);
   if (rc) return rc;
   const unsigned grid = fsb_grid(nf, 256, 256);
+  const int stride = mesh->degree == 2 ? mesh->tdim * (mesh->tdim + 1) / 2 : mesh->tdim;
   if (mesh->tdim == 3)
-    k_facet_area<3><<<grid, 256, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, ctx->d_partials);
+    k_facet_area<3><<<grid, 256, 0, ctx->stream>>>(nf, up.fverts, stride, mesh->xyz, ctx->d_partials);
   else
-    k_facet_area<2><<<grid, 256, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, ctx->d_partials);
+    k_facet_area<2><<<grid, 256, 0, ctx->stream>>>(nf, up.fverts, stride, mesh->xyz, ctx->d_partials);
   FSB_LAUNCH_CHECK(ctx);
   std::vector<double> part(grid);
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(part.data(), ctx->d_partials, sizeof(double) * grid, cudaMemcpyDeviceToHost, ctx->stream));

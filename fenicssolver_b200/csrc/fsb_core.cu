@@ -200,6 +200,7 @@ extern "C" int fsb_mesh_upload(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->xyz, xyz, sizeof(double) * nverts * gdim, cudaMemcpyHostToDevice, ctx->stream));
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->cells, cells, sizeof(int32_t) * ncells * (tdim + 1), cudaMemcpyHostToDevice, ctx->stream));
   FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->degree = 1; m->nl = m->tdim + 1; m->nnodes = m->nverts; m->cell_nodes = m->cells;
   *out = m;
   return FSB_OK;
 }
@@ -285,6 +286,7 @@ extern "C" int fsb_mesh_box(fsb_ctx* ctx, int32_t tdim, const int32_t* n, const 
     k_box_cells2<<<fsb_grid(nbox, 256, cap), 256, 0, ctx->stream>>>(m->cells, nbox, nx);
     FSB_LAUNCH_CHECK(ctx);
   }
+  m->degree = 1; m->nl = m->tdim + 1; m->nnodes = m->nverts; m->cell_nodes = m->cells;
   *out = m;
   return FSB_OK;
 }
@@ -307,9 +309,40 @@ extern "C" int fsb_mesh_download(fsb_mesh* m, double* xyz, int32_t* cells) {
   return FSB_OK;
 }
 
+// FunctionSpace(mesh, "Lagrange", 2): the mesh plus a degree-2 node layout (vertices, then edge nodes).
+extern "C" int fsb_mesh_upload_p2(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz, int64_t ncells,
+                                  const int32_t* cell_nodes, int64_t nnodes, fsb_mesh** out) {
+  if (!ctx || !out || !xyz || !cell_nodes) return FSB_ERR_ARG;
+  if (gdim != tdim || (tdim != 2 && tdim != 3)) FSB_FAIL(ctx, FSB_ERR_ARG, "only gdim==tdim in {2,3} is supported");
+  if (nverts <= 0 || ncells <= 0 || nnodes < nverts || nnodes > 0x7fffffffll) FSB_FAIL(ctx, FSB_ERR_ARG, "bad mesh sizes");
+  const int nv_loc = tdim + 1, nl = (tdim + 1) * (tdim + 2) / 2;
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int a = 0; a < nl; ++a) {
+      const int32_t v = cell_nodes[c * nl + a];
+      if (v < 0 || v >= nnodes || (a < nv_loc && v >= nverts)) FSB_FAIL(ctx, FSB_ERR_ARG, "cell_nodes entry out of range");
+    }
+  fsb_mesh* m = new fsb_mesh{ctx, gdim, tdim, nverts, ncells};
+  int rc = fsb_dmalloc(ctx, &m->xyz, (size_t)nverts * gdim);
+  if (!rc) rc = fsb_dmalloc(ctx, &m->cells, (size_t)ncells * nv_loc);
+  if (!rc) rc = fsb_dmalloc(ctx, &m->cell_nodes, (size_t)ncells * nl);
+  if (rc) { fsb_mesh_destroy(m); return rc; }
+  m->degree = 2; m->nl = nl; m->nnodes = nnodes;
+  std::vector<int32_t> verts((size_t)ncells * nv_loc);
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int a = 0; a < nv_loc; ++a) verts[c * nv_loc + a] = cell_nodes[c * nl + a];
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->xyz, xyz, sizeof(double) * nverts * gdim, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->cells, verts.data(), sizeof(int32_t) * verts.size(), cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->cell_nodes, cell_nodes, sizeof(int32_t) * ncells * nl, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = m;
+  return FSB_OK;
+}
+
 extern "C" void fsb_mesh_destroy(fsb_mesh* m) {
   if (!m) return;
   fsb_dfree(m->ctx, m->xyz);
+  if (m->cell_nodes != m->cells) fsb_dfree(m->ctx, m->cell_nodes);
   fsb_dfree(m->ctx, m->cells);
+  fsb_dfree(m->ctx, m->p2_tables);
   delete m;
 }

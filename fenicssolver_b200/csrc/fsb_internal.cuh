@@ -48,6 +48,13 @@ struct fsb_mesh {
   int64_t nverts, ncells;
   double* xyz = nullptr;     // [nverts][gdim]
   int32_t* cells = nullptr;  // [ncells][tdim+1] sorted per cell
+  // Lagrange node layout the pattern and the element kernels work on.  Degree 1: the vertices themselves
+  // (cell_nodes == cells, nl == tdim+1, nnodes == nverts).  Degree 2: vertices then edge nodes.
+  int degree = 1;
+  int nl = 0;                      // nodes per cell
+  int64_t nnodes = 0;
+  int32_t* cell_nodes = nullptr;   // [ncells][nl]; owned only when degree == 2
+  double* p2_tables = nullptr;     // device copy of the P2 reference tensors for this dimension (degree 2)
 };
 
 struct fsb_vec {
@@ -151,6 +158,15 @@ struct fsb_spmv_dist;   // fsb_device.cuh: peer-memory wait/post instructions fo
 int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done,
                     const fsb_spmv_dist* dd = nullptr);
 bool fsb_spmv_supports_p2p(fsb_mat* A);
+// degree-2 element kernels [fsb_assemble_p2.cu]; A == nullptr selects the matrix-free action y += (...) x
+int fsb_p2_scalar(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, fsb_vec* y, double kscale, const double* ktensor, double mass, double adv,
+                  const double* vel);
+int fsb_p2_elasticity(fsb_mesh* mesh, fsb_mat* A, double mu, double lambda);
+int fsb_p2_source(fsb_mesh* mesh, double* b, int ncomp, const double* S_const, const double* S_nodal, double scale, const int32_t* d_tags,
+                  int tag);
+int fsb_p2_facet_load(fsb_mesh* mesh, double* b, int ncomp, int64_t nf, const int32_t* d_fnodes, const int32_t* d_opp, int mode,
+                      const double* g, double scale);
+int fsb_p2_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, const int32_t* d_fnodes, double h);
 // distributed hooks [fsb_dist.cu]
 bool fsb_dist_active(fsb_ctx* ctx);
 int fsb_dist_halo_raw(fsb_ctx* ctx, double* v, int64_t n);

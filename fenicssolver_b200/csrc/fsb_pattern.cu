@@ -224,7 +224,7 @@ k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vp
 __global__ void k_posmap(const int32_t* __restrict__ cells, int64_t ncells, int nl, const int64_t* __restrict__ row_ptr,
                          const int32_t* __restrict__ col_idx, uint8_t* __restrict__ posmap) {
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
-    int v[4];
+    int v[10];
     for (int a = 0; a < nl; ++a) v[a] = cells[c * nl + a];
     for (int a = 0; a < nl; ++a) {
       const int64_t base = row_ptr[v[a]];
@@ -267,8 +267,8 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   if (!mesh || !out) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
   if (ncomp < 1 || ncomp > 3) FSB_FAIL(ctx, FSB_ERR_ARG, "ncomp must be 1..3");
-  const int nl = mesh->tdim + 1;
-  const int64_t nv = mesh->nverts, nc = mesh->ncells;
+  const int nl = mesh->nl;
+  const int64_t nv = mesh->nnodes, nc = mesh->ncells;
   const int cap = ctx->sm_count * 16;
   fsb_mat* A = new fsb_mat();
   A->ctx = ctx; A->mesh = mesh; A->bs = ncomp; A->nbrows = nv; A->own0 = 0; A->own1 = nv;
@@ -283,15 +283,15 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   TRY(fsb_dmalloc(ctx, &v2c, (size_t)nc * nl));
   TRY(fsb_dmalloc(ctx, &d_max, 1));
   TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
-  k_v2c_count<<<fsb_grid(nc * nl, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc * nl, deg);
+  k_v2c_count<<<fsb_grid(nc * nl, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc * nl, deg);
   ctx->launches++; TRYCUDA(cudaGetLastError());
   TRY(fsb_exclusive_scan(ctx, deg, vptr, nv));
   TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
-  k_v2c_fill<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, nl, vptr, deg, v2c);
+  k_v2c_fill<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc, nl, vptr, deg, v2c);
   ctx->launches++; TRYCUDA(cudaGetLastError());
   // row lengths -> row_ptr
   TRY(fsb_dmalloc(ctx, &A->row_ptr, (size_t)nv + 1));
-  k_rows<false><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cells, nl, vptr, v2c, nv, deg, nullptr, nullptr);
+  k_rows<false><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cell_nodes, nl, vptr, v2c, nv, deg, nullptr, nullptr);
   ctx->launches++; TRYCUDA(cudaGetLastError());
   TRYCUDA(cudaMemsetAsync(d_max, 0, sizeof(int32_t), ctx->stream));
   k_max_i32<<<fsb_grid(nv, 256, cap), 256, 0, ctx->stream>>>(deg, nv, d_max);
@@ -305,7 +305,7 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   A->nnzb = nnzb;
   A->max_row_len = maxlen;
   TRY(fsb_dmalloc(ctx, &A->col_idx, (size_t)nnzb));
-  k_rows<true><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cells, nl, vptr, v2c, nv, nullptr, A->row_ptr, A->col_idx);
+  k_rows<true><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cell_nodes, nl, vptr, v2c, nv, nullptr, A->row_ptr, A->col_idx);
   ctx->launches++; TRYCUDA(cudaGetLastError());
   TRYCUDA(cudaStreamSynchronize(ctx->stream));
   fsb_dfree(ctx, v2c); v2c = nullptr;
@@ -314,7 +314,7 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   TRYCUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * nnzb * ncomp * ncomp + 512, ctx->stream));
   if (maxlen <= 256) {
     TRY(fsb_dmalloc(ctx, &A->posmap, (size_t)nc * nl * nl));
-    k_posmap<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, nl, A->row_ptr, A->col_idx, A->posmap);
+    k_posmap<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc, nl, A->row_ptr, A->col_idx, A->posmap);
     ctx->launches++; TRYCUDA(cudaGetLastError());
   }
   TRY(fsb_mat_setup_tiles(A));

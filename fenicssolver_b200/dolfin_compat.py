@@ -425,24 +425,80 @@ class _UflElement:
         return self._degree
 
 
+_UFC_EDGES = {1: ((0, 1),), 2: ((1, 2), (0, 2), (0, 1)), 3: ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))}
+
+
 class FunctionSpace:
-    """P1 Lagrange on a mesh; ncomp = 1 (scalar) or dim (vector).  DoF numbering is vertex order."""
+    """P1 or P2 Lagrange on a mesh; ncomp = 1 (scalar) or dim (vector).
+
+    Node numbering: vertices in vertex order, then (degree 2) one node per edge, edges numbered
+    by the lexicographic rank of their sorted vertex pair; vector dof = ncomp*node + component.  Local node
+    order of a cell: its vertices sorted ascending, then its edges in UFC order."""
 
     def __init__(self, mesh, family="CG", degree=1, ncomp=1, constrained_domain=None):
         if family not in ("CG", "Lagrange", "P"):
             raise SolverError("element family %r is not supported (CG/Lagrange only)" % family)
-        if degree != 1:
-            raise SolverError("fe_degree %r is not implemented yet: only P1 runs on the device path" % degree)
+        if degree not in (1, 2):
+            raise SolverError("fe_degree %r is not implemented: P1 and P2 run on the device path" % degree)
         if constrained_domain is not None:
             raise SolverError("periodic boundaries are not implemented")
-        self._mesh, self.ncomp = mesh, ncomp
+        self._mesh, self.ncomp, self.degree = mesh, ncomp, degree
         self._ufl_element = _UflElement(degree)
+        self._edges = self._cell_nodes = self._node_coords = None
 
     def mesh(self):
         return self._mesh
 
+    def num_nodes(self):
+        if self.degree == 1:
+            return self._mesh.num_vertices()
+        return self._mesh.num_vertices() + self.edges().shape[0]
+
     def dim(self):
-        return self._mesh.num_vertices() * self.ncomp
+        return self.num_nodes() * self.ncomp
+
+    # ---- degree 2: edge nodes (host integer work, K1) ----------------------------------------------
+    def edges(self):
+        if self._edges is None:
+            cells = self._mesh.cells().astype(np.int64)
+            nv = self._mesh.num_vertices()
+            loc = _UFC_EDGES[self._mesh.tdim]
+            keys = np.stack([cells[:, a] * nv + cells[:, b] for a, b in loc], axis=1)       # cells are sorted: a < b
+            uniq, inv = np.unique(keys.ravel(), return_inverse=True)
+            self._edge_keys = uniq
+            self._edges = np.stack([uniq // nv, uniq % nv], axis=1)
+            self._cell_nodes = np.hstack([cells, nv + inv.reshape(keys.shape)]).astype(np.int32)
+        return self._edges
+
+    def cell_nodes(self):
+        if self.degree == 1:
+            return self._mesh.cells()
+        self.edges()
+        return self._cell_nodes
+
+    def node_coordinates(self):
+        c = self._mesh.coordinates()
+        if self.degree == 1:
+            return c
+        if self._node_coords is None:
+            e = self.edges()
+            self._node_coords = np.vstack([c, 0.5 * (c[e[:, 0]] + c[e[:, 1]])])
+        return self._node_coords
+
+    def facet_nodes(self, fverts):
+        """Nodes of facets given by their (sorted) vertices: the vertices, then (degree 2) the facet's edges."""
+        fv = np.asarray(fverts, dtype=np.int64)
+        if self.degree == 1 or fv.shape[0] == 0:
+            return fv.astype(np.int32) if self.degree == 1 else np.zeros((0, fv.shape[1] * (fv.shape[1] + 1) // 2), dtype=np.int32)
+        self.edges()
+        nv = self._mesh.num_vertices()
+        fv = np.sort(fv, axis=1)
+        loc = _UFC_EDGES[fv.shape[1] - 1]
+        keys = np.stack([fv[:, a] * nv + fv[:, b] for a, b in loc], axis=1)
+        pos = np.searchsorted(self._edge_keys, keys)
+        if not np.array_equal(self._edge_keys[np.minimum(pos, self._edge_keys.size - 1)], keys):
+            raise SolverError("facet edge not found in the mesh edge table")
+        return np.hstack([fv, nv + pos]).astype(np.int32)
 
 
 def VectorFunctionSpace(mesh, family="CG", degree=1, dim=None, constrained_domain=None):
@@ -542,7 +598,8 @@ class Function:
     def compute_vertex_values(self, mesh=None):
         a = self.array()
         nc = self.function_space.ncomp
-        return a if nc == 1 else a.reshape(-1, nc).T.reshape(-1)     # dolfin returns component-major
+        nv = self.function_space.mesh().num_vertices()               # P2: the vertex nodes come first
+        return a[:nv].copy() if nc == 1 else a.reshape(-1, nc)[:nv].T.reshape(-1)     # dolfin returns component-major
 
     @property
     def values(self):
@@ -570,7 +627,8 @@ class DirichletBC:
         self.V, self.value, self.markers, self.marker_id, self.component = V, value, markers, marker_id, component
 
     def dofs_and_values(self, coords):
-        verts = self.markers.vertices(self.marker_id)
+        # `coords` are the node coordinates of V (vertices, then edge midpoints for degree 2)
+        verts = np.unique(self.V.facet_nodes(self.markers.facets(self.marker_id)[0])).astype(np.int64)
         nc = self.V.ncomp
         comps = range(nc) if self.component is None else [self.component]
         comps = list(comps)

@@ -80,6 +80,14 @@ int fsb_mesh_upload(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, co
  * slab: global id - layer0*plane_size. */
 int fsb_mesh_box(fsb_ctx* ctx, int32_t tdim, const int32_t* n, const double* p0, const double* p1,
                  int32_t layer0, int32_t layer1, fsb_mesh** mesh);
+/* FunctionSpace(mesh, "Lagrange", 2) (examples/test_linear_elasticity.py:105-106): the mesh together with
+ * a degree-2 node layout.  cell_nodes[ncells][nl], nl = 6 (triangles) / 10 (tetrahedra): the tdim+1 vertices,
+ * sorted ascending, then the edge nodes in UFC order (triangle (1,2)(0,2)(0,1); tetrahedron
+ * (2,3)(1,3)(1,2)(0,3)(0,2)(0,1)); node ids < nverts are vertices, nnodes = nverts + nedges.  Every entry point
+ * below accepts such a mesh: matrices/vectors then have nnodes*ncomp rows, and facet lists hold each facet's P2
+ * nodes (its tdim vertices followed by its edge nodes) instead of its vertices only. */
+int fsb_mesh_upload_p2(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz,
+                       int64_t ncells, const int32_t* cell_nodes, int64_t nnodes, fsb_mesh** mesh);
 int fsb_mesh_sizes(fsb_mesh* mesh, int32_t* gdim, int32_t* tdim, int64_t* nverts, int64_t* ncells);
 int fsb_mesh_download(fsb_mesh* mesh, double* xyz, int32_t* cells);
 void fsb_mesh_destroy(fsb_mesh* mesh);

@@ -140,7 +140,7 @@ def test_settings_errors_mirror_reference():
     with pytest.raises(NameError):
         main({'solver_name': 'NoSuchSolver'})                                   # main.py:92-93
     with pytest.raises(SolverBase.SolverError):
-        FunctionSpace(UnitSquareMesh(2, 2), "CG", 2)                            # P2 is next-tier: loud, not silent P1
+        FunctionSpace(UnitSquareMesh(2, 2), "CG", 3)                            # degrees 1 and 2 exist: loud, not silent P1
     m = UnitSquareMesh(2, 2)
     s = heat_settings(m)
     s['mesh'] = "/no/such/mesh.xml"
@@ -219,6 +219,31 @@ def test_expression_evaluation():
     assert Expression(("10*rho", "0", "0.0"), rho=7800, degree=2)(np.zeros((3, 3))).shape == (3, 3)
     with pytest.raises(SolverBase.SolverError):
         Expression("__import__('os')")(c)
+
+
+@pytest.mark.parametrize("mesh", [UnitSquareMesh(3, 2), UnitCubeMesh(2, 2, 3)], ids=["2d", "3d"])
+def test_degree2_space_numbering_matches_oracle(mesh):
+    """Host integer work of the P2 space (edge numbering, cell node lists, facet node lists, Dirichlet dofs)
+    against the oracle's independent construction."""
+    from oracle import fem_oracle_p2 as p2
+    V = FunctionSpace(mesh, "Lagrange", 2)
+    cn, xc, edges = p2.p2_dofmap(mesh.coordinates(), mesh.cells())
+    assert V.num_nodes() == xc.shape[0] and np.array_equal(V.edges(), edges)
+    assert np.array_equal(V.cell_nodes(), cn) and np.array_equal(V.node_coordinates(), xc)
+    fv, _, _ = fo.exterior_facets(mesh.cells())
+    assert np.array_equal(V.facet_nodes(fv), p2.facet_nodes(fv, edges, mesh.num_vertices()))
+    W = VectorFunctionSpace(mesh, "CG", 2)
+    assert W.dim() == xc.shape[0] * mesh.geometry().dim()
+    # Dirichlet on x = 0 takes the edge midpoints of the marked facets as well as their vertices
+    markers = FacetMarkers(mesh)
+    markers.set_all(0)
+    AutoSubDomain(lambda x: near(x[0], 0.0)).mark(markers, 1)
+    from fenicssolver_b200.dolfin_compat import DirichletBC
+    d, v = SolverBase.collect_dirichlet([DirichletBC(V, Constant(2.0), markers, 1)], V)
+    assert np.array_equal(np.sort(d), np.flatnonzero(xc[:, 0] == 0.0)) and np.all(v == 2.0)
+    f = Expression("x[0]*x[0] + x[1]", degree=2)
+    d, v = SolverBase.collect_dirichlet([DirichletBC(V, f, markers, 1)], V)
+    assert np.allclose(v, xc[d, 0] ** 2 + xc[d, 1])
 
 
 def test_slab_partition_and_index_maps():
