@@ -231,6 +231,7 @@ __global__ void k_posmap(const int32_t* __restrict__ cells, int64_t ncells, int 
       const int len = (int)(row_ptr[v[a] + 1] - base);
       int lo = 0;
       for (int b = 0; b < nl; ++b) {
+        if (b > 0 && v[b] < v[b - 1]) lo = 0;      // P2 node lists are ascending only within vertices / within runs of edges
         lo = row_find(col_idx + base, lo, len, v[b]);
         posmap[c * nl * nl + a * nl + b] = (uint8_t)lo;
         ++lo;
