@@ -478,7 +478,6 @@ def collect_dirichlet(bcs, space):
     if not bcs:
         return np.zeros(0, dtype=np.int64), np.zeros(0)
     coords = space.node_coordinates() if hasattr(space, "node_coordinates") else space.coordinates()
-    merged = {}
     dofs_all, vals_all = [], []
     for bc in bcs:
         if not isinstance(bc, DirichletBC):
@@ -488,11 +487,18 @@ def collect_dirichlet(bcs, space):
         vals_all.append(v)
     d = np.concatenate(dofs_all)
     v = np.concatenate(vals_all)
-    # keep the last occurrence of each dof
-    _, idx = np.unique(d[::-1], return_index=True)
-    idx = d.size - 1 - idx
-    del merged
-    return d[idx], v[idx]
+    # keep the last occurrence of each dof; the selection depends only on the marked sets, so a transient
+    # loop (new DirichletBC objects, same markers, every step) reuses it
+    key = tuple((id(bc.markers), bc.marker_id, bc.component, getattr(bc.markers, "version", None)) for bc in bcs)
+    cache = getattr(space, "__dict__", {}).setdefault("_bc_merge", {})
+    hit = cache.get(key)
+    if hit is None or hit[0].size != d.size:
+        _, idx = np.unique(d[::-1], return_index=True)
+        idx = d.size - 1 - idx
+        if len(cache) > 16:
+            cache.clear()
+        hit = cache[key] = (d, idx, d[idx])
+    return hit[2], v[hit[1]]
 
 
 def mesh_from_dict(m):

@@ -62,6 +62,34 @@ __device__ __forceinline__ void finish_partials(const double (&mine)[NV], double
 }
 
 
+// as finish_partials; returns true in every thread of the CTA that combined the partials (out[] is written)
+template <int NV>
+__device__ __forceinline__ bool finish_partials_last(const double (&mine)[NV], double* __restrict__ partials, int stride,
+                                                     double* __restrict__ out, unsigned* counter, double* sm) {
+  __shared__ bool is_last_f;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) partials[k * stride + blockIdx.x] = mine[k];
+    __threadfence();
+    unsigned t = atomicAdd(counter, 1u);
+    is_last_f = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last_f) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partials + k * stride + i);
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) out[k] = s;
+  }
+  if (threadIdx.x == 0) { *counter = 0; __threadfence(); }
+  __syncthreads();
+  return true;
+}
+
+
 // ------------------------------------------------------------------------------------ peer memory (one node)
 // Distributed CG without collective launches.  Every rank owns a small CommBuf that all ranks map through
 // CUDA IPC (NVLink / NVSwitch peer memory):

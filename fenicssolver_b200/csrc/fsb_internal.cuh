@@ -98,6 +98,7 @@ struct fsb_mat {
   // Krylov work vectors, kept across solves (transient runs re-solve every step)
   double* work[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int work_count = 0;
+  int last_iters = 0;          // iterations of the previous Krylov solve on this matrix (sizes the first launch batch)
 };
 
 #define FSB_CHECK_CUDA(ctx, call)                                                         \
@@ -156,7 +157,7 @@ int fsb_exclusive_scan(fsb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n)
 int fsb_mat_setup_tiles(fsb_mat* A);
 struct fsb_spmv_dist;   // fsb_device.cuh: peer-memory wait/post instructions for one launch
 int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done,
-                    const fsb_spmv_dist* dd = nullptr);
+                    const fsb_spmv_dist* dd = nullptr, const double* w2 = nullptr);
 bool fsb_spmv_supports_p2p(fsb_mat* A);
 // degree-2 element kernels [fsb_assemble_p2.cu]; A == nullptr selects the matrix-free action y += (...) x
 int fsb_p2_scalar(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, fsb_vec* y, double kscale, const double* ktensor, double mass, double adv,

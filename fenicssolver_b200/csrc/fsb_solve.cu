@@ -46,7 +46,8 @@ __global__ void k_extract_dinv(int64_t n0, int64_t n1, const int64_t* __restrict
 // scalar slots in ctx->d_scalars
 enum { S_PQ0 = 0, S_PQ1 = 1, S_RZ0 = 2, S_RR0 = 3, S_BB = 4, S_RZ1 = 5, S_RR1 = 6, S_FINAL_RR = 7,
        // BiCGStab
-       S_RHO0 = 8, S_RRB0 = 9, S_BBB = 10, S_RHO1 = 11, S_RRB1 = 12, S_RV = 13, S_TS = 14, S_TT = 15, S_SPARE = 16 };
+       S_RHO0 = 8, S_RRB0 = 9, S_BBB = 10, S_RHO1 = 11, S_RRB1 = 12, S_RV = 13, S_TS = 14, S_TT = 15, S_RT = 16, S_RS = 17,
+       S_SPARE = 18 };
 // state ints in ctx->d_state: [0] done, [1] iterations, [2] outcome (1 converged, 0 maxit, -1 breakdown)
 
 // r = b - q ; p = z = dinv r ; sums r.z, z.z, (dinv b).(dinv b) -> out[0..3)
@@ -251,6 +252,17 @@ struct SpmvTimer {
   ~SpmvTimer() { for (int h = 0; h < 2; ++h) for (auto e : ev[h]) cudaEventDestroy(e); }
 };
 
+// Iterations launched per host poll.  A transient run solves a similar system every step: the previous
+// solve's iteration count sizes the first batch, so a 20-iteration solve does not pay for 32 launches.
+static void batch_plan(const fsb_ctx* ctx, int last_iters, int* first, int* rest) {
+  const int full = std::max(2, ctx->check_every & ~1);
+  *first = *rest = full;
+  if (last_iters > 0 && last_iters < full) {
+    *first = std::min(full, (last_iters + 2) & ~1);
+    *rest = std::max(2, (full / 4) & ~1);
+  }
+}
+
 static int read_outcome(fsb_ctx* ctx, int rr_slot_final, int bb_slot, fsb_solve_info* info) {
   int st[4];
   double sc[32];
@@ -323,15 +335,17 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   }
 
   // iteration batches; the host polls the state one batch behind the launches
-  const int batch = std::max(2, ctx->check_every & ~1);
+  int batch_first, batch_rest;
+  batch_plan(ctx, A->last_iters, &batch_first, &batch_rest);
   cudaEvent_t polled[2];
   FSB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&polled[0], cudaEventDisableTiming));
   FSB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&polled[1], cudaEventDisableTiming));
   struct PollGuard { cudaEvent_t* e; ~PollGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } pguard{polled};
-  if (ctx->profile) timer.ensure(batch);
+  if (ctx->profile) timer.ensure(std::max(batch_first, batch_rest));
   int launched = 0;
   for (int nb = 0;; ++nb) {
     const int slot = nb & 1;
+    const int batch = nb == 0 ? batch_first : batch_rest;
     const bool more = launched < maxit;
     if (more) {
       for (int k = 0; k < batch; ++k) {
@@ -372,6 +386,7 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   FSB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
   rc = read_outcome(ctx, S_FINAL_RR, S_BB, info);
   if (rc) return rc;
+  A->last_iters = info->iterations;
   if (p2p) fsb_dist_seq_reserve(ctx, (unsigned long long)info->iterations + 2);   // identical on every rank
   if (ctx->profile) { timer.collect(0); timer.collect(1); info->spmv_ms = timer.total_ms; }
   float ms = 0;
@@ -398,86 +413,98 @@ extern "C" int fsb_dot(fsb_vec* x, fsb_vec* y, double* result) {
 }
 
 // ------------------------------------------------------------------------------------ BiCGStab
-// r = b - q ; rhat = r ; sums rho=rhat.r, |dinv r|^2, |dinv b|^2 -> out[0..3)
+// Right-Jacobi BiCGStab with two synchronisation-free fusions (4 kernels per iteration instead of 7):
+//   v = A ph            (+ rhat.v)                                   SpMV
+//   s = r - alpha v ; sh = dinv s                 (+ rhat.s)         k_bcg_s
+//   t = A sh            (+ t.s, t.t, rhat.t)                         SpMV
+//   omega = ts/tt ; rho' = rhat.s - omega rhat.t  (= rhat.r_new, so no reduction separates the two updates)
+//   x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v) ; ph = dinv p   (+ |dinv r|^2)   k_bcg_xp
+// The last CTA of k_bcg_xp holds the reduced norm and advances the iteration state itself (single GPU);
+// distributed runs all-reduce first and use the one-thread k_bcg_check.
+
+// r = b - q ; rhat = p = r ; ph = dinv r ; sums rho=rhat.r, |dinv r|^2, |dinv b|^2 -> out[0..3)
 __global__ void __launch_bounds__(kVecThreads)
 k_bcg_init(int64_t n0, int64_t n1, const double* __restrict__ b, const double* __restrict__ q, const double* __restrict__ dinv,
-           double* __restrict__ r, double* __restrict__ rhat, double* partials, double* out, unsigned* counter) {
+           double* __restrict__ r, double* __restrict__ rhat, double* __restrict__ p, double* __restrict__ ph,
+           double* partials, double* out, unsigned* counter) {
   __shared__ double red[32];
   double s0 = 0, s1 = 0, s2 = 0;
   for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
     const double bi = b[i], ri = bi - q[i];
-    r[i] = ri; rhat[i] = ri;
+    r[i] = ri; rhat[i] = ri; p[i] = ri;
     const double zi = dinv[i] * ri, zb = dinv[i] * bi;
+    ph[i] = zi;
     s0 += ri * ri; s1 += zi * zi; s2 += zb * zb;
   }
   double mine[3] = {block_sum(s0, red), block_sum(s1, red), block_sum(s2, red)};
   finish_partials<3>(mine, partials, kMaxPartials, out, counter, red);
 }
 
-// p = r + beta (p - omega v), beta = (rho/rho_prev)(alpha/omega) ; ph = dinv p      (first: p = r)
-__global__ void __launch_bounds__(kVecThreads)
-k_bcg_p(int64_t n0, int64_t n1, const double* __restrict__ scal, int rho_cur, int rho_prev, int first,
-        const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv, double* __restrict__ p,
-        double* __restrict__ ph, const int* done) {
-  if (*done) return;
-  double beta = 0.0, omega = 0.0;
-  if (!first) {
-    const double alpha = scal[rho_prev] / scal[S_RV];
-    omega = scal[S_TS] / scal[S_TT];
-    beta = (scal[rho_cur] / scal[rho_prev]) * (alpha / omega);
-  }
-  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
-    const double pi = first ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
-    p[i] = pi;
-    ph[i] = dinv[i] * pi;
-  }
-}
-
-// alpha = rho/(rhat.v) ; s = r - alpha v (stored in r) ; sh = dinv s
+// alpha = rho/(rhat.v) ; s = r - alpha v (stored in r) ; sh = dinv s ; sum rhat.s -> out[0]
 __global__ void __launch_bounds__(kVecThreads)
 k_bcg_s(int64_t n0, int64_t n1, const double* __restrict__ scal, int rho_cur, const double* __restrict__ v,
-        const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ sh, const int* done) {
+        const double* __restrict__ rhat, const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ sh,
+        double* partials, double* out, unsigned* counter, const int* done) {
+  __shared__ double red[32];
   if (*done) return;
   const double alpha = scal[rho_cur] / scal[S_RV];
+  double s0 = 0;
   for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
     const double si = r[i] - alpha * v[i];
     r[i] = si;
     sh[i] = dinv[i] * si;
+    s0 += rhat[i] * si;
   }
+  double mine[1] = {block_sum(s0, red)};
+  finish_partials<1>(mine, partials, kMaxPartials, out, counter, red);
 }
 
-// omega = (t.s)/(t.t) ; x += alpha ph + omega sh ; r = s - omega t ; sums rho'=rhat.r, rr -> out[0..2)
-__global__ void __launch_bounds__(kVecThreads)
-k_bcg_x(int64_t n0, int64_t n1, const double* __restrict__ scal, int rho_cur, const double* __restrict__ ph,
-        const double* __restrict__ sh, const double* __restrict__ t, const double* __restrict__ rhat,
-        const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, double* partials, double* out, unsigned* counter, const int* done) {
-  __shared__ double red[32];
-  if (*done) return;
-  const double alpha = scal[rho_cur] / scal[S_RV];
-  const double omega = scal[S_TS] / scal[S_TT];
-  double s0 = 0, s1 = 0;
-  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
-    x[i] += alpha * ph[i] + omega * sh[i];
-    const double ri = r[i] - omega * t[i];
-    r[i] = ri;
-    const double zi = dinv[i] * ri;
-    s0 += rhat[i] * ri;
-    s1 += zi * zi;
-  }
-  double mine[2] = {block_sum(s0, red), block_sum(s1, red)};
-  finish_partials<2>(mine, partials, kMaxPartials, out, counter, red);
-}
-
-__global__ void k_bcg_check(double* __restrict__ scal, int rho_new, int rr_new, double rtol, double atol, int maxit, int* state) {
-  if (state[0]) return;
-  const double rr = scal[rr_new], bb = scal[S_BBB], rho = scal[rho_new], tt = scal[S_TT], rv = scal[S_RV];
+__device__ __forceinline__ void bcg_advance(double* __restrict__ scal, int rr_new, double rho_new, double rtol, double atol, int maxit,
+                                            int* state) {
+  const double rr = scal[rr_new], bb = scal[S_BBB], tt = scal[S_TT], rv = scal[S_RV];
   const double tol2 = fmax(rtol * rtol * bb, atol * atol);
   const int it = state[1] + 1;
   state[1] = it;
   scal[S_FINAL_RR] = rr;
   if (rr <= tol2) { state[2] = 1; state[0] = 1; }
-  else if (!(rr == rr) || rho == 0.0 || tt == 0.0 || rv == 0.0 || !(rho == rho)) { state[2] = -1; state[0] = 1; }
+  else if (!(rr == rr) || rho_new == 0.0 || tt == 0.0 || rv == 0.0 || !(rho_new == rho_new)) { state[2] = -1; state[0] = 1; }
   else if (it >= maxit) { state[2] = 0; state[0] = 1; }
+}
+
+// the two updates of one iteration in one pass; sum |dinv r|^2 -> out[0]; rho' -> scal[rho_next]
+__global__ void __launch_bounds__(kVecThreads)
+k_bcg_xp(int64_t n0, int64_t n1, double* __restrict__ scal, int rho_cur, int rho_next, int rr_new, const double* __restrict__ sh,
+         const double* __restrict__ t, const double* __restrict__ v, const double* __restrict__ dinv, double* __restrict__ x,
+         double* __restrict__ r, double* __restrict__ p, double* __restrict__ ph, double* partials, unsigned* counter,
+         double rtol, double atol, int maxit, int* state, int advance) {
+  __shared__ double red[32];
+  if (state[0]) return;
+  const double rho = scal[rho_cur];
+  const double alpha = rho / scal[S_RV];
+  const double omega = scal[S_TS] / scal[S_TT];
+  const double rho_new = scal[S_RS] - omega * scal[S_RT];
+  const double beta = (rho_new / rho) * (alpha / omega);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[rho_next] = rho_new;
+  double s0 = 0;
+  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
+    const double di = dinv[i], shi = sh[i];
+    x[i] += alpha * ph[i] + omega * shi;
+    const double ri = r[i] - omega * t[i];
+    r[i] = ri;
+    const double zi = di * ri;
+    s0 += zi * zi;
+    const double pi = ri + beta * (p[i] - omega * v[i]);
+    p[i] = pi;
+    ph[i] = di * pi;
+  }
+  double mine[1] = {block_sum(s0, red)};
+  const bool last = finish_partials_last<1>(mine, partials, kMaxPartials, scal + rr_new, counter, red);
+  if (advance && last && threadIdx.x == 0) bcg_advance(scal, rr_new, rho_new, rtol, atol, maxit, state);
+}
+
+__global__ void k_bcg_check(double* __restrict__ scal, int rho_new, int rr_new, double rtol, double atol, int maxit, int* state) {
+  if (state[0]) return;
+  bcg_advance(scal, rr_new, scal[rho_new], rtol, atol, maxit, state);
 }
 
 extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit,
@@ -512,34 +539,37 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   FSB_LAUNCH_CHECK(ctx);
   if (dist && (rc = fsb_dist_halo_raw(ctx, x->d, n))) return rc;
   if ((rc = fsb_launch_spmv(A, x->d, v, nullptr, 0, nullptr, nullptr))) return rc;
-  k_bcg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, v, dinv, r, rhat, ctx->d_partials, scal + S_RHO0, ctx->d_counters + 1);
+  k_bcg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, v, dinv, r, rhat, p, ph, ctx->d_partials, scal + S_RHO0, ctx->d_counters + 1);
   FSB_LAUNCH_CHECK(ctx);
   if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RHO0, 3))) return rc;
   k_check0<<<1, 1, 0, ctx->stream>>>(scal, S_RRB0, S_BBB, rtol, atol, maxit, state, scal + S_FINAL_RR);
   FSB_LAUNCH_CHECK(ctx);
 
-  const int batch = std::max(2, ctx->check_every & ~1);
+  int first, rest;
+  batch_plan(ctx, A->last_iters, &first, &rest);
   int launched = 0;
   bool finished = false;
   while (!finished) {
+    const int batch = launched == 0 ? first : rest;
     for (int k = 0; k < batch; ++k) {
       const int par = (launched + k) & 1;
       const int rho = par ? S_RHO1 : S_RHO0, rhon = par ? S_RHO0 : S_RHO1, rrn = par ? S_RRB0 : S_RRB1;
-      k_bcg_p<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, rhon, (launched + k) == 0, r, v, dinv, p, ph, state);
-      FSB_LAUNCH_CHECK(ctx);
       if (dist && (rc = fsb_dist_halo_raw(ctx, ph, n))) return rc;
       if ((rc = fsb_launch_spmv(A, ph, v, rhat, 0, scal + S_RV, state))) return rc;
       if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RV, 1))) return rc;
-      k_bcg_s<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, v, dinv, r, sh, state);
+      k_bcg_s<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, v, rhat, dinv, r, sh, ctx->d_partials, scal + S_RS, ctx->d_counters + 5, state);
       FSB_LAUNCH_CHECK(ctx);
       if (dist && (rc = fsb_dist_halo_raw(ctx, sh, n))) return rc;
-      if ((rc = fsb_launch_spmv(A, sh, t, r, 1, scal + S_TS, state))) return rc;
-      if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_TS, 2))) return rc;
-      k_bcg_x<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, ph, sh, t, rhat, dinv, x->d, r, ctx->d_partials, scal + rhon, ctx->d_counters + 2, state);
+      if ((rc = fsb_launch_spmv(A, sh, t, r, 1, scal + S_TS, state, nullptr, rhat))) return rc;
+      if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_TS, 4))) return rc;        // t.s, t.t, rhat.t, rhat.s
+      k_bcg_xp<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, rhon, rrn, sh, t, v, dinv, x->d, r, p, ph, ctx->d_partials,
+                                                    ctx->d_counters + 2, rtol, atol, maxit, state, dist ? 0 : 1);
       FSB_LAUNCH_CHECK(ctx);
-      if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + rhon, 2))) return rc;
-      k_bcg_check<<<1, 1, 0, ctx->stream>>>(scal, rhon, rrn, rtol, atol, maxit, state);
-      FSB_LAUNCH_CHECK(ctx);
+      if (dist) {
+        if ((rc = fsb_dist_allreduce_sum_dev(ctx, scal + rrn, 1))) return rc;
+        k_bcg_check<<<1, 1, 0, ctx->stream>>>(scal, rhon, rrn, rtol, atol, maxit, state);
+        FSB_LAUNCH_CHECK(ctx);
+      }
     }
     launched += batch;
     FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, state, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -549,6 +579,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   FSB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
   rc = read_outcome(ctx, S_FINAL_RR, S_BBB, info);
   if (rc) return rc;
+  A->last_iters = info->iterations;
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   info->solve_ms = ms;

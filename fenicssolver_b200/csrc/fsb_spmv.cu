@@ -31,6 +31,7 @@ struct SpmvArgs {
   double* y;
   const double* w;          // optional: d0 = sum y.w
   int want_yy;              // d1 = sum y.y
+  const double* w2;         // optional: d2 = sum y.w2 (then out has 3 entries)
   double* partials;
   double* out;              // out[0]=d0, out[1]=d1
   unsigned* counter;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(THREADS) k_spmv_tma(SpmvArgs a) {
     bulk_g2s((void*)cols_s(s), a.col_idx + al0, cnt * 4, &bar[s]);
   };
 
-  double d0 = 0.0, d1 = 0.0;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   int64_t tile = blockIdx.x;
   if (threadIdx.x == 0 && tile < a.ntiles) issue(tile, 0);
   for (int it = 0; tile < a.ntiles; tile += gridDim.x, ++it) {
@@ -101,15 +102,19 @@ __global__ void __launch_bounds__(THREADS) k_spmv_tma(SpmvArgs a) {
         a.y[row] = acc;
         if (a.w) d0 += acc * a.w[row];
         if (a.want_yy) d1 += acc * acc;
+        if (a.w2) d2 += acc * a.w2[row];
       }
     }
     __syncthreads();   // stage s is free for the prefetch issued at the top of the next iteration
   }
   if (a.out) {
-    double mine[2];
-    mine[0] = block_sum(d0, red);
-    mine[1] = block_sum(d1, red);
-    finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    if (a.w2) {
+      double mine[3] = {block_sum(d0, red), block_sum(d1, red), block_sum(d2, red)};
+      finish_partials<3>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    } else {
+      double mine[2] = {block_sum(d0, red), block_sum(d1, red)};
+      finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    }
   }
 }
 
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
   }
   __syncthreads();
 
-  double d0 = 0.0, d1 = 0.0;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   if (threadIdx.x >= CONSUMERS) {
     // ===== producer warp: lane 0 walks the tiles and issues the bulk copies (the warp stays converged) =====
     int it = 0;
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
           else { ks = (int)(a.row_ptr[R] - al0); ke = (int)(a.row_ptr[R + 1] - al0); }
           if (!live) ke = ks;
           const double wv = (a.w && live && sub == 0) ? __ldg(a.w + row) : 0.0;   // issued with the gathers
+          const double wv2 = (a.w2 && live && sub == 0) ? __ldg(a.w2 + row) : 0.0;
           double acc = 0.0;
           for (int k = ks + sub; k < ke; k += LPR * UNR) {
             double v[UNR][BS], xg[UNR][BS];
@@ -231,6 +237,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
             a.y[row] = acc;
             d0 += acc * wv;
             if (a.want_yy) d1 += acc * acc;
+            d2 += acc * wv2;
           }
         }
       }
@@ -244,10 +251,13 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
     mine[1] = block_sum(d1, red);
     finish_partials_mail<2>(mine, a.partials, kMaxPartials, a.counter, red, a.pc, a.mail_slot, a.mail_seq);
   } else if (a.out) {
-    double mine[2];
-    mine[0] = block_sum(d0, red);
-    mine[1] = block_sum(d1, red);
-    finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    if (a.w2) {
+      double mine[3] = {block_sum(d0, red), block_sum(d1, red), block_sum(d2, red)};
+      finish_partials<3>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    } else {
+      double mine[2] = {block_sum(d0, red), block_sum(d1, red)};
+      finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    }
   }
 }
 
@@ -256,7 +266,7 @@ template <int BS>
 __global__ void __launch_bounds__(256) k_spmv_plain(SpmvArgs a) {
   __shared__ double red[32];
   if (a.done && *a.done) return;
-  double d0 = 0.0, d1 = 0.0;
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   const int64_t n0 = a.own0 * BS, n1 = a.own1 * BS;
   for (int64_t row = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < n1; row += (int64_t)gridDim.x * blockDim.x) {
     const int64_t R = row / BS;
@@ -270,12 +280,16 @@ __global__ void __launch_bounds__(256) k_spmv_plain(SpmvArgs a) {
     a.y[row] = acc;
     if (a.w) d0 += acc * a.w[row];
     if (a.want_yy) d1 += acc * acc;
+    if (a.w2) d2 += acc * a.w2[row];
   }
   if (a.out) {
-    double mine[2];
-    mine[0] = block_sum(d0, red);
-    mine[1] = block_sum(d1, red);
-    finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    if (a.w2) {
+      double mine[3] = {block_sum(d0, red), block_sum(d1, red), block_sum(d2, red)};
+      finish_partials<3>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    } else {
+      double mine[2] = {block_sum(d0, red), block_sum(d1, red)};
+      finish_partials<2>(mine, a.partials, kMaxPartials, a.out, a.counter, red);
+    }
   }
 }
 
@@ -352,7 +366,7 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
 bool fsb_spmv_supports_p2p(fsb_mat* A) { return A->ctx->spmv_mode == 0 && A->ntiles > 0; }
 
 int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done,
-                    const fsb_spmv_dist* dd) {
+                    const fsb_spmv_dist* dd, const double* w2) {
   fsb_ctx* ctx = A->ctx;
   if (A->own1 <= A->own0) return FSB_OK;
   if (ctx->spmv_mode != 1 && A->tile_rows != spmv_rows(ctx, A->bs)) {
@@ -363,7 +377,7 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
   a.row_ptr = A->row_ptr; a.col_idx = A->col_idx; a.vals = A->vals;
   a.tile_row = A->tile_row; a.tile_k = A->tile_row ? A->tile_row + A->ntiles + 1 : nullptr;
   a.ntiles = A->ntiles; a.own0 = A->own0; a.own1 = A->own1; a.cap = A->tile_cap;
-  a.x = x; a.y = y; a.w = w; a.want_yy = want_yy;
+  a.x = x; a.y = y; a.w = w; a.want_yy = want_yy; a.w2 = w2;
   a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
   memset(&a.pc, 0, sizeof(a.pc));
   a.halo_seq = 0; a.mail_slot = -1; a.mail_seq = 0;

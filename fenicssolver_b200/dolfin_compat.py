@@ -362,10 +362,27 @@ class FacetMarkers:
     def __init__(self, mesh):
         self.mesh = mesh
         self.fverts, self.opp = mesh.exterior_facets()
+        self._cache = {}
+        self.version = 0          # bumped by every marking call; keys the per-marker caches (transient loops ask each step)
         self.values = np.zeros(self.fverts.shape[0], dtype=np.int64)
 
+    @property
+    def values(self):
+        return self._values
+
+    @values.setter
+    def values(self, v):
+        self._values = v
+        self.touch()
+
+    def touch(self):
+        """Call after editing `values` in place (set_all / SubDomain.mark do it themselves)."""
+        self.version += 1
+        self._cache.clear()
+
     def set_all(self, v):
-        self.values[:] = v
+        self._values[:] = v
+        self.touch()
 
     def mark_subdomain(self, sub, value):
         """SubDomain.mark: a facet is marked iff all its vertices and its midpoint are inside
@@ -378,11 +395,15 @@ class FacetMarkers:
             geom = self.mesh._boundary_geometry = (inv, pts, pts[inv].mean(axis=1))
         inv, pts, mid = geom
         ok = _evaluate_predicate(sub, mid) & _evaluate_predicate(sub, pts)[inv].all(axis=1)
-        self.values[ok] = value
+        self._values[ok] = value
+        self.touch()
 
     def facets(self, marker):
-        sel = self.values == marker
-        return self.fverts[sel], self.opp[sel]
+        hit = self._cache.get(marker)
+        if hit is None:
+            sel = self._values == marker
+            hit = self._cache[marker] = (self.fverts[sel], self.opp[sel])
+        return hit
 
     def vertices(self, marker):
         return np.unique(self.fverts[self.values == marker])
@@ -628,7 +649,13 @@ class DirichletBC:
 
     def dofs_and_values(self, coords):
         # `coords` are the node coordinates of V (vertices, then edge midpoints for degree 2)
-        verts = np.unique(self.V.facet_nodes(self.markers.facets(self.marker_id)[0])).astype(np.int64)
+        cache = self.V.__dict__.setdefault("_bc_nodes", {})
+        key = (id(self.markers), self.marker_id, getattr(self.markers, "version", None))
+        verts = cache.get(key)
+        if verts is None:
+            if len(cache) > 64:
+                cache.clear()
+            verts = cache[key] = np.unique(self.V.facet_nodes(self.markers.facets(self.marker_id)[0])).astype(np.int64)
         nc = self.V.ncomp
         comps = range(nc) if self.component is None else [self.component]
         comps = list(comps)
@@ -636,23 +663,25 @@ class DirichletBC:
         if isinstance(val, Constant):
             val = val.values()
             val = val[0] if val.size == 1 else val
-        if isinstance(val, Expression):
-            val = val(coords)                       # nodal values over the whole mesh
+        at_nodes = isinstance(val, Expression)
+        if at_nodes:
+            val = val(coords[verts])                # evaluated at the constrained nodes only
         elif isinstance(val, Function):
             val = val.values
         val = np.asarray(val, dtype=np.float64)
-        nv = coords.shape[0]
+        nv = verts.size if at_nodes else coords.shape[0]
+        pick = (lambda a: a) if at_nodes else (lambda a: a[verts])
         dofs, vals = [], []
         for k, c in enumerate(comps):
-            dofs.append(verts.astype(np.int64) * nc + c)
+            dofs.append(verts * nc + c)
             if val.ndim == 0:                                        # one constant
                 v = np.full(verts.size, float(val))
-            elif val.ndim == 1 and len(comps) > 1 and val.size == len(comps):   # constant vector
+            elif val.ndim == 1 and len(comps) > 1 and val.size == len(comps) and not at_nodes:   # constant vector
                 v = np.full(verts.size, val[k])
             elif val.ndim == 1 and val.size == nv:                   # nodal scalar field
-                v = val[verts]
+                v = pick(val)
             elif val.ndim == 2 and val.shape[0] == nv:               # nodal vector field
-                v = val[verts, c if self.component is None else 0]
+                v = pick(val)[:, c if self.component is None else 0]
             else:
                 raise SolverError("cannot interpret a Dirichlet value of shape %r" % (val.shape,))
             vals.append(v)
