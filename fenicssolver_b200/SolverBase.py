@@ -427,7 +427,8 @@ class SolverBase():
         if parity:
             rtol, maxit = min(rtol, PARITY_RTOL), max(maxit, PARITY_MAXIT)
         return {'rtol': rtol, 'atol': float(sp.get('absolute_tolerance', 0.0)), 'maxit': maxit,
-                'method': sp.get('linear_solver'), 'precond': sp.get('preconditioner', 'jacobi')}
+                'method': sp.get('linear_solver'), 'precond': sp.get('preconditioner', 'jacobi'),
+                'drop_zeros': bool(sp.get('drop_zeros', False))}
 
     def solve_linear_problem(self, F, u, Dirichlet_bcs):
         """assemble A and b, apply the Dirichlet conditions, solve (SolverBase.py:592-613).  F is the
@@ -446,6 +447,9 @@ class SolverBase():
         space.ctx.sync()
         self.timings['assemble'] = time.perf_counter() - t0
         t0 = time.perf_counter()
+        # 'drop_zeros': the Krylov SpMVs skip the entries that are exactly zero after assembly (same solution;
+        # the assembled pattern, which is the parity object, keeps them as dolfin/PETSc do)
+        space.ctx.set_option("drop_zeros", int(kp['drop_zeros']))
         info = space.solve(b, x, method=method, rtol=kp['rtol'], atol=kp['atol'], maxit=kp['maxit'], precond=kp['precond'])
         self.timings['solve'] = time.perf_counter() - t0
         self.solve_info = info

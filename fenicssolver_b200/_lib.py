@@ -24,7 +24,7 @@ P = C.POINTER
 
 class SolveInfo(C.Structure):
     _fields_ = [("iterations", c_i32), ("converged", c_i32), ("rnorm", c_dbl), ("bnorm", c_dbl),
-                ("solve_ms", c_dbl), ("spmv_ms", c_dbl)]
+                ("solve_ms", c_dbl), ("spmv_ms", c_dbl), ("operand_nnzb", c_i64)]
 
 
 # name -> (restype, argtypes); must list every symbol include/fsb.h declares (tests check this)
@@ -351,7 +351,7 @@ class DeviceMatrix(_Handle):
         pc = {"none": 0, None: 0, "jacobi": 1}[precond]
         self.ctx.check(fn(self.h, b.h, x.h, float(rtol), float(atol), int(maxit), pc, C.byref(info)))
         return {"iterations": info.iterations, "converged": info.converged, "rnorm": info.rnorm, "bnorm": info.bnorm,
-                "solve_ms": info.solve_ms, "spmv_ms": info.spmv_ms}
+                "solve_ms": info.solve_ms, "spmv_ms": info.spmv_ms, "operand_nnzb": info.operand_nnzb}
 
 
 def apply_scalar(mesh, x, y, kscale=1.0, ktensor=None, mass=0.0, adv=0.0, vel=None):

@@ -28,6 +28,7 @@ struct fsb_ctx {
   int profile = 0;
   int use_graph = 1;
   int check_every = 32;
+  int drop_zeros = 0;    // Krylov SpMVs run on a copy without the exactly-zero blocks (fsb_squeeze.cu)
   // scratch for reductions: per-CTA partials + a few scalars, and a pinned host mirror
   double* d_partials = nullptr;   // [kMaxPartials * 4]
   double* d_scalars = nullptr;    // [64]
@@ -99,6 +100,9 @@ struct fsb_mat {
   double* work[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int work_count = 0;
   int last_iters = 0;          // iterations of the previous Krylov solve on this matrix (sizes the first launch batch)
+  // "drop_zeros": compacted copy (blocks with a non-zero entry only) the Krylov SpMVs run on   [fsb_squeeze.cu]
+  fsb_mat* sq = nullptr;
+  int64_t sq_cap = 0;          // capacity (blocks) of sq's col_idx / vals, kept on the squeezed matrix itself
 };
 
 #define FSB_CHECK_CUDA(ctx, call)                                                         \
@@ -159,6 +163,7 @@ struct fsb_spmv_dist;   // fsb_device.cuh: peer-memory wait/post instructions fo
 int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done,
                     const fsb_spmv_dist* dd = nullptr, const double* w2 = nullptr);
 bool fsb_spmv_supports_p2p(fsb_mat* A);
+int fsb_mat_squeeze(fsb_mat* A, fsb_mat** out);   // [fsb_squeeze.cu]
 // degree-2 element kernels [fsb_assemble_p2.cu]; A == nullptr selects the matrix-free action y += (...) x
 int fsb_p2_scalar(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, fsb_vec* y, double kscale, const double* ktensor, double mass, double adv,
                   const double* vel);

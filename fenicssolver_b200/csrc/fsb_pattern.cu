@@ -261,6 +261,7 @@ extern "C" void fsb_mat_destroy(fsb_mat* A) {
   fsb_dfree(A->ctx, A->bc_vals);
   for (double* w : A->work) fsb_dfree(A->ctx, w);
   fsb_dist_release_mat(A);
+  if (A->sq) fsb_mat_destroy(A->sq);
   delete A;
 }
 

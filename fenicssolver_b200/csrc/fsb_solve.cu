@@ -285,11 +285,19 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   memset(info, 0, sizeof(*info));
   const int64_t n0 = A->own0 * A->bs, n1 = A->own1 * A->bs;
   const bool dist = fsb_dist_active(ctx);
+  cudaEvent_t e0, e1;
+  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e0));
+  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{e0, e1};
+  FSB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  int rc;
+  fsb_mat* S = A;             // the SpMV operand: A itself, or its copy without the exactly-zero blocks
+  if (ctx->drop_zeros && (rc = fsb_mat_squeeze(A, &S))) return rc;
+  info->operand_nnzb = S->nnzb;
   // peer-memory path: mailboxes mapped on every rank, staged SpMV kernel; the decision is the same on every rank
-  const bool p2p = dist && fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(A);
+  const bool p2p = dist && fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(S);
   Workspace ws{A};
   double *r, *p, *q, *dinv;
-  int rc;
   if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&q, n)) || (rc = ws.alloc(&dinv, n))) return rc;
   CgPeer cp;
   memset(&cp, 0, sizeof(cp));
@@ -307,12 +315,7 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   double* scal = ctx->d_scalars;
   int* state = ctx->d_state;
   const unsigned vg = vec_grid(ctx, n1 - n0);
-  cudaEvent_t e0, e1;
-  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e0));
-  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e1));
-  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{e0, e1};
   SpmvTimer timer;
-  FSB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
 
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(state, 0, sizeof(int) * 8, ctx->stream));
   // last-CTA counters: a kernel that observes `done` half-way may leave one partially counted
@@ -323,7 +326,7 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   FSB_LAUNCH_CHECK(ctx);
   // r0 = b - A x0
   if (dist && (rc = fsb_dist_halo_raw(ctx, x->d, n))) return rc;
-  if ((rc = fsb_launch_spmv(A, x->d, q, nullptr, 0, nullptr, nullptr))) return rc;
+  if ((rc = fsb_launch_spmv(S, x->d, q, nullptr, 0, nullptr, nullptr))) return rc;
   k_cg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, q, dinv, r, p, ctx->d_partials, scal + S_RZ0, ctx->d_counters + 1);
   FSB_LAUNCH_CHECK(ctx);
   if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RZ0, 3))) return rc;
@@ -357,8 +360,8 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
         if (ctx->profile) cudaEventRecord(timer.next(slot), ctx->stream);
         if (p2p) {
           fsb_spmv_dist dd{cp.pc, it > 0 ? cp.seq : 0ull, MAIL_PQ + par, cp.seq + 1};
-          if ((rc = fsb_launch_spmv(A, p, q, p, 0, nullptr, state, &dd))) return rc;
-        } else if ((rc = fsb_launch_spmv(A, p, q, p, 0, scal + pq, state))) {
+          if ((rc = fsb_launch_spmv(S, p, q, p, 0, nullptr, state, &dd))) return rc;
+        } else if ((rc = fsb_launch_spmv(S, p, q, p, 0, scal + pq, state))) {
           return rc;
         }
         if (ctx->profile) cudaEventRecord(timer.next(slot), ctx->stream);
@@ -516,20 +519,23 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   memset(info, 0, sizeof(*info));
   const int64_t n0 = A->own0 * A->bs, n1 = A->own1 * A->bs;
   const bool dist = fsb_dist_active(ctx);
+  cudaEvent_t e0, e1;
+  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e0));
+  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{e0, e1};
+  FSB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  int rc;
+  fsb_mat* S = A;
+  if (ctx->drop_zeros && (rc = fsb_mat_squeeze(A, &S))) return rc;
+  info->operand_nnzb = S->nnzb;
   Workspace ws{A};
   double *r, *rhat, *p, *ph, *v, *sh, *t, *dinv;
-  int rc;
   if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&rhat, n)) || (rc = ws.alloc(&p, n)) || (rc = ws.alloc(&ph, n)) ||
       (rc = ws.alloc(&v, n)) || (rc = ws.alloc(&sh, n)) || (rc = ws.alloc(&t, n)) || (rc = ws.alloc(&dinv, n)))
     return rc;
   double* scal = ctx->d_scalars;
   int* state = ctx->d_state;
   const unsigned vg = vec_grid(ctx, n1 - n0);
-  cudaEvent_t e0, e1;
-  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e0));
-  FSB_CHECK_CUDA(ctx, cudaEventCreate(&e1));
-  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } guard{e0, e1};
-  FSB_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(state, 0, sizeof(int) * 8, ctx->stream));
   // last-CTA counters: a kernel that observes `done` half-way may leave one partially counted
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 16, ctx->stream));
@@ -538,7 +544,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
 #undef DINV_LAUNCH
   FSB_LAUNCH_CHECK(ctx);
   if (dist && (rc = fsb_dist_halo_raw(ctx, x->d, n))) return rc;
-  if ((rc = fsb_launch_spmv(A, x->d, v, nullptr, 0, nullptr, nullptr))) return rc;
+  if ((rc = fsb_launch_spmv(S, x->d, v, nullptr, 0, nullptr, nullptr))) return rc;
   k_bcg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, v, dinv, r, rhat, p, ph, ctx->d_partials, scal + S_RHO0, ctx->d_counters + 1);
   FSB_LAUNCH_CHECK(ctx);
   if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RHO0, 3))) return rc;
@@ -555,12 +561,12 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
       const int par = (launched + k) & 1;
       const int rho = par ? S_RHO1 : S_RHO0, rhon = par ? S_RHO0 : S_RHO1, rrn = par ? S_RRB0 : S_RRB1;
       if (dist && (rc = fsb_dist_halo_raw(ctx, ph, n))) return rc;
-      if ((rc = fsb_launch_spmv(A, ph, v, rhat, 0, scal + S_RV, state))) return rc;
+      if ((rc = fsb_launch_spmv(S, ph, v, rhat, 0, scal + S_RV, state))) return rc;
       if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RV, 1))) return rc;
       k_bcg_s<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, v, rhat, dinv, r, sh, ctx->d_partials, scal + S_RS, ctx->d_counters + 5, state);
       FSB_LAUNCH_CHECK(ctx);
       if (dist && (rc = fsb_dist_halo_raw(ctx, sh, n))) return rc;
-      if ((rc = fsb_launch_spmv(A, sh, t, r, 1, scal + S_TS, state, nullptr, rhat))) return rc;
+      if ((rc = fsb_launch_spmv(S, sh, t, r, 1, scal + S_TS, state, nullptr, rhat))) return rc;
       if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_TS, 4))) return rc;        // t.s, t.t, rhat.t, rhat.s
       k_bcg_xp<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, rhon, rrn, sh, t, v, dinv, x->d, r, p, ph, ctx->d_partials,
                                                     ctx->d_counters + 2, rtol, atol, maxit, state, dist ? 0 : 1);

@@ -53,6 +53,7 @@ typedef struct {
   double bnorm;          /* ||M^-1 b||_2 */
   double solve_ms;       /* device time of the iteration loop (CUDA events on the ctx stream) */
   double spmv_ms;        /* accumulated device time of the SpMV launches when profiling is on, else 0 */
+  int64_t operand_nnzb;  /* blocks in the matrix the SpMVs ran on (< the assembled count with "drop_zeros") */
 } fsb_solve_info;
 
 /* ---- context --------------------------------------------------------------------------------- */
@@ -65,7 +66,8 @@ int fsb_sync(fsb_ctx* ctx);
 int fsb_device_info(fsb_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes);
 /* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 position-map+atomics),
  * "spmv_mode" (0 TMA-staged tiles, 1 plain row-per-thread), "profile" (0/1), "graph" (0/1),
- * "check_every" (iterations between host convergence polls). */
+ * "check_every" (iterations between host convergence polls), "drop_zeros" (0/1: the Krylov SpMVs run on a
+ * compacted copy without the blocks that are exactly zero after assembly; the assembled CSR is untouched). */
 int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value);
 int64_t fsb_launch_count(fsb_ctx* ctx);   /* kernels launched by this library on ctx so far */
 
