@@ -82,6 +82,7 @@ struct fsb_mat {
   int64_t* tile_row = nullptr; // [2*(ntiles+1)]: first block row of each tile, then row_ptr at that row
   int tile_cap = 0;            // smem capacity in blocks per stage
   int tile_rows = 0;           // scalar rows per tile this tiling was built for
+  double avg_row = 0.0;        // blocks per owned block row (picks the SpMV configuration)
   size_t stage_bytes = 0;      // shared memory per pipeline stage (values + columns + row_ptr slice)
   // dirichlet scratch
   uint8_t* bc_flag = nullptr;  // [nbrows*bs]

@@ -318,13 +318,17 @@ __global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, i
 // block size on B200 (profiles/spmv_sweep_r1.txt): CSR 256 rows x 2 lanes x 2 stages (two CTAs per SM beat
 // a deeper pipeline with one); 3x3 blocks 192 rows x 2 lanes x 3 stages (one CTA per SM either way, so
 // the third stage is free and keeps two 73 KB tiles in flight).
-static int spmv_rows(fsb_ctx* ctx, int bs) {
-  const int big = bs == 3 ? 192 : 256;
+// Short rows (<= ~8 entries: a squeezed P1 operand, 2-D P1 matrices) are bound by per-row cost, not bytes,
+// with 2 lanes x 8 slots per row: they get one lane per row (tools/spmv_short_rows.py on the squeezed C2
+// operand: 256 rows x 1 lane x 2 stages 6 265 GB/s, x 2 lanes 3 062 GB/s; deeper pipelines lose the second CTA).
+static bool spmv_short_rows(const fsb_mat* A) { return A->bs == 1 && A->avg_row > 0.0 && A->avg_row <= 8.5; }
+static int spmv_rows(fsb_ctx* ctx, const fsb_mat* A) {
+  const int big = A->bs == 3 ? 192 : 256;
   const int opt = ctx->spmv_rows ? ctx->spmv_rows : 256;
-  return opt == 128 ? big / 2 : big;
+  return opt == 128 ? big / 2 : (opt == 512 && A->bs == 1 ? 512 : big);
 }
-static int spmv_lpr(fsb_ctx* ctx, int bs) { return ctx->spmv_lpr ? ctx->spmv_lpr : 2; }
-static int spmv_stages(fsb_ctx* ctx, int bs) { return ctx->spmv_stages ? ctx->spmv_stages : (bs == 3 ? 3 : 2); }
+static int spmv_lpr(fsb_ctx* ctx, const fsb_mat* A) { return ctx->spmv_lpr ? ctx->spmv_lpr : (spmv_short_rows(A) ? 1 : 2); }
+static int spmv_stages(fsb_ctx* ctx, const fsb_mat* A) { return ctx->spmv_stages ? ctx->spmv_stages : (A->bs == 3 ? 3 : 2); }
 static constexpr size_t kSmemBudget = 200 * 1024;
 
 int fsb_mat_setup_tiles(fsb_mat* A) {
@@ -332,7 +336,8 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
   fsb_dfree(A->ctx, A->tile_row);
   A->tile_row = nullptr;
   A->ntiles = 0; A->tile_nnz = 0; A->tile_cap = 0; A->stage_bytes = 0;
-  A->tile_rows = spmv_rows(ctx, A->bs);
+  A->avg_row = 0.0;
+  A->tile_rows = spmv_rows(ctx, A);
   const int64_t nrows = A->own1 - A->own0;
   if (nrows <= 0) return FSB_OK;
   int64_t k01[2];
@@ -342,8 +347,10 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
   const int64_t nnz = k01[1] - k01[0];
   if (nnz <= 0) return FSB_OK;
   const int bs = A->bs;
-  const int rows_target = A->tile_rows / bs;
   const double avg = (double)nnz / (double)nrows;
+  A->avg_row = avg;
+  A->tile_rows = spmv_rows(ctx, A);
+  const int rows_target = A->tile_rows / bs;
   int64_t T = (int64_t)std::ceil(avg * rows_target);
   T = (T + 15) & ~15ll;
   int64_t cap = T + A->max_row_len + 8;
@@ -369,7 +376,7 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
                     const fsb_spmv_dist* dd, const double* w2) {
   fsb_ctx* ctx = A->ctx;
   if (A->own1 <= A->own0) return FSB_OK;
-  if (ctx->spmv_mode != 1 && A->tile_rows != spmv_rows(ctx, A->bs)) {
+  if (ctx->spmv_mode != 1 && A->tile_rows != spmv_rows(ctx, A)) {
     int rc = fsb_mat_setup_tiles(A);      // the tile size option changed since the matrix was set up
     if (rc) return rc;
   }
@@ -387,9 +394,9 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
   }
   const bool tiled = ctx->spmv_mode != 1 && A->ntiles > 0;
   if (tiled && ctx->spmv_mode == 0) {
-    const int lpr = spmv_lpr(ctx, A->bs);
+    const int lpr = spmv_lpr(ctx, A);
     const int rows = A->tile_rows;
-    const int nst = std::max(2, std::min(spmv_stages(ctx, A->bs), (int)((224 * 1024) / A->stage_bytes)));
+    const int nst = std::max(2, std::min(spmv_stages(ctx, A), (int)((224 * 1024) / A->stage_bytes)));
     const size_t smem = (size_t)nst * A->stage_bytes;
     bool launched = false;
 #define FSB_SPMV_CASE(BS, ROWS, LPR, NST)                                                                              \
@@ -406,7 +413,7 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
     launched = true;                                                                                                   \
   }
 #define FSB_SPMV_NST(BS, ROWS, LPR) FSB_SPMV_CASE(BS, ROWS, LPR, 2) FSB_SPMV_CASE(BS, ROWS, LPR, 3) FSB_SPMV_CASE(BS, ROWS, LPR, 4)
-    FSB_SPMV_NST(1, 256, 1) FSB_SPMV_NST(1, 256, 2) FSB_SPMV_NST(1, 128, 1) FSB_SPMV_NST(1, 128, 2) FSB_SPMV_NST(1, 128, 4)
+    FSB_SPMV_NST(1, 512, 1) FSB_SPMV_NST(1, 256, 1) FSB_SPMV_NST(1, 256, 2) FSB_SPMV_NST(1, 128, 1) FSB_SPMV_NST(1, 128, 2) FSB_SPMV_NST(1, 128, 4)
     FSB_SPMV_NST(2, 256, 2) FSB_SPMV_NST(2, 128, 2)
     FSB_SPMV_NST(3, 192, 2) FSB_SPMV_NST(3, 192, 4) FSB_SPMV_NST(3, 96, 2) FSB_SPMV_NST(3, 96, 4) FSB_SPMV_NST(3, 96, 8)
 #undef FSB_SPMV_NST
