@@ -154,7 +154,7 @@ k_scalar_form(int64_t ncells, const int32_t* __restrict__ cells, const double* _
 #pragma unroll
       for (int a = 0; a < NL; ++a)
 #pragma unroll
-        for (int b = 0; b < NL; ++b) atomicAdd(vals + base[a] + pos[a][b], Ke[a][b]);
+        for (int b = 0; b < NL; ++b) add_nz(vals + base[a] + pos[a][b], Ke[a][b]);
     }
   }
 }
@@ -187,7 +187,7 @@ k_elasticity(int64_t ncells, const int32_t* __restrict__ cells, const double* __
         for (int i = 0; i < D; ++i)
 #pragma unroll
           for (int j = 0; j < D; ++j)
-            atomicAdd(blk + i * D + j, wmu * ((i == j ? gg : 0.0) + g.G[a][j] * g.G[b][i]) + wl * g.G[a][i] * g.G[b][j]);
+            add_nz(blk + i * D + j, wmu * ((i == j ? gg : 0.0) + g.G[a][j] * g.G[b][i]) + wl * g.G[a][i] * g.G[b][j]);
       }
   }
 }

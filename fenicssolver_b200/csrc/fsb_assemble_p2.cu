@@ -243,7 +243,7 @@ k_p2_scalar(int64_t ncells, const int32_t* __restrict__ cell_nodes, const double
 #pragma unroll
         for (int e = 0; e < NL; ++e) s += __ldg(tS + (i * NN + j) * NL + e) * vgl[e];
         if (ACTION) yi += s * xl[j];
-        else atomicAdd(vals + base + entry_pos(posmap, c, NN, i, j, col_idx + base, len, nd[j]), s);
+        else add_nz(vals + base + entry_pos(posmap, c, NN, i, j, col_idx + base, len, nd[j]), s);
       }
       if (ACTION) atomicAdd(y + nd[i], yi);
     }
@@ -294,7 +294,7 @@ k_p2_elasticity(int64_t ncells, const int32_t* __restrict__ cell_nodes, const do
         for (int a = 0; a < D; ++a)
 #pragma unroll
           for (int b = 0; b < D; ++b)
-            atomicAdd(blk + a * D + b, g.vol * (mu * ((a == b ? tr : 0.0) + W[b][a]) + lambda * W[a][b]));
+            add_nz(blk + a * D + b, g.vol * (mu * ((a == b ? tr : 0.0) + W[b][a]) + lambda * W[a][b]));
       }
     }
   }
