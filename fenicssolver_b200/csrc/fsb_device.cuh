@@ -169,24 +169,52 @@ __device__ __forceinline__ void finish_partials_mail(const double (&mine)[NV], d
   if (threadIdx.x == 0) *counter = 0;
 }
 
-// wait for all ranks' entries of `slot` (sequence >= seq) and add them in rank order; every thread gets v[]
+// wait for all ranks' entries of `slot` (sequence >= seq) and add them in rank order; every thread gets v[].
+// One lane per rank polls (the waits overlap instead of queueing behind each other).
 template <int NV>
-__device__ __forceinline__ void mail_sum(const PeerComm& pc, int slot, unsigned long long seq, double (&v)[NV], double* sm4) {
-  if (threadIdx.x == 0) {
-    double acc[NV];
+__device__ __forceinline__ void mail_sum(const PeerComm& pc, int slot, unsigned long long seq, double (&v)[NV], double* /*unused*/) {
+  __shared__ double s_mail[kMaxRanks][3];
+  if ((int)threadIdx.x < pc.nranks) {
+    const MailEntry* e = &pc.buf[pc.rank]->mail[slot][threadIdx.x];
+    while (ld_acquire_sys(&e->seq) < seq) { }
 #pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    for (int r = 0; r < pc.nranks; ++r) {
-      const MailEntry* e = &pc.buf[pc.rank]->mail[slot][r];
-      while (ld_acquire_sys(&e->seq) < seq) { }
-#pragma unroll
-      for (int k = 0; k < NV; ++k) acc[k] += *reinterpret_cast<const volatile double*>(&e->v[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < NV; ++k) sm4[k] = acc[k];
+    for (int k = 0; k < NV; ++k) s_mail[threadIdx.x][k] = *reinterpret_cast<const volatile double*>(&e->v[k]);
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) v[k] = sm4[k];
+  for (int k = 0; k < NV; ++k) {
+    double acc = 0.0;
+    for (int r = 0; r < pc.nranks; ++r) acc += s_mail[r][k];
+    v[k] = acc;
+  }
+  __syncthreads();
+}
+
+// two slots at once (lanes [0, kMaxRanks) poll slot A, lanes [kMaxRanks, 2 kMaxRanks) slot B)
+template <int NA, int NB>
+__device__ __forceinline__ void mail_sum_pair(const PeerComm& pc, int slot_a, unsigned long long seq_a, double (&a)[NA], int slot_b,
+                                              unsigned long long seq_b, double (&b)[NB]) {
+  __shared__ double s_pair[2][kMaxRanks][3];
+  const int which = threadIdx.x / kMaxRanks, r = threadIdx.x % kMaxRanks;
+  if (which < 2 && r < pc.nranks) {
+    const MailEntry* e = &pc.buf[pc.rank]->mail[which ? slot_b : slot_a][r];
+    const unsigned long long seq = which ? seq_b : seq_a;
+    while (ld_acquire_sys(&e->seq) < seq) { }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s_pair[which][r][k] = *reinterpret_cast<const volatile double*>(&e->v[k]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NA; ++k) {
+    double acc = 0.0;
+    for (int q = 0; q < pc.nranks; ++q) acc += s_pair[0][q][k];
+    a[k] = acc;
+  }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    double acc = 0.0;
+    for (int q = 0; q < pc.nranks; ++q) acc += s_pair[1][q][k];
+    b[k] = acc;
+  }
   __syncthreads();
 }

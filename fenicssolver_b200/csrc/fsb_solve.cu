@@ -276,6 +276,219 @@ static int read_outcome(fsb_ctx* ctx, int rr_slot_final, int bb_slot, fsb_solve_
   return FSB_OK;
 }
 
+// ------------------------------------------------------------------------------------ single-reduction CG
+// Chronopoulos-Gear form of Jacobi-PCG: with u = M^-1 r and w = A u,
+//   beta = g/g_prev ; alpha = g / (d - beta g / alpha_prev)            g = r.u, d = w.u
+//   p = u + beta p ; s = w + beta s (= A p) ; x += alpha p ; r -= alpha s ; u = M^-1 r
+// Both inner products of an iteration are available after ONE SpMV, so an iteration is two kernels (update,
+// SpMV) with one global synchronisation point instead of three kernels with two.  On one GPU that trades 8 more
+// bytes per row for one kernel boundary (a wash), so it is the distributed default: each rank waits for its peers
+// once per iteration, and the reduction of (r.u, u.u) posted by the update kernel travels while the SpMV runs.
+// Same iterates as classic PCG in exact arithmetic; convergence is tested on the same norm ||M^-1 r||.
+enum { C1_G0 = 20, C1_Z0 = 21, C1_D0 = 22, C1_G1 = 24, C1_Z1 = 25, C1_D1 = 26, C1_A0 = 28, C1_A1 = 29 };
+
+// start values -> parity-0 slots (and, peer path, the local mailboxes as rank 0's contribution)
+__global__ void k_cg1_seed(double* __restrict__ scal, PeerComm pc, unsigned long long seq) {
+  if (threadIdx.x == 0) { scal[C1_G0] = scal[S_RZ0]; scal[C1_Z0] = scal[S_RR0]; }
+  if (pc.nranks > 1 && (int)threadIdx.x < pc.nranks) {
+    MailEntry* e = &pc.buf[pc.rank]->mail[MAIL_RZ][threadIdx.x];
+    e->v[0] = threadIdx.x == 0 ? scal[S_RZ0] : 0.0;
+    e->v[1] = threadIdx.x == 0 ? scal[S_RR0] : 0.0;
+    e->v[2] = 0.0;
+    MailEntry* f = &pc.buf[pc.rank]->mail[MAIL_PQ][threadIdx.x];
+    f->v[0] = threadIdx.x == 0 ? scal[C1_D0] : 0.0;
+    f->v[1] = 0.0; f->v[2] = 0.0;
+    __threadfence();
+    e->seq = seq;
+    f->seq = seq;
+  }
+}
+
+// iteration `it` (parity par): test convergence of the current iterate, then the five vector updates in one pass;
+// sums r.u, u.u of the new residual -> slots of parity par^1 (or the mailboxes); peer path: the boundary planes
+// of the new u go straight into the neighbours' ghost planes and the last CTA raises their halo flags
+__global__ void __launch_bounds__(kVecThreads)
+k_cg1_update(int64_t n0, int64_t n1, double* __restrict__ scal, int par, int it, int maxit, double rtol, double atol,
+             const double* __restrict__ dinv, double* __restrict__ u, const double* __restrict__ w, double* __restrict__ p,
+             double* __restrict__ s, double* __restrict__ x, double* __restrict__ r, double* partials, unsigned* counter,
+             unsigned* halo_counter, int* state, CgPeer cp) {
+  __shared__ double red[32];
+  if (state[0]) return;
+  const bool peer = cp.pc.nranks > 1;
+  const int G = par ? C1_G1 : C1_G0, Gp = par ? C1_G0 : C1_G1, Ap = par ? C1_A0 : C1_A1, Ac = par ? C1_A1 : C1_A0;
+  double g, zz, d;
+  if (peer) {
+    double a[2], b[1];
+    mail_sum_pair<2, 1>(cp.pc, MAIL_RZ + par, cp.seq, a, MAIL_PQ + par, cp.seq, b);
+    g = a[0]; zz = a[1]; d = b[0];
+  } else {
+    g = scal[G]; zz = scal[G + 1]; d = scal[G + 2];
+  }
+  const double bb = scal[S_BB];
+  const double tol2 = fmax(rtol * rtol * bb, atol * atol);
+  const double g_prev = it > 0 ? scal[Gp] : 1.0, a_prev = it > 0 ? scal[Ap] : 1.0;
+  const double beta = it > 0 ? g / g_prev : 0.0;
+  const double denom = it > 0 ? d - beta * g / a_prev : d;
+  const double alpha = g / denom;
+  const bool conv = zz <= tol2;
+  const bool broken = !(zz == zz) || !(alpha == alpha) || denom == 0.0 || (it > 0 && g_prev == 0.0);
+  if (conv || broken || it >= maxit) {          // the same decision in every CTA (and on every rank)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      state[1] = it;
+      state[2] = conv ? 1 : (broken ? -1 : 0);
+      scal[S_FINAL_RR] = zz;
+      __threadfence();
+      state[0] = 1;
+    }
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[Ac] = alpha;
+    if (peer) scal[G] = g;                      // next iteration's g_prev (single GPU / NCCL: already there)
+    state[1] = it + 1;
+    scal[S_FINAL_RR] = zz;
+  }
+  const int64_t plane = cp.pc.plane;
+  double s0 = 0, s1 = 0;
+  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
+    const double pi = u[i] + beta * p[i];
+    const double si = w[i] + beta * s[i];
+    p[i] = pi; s[i] = si;
+    x[i] += alpha * pi;
+    const double ri = r[i] - alpha * si;
+    r[i] = ri;
+    const double ui = dinv[i] * ri;
+    u[i] = ui;
+    s0 += ri * ui; s1 += ui * ui;
+    if (peer) {
+      if (cp.pc.lo_dst && i < n0 + plane) cp.pc.lo_dst[i - n0] = ui;
+      if (cp.pc.hi_dst && i >= n1 - plane) cp.pc.hi_dst[i - (n1 - plane)] = ui;
+    }
+  }
+  if (peer) {
+    __threadfence_system();           // this CTA's peer stores are visible system-wide before it counts itself done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(halo_counter, 1u);
+      if (t == gridDim.x - 1) {
+        *halo_counter = 0;
+        __threadfence_system();
+        if (cp.pc.rank > 0) st_release_sys(&cp.pc.buf[cp.pc.rank - 1]->halo_flag[1], cp.seq + 1);
+        if (cp.pc.rank < cp.pc.nranks - 1) st_release_sys(&cp.pc.buf[cp.pc.rank + 1]->halo_flag[0], cp.seq + 1);
+      }
+    }
+  }
+  double mine[2] = {block_sum(s0, red), block_sum(s1, red)};
+  if (peer) finish_partials_mail<2>(mine, partials, kMaxPartials, counter, red, cp.pc, MAIL_RZ + (par ^ 1), cp.seq + 1);
+  else finish_partials<2>(mine, partials, kMaxPartials, scal + (par ? C1_G0 : C1_G1), counter, red);
+}
+
+static int solve_cg1(fsb_mat* A, fsb_mat* S, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit, int32_t precond,
+                     fsb_solve_info* info, cudaEvent_t e0, cudaEvent_t e1) {
+  fsb_ctx* ctx = A->ctx;
+  const int64_t n = A->nbrows * A->bs;
+  const int64_t n0 = A->own0 * A->bs, n1 = A->own1 * A->bs;
+  const bool dist = fsb_dist_active(ctx);
+  const bool p2p = dist && fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(S);
+  Workspace ws{A};
+  double *r, *u, *w, *p, *s, *dinv;
+  int rc;
+  if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&w, n)) || (rc = ws.alloc(&dinv, n)) || (rc = ws.alloc(&p, n)) || (rc = ws.alloc(&s, n))) return rc;
+  CgPeer cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.pc.nranks = 1;
+  unsigned long long seq_base = 0;
+  if (p2p) {
+    if ((rc = fsb_dist_share_p(A, n))) return rc;          // collective; here the shared vector is u, the SpMV input
+    u = A->p_dist;
+    FSB_CHECK_CUDA(ctx, cudaMemsetAsync(u, 0, sizeof(double) * n, ctx->stream));
+    if ((rc = fsb_dist_peer_comm(A, &cp.pc))) return rc;
+    seq_base = fsb_dist_seq_reserve(ctx, 0);
+  } else if ((rc = ws.alloc(&u, n))) {
+    return rc;
+  }
+  double* scal = ctx->d_scalars;
+  int* state = ctx->d_state;
+  const unsigned vg = vec_grid(ctx, n1 - n0);
+  SpmvTimer timer;
+  FSB_CHECK_CUDA(ctx, cudaMemsetAsync(state, 0, sizeof(int) * 8, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 16, ctx->stream));
+#define DINV_LAUNCH(BS) k_extract_dinv<BS><<<fsb_grid(n1 - n0, 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(n0, n1, A->row_ptr, A->col_idx, A->vals, dinv, precond == 1)
+  if (A->bs == 1) DINV_LAUNCH(1); else if (A->bs == 2) DINV_LAUNCH(2); else DINV_LAUNCH(3);
+#undef DINV_LAUNCH
+  FSB_LAUNCH_CHECK(ctx);
+  // r0 = b - A x0 ; u0 = M^-1 r0 ; w0 = A u0
+  if (dist && (rc = fsb_dist_halo_raw(ctx, x->d, n))) return rc;
+  if ((rc = fsb_launch_spmv(S, x->d, w, nullptr, 0, nullptr, nullptr))) return rc;
+  k_cg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, w, dinv, r, u, ctx->d_partials, scal + S_RZ0, ctx->d_counters + 1);
+  FSB_LAUNCH_CHECK(ctx);
+  if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RZ0, 3))) return rc;
+  k_check0<<<1, 1, 0, ctx->stream>>>(scal, S_RR0, S_BB, rtol, atol, maxit, state, scal + S_FINAL_RR);
+  FSB_LAUNCH_CHECK(ctx);
+  if (dist && (rc = fsb_dist_halo_raw(ctx, u, n))) return rc;
+  if ((rc = fsb_launch_spmv(S, u, w, u, 0, scal + C1_D0, state))) return rc;
+  if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + C1_D0, 1))) return rc;
+  k_cg1_seed<<<1, 32, 0, ctx->stream>>>(scal, cp.pc, seq_base);
+  FSB_LAUNCH_CHECK(ctx);
+
+  int batch_first, batch_rest;
+  batch_plan(ctx, A->last_iters, &batch_first, &batch_rest);
+  cudaEvent_t polled[2];
+  FSB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&polled[0], cudaEventDisableTiming));
+  FSB_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&polled[1], cudaEventDisableTiming));
+  struct PollGuard { cudaEvent_t* e; ~PollGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } pguard{polled};
+  if (ctx->profile) timer.ensure(std::max(batch_first, batch_rest));
+  int launched = 0;
+  for (int nb = 0;; ++nb) {
+    const int slot = nb & 1;
+    const int batch = nb == 0 ? batch_first : batch_rest;
+    const bool more = launched <= maxit;          // iteration `maxit` is the launch that records the maxit outcome
+    if (more) {
+      for (int k = 0; k < batch; ++k) {
+        const int it = launched + k, par = it & 1;
+        cp.seq = seq_base + (unsigned long long)it;
+        k_cg1_update<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, par, it, maxit, rtol, atol, dinv, u, w, p, s, x->d, r, ctx->d_partials,
+                                                          ctx->d_counters + 2, ctx->d_counters + 4, state, cp);
+        FSB_LAUNCH_CHECK(ctx);
+        if (dist && !p2p && (rc = fsb_dist_halo_raw(ctx, u, n))) return rc;
+        if (ctx->profile) cudaEventRecord(timer.next(slot), ctx->stream);
+        if (p2p) {
+          fsb_spmv_dist dd{cp.pc, cp.seq + 1, MAIL_PQ + (par ^ 1), cp.seq + 1};
+          if ((rc = fsb_launch_spmv(S, u, w, u, 0, nullptr, state, &dd))) return rc;
+        } else if ((rc = fsb_launch_spmv(S, u, w, u, 0, scal + (par ? C1_D0 : C1_D1), state))) {
+          return rc;
+        }
+        if (ctx->profile) cudaEventRecord(timer.next(slot), ctx->stream);
+        // one all-reduce per iteration: (r.u, u.u, w.u) sit next to each other
+        if (dist && !p2p && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + (par ? C1_G0 : C1_G1), 3))) return rc;
+      }
+      launched += batch;
+    }
+    FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_state + 8 * slot, state, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FSB_CHECK_CUDA(ctx, cudaEventRecord(polled[slot], ctx->stream));
+    if (nb > 0) {
+      FSB_CHECK_CUDA(ctx, cudaEventSynchronize(polled[slot ^ 1]));
+      if (ctx->profile) timer.collect(slot ^ 1);
+      if (ctx->h_state[8 * (slot ^ 1)]) break;
+    }
+    if (!more) {
+      FSB_CHECK_CUDA(ctx, cudaEventSynchronize(polled[slot]));
+      break;
+    }
+  }
+  FSB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  rc = read_outcome(ctx, S_FINAL_RR, S_BB, info);
+  if (rc) return rc;
+  A->last_iters = info->iterations;
+  if (p2p) fsb_dist_seq_reserve(ctx, (unsigned long long)info->iterations + 2);   // identical on every rank
+  if (ctx->profile) { timer.collect(0); timer.collect(1); info->spmv_ms = timer.total_ms; }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  info->solve_ms = ms;
+  if (info->converged < 0) FSB_FAIL(ctx, FSB_ERR_BREAKDOWN, "CG breakdown (non-finite or zero recurrence scalar)");
+  return FSB_OK;
+}
+
 extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit, int32_t precond,
                             fsb_solve_info* info) {
   if (!A || !b || !x || !info) return FSB_ERR_ARG;
@@ -294,6 +507,8 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   fsb_mat* S = A;             // the SpMV operand: A itself, or its copy without the exactly-zero blocks
   if (ctx->drop_zeros && (rc = fsb_mat_squeeze(A, &S))) return rc;
   info->operand_nnzb = S->nnzb;
+  // cg_variant: 0 = classic on one GPU, single-reduction when distributed; 1 = classic; 2 = single-reduction
+  if (ctx->cg_variant == 2 || (ctx->cg_variant == 0 && dist)) return solve_cg1(A, S, b, x, rtol, atol, maxit, precond, info, e0, e1);
   // peer-memory path: mailboxes mapped on every rank, staged SpMV kernel; the decision is the same on every rank
   const bool p2p = dist && fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(S);
   Workspace ws{A};

@@ -578,3 +578,53 @@ def test_drop_zeros_block_matrix(ctx):
         sols.append((x.numpy(), info))
     assert sols[1][1]["operand_nnzb"] <= sols[0][1]["operand_nnzb"]
     assert fo.relative_l2(sols[1][0], sols[0][0]) < 1e-9
+
+
+@pytest.mark.parametrize("drop_zeros", [0, 1])
+def test_single_reduction_cg_matches_classic(ctx, drop_zeros):
+    """cg_variant 2 (Chronopoulos-Gear recurrences, two kernels and one synchronisation point per iteration; the
+    distributed default) against the classic three-kernel chain: same solution, iteration count within rounding,
+    maxit honoured, zero right-hand side / converged start handled."""
+    N = 14
+    c, t, z0, z1 = heat_problem(N, jit=True)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    dofs = np.concatenate([z0, z1])
+    vals = np.concatenate([np.full(z0.size, 350.0), np.full(z1.size, 300.0)])
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=20.0)
+    b = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_source(m, b, 1000.0)
+    x = _lib.DeviceVector(ctx, nv)
+    A.apply_dirichlet(b, dofs, vals, symmetric=True, x=x)
+    x0 = x.numpy()
+    res = {}
+    ctx.set_option("drop_zeros", drop_zeros)
+    try:
+        for variant in (1, 2):
+            ctx.set_option("cg_variant", variant)
+            xv = _lib.DeviceVector.from_numpy(ctx, x0)
+            info = A.solve(b, xv, "cg", rtol=1e-12)
+            assert info["converged"] == 1 and info["rnorm"] <= 1e-12 * info["bnorm"]
+            res[variant] = (xv.numpy(), info["iterations"])
+        assert fo.relative_l2(res[2][0], res[1][0]) < 1e-11
+        assert abs(res[2][1] - res[1][1]) <= 2
+        # maxit: exactly that many updates, outcome 0
+        ctx.set_option("cg_variant", 2)
+        for maxit in (5, 32, 64):
+            xv = _lib.DeviceVector.from_numpy(ctx, x0)
+            info = A.solve(b, xv, "cg", rtol=1e-30, maxit=maxit)
+            assert info["converged"] == 0 and info["iterations"] == maxit
+            ctx.set_option("cg_variant", 1)
+            xc = _lib.DeviceVector.from_numpy(ctx, x0)
+            A.solve(b, xc, "cg", rtol=1e-30, maxit=maxit)
+            ctx.set_option("cg_variant", 2)
+            assert fo.relative_l2(xv.numpy(), xc.numpy()) < 1e-9
+        # start vector already converged: zero iterations, x untouched
+        xs = _lib.DeviceVector.from_numpy(ctx, res[1][0])
+        info = A.solve(b, xs, "cg", rtol=1e-9)
+        assert info["converged"] == 1 and info["iterations"] == 0
+        assert np.array_equal(xs.numpy(), res[1][0])
+    finally:
+        ctx.set_option("cg_variant", 0)
+        ctx.set_option("drop_zeros", 0)
