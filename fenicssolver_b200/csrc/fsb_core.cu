@@ -88,6 +88,7 @@ extern "C" int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value) {
   if (s == "asm_mode") ctx->asm_mode = (int)value;
   else if (s == "drop_zeros") ctx->drop_zeros = (int)value;
   else if (s == "cg_variant") ctx->cg_variant = (int)value;
+  else if (s == "spmv_hint") ctx->spmv_hint = (int)value;
   else if (s == "spmv_mode") ctx->spmv_mode = (int)value;
   else if (s == "dist_p2p") ctx->dist_p2p = (int)value;
   else if (s == "spmv_lpr") ctx->spmv_lpr = (int)value;

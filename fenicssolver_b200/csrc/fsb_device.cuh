@@ -34,6 +34,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// the same with an L2 eviction-priority hint: the matrix streams through once per SpMV and should not push the
+// gathered vector out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------ reductions
 // Combine per-CTA partials: the last CTA to arrive sums partials[k*stride + 0..nblocks) for k < NV in a
 // fixed order and stores the NV results to out[0..NV).  `counter` must be 0 on entry and is reset.

@@ -28,6 +28,7 @@ struct fsb_ctx {
   int profile = 0;
   int use_graph = 1;
   int check_every = 32;
+  int spmv_hint = 1;     // L2 evict-first on the matrix stream + streaming stores of y (0: plain)
   int cg_variant = 0;    // 0 auto (classic on one GPU, single-reduction when distributed), 1 classic, 2 single-reduction
   int drop_zeros = 0;    // Krylov SpMVs run on a copy without the exactly-zero blocks (fsb_squeeze.cu)
   // scratch for reductions: per-CTA partials + a few scalars, and a pinned host mirror

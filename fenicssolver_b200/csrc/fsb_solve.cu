@@ -350,20 +350,50 @@ k_cg1_update(int64_t n0, int64_t n1, double* __restrict__ scal, int par, int it,
   }
   const int64_t plane = cp.pc.plane;
   double s0 = 0, s1 = 0;
-  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
-    const double pi = u[i] + beta * p[i];
-    const double si = w[i] + beta * s[i];
-    p[i] = pi; s[i] = si;
-    x[i] += alpha * pi;
-    const double ri = r[i] - alpha * si;
-    r[i] = ri;
-    const double ui = dinv[i] * ri;
+  auto push = [&](int64_t i, double v) {       // owned boundary planes -> neighbours' ghost planes
+    if (cp.pc.lo_dst && i < n0 + plane) cp.pc.lo_dst[i - n0] = v;
+    if (cp.pc.hi_dst && i >= n1 - plane) cp.pc.hi_dst[i - (n1 - plane)] = v;
+  };
+  // p, s, x, r, w and dinv are touched once per iteration: streaming (evict-first) accesses, so that the new u,
+  // which the SpMV gathers next, is what stays in L2
+  auto one = [&](int64_t i) {
+    const double pi = u[i] + beta * __ldcs(p + i);
+    const double si = __ldcs(w + i) + beta * __ldcs(s + i);
+    __stcs(p + i, pi); __stcs(s + i, si);
+    __stcs(x + i, __ldcs(x + i) + alpha * pi);
+    const double ri = __ldcs(r + i) - alpha * si;
+    __stcs(r + i, ri);
+    const double ui = __ldcs(dinv + i) * ri;
     u[i] = ui;
     s0 += ri * ui; s1 += ui * ui;
-    if (peer) {
-      if (cp.pc.lo_dst && i < n0 + plane) cp.pc.lo_dst[i - n0] = ui;
-      if (cp.pc.hi_dst && i >= n1 - plane) cp.pc.hi_dst[i - (n1 - plane)] = ui;
-    }
+    if (peer) push(i, ui);
+  };
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const int64_t a_up = (n0 + 1) & ~(int64_t)1;
+  const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
+  if (tid == 0 && a0 > n0) one(n0);
+  if (tid == 1 && a0 + 2 * npair < n1) one(n1 - 1);
+  for (int64_t j = tid; j < npair; j += nth) {
+    const int64_t i = a0 + 2 * j;
+    const double2 uv = *reinterpret_cast<const double2*>(u + i);
+    const double2 wv = __ldcs(reinterpret_cast<const double2*>(w + i));
+    double2 pv = __ldcs(reinterpret_cast<const double2*>(p + i)), sv = __ldcs(reinterpret_cast<const double2*>(s + i));
+    double2 xv = __ldcs(reinterpret_cast<const double2*>(x + i)), rv = __ldcs(reinterpret_cast<const double2*>(r + i));
+    const double2 dv = __ldcs(reinterpret_cast<const double2*>(dinv + i));
+    pv.x = uv.x + beta * pv.x; pv.y = uv.y + beta * pv.y;
+    sv.x = wv.x + beta * sv.x; sv.y = wv.y + beta * sv.y;
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * sv.x; rv.y -= alpha * sv.y;
+    double2 un;
+    un.x = dv.x * rv.x; un.y = dv.y * rv.y;
+    __stcs(reinterpret_cast<double2*>(p + i), pv);
+    __stcs(reinterpret_cast<double2*>(s + i), sv);
+    __stcs(reinterpret_cast<double2*>(x + i), xv);
+    __stcs(reinterpret_cast<double2*>(r + i), rv);
+    *reinterpret_cast<double2*>(u + i) = un;
+    s0 += rv.x * un.x + rv.y * un.y;
+    s1 += un.x * un.x + un.y * un.y;
+    if (peer) { push(i, un.x); push(i + 1, un.y); }
   }
   if (peer) {
     __threadfence_system();           // this CTA's peer stores are visible system-wide before it counts itself done

@@ -32,6 +32,7 @@ struct SpmvArgs {
   const double* w;          // optional: d0 = sum y.w
   int want_yy;              // d1 = sum y.y
   const double* w2;         // optional: d2 = sum y.w2 (then out has 3 entries)
+  int l2_hint;              // 1: matrix stream marked evict-first in L2, y written with streaming stores
   double* partials;
   double* out;              // out[0]=d0, out[1]=d1
   unsigned* counter;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
   if (threadIdx.x >= CONSUMERS) {
     // ===== producer warp: lane 0 walks the tiles and issues the bulk copies (the warp stays converged) =====
+    const uint64_t policy = a.l2_hint ? l2_evict_first_policy() : 0ull;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const int s = it % NST;
@@ -179,9 +181,15 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
           const uint32_t nrp = stage_rp ? (uint32_t)(((r1 - ra0 + 1) + 1) & ~1ll) : 0u;
           s_info[s][2] = al0; s_info[s][3] = stage_rp ? ra0 : -1;
           mbar_expect_tx(&full[s], cnt * (VB + 4) + nrp * 8);
-          bulk_g2s((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &full[s]);
-          bulk_g2s((void*)cols_s(s), a.col_idx + al0, cnt * 4, &full[s]);
-          if (stage_rp) bulk_g2s((void*)rptr_s(s), a.row_ptr + ra0, nrp * 8, &full[s]);
+          if (a.l2_hint) {
+            bulk_g2s_hint((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &full[s], policy);
+            bulk_g2s_hint((void*)cols_s(s), a.col_idx + al0, cnt * 4, &full[s], policy);
+            if (stage_rp) bulk_g2s_hint((void*)rptr_s(s), a.row_ptr + ra0, nrp * 8, &full[s], policy);
+          } else {
+            bulk_g2s((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &full[s]);
+            bulk_g2s((void*)cols_s(s), a.col_idx + al0, cnt * 4, &full[s]);
+            if (stage_rp) bulk_g2s((void*)rptr_s(s), a.row_ptr + ra0, nrp * 8, &full[s]);
+          }
         }
       }
       __syncwarp();
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
 #pragma unroll
           for (int o = LPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
           if (live && sub == 0) {
-            a.y[row] = acc;
+            if (a.l2_hint) __stcs(a.y + row, acc); else a.y[row] = acc;
             d0 += acc * wv;
             if (a.want_yy) d1 += acc * acc;
             d2 += acc * wv2;
@@ -384,7 +392,7 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
   a.row_ptr = A->row_ptr; a.col_idx = A->col_idx; a.vals = A->vals;
   a.tile_row = A->tile_row; a.tile_k = A->tile_row ? A->tile_row + A->ntiles + 1 : nullptr;
   a.ntiles = A->ntiles; a.own0 = A->own0; a.own1 = A->own1; a.cap = A->tile_cap;
-  a.x = x; a.y = y; a.w = w; a.want_yy = want_yy; a.w2 = w2;
+  a.x = x; a.y = y; a.w = w; a.want_yy = want_yy; a.w2 = w2; a.l2_hint = ctx->spmv_hint;
   a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
   memset(&a.pc, 0, sizeof(a.pc));
   a.halo_seq = 0; a.mail_slot = -1; a.mail_seq = 0;
