@@ -31,6 +31,8 @@ extern "C" int fsb_init(int device, void* stream, fsb_ctx** out) {
     uint64_t keep = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_limit = total_b / 3;   // bound on blocks held for reuse
   bool ok = cudaMalloc((void**)&ctx->d_partials, sizeof(double) * kMaxPartials * 4) == cudaSuccess &&
             cudaMalloc((void**)&ctx->d_scalars, sizeof(double) * 64) == cudaSuccess &&
             cudaMalloc((void**)&ctx->d_counters, sizeof(unsigned) * 16) == cudaSuccess &&
@@ -49,6 +51,7 @@ extern "C" void fsb_destroy(fsb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   fsb_dist_destroy(ctx);
+  fsb_cache_flush(ctx);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_partials);
   cudaFree(ctx->d_scalars);
@@ -95,6 +98,7 @@ extern "C" int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value) {
   else if (s == "spmv_rows") ctx->spmv_rows = (int)value;
   else if (s == "spmv_stages") ctx->spmv_stages = (int)value;
   else if (s == "profile") ctx->profile = (int)value;
+  else if (s == "alloc_cache_mb") { ctx->cache_limit = (size_t)(value < 0 ? 0 : value) << 20; if (!value) fsb_cache_flush(ctx); }
   else if (s == "graph") ctx->use_graph = (int)value;
   else if (s == "check_every") ctx->check_every = value < 1 ? 1 : (int)value;
   else FSB_FAIL(ctx, FSB_ERR_ARG, "unknown option " + s);

@@ -4,7 +4,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <cstdlib>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "fsb.h"
@@ -41,6 +44,11 @@ struct fsb_ctx {
   void* h_stage[2] = {nullptr, nullptr};   // pinned staging chunks for large downloads into pageable memory
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
   fsb_dist* dist = nullptr;
+  // exact-size block cache in front of the stream-ordered pool (see fsb_dmalloc)
+  std::unordered_multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> live_blocks;
+  size_t cached_bytes = 0;
+  size_t cache_limit = (size_t)96 << 30;
 };
 
 static constexpr int kMaxPartials = 4096;
@@ -130,24 +138,70 @@ struct fsb_mat {
     FSB_CHECK_CUDA(ctx, cudaGetLastError());    \
   } while (0)
 
-template <typename T>
-static inline int fsb_dmalloc(fsb_ctx* ctx, T** p, size_t count, size_t pad_bytes = 512) {
+// Device buffers.  Every kernel of a context runs on ctx->stream, so a block released by the host can be handed
+// to the next request of the same size without waiting: work already queued on the old owner is ordered before
+// anything the new owner enqueues.  A solver rebuilt on the same mesh (every transient restart, every bench
+// step) asks for exactly the sizes the previous one released, so it is served from this cache and never reaches
+// the driver allocator (whose pool grows by mapping fresh physical memory: ~0.1 ms per 2 MB, measured as
+// 0.4-1.0 s per 256^3 solver construction).  Misses fall through to cudaMallocAsync.
+static inline void fsb_cache_flush(fsb_ctx* ctx) {
+  for (auto& kv : ctx->free_blocks) cudaFreeAsync(kv.second, ctx->stream);
+  ctx->free_blocks.clear();
+  ctx->cached_bytes = 0;
+}
+
+static inline int fsb_dmalloc_bytes(fsb_ctx* ctx, void** p, size_t bytes) {
+  auto hit = ctx->free_blocks.find(bytes);
+  if (hit != ctx->free_blocks.end()) {
+    *p = hit->second;
+    ctx->free_blocks.erase(hit);
+    ctx->cached_bytes -= bytes;
+    ctx->live_blocks[*p] = bytes;
+    return FSB_OK;
+  }
+  static const bool trace = getenv("FSB_ALLOC_TRACE") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   void* q = nullptr;
-  // stream-ordered pool allocation (the pool keeps freed blocks: repeated solver construction does not pay
-  // cudaMalloc/cudaFree device synchronisations); pad: TMA tiles may over-read a few entries
-  cudaError_t e = cudaMallocAsync(&q, count * sizeof(T) + pad_bytes, ctx->stream);
+  cudaError_t e = cudaMallocAsync(&q, bytes, ctx->stream);
+  if (e != cudaSuccess && !ctx->free_blocks.empty()) {     // give the cached blocks back and try once more
+    cudaGetLastError();
+    fsb_cache_flush(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaMallocAsync(&q, bytes, ctx->stream);
+  }
+  if (trace) {
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > 0.5) fprintf(stderr, "libfsb: cudaMallocAsync(%zu MB) took %.2f ms\n", bytes >> 20, ms);
+  }
   if (e != cudaSuccess) {
-    ctx->err = std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) + " bytes: " + cudaGetErrorString(e);
+    ctx->err = std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes: " + cudaGetErrorString(e);
     *p = nullptr;
     cudaGetLastError();
     return FSB_ERR_NOMEM;
   }
-  *p = (T*)q;
+  *p = q;
+  ctx->live_blocks[q] = bytes;
   return FSB_OK;
 }
 
+// pad: TMA tiles may over-read a few entries
+template <typename T>
+static inline int fsb_dmalloc(fsb_ctx* ctx, T** p, size_t count, size_t pad_bytes = 512) {
+  void* q = nullptr;
+  int rc = fsb_dmalloc_bytes(ctx, &q, count * sizeof(T) + pad_bytes);
+  *p = (T*)q;
+  return rc;
+}
+
 static inline void fsb_dfree(fsb_ctx* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto it = ctx->live_blocks.find(p);
+  if (it == ctx->live_blocks.end()) { cudaFreeAsync(p, ctx->stream); return; }
+  const size_t bytes = it->second;
+  ctx->live_blocks.erase(it);
+  if (ctx->cached_bytes + bytes > ctx->cache_limit) { cudaFreeAsync(p, ctx->stream); return; }
+  ctx->free_blocks.emplace(bytes, p);
+  ctx->cached_bytes += bytes;
 }
 
 static inline unsigned fsb_grid(int64_t n, int block, int64_t cap = (1ll << 31) - 1) {

@@ -67,7 +67,8 @@ int fsb_device_info(fsb_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_
 /* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 position-map+atomics),
  * "spmv_mode" (0 TMA-staged tiles, 1 plain row-per-thread), "profile" (0/1), "graph" (0/1),
  * "check_every" (iterations between host convergence polls), "drop_zeros" (0/1: the Krylov SpMVs run on a
- * compacted copy without the blocks that are exactly zero after assembly; the assembled CSR is untouched). */
+ * compacted copy without the blocks that are exactly zero after assembly; the assembled CSR is untouched),
+ * "alloc_cache_mb" (bound on released device blocks kept for exact-size reuse; 0 releases them and disables it). */
 int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value);
 int64_t fsb_launch_count(fsb_ctx* ctx);   /* kernels launched by this library on ctx so far */
 
