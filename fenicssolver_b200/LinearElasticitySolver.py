@@ -9,8 +9,9 @@ form :206-245, solve :247-253.
 The minus sign is the reference's: it appends the load integrals with `F += item`
 (:242-243) and then solves lhs(F) == rhs(F), so tractions and body forces act with the opposite sign
 to the scalar solver's convention.  This is reproduced by default (settings['reference_load_sign'] =
-True); set it False for the conventional sign.  Out of scope: thermal stress, dynamics, modal
-analysis, von Mises projection -> SolverError / not provided.
+True); set it False for the conventional sign.  Thermal stress enters with the conventional sign, as in the
+reference (`F -= inner(stress_t, grad(v))*dx`, :238).  von_Mises(u) is the L2 projection onto P1 (:71-76).
+Out of scope: elastodynamics, modal analysis -> SolverError.
 """
 from __future__ import annotations
 
@@ -29,6 +30,7 @@ class ElasticityForm:
         self.tractions = []      # (marker id, constant vector)
         self.pressures = []      # (marker id, scalar along the outward normal)
         self.body_forces = []    # constant vector | nodal array
+        self.thermal = None      # (beta, T: number | nodal array, T_ref)
         self.load_sign = -1.0
 
     def assemble(self, space):
@@ -49,6 +51,15 @@ class ElasticityForm:
                 _lib.assemble_source(space.dmesh, b, f, ncomp=dim, scale=self.load_sign)
             else:
                 _lib.assemble_source_nodal(space.dmesh, b, space.vector_from_global(np.asarray(f).reshape(-1)), ncomp=dim, scale=self.load_sign)
+        if self.thermal is not None:
+            beta, T, T_ref = self.thermal
+            if isinstance(T, np.ndarray):
+                if space.comm.nranks > 1:
+                    raise SolverError('a nodal temperature distribution is not implemented for distributed runs')
+                Td = _lib.DeviceVector.from_numpy(space.ctx, T)
+                _lib.assemble_thermal_load(space.dmesh, b, beta, T=Td, T_ref=T_ref)
+            else:
+                _lib.assemble_thermal_load(space.dmesh, b, beta, T_const=float(T), T_ref=T_ref)
         return b, True
 
 
@@ -68,6 +79,50 @@ class LinearElasticitySolver(SolverBase):
 
     def get_flux(self, u, mag_vector):
         return mag_vector
+
+    def thermal_stress(self, T):
+        """Isotropic thermal stress magnitude E/(1-2nu) * tec * (T - T_ref) (times the identity), :78-85.
+        T: number or nodal array."""
+        elasticity = self.material['elastic_modulus']
+        nu = self.material['poisson_ratio']
+        tec = self.material['thermal_expansion_coefficient']
+        return elasticity / (1.0 - 2.0 * nu) * tec * (T - self.reference_values['temperature'])
+
+    def von_Mises(self, u):
+        """project(sqrt(3/2 s:s), FunctionSpace(mesh, 'P', 1)), s the deviatoric stress of u (:71-76): the load
+        int vm phi_a and the P1 mass matrix are assembled on the device and solved by Jacobi-CG."""
+        from .backend import DeviceSpace
+        from .dolfin_compat import Function, FunctionSpace
+        space = self.device_space()
+        if space.comm.nranks > 1:
+            raise SolverError('von_Mises projection is not implemented for distributed runs')
+        mu, lmbda = self.lame_parameters()
+        V1 = FunctionSpace(self.mesh, 'P', 1)
+        proj = getattr(self, '_vm_space', None)
+        if proj is None:
+            # the scalar P1 pattern: on the displacement's own device mesh when that is degree 1
+            if space.degree == 1:
+                proj = (space.dmesh, _lib.DeviceMatrix.create(space.dmesh, 1), None)
+            else:
+                s1 = DeviceSpace(self.mesh, 1, ctx=space.ctx)
+                proj = (s1.dmesh, s1.A, s1)
+            self._vm_space = proj
+        dmesh1, M, _keep = proj
+        ud = u.device_vector() if isinstance(u, Function) else None
+        if ud is None or ud.n != space.ndof_local:
+            ud = space.vector_from_global(u.array() if isinstance(u, Function) else np.asarray(u).reshape(-1))
+        nv = self.mesh.num_vertices()
+        b = _lib.DeviceVector(space.ctx, nv)
+        _lib.assemble_von_mises_load(space.dmesh, ud, mu, lmbda, b)
+        M.zero()
+        M.assemble_scalar(kscale=0.0, mass=1.0)
+        x = _lib.DeviceVector(space.ctx, nv)
+        info = M.solve(b, x, method='cg', rtol=1e-12, maxit=100000)
+        if info['converged'] != 1:
+            self.logger.warning('von Mises projection did not converge: %s', info)
+        out = Function(V1)
+        out.set_device(x)
+        return out
 
     def _vector_constant(self, value, what):
         v = self.translate_value(value)
@@ -144,8 +199,20 @@ class LinearElasticitySolver(SolverBase):
         if self.body_source is not None:
             f = self.translate_value(self.body_source)
             F.body_forces.append(f)
-        if self.settings.get('temperature_distribution') or getattr(self, 'temperature_distribution', None):
-            raise SolverError('thermal stress is not implemented on the device path')
+        # thermal stress (:230-238): settings['temperature_distribution'] or an attribute set by a coupler
+        if not hasattr(self, 'temperature_distribution'):
+            td = self.settings.get('temperature_distribution')
+            if td is not None and not (isinstance(td, (int, float)) and not td):
+                self.temperature_distribution = td
+        td = getattr(self, 'temperature_distribution', None)
+        if td is not None:
+            T = self.translate_value(td, self.function_space)
+            if isinstance(T, np.ndarray):
+                T = np.asarray(T, dtype=np.float64).reshape(-1)
+                if T.size != self.function_space.num_nodes():
+                    raise SolverError('temperature_distribution must be a number or one value per node of the space')
+            beta = self.thermal_stress(1.0 + self.reference_values['temperature'])      # E/(1-2nu)*tec
+            F.thermal = (beta, T, float(self.reference_values['temperature']))
         return F, bcs
 
     def solve_form(self, F, u_, bcs):

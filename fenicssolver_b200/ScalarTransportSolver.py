@@ -10,8 +10,10 @@ replaced by a ScalarForm record that libfsb assembles:
   transient  A = (c/dt) M + theta K(k) + c C(v) + sum h M_F        theta = 0.5 (Crank-Nicolson)
              b = (c/dt) M T_prev - (1-theta) K(k) T_prev + loads
 (convection and the boundary/source loads are fully implicit, exactly as the reference writes them,
-:297-311).  Out of scope on the device path: radiation, nonlinear material, SUPG/IP stabilisation,
-point sources -> SolverError.
+:297-311).  Radiation (:334-374) adds the nonlinear boundary term -m (Ta^4 - T^4) q ds over the whole exterior
+surface; the problem is then solved by Newton's method (SolverBase.solve_nonlinear_problem), the Jacobian term
+4 m T^3 u q ds and the residual being assembled on the device.  Out of scope on the device path: nonlinear
+material functions, SUPG/IP stabilisation, point sources -> SolverError.
 """
 from __future__ import annotations
 
@@ -21,7 +23,7 @@ import numpy as np
 
 from . import _lib
 from .SolverBase import SolverBase, SolverError
-from .dolfin_compat import Constant, DirichletBC, Function
+from .dolfin_compat import Constant, DirichletBC, Function, Point, PointSource
 
 supported_scalars = {'temperature', 'electric_potential', 'species_concentration'}
 electric_permittivity_in_vacumm = 8.854187817e-12
@@ -42,6 +44,8 @@ class ScalarForm:
         self.robin = []                  # (marker id, h, T_ambient)
         self.sources = []                # (value (number | nodal array), subdomain id | None)
         self.T_prev = None
+        self.radiation = None            # (m = emissivity * Stefan-Boltzmann, T_ambient)
+        self.point_sources = []          # PointSource objects
 
     def _k(self):
         k = self.conductivity
@@ -88,8 +92,20 @@ class ScalarForm:
                         raise SolverError('body_source per subdomain needs cell markers (mesh_physical_region.xml)')
                     tags = s.subdomains.array()
                 _lib.assemble_source(space.dmesh, b, float(value), cell_tags=tags, tag=sub_id or 0)
+        for ps in self.point_sources:
+            nodes, w = ps.entries()
+            if space.comm.nranks > 1:
+                raise SolverError('point sources are not implemented for distributed runs')
+            b.add_entries(nodes, w)
         symmetric = vel is None and (ktensor is None or np.allclose(ktensor, ktensor.T, rtol=0, atol=0))
         return b, symmetric
+
+    def add_newton_terms(self, space, x, r):
+        """Nonlinear part at the iterate x: space.A += dR/dT(x), r -= R(x) (r holds b - A_lin x)."""
+        if self.radiation is not None:
+            m, Ta = self.radiation
+            fv, _ = space.local_facets(*self.solver.mesh.exterior_facets()[:2])
+            _lib.assemble_facet_radiation(space.dmesh, space.A, r, x, fv, m, Ta, rscale=-1.0)
 
 
 class ScalarTransportSolver(SolverBase):
@@ -164,7 +180,15 @@ class ScalarTransportSolver(SolverBase):
         capacity = self.capacity(T)
         bcs = []
         if 'point_source' in self.settings and self.settings['point_source']:
-            raise SolverError('point_source is not implemented on the device path')
+            ps = self.settings['point_source']
+            # a PointSource, or a list of (point, magnitude) tuples (:150-158); they go into the right-hand side
+            # before the Dirichlet rows are imposed, the order of the reference's bcs list
+            if isinstance(ps, PointSource):
+                F.point_sources.append(ps)
+            else:
+                for si in ps:
+                    pt = si[0] if isinstance(si[0], Point) else Point(*np.atleast_1d(si[0]))
+                    F.point_sources.append(PointSource(self.function_space, pt, si[1]))
         if 'surface_source' in self.settings and self.settings['surface_source']:
             raise SolverError('surface_source is broken in the reference scalar solver (undefined get_flux) and not implemented')
 
@@ -213,7 +237,7 @@ class ScalarTransportSolver(SolverBase):
         F = ScalarForm(self)
         conductivity = self.conductivity(T)
         capacity = self.capacity(T)
-        if self.nonlinear or self.nonlinear_material:
+        if self.nonlinear_material or any(callable(v) and not isinstance(v, Constant) for v in self.material.values()):
             raise SolverError('nonlinear material is outside the device hot path')
         if isinstance(conductivity, (Function,)) or callable(conductivity):
             raise SolverError('conductivity must be a number or a constant tensor on the device path')
@@ -245,11 +269,42 @@ class ScalarTransportSolver(SolverBase):
             F.sources.extend(bs_items)
 
         if self.scalar_name == "temperature":
-            if self.settings.get('radiation_settings') or getattr(self, 'radiation_settings', None):
-                raise SolverError('radiation is nonlinear and outside the device hot path')
+            if ('radiation_settings' in self.settings and self.settings['radiation_settings']):
+                self.radiation_settings = self.settings['radiation_settings']
+                self.has_radiation = True
+            elif hasattr(self, 'radiation_settings') and self.radiation_settings:
+                self.has_radiation = True
+            else:
+                self.has_radiation = False
+            if self.has_radiation:
+                if self.function_space.degree != 1:
+                    raise SolverError('radiation is implemented for degree-1 spaces')
+                self.nonlinear = True
+                m_, Ta = self.radiation_coefficients()
+                F.radiation = (m_, Ta)           # F -= radiation_flux(T)*Tq*ds: all exterior facets (:359)
         return F, bcs
+
+    def radiation_coefficients(self):
+        """(emissivity * Stefan constant, ambient temperature) with the reference's look-up order (:361-374)."""
+        Stefan_constant = 5.670367e-8
+        if 'emissivity' in self.material:
+            emissivity = self.material['emissivity']
+        elif 'emissivity' in self.radiation_settings:
+            emissivity = self.radiation_settings['emissivity']
+        else:
+            emissivity = 1.0
+        if 'ambient_temperature' in self.radiation_settings:
+            T_ambient_radiaton = self.radiation_settings['ambient_temperature']
+        else:
+            T_ambient_radiaton = self.reference_values['temperature']
+        return float(emissivity) * Stefan_constant, float(T_ambient_radiaton)
+
+    def radiation_flux(self, T):
+        m_, Ta = self.radiation_coefficients()
+        return m_ * (Ta ** 4 - np.asarray(T, dtype=np.float64) ** 4)
 
     def solve_form(self, F, T_current, bcs):
         if self.nonlinear:
-            raise SolverError('nonlinear solve is outside the device hot path')
-        return self.solve_linear_problem(F, T_current, bcs)
+            return self.solve_nonlinear_problem(F, T_current, bcs, None)
+        else:
+            return self.solve_linear_problem(F, T_current, bcs)

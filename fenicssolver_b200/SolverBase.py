@@ -401,14 +401,25 @@ class SolverBase():
             plt.show()
 
     def save(self, result_filename):
-        """Nodal values in vertex order: `.npy` (restartable through initial_values) or legacy-ASCII `.vtk`."""
+        """`File(result_filename) << (w_current, current_time)` (SolverBase.py:570-577): `.pvd` writes the ParaView
+        collection plus one ASCII `.vtu` piece per call (`name000000.vtu`, ... as dolfin's VTKFile numbers them);
+        also `.vtu` alone, legacy-ASCII `.vtk`, and `.npy` (nodal values, restartable through initial_values)."""
         values = self.w_current.values
+        name = self.get_variable_name()
         if result_filename.endswith('.npy'):
             np.save(result_filename, values)
-        elif result_filename.endswith('.vtk') or result_filename.endswith('.pvd'):
-            write_vtk(result_filename[:-4] + '.vtk', self.mesh, values, self.get_variable_name())
+        elif result_filename.endswith('.vtk'):
+            write_vtk(result_filename, self.mesh, values, name)
+        elif result_filename.endswith('.vtu'):
+            write_vtu(result_filename, self.mesh, values, name)
+        elif result_filename.endswith('.pvd'):
+            series = self.__dict__.setdefault('_pvd_series', {}).setdefault(result_filename, [])
+            piece = '%s%06d.vtu' % (result_filename[:-4], len(series))
+            write_vtu(piece, self.mesh, values, name)
+            series.append((float(getattr(self, 'current_time', 0.0)), os.path.basename(piece)))
+            write_pvd(result_filename, series)
         else:
-            raise SolverError('result file must end in .npy, .vtk or .pvd')
+            raise SolverError('result file must end in .pvd, .vtu, .vtk or .npy')
 
     # ------------------------------------------------------------------ linear solve (the hot path)
     def device_space(self):
@@ -473,7 +484,54 @@ class SolverBase():
         return self.solve_linear_problem(F, u, bcs)
 
     def solve_nonlinear_problem(self, F, u_current, Dirichlet_bcs, J):
-        raise SolverError('nonlinear problems (Newton) are outside the device hot path')
+        """Newton's method on the device (NonlinearVariationalSolver, SolverBase.py:615-626).  Each iteration
+        assembles the linear part (A, b) and lets the form add its nonlinear Jacobian / residual terms at the
+        iterate x; the update solves J dx = -F(x) with homogeneous Dirichlet rows (x carries the boundary values
+        from the start).  Stops on ||F|| <= newton_rtol * ||F_0|| (default 1e-11; dolfin's own default is 1e-9) or
+        newton_atol.  `J` is unused: the forms know their own derivative."""
+        space = self.device_space()
+        if space.comm.nranks > 1:
+            raise SolverError('the Newton solver is not implemented for distributed runs')
+        kp = self.krylov_parameters()
+        sp = self.solver_settings.get('solver_parameters') or {}
+        n_rtol, n_atol = float(sp.get('newton_relative_tolerance', 1e-11)), float(sp.get('newton_absolute_tolerance', 1e-14))
+        n_maxit = int(sp.get('newton_maximum_iterations', 50))
+        dofs, vals = collect_dirichlet(Dirichlet_bcs, self.function_space)
+        ldofs, lvals = space.local_dofs(dofs, vals)
+        xh = u_current.array().copy()
+        xh[ldofs] = lvals
+        x = space.vector_from_global(xh)
+        y, dx = space.scratch_vector('newton_y'), space.scratch_vector('newton_dx')
+        t0 = time.perf_counter()
+        r0, history, lin_iters = None, [], 0
+        for it in range(n_maxit + 1):
+            b, symmetric_form = F.assemble(space)                 # linear part: space.A, b
+            space.A.spmv(x, y)
+            b.axpy(-1.0, y)                                       # b <- b - A_lin x
+            F.add_newton_terms(space, x, b)                       # A += dR/dx, b -= R(x)
+            method = kp['method'] or ('cg' if symmetric_form else 'bicgstab')
+            space.apply_dirichlet(b, dofs, np.zeros(len(dofs)), symmetric=(method == 'cg'))
+            rn = float(np.sqrt(b.dot(b)))
+            history.append(rn)
+            r0 = rn if r0 is None else r0
+            if rn <= max(n_rtol * r0, n_atol) or it == n_maxit:
+                break
+            dx.fill(0.0)
+            info = space.solve(b, dx, method=method, rtol=kp['rtol'], atol=kp['atol'], maxit=kp['maxit'], precond=kp['precond'])
+            lin_iters += info['iterations']
+            if info['converged'] != 1:
+                self.logger.warning("%s did not converge inside Newton iteration %d: %s", method, it, info)
+            x.axpy(1.0, dx)
+        self.timings['solve'] = time.perf_counter() - t0
+        converged = history[-1] <= max(n_rtol * r0, n_atol)
+        self.solve_info = {'iterations': lin_iters, 'converged': int(converged), 'newton_iterations': len(history) - 1,
+                           'newton_residuals': history, 'rnorm': history[-1], 'bnorm': r0, 'solve_ms': self.timings['solve'] * 1e3,
+                           'spmv_ms': 0.0, 'operand_nnzb': 0}
+        if not converged:
+            self.logger.warning("Newton did not converge: residuals %s", history)
+        self._last_x = x
+        u_current.set_device(x)
+        return u_current
 
 
 def collect_dirichlet(bcs, space):
@@ -545,3 +603,45 @@ def write_vtk(path, mesh, values, name):
             v3[:, :vals.shape[1]] = vals
             f.write("VECTORS %s double\n" % name)
             np.savetxt(f, v3, fmt="%.16g")
+
+
+def write_vtu(path, mesh, values, name):
+    """One ASCII VTK XML UnstructuredGrid piece, the layout dolfin's VTKFile writes for a P1 function: points,
+    connectivity/offsets/types (5 = triangle, 10 = tetrahedron), one PointData array (vectors padded to 3
+    components).  Degree-2 results are written at the vertices (dolfin does the same for `File << u`)."""
+    c, t = mesh.coordinates(), mesh.cells()
+    nv, d = c.shape
+    nc, nl = t.shape
+    pts = np.zeros((nv, 3))
+    pts[:, :d] = c
+    vals = np.asarray(values)[:nv]
+    with open(path, 'w') as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1">\n<UnstructuredGrid>\n')
+        f.write('<Piece NumberOfPoints="%d" NumberOfCells="%d">\n' % (nv, nc))
+        f.write('<Points>\n<DataArray type="Float64" NumberOfComponents="3" format="ascii">\n')
+        np.savetxt(f, pts, fmt="%.16g")
+        f.write('</DataArray>\n</Points>\n<Cells>\n<DataArray type="UInt32" Name="connectivity" format="ascii">\n')
+        np.savetxt(f, t, fmt="%d")
+        f.write('</DataArray>\n<DataArray type="UInt32" Name="offsets" format="ascii">\n')
+        np.savetxt(f, (np.arange(1, nc + 1) * nl)[None, :], fmt="%d")
+        f.write('</DataArray>\n<DataArray type="UInt8" Name="types" format="ascii">\n')
+        np.savetxt(f, np.full((1, nc), 10 if nl == 4 else 5), fmt="%d")
+        f.write('</DataArray>\n</Cells>\n')
+        if vals.ndim == 1:
+            f.write('<PointData Scalars="%s">\n<DataArray type="Float64" Name="%s" format="ascii">\n' % (name, name))
+            np.savetxt(f, vals, fmt="%.16g")
+        else:
+            v3 = np.zeros((nv, 3))
+            v3[:, :vals.shape[1]] = vals
+            f.write('<PointData Vectors="%s">\n<DataArray type="Float64" Name="%s" NumberOfComponents="3" format="ascii">\n' % (name, name))
+            np.savetxt(f, v3, fmt="%.16g")
+        f.write('</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n')
+
+
+def write_pvd(path, series):
+    """ParaView collection: one DataSet per (time, piece file)."""
+    with open(path, 'w') as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="Collection" version="0.1">\n<Collection>\n')
+        for t, piece in series:
+            f.write('<DataSet timestep="%.16g" part="0" file="%s" />\n' % (t, piece))
+        f.write('</Collection>\n</VTKFile>\n')

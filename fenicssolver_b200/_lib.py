@@ -48,6 +48,7 @@ SIGNATURES = {
     "fsb_vec_download": (C.c_int, [c_vp, c_vp, c_i64]),
     "fsb_vec_copy": (C.c_int, [c_vp, c_vp]),
     "fsb_vec_axpy": (C.c_int, [c_vp, c_dbl, c_vp]),
+    "fsb_vec_add_entries": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "fsb_vec_size": (C.c_int, [c_vp, P(c_i64)]),
     "fsb_vec_ptr": (c_vp, [c_vp]),
     "fsb_vec_destroy": (None, [c_vp]),
@@ -66,6 +67,9 @@ SIGNATURES = {
     "fsb_assemble_facet_load": (C.c_int, [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_vp, c_dbl]),
     "fsb_assemble_facet_mass": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_dbl]),
     "fsb_facet_area": (C.c_int, [c_vp, c_i64, c_vp, P(c_dbl)]),
+    "fsb_assemble_thermal_load": (C.c_int, [c_vp, c_vp, c_dbl, c_vp, c_dbl, c_dbl, c_dbl]),
+    "fsb_assemble_von_mises_load": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, c_vp]),
+    "fsb_assemble_facet_radiation": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl]),
     "fsb_apply_dirichlet": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32]),
     "fsb_spmv": (C.c_int, [c_vp, c_vp, c_vp]),
     "fsb_dot": (C.c_int, [c_vp, c_vp, P(c_dbl)]),
@@ -272,6 +276,10 @@ class DeviceVector(_Handle):
     def axpy(self, a, x):
         self.ctx.check(self.ctx.lib.fsb_vec_axpy(self.h, float(a), x.h))
 
+    def add_entries(self, idx, vals):
+        i, v = _np(idx, np.int64).ravel(), _np(vals, np.float64).ravel()
+        self.ctx.check(self.ctx.lib.fsb_vec_add_entries(self.h, i.size, _ptr(i), _ptr(v)))
+
     def dot(self, other):
         r = c_dbl()
         self.ctx.check(self.ctx.lib.fsb_dot(self.h, other.h, C.byref(r)))
@@ -382,3 +390,20 @@ def facet_area(mesh, fverts):
     a = c_dbl()
     mesh.ctx.check(mesh.ctx.lib.fsb_facet_area(mesh.h, fv.shape[0], _ptr(fv), C.byref(a)))
     return a.value
+
+
+def assemble_thermal_load(mesh, b, beta, T=None, T_const=0.0, T_ref=0.0, scale=1.0):
+    """b += scale * beta * int (T - T_ref) div(v) dx; T: DeviceVector of nodal temperatures or None (constant T_const)."""
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_thermal_load(mesh.h, b.h, float(beta), T.h if T is not None else None,
+                                                          float(T_const), float(T_ref), float(scale)))
+
+
+def assemble_von_mises_load(mesh, u, mu, lmbda, b):
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_von_mises_load(mesh.h, u.h, float(mu), float(lmbda), b.h))
+
+
+def assemble_facet_radiation(mesh, A, r, T, fverts, m, T_ambient, rscale=1.0):
+    """A += int 4 m T^3 u v ds, r += rscale * int m (T^4 - Ta^4) v ds over the facets (A or r may be None)."""
+    fv = _np(fverts, np.int32)
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_facet_radiation(mesh.h, A.h if A is not None else None, r.h if r is not None else None,
+                                                             T.h, fv.shape[0], _ptr(fv), float(m), float(T_ambient), float(rscale)))

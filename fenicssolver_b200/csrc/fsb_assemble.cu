@@ -302,6 +302,99 @@ __global__ void k_facet_area(int64_t nf, const int32_t* __restrict__ fverts, int
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// ------------------------------------------------------------------------------------ thermal stress, von Mises, radiation
+// b[(a,i)] += w |T| mean_a(T_a - T_ref) G_a[i]: the load of sigma_t = beta (T - T_ref) I tested with grad v
+// (LinearElasticitySolver.py:78-85, 232-238), T the P1 interpolant of the nodal temperatures (or a constant)
+template <int D>
+__global__ void k_thermal_load(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz,
+                               const double* __restrict__ T, double T_const, double T_ref, double w, double* __restrict__ b) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    double dT = 0.0;
+#pragma unroll
+    for (int a = 0; a < NL; ++a) dT += (T ? __ldg(T + v[a]) : T_const) - T_ref;
+    const double f = w * g.vol * dT / (double)NL;
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int i = 0; i < D; ++i) atomicAdd(b + (int64_t)v[a] * D + i, f * g.G[a][i]);
+  }
+}
+
+// b_a += |T|/(D+1) vm(u_h): load of the L2 projection of the (cell-wise constant) von Mises stress onto P1
+// (LinearElasticitySolver.py:71-76)
+template <int D>
+__global__ void k_von_mises_load(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz,
+                                 const double* __restrict__ u, double mu, double lambda, double* __restrict__ b) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    double H[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) H[i][k] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const double ua = __ldg(u + (int64_t)v[a] * D + i);
+#pragma unroll
+        for (int k = 0; k < D; ++k) H[i][k] += ua * g.G[a][k];
+      }
+    const double w = g.vol / (double)NL * fsb_von_mises<D>(H, mu, lambda);
+#pragma unroll
+    for (int a = 0; a < NL; ++a) atomicAdd(b + v[a], w);
+  }
+}
+
+// Newton terms of the grey-body boundary flux m (Ta^4 - T^4) (ScalarTransportSolver.py:334-359, 361-374):
+//   A_ab += int 4 m T_h^3 phi_a phi_b ds      r_a += rscale int m (T_h^4 - Ta^4) phi_a ds
+// T_h is linear on the facet, so the integrands are polynomials of degree 5: the rule integrates them exactly.
+struct FacetRule { int n; double l[16][3]; double w[16]; };
+
+template <int D>
+__global__ void k_facet_radiation(int64_t nf, const int32_t* __restrict__ fverts, const double* __restrict__ xyz,
+                                  const double* __restrict__ T, double m, double Ta4, double rscale, FacetRule q,
+                                  const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                  double* __restrict__ vals, double* __restrict__ r) {
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nf; f += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t* fv = fverts + f * D;
+    double n[3], x0[3];
+    const double meas = facet_geom<D>(xyz, fv, n, x0);
+    double t[D], Jab[D][D], ra[D];
+    for (int a = 0; a < D; ++a) {
+      t[a] = T[fv[a]];
+      ra[a] = 0.0;
+      for (int b = 0; b < D; ++b) Jab[a][b] = 0.0;
+    }
+    for (int p = 0; p < q.n; ++p) {
+      double Tq = 0.0;
+      for (int a = 0; a < D; ++a) Tq += t[a] * q.l[p][a];
+      const double T3 = Tq * Tq * Tq, wp = q.w[p] * meas;
+      for (int a = 0; a < D; ++a) {
+        ra[a] += wp * m * (T3 * Tq - Ta4) * q.l[p][a];
+        for (int b = 0; b < D; ++b) Jab[a][b] += wp * 4.0 * m * T3 * q.l[p][a] * q.l[p][b];
+      }
+    }
+    for (int a = 0; a < D; ++a) {
+      if (r) atomicAdd(r + fv[a], rscale * ra[a]);
+      if (vals) {
+        const int64_t base = row_ptr[fv[a]];
+        const int len = (int)(row_ptr[fv[a] + 1] - base);
+        for (int b = 0; b < D; ++b) atomicAdd(vals + base + row_find(col_idx + base, 0, len, fv[b]), Jab[a][b]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ Dirichlet
 __global__ void k_bc_scatter(int64_t nbc, const int64_t* __restrict__ dofs, const double* __restrict__ g,
                              uint8_t* __restrict__ flag, double* __restrict__ val, double* __restrict__ x) {
@@ -537,6 +630,68 @@ extern "C" int fsb_facet_area(fsb_mesh* mesh, int64_t nf, const int32_t* fverts,
   double s = 0.0;
   for (double p : part) s += p;
   *area = s;
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_thermal_load(fsb_mesh* mesh, fsb_vec* b, double beta, fsb_vec* T, double T_const, double T_ref,
+                                         double scale) {
+  if (!mesh || !b) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (b->n != mesh->nnodes * mesh->tdim) FSB_FAIL(ctx, FSB_ERR_ARG, "thermal load needs a vector rhs with ncomp == dim");
+  if (T && T->n != mesh->nnodes) FSB_FAIL(ctx, FSB_ERR_ARG, "temperature must be a nodal scalar field of the same space");
+  const double* Tp = T ? T->d : nullptr;
+  if (mesh->degree == 2) return fsb_p2_thermal_load(mesh, b->d, Tp, T_const, T_ref, beta * scale);
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3) k_thermal_load<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, Tp, T_const, T_ref, beta * scale, b->d);
+  else k_thermal_load<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, Tp, T_const, T_ref, beta * scale, b->d);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_von_mises_load(fsb_mesh* mesh, fsb_vec* u, double mu, double lambda, fsb_vec* b) {
+  if (!mesh || !u || !b) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (u->n != mesh->nnodes * mesh->tdim) FSB_FAIL(ctx, FSB_ERR_ARG, "displacement must have ncomp == dim on this mesh");
+  if (b->n != mesh->nverts) FSB_FAIL(ctx, FSB_ERR_ARG, "the projection load lives on the vertices (P1)");
+  if (mesh->degree == 2) return fsb_p2_von_mises_load(mesh, u->d, mu, lambda, b->d);
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3) k_von_mises_load<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, u->d, mu, lambda, b->d);
+  else k_von_mises_load<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, u->d, mu, lambda, b->d);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_facet_radiation(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec* T, int64_t nf, const int32_t* fverts,
+                                            double m, double T_ambient, double rscale) {
+  if (!mesh || !T || (!A && !r) || (nf > 0 && !fverts)) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (mesh->degree != 1) FSB_FAIL(ctx, FSB_ERR_ARG, "radiation is implemented for degree-1 spaces");
+  if (T->n != mesh->nnodes || (r && r->n != mesh->nnodes) || (A && (A->bs != 1 || A->nbrows != mesh->nnodes)))
+    FSB_FAIL(ctx, FSB_ERR_ARG, "radiation needs the scalar matrix / vectors of this mesh");
+  if (nf == 0) return FSB_OK;
+  FacetUpload up(ctx);
+  int rc = upload_facets(mesh, nf, fverts, nullptr, up);
+  if (rc) return rc;
+  std::vector<double> bary, w;
+  const int fd = mesh->tdim - 1;
+  fsb_simplex_rule(fd, fd == 1 ? 3 : 4, bary, w);
+  FacetRule q;
+  memset(&q, 0, sizeof(q));
+  q.n = (int)w.size();
+  for (int p = 0; p < q.n; ++p) {
+    for (int a = 0; a <= fd; ++a) q.l[p][a] = bary[(size_t)p * (fd + 1) + a];
+    q.w[p] = w[p];
+  }
+  const double Ta2 = T_ambient * T_ambient;
+  const unsigned grid = fsb_grid(nf, 128, (int64_t)ctx->sm_count * 16);
+  if (mesh->tdim == 3)
+    k_facet_radiation<3><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, T->d, m, Ta2 * Ta2, rscale, q, A ? A->row_ptr : nullptr,
+                                                        A ? A->col_idx : nullptr, A ? A->vals : nullptr, r ? r->d : nullptr);
+  else
+    k_facet_radiation<2><<<grid, 128, 0, ctx->stream>>>(nf, up.fverts, mesh->xyz, T->d, m, Ta2 * Ta2, rscale, q, A ? A->row_ptr : nullptr,
+                                                        A ? A->col_idx : nullptr, A ? A->vals : nullptr, r ? r->d : nullptr);
+  FSB_LAUNCH_CHECK(ctx);
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FSB_OK;
 }
 

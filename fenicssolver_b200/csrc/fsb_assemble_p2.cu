@@ -395,6 +395,103 @@ __global__ void k_p2_facet_mass(int64_t nf, const int32_t* __restrict__ fnodes, 
   }
 }
 
+
+// P2 basis gradients d(phi_j)/d(lambda_e) at the barycentric point l
+template <int D>
+__device__ __forceinline__ void p2_dphi(const double* l, double (&dphi)[(D + 1) * (D + 2) / 2][D + 1]) {
+  constexpr int NL = D + 1, NN = (D + 1) * (D + 2) / 2;
+#pragma unroll
+  for (int j = 0; j < NN; ++j)
+#pragma unroll
+    for (int e = 0; e < NL; ++e) dphi[j][e] = 0.0;
+#pragma unroll
+  for (int a = 0; a < NL; ++a) dphi[a][a] = 4.0 * l[a] - 1.0;
+  if constexpr (D == 2) {
+    dphi[3][1] = 4.0 * l[2]; dphi[3][2] = 4.0 * l[1];
+    dphi[4][0] = 4.0 * l[2]; dphi[4][2] = 4.0 * l[0];
+    dphi[5][0] = 4.0 * l[1]; dphi[5][1] = 4.0 * l[0];
+  } else {
+    dphi[4][2] = 4.0 * l[3]; dphi[4][3] = 4.0 * l[2];
+    dphi[5][1] = 4.0 * l[3]; dphi[5][3] = 4.0 * l[1];
+    dphi[6][1] = 4.0 * l[2]; dphi[6][2] = 4.0 * l[1];
+    dphi[7][0] = 4.0 * l[3]; dphi[7][3] = 4.0 * l[0];
+    dphi[8][0] = 4.0 * l[2]; dphi[8][2] = 4.0 * l[0];
+    dphi[9][0] = 4.0 * l[1]; dphi[9][1] = 4.0 * l[0];
+  }
+}
+
+// b[(a,i)] += scale beta int (T_h - T_ref) d(phi_a)/dx_i = scale beta |T| sum_j dT_j sum_e S[j][a][e] G_e[i]
+template <int D>
+__global__ void k_p2_thermal_load(int64_t ncells, const int32_t* __restrict__ cell_nodes, const double* __restrict__ xyz,
+                                  const double* __restrict__ tS, const double* __restrict__ T, double T_const, double T_ref,
+                                  double w, double* __restrict__ b) {
+  constexpr int NL = D + 1, NN = (D + 1) * (D + 2) / 2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int nd[NN];
+    for (int a = 0; a < NN; ++a) nd[a] = cell_nodes[c * NN + a];
+    Cell<D> g;
+    cell_geometry<D>(xyz, nd, g);
+    double dT[NN];
+    for (int j = 0; j < NN; ++j) dT[j] = (T ? T[nd[j]] : T_const) - T_ref;
+    for (int a = 0; a < NN; ++a) {
+      double se[NL];
+      for (int e = 0; e < NL; ++e) {
+        double s = 0.0;
+        for (int j = 0; j < NN; ++j) s += dT[j] * tS[(j * NN + a) * NL + e];
+        se[e] = s;
+      }
+      for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+        for (int e = 0; e < NL; ++e) s += se[e] * g.G[e][i];
+        atomicAdd(b + (int64_t)nd[a] * D + i, w * g.vol * s);
+      }
+    }
+  }
+}
+
+struct QRule { int n; double l[64][4]; double w[64]; };
+
+// b_a += int vm(u_h) lambda_a dx over the vertices a of each cell, u_h degree 2: quadrature rule `q`
+template <int D>
+__global__ void k_p2_von_mises_load(int64_t ncells, const int32_t* __restrict__ cell_nodes, const double* __restrict__ xyz,
+                                    const double* __restrict__ u, double mu, double lambda, const QRule* __restrict__ q,
+                                    double* __restrict__ b) {
+  constexpr int NL = D + 1, NN = (D + 1) * (D + 2) / 2;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int nd[NN];
+    for (int a = 0; a < NN; ++a) nd[a] = cell_nodes[c * NN + a];
+    Cell<D> g;
+    cell_geometry<D>(xyz, nd, g);
+    double ul[NN][D];
+    for (int j = 0; j < NN; ++j)
+      for (int i = 0; i < D; ++i) ul[j][i] = u[(int64_t)nd[j] * D + i];
+    double acc[NL];
+    for (int a = 0; a < NL; ++a) acc[a] = 0.0;
+    for (int p = 0; p < q->n; ++p) {
+      double l[NL];
+      for (int a = 0; a < NL; ++a) l[a] = q->l[p][a];
+      double dphi[NN][NL];
+      p2_dphi<D>(l, dphi);
+      double H[D][D];                       // grad u [i][k] = sum_j u_j[i] sum_e dphi_j/dl_e G_e[k]
+      for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) H[i][k] = 0.0;
+      for (int j = 0; j < NN; ++j) {
+        double gj[D];
+        for (int k = 0; k < D; ++k) {
+          double s = 0.0;
+          for (int e = 0; e < NL; ++e) s += dphi[j][e] * g.G[e][k];
+          gj[k] = s;
+        }
+        for (int i = 0; i < D; ++i)
+          for (int k = 0; k < D; ++k) H[i][k] += ul[j][i] * gj[k];
+      }
+      const double vm = fsb_von_mises<D>(H, mu, lambda);
+      for (int a = 0; a < NL; ++a) acc[a] += q->w[p] * vm * l[a];
+    }
+    for (int a = 0; a < NL; ++a) atomicAdd(b + nd[a], g.vol * acc[a]);
+  }
+}
+
 void fill_form(Form& f, int D, double kscale, const double* ktensor, double mass, double adv, const double* vel) {
   memset(&f, 0, sizeof(f));
   f.kscale = kscale; f.mass = mass; f.adv = adv;
@@ -483,5 +580,52 @@ int fsb_p2_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, const int32_t* d_f
   if (mesh->tdim == 3) k_p2_facet_mass<3><<<grid, 128, 0, ctx->stream>>>(nf, d_fnodes, mesh->xyz, h, mesh->p2_tables + L.oMf, A->row_ptr, A->col_idx, A->vals);
   else k_p2_facet_mass<2><<<grid, 128, 0, ctx->stream>>>(nf, d_fnodes, mesh->xyz, h, mesh->p2_tables + L.oMf, A->row_ptr, A->col_idx, A->vals);
   FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+void fsb_simplex_rule(int d, int n, std::vector<double>& bary, std::vector<double>& w) {
+  bary.clear(); w.clear();
+  integrate_simplex(d, n, [&](const double* l, double wt) {
+    for (int a = 0; a <= d; ++a) bary.push_back(l[a]);
+    w.push_back(wt);
+  });
+}
+
+int fsb_p2_thermal_load(fsb_mesh* mesh, double* b, const double* T, double T_const, double T_ref, double w) {
+  fsb_ctx* ctx = mesh->ctx;
+  int rc = ensure_tables(mesh);
+  if (rc) return rc;
+  P2Layout L(mesh->tdim);
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3) k_p2_thermal_load<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, mesh->p2_tables + L.oS, T, T_const, T_ref, w, b);
+  else k_p2_thermal_load<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, mesh->p2_tables + L.oS, T, T_const, T_ref, w, b);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+// the projection integrand sqrt(3/2 s:s) is not a polynomial: a collapsed Gauss rule with 4 points per axis
+// (exact to degree 5, the degree UFL estimates for this integrand on a degree-2 displacement)
+int fsb_p2_von_mises_load(fsb_mesh* mesh, const double* u, double mu, double lambda, double* b) {
+  fsb_ctx* ctx = mesh->ctx;
+  const int D = mesh->tdim;
+  std::vector<double> bary, w;
+  fsb_simplex_rule(D, 4, bary, w);
+  QRule q;
+  memset(&q, 0, sizeof(q));
+  q.n = (int)w.size();
+  for (int p = 0; p < q.n; ++p) {
+    for (int a = 0; a <= D; ++a) q.l[p][a] = bary[(size_t)p * (D + 1) + a];
+    q.w[p] = w[p];
+  }
+  QRule* dq = nullptr;
+  int rc = fsb_dmalloc(ctx, &dq, 1);
+  if (rc) return rc;
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(dq, &q, sizeof(q), cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned grid = fsb_grid(mesh->ncells, 64, (int64_t)ctx->sm_count * 64);
+  if (D == 3) k_p2_von_mises_load<3><<<grid, 64, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, u, mu, lambda, dq, b);
+  else k_p2_von_mises_load<2><<<grid, 64, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, u, mu, lambda, dq, b);
+  FSB_LAUNCH_CHECK(ctx);
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // q lives on the host stack
+  fsb_dfree(ctx, dq);
   return FSB_OK;
 }

@@ -115,6 +115,31 @@ __global__ void k_axpy(double* __restrict__ y, double a, const double* __restric
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];
 }
 
+__global__ void k_add_entries(double* __restrict__ v, int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ val) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(v + idx[i], val[i]);
+}
+
+extern "C" int fsb_vec_add_entries(fsb_vec* v, int64_t n, const int64_t* idx, const double* vals) {
+  if (!v || (n > 0 && (!idx || !vals))) return FSB_ERR_ARG;
+  fsb_ctx* ctx = v->ctx;
+  for (int64_t i = 0; i < n; ++i)
+    if (idx[i] < 0 || idx[i] >= v->n) FSB_FAIL(ctx, FSB_ERR_ARG, "entry index out of range");
+  if (n == 0) return FSB_OK;
+  int64_t* d_idx = nullptr;
+  double* d_val = nullptr;
+  int rc = fsb_dmalloc(ctx, &d_idx, (size_t)n);
+  if (!rc) rc = fsb_dmalloc(ctx, &d_val, (size_t)n);
+  if (rc) { fsb_dfree(ctx, d_idx); return rc; }
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_idx, idx, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d_val, vals, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_add_entries<<<fsb_grid(n, 128, 1024), 128, 0, ctx->stream>>>(v->d, n, d_idx, d_val);
+  FSB_LAUNCH_CHECK(ctx);
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // idx/vals are caller-owned pageable memory
+  fsb_dfree(ctx, d_idx);
+  fsb_dfree(ctx, d_val);
+  return FSB_OK;
+}
+
 extern "C" int fsb_vec_create(fsb_ctx* ctx, int64_t n, fsb_vec** out) {
   if (!ctx || !out || n < 0) return FSB_ERR_ARG;
   fsb_vec* v = new fsb_vec{ctx, n, nullptr};

@@ -230,6 +230,11 @@ int fsb_p2_source(fsb_mesh* mesh, double* b, int ncomp, const double* S_const, c
 int fsb_p2_facet_load(fsb_mesh* mesh, double* b, int ncomp, int64_t nf, const int32_t* d_fnodes, const int32_t* d_opp, int mode,
                       const double* g, double scale);
 int fsb_p2_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, const int32_t* d_fnodes, double h);
+int fsb_p2_thermal_load(fsb_mesh* mesh, double* b, const double* T, double T_const, double T_ref, double w);
+int fsb_p2_von_mises_load(fsb_mesh* mesh, const double* u, double mu, double lambda, double* b);
+// collapsed Gauss-Legendre rule on the reference d-simplex, n points per axis: barycentric points [np][d+1] and
+// weights normalised to sum 1 (so int f = |T| sum w f)   [fsb_assemble_p2.cu]
+void fsb_simplex_rule(int d, int n, std::vector<double>& bary, std::vector<double>& w);
 // distributed hooks [fsb_dist.cu]
 bool fsb_dist_active(fsb_ctx* ctx);
 int fsb_dist_halo_raw(fsb_ctx* ctx, double* v, int64_t n);
@@ -270,6 +275,32 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
   v = (threadIdx.x < nw) ? smem[threadIdx.x] : 0.0;
   if (w == 0) v = warp_sum(v);
   return v;
+}
+
+// von Mises stress of the small-strain state with displacement gradient H = grad u:
+// sigma = 2 mu sym(H) + lambda tr(H) I, s = sigma - (1/3) tr(sigma) I, sqrt(3/2 s:s)   (LinearElasticitySolver.py:71-76;
+// the 1/3 is the reference's in 2D as well)
+template <int D>
+__device__ __forceinline__ double fsb_von_mises(const double (&H)[D][D], double mu, double lambda) {
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) tr += H[i][i];
+  double sig[D][D], trs = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) sig[i][j] = mu * (H[i][j] + H[j][i]) + (i == j ? lambda * tr : 0.0);
+#pragma unroll
+  for (int i = 0; i < D; ++i) trs += sig[i][i];
+  double ss = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double sij = sig[i][j] - (i == j ? trs * (1.0 / 3.0) : 0.0);
+      ss += sij * sij;
+    }
+  return sqrt(1.5 * ss);
 }
 
 // in-row search: position of `col` in the sorted list cols[0..len), starting the search at lo

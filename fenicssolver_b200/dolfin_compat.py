@@ -23,7 +23,7 @@ from ._lib import SolverError
 DOLFIN_EPS = 3.0e-16
 __all__ = ["DOLFIN_EPS", "near", "Point", "Constant", "Expression", "Mesh", "UnitSquareMesh", "RectangleMesh",
            "UnitCubeMesh", "BoxMesh", "SubDomain", "AutoSubDomain", "MeshFunction", "FacetMarkers", "FunctionSpace",
-           "VectorFunctionSpace", "Function", "DirichletBC", "SolverError"]
+           "VectorFunctionSpace", "Function", "DirichletBC", "PointSource", "SolverError"]
 
 
 def near(a, b, eps=DOLFIN_EPS):
@@ -170,6 +170,27 @@ class Mesh:
                 order = np.argsort(fid, kind="stable")
                 self._exterior = (facets[fid[order]].astype(np.int32), self._cells[ci[order], li[order]].astype(np.int32), fid[order])
         return self._exterior[0], self._exterior[1]
+
+    def locate_point(self, p, tol=1e-12):
+        """(cell index, barycentric coordinates) of a cell containing point p (the first one in cell order, as a
+        linear search would find it); SolverError if p is outside the mesh."""
+        x = np.asarray(p.x if isinstance(p, Point) else p, dtype=np.float64)[:self.gdim]
+        c, t = self.coordinates(), self.cells()
+        d = self.tdim
+        best = None
+        for s0 in range(0, t.shape[0], 1 << 20):                     # chunks bound the temporary memory
+            tc = t[s0:s0 + (1 << 20)]
+            X = c[tc]                                                # [n, d+1, d]
+            J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))
+            lam = np.linalg.solve(J, np.broadcast_to(x - X[:, 0, :], (tc.shape[0], d))[..., None])[..., 0]
+            lam = np.concatenate([1.0 - lam.sum(axis=1, keepdims=True), lam], axis=1)
+            inside = np.nonzero(lam.min(axis=1) >= -tol)[0]
+            if inside.size:
+                best = (s0 + int(inside[0]), lam[inside[0]])
+                break
+        if best is None:
+            raise SolverError("point %s is outside the mesh" % (x,))
+        return best
 
     def exterior_facet_ids(self):
         """dolfin facet indices of the exterior facets (file meshes only)."""
@@ -506,6 +527,15 @@ class FunctionSpace:
             self._node_coords = np.vstack([c, 0.5 * (c[e[:, 0]] + c[e[:, 1]])])
         return self._node_coords
 
+    def point_weights(self, p):
+        """(nodes, basis values) of the cell containing point p: what PointSource adds to the right-hand side."""
+        cell, lam = self._mesh.locate_point(p)
+        nodes = self.cell_nodes()[cell].astype(np.int64)
+        if self.degree == 1:
+            return nodes, lam
+        phi = [l * (2.0 * l - 1.0) for l in lam] + [4.0 * lam[a] * lam[b] for a, b in _UFC_EDGES[self._mesh.tdim]]
+        return nodes, np.array(phi)
+
     def facet_nodes(self, fverts):
         """Nodes of facets given by their (sorted) vertices: the vertices, then (degree 2) the facet's edges."""
         fv = np.asarray(fverts, dtype=np.int64)
@@ -638,6 +668,18 @@ class Function:
 
     def __call__(self, *x):
         raise SolverError("point evaluation is not implemented; use .values (vertex order)")
+
+
+class PointSource:
+    """PointSource(V, point, magnitude): adds magnitude * phi_a(point) to the right-hand side
+    (ScalarTransportSolver.py:150-158; applied with bc.apply(b), SolverBase.py:598-602)."""
+
+    def __init__(self, V, p, magnitude=1.0):
+        self.V, self.point, self.magnitude = V, p, float(magnitude)
+
+    def entries(self):
+        nodes, w = self.V.point_weights(self.point)
+        return nodes, self.magnitude * np.asarray(w)
 
 
 class DirichletBC:

@@ -102,6 +102,8 @@ int fsb_vec_upload(fsb_vec* v, const double* host, int64_t n);
 int fsb_vec_download(fsb_vec* v, double* host, int64_t n);
 int fsb_vec_copy(fsb_vec* dst, fsb_vec* src);
 int fsb_vec_axpy(fsb_vec* y, double a, fsb_vec* x);            /* y += a x */
+/* v[idx[i]] += vals[i] (host lists; repeated indices accumulate): PointSource.apply(b), SolverBase.py:598-602 */
+int fsb_vec_add_entries(fsb_vec* v, int64_t n, const int64_t* idx, const double* vals);
 int fsb_vec_size(fsb_vec* v, int64_t* n);
 void* fsb_vec_ptr(fsb_vec* v);                                 /* device pointer (for interop) */
 void fsb_vec_destroy(fsb_vec* v);
@@ -147,6 +149,20 @@ int fsb_assemble_facet_load(fsb_mesh* mesh, fsb_vec* b, int32_t ncomp, int64_t n
 int fsb_assemble_facet_mass(fsb_mesh* mesh, fsb_mat* A, int64_t nf, const int32_t* fverts, double h);
 /* assemble(Constant(1)*ds(id))  (LinearElasticitySolver.py:171) */
 int fsb_facet_area(fsb_mesh* mesh, int64_t nf, const int32_t* fverts, double* area);
+
+/* b += scale * beta * int (T - T_ref) div(v) dx: the thermal-stress load of sigma_t = beta (T - T_ref) I, beta =
+ * E/(1-2 nu) * expansion coefficient (LinearElasticitySolver.py:78-85 thermal_stress, :232-238).  T: nodal scalar
+ * field on the space's nodes, or NULL for the constant T_const.  b has ncomp == dim. */
+int fsb_assemble_thermal_load(fsb_mesh* mesh, fsb_vec* b, double beta, fsb_vec* T, double T_const, double T_ref,
+                              double scale);
+/* b_a += int vonMises(u) phi_a dx with phi_a the P1 vertex basis: right-hand side of project(von_Mises, P1)
+ * (LinearElasticitySolver.py:71-76); u: displacement on the mesh's nodes (ncomp == dim), b: nverts entries. */
+int fsb_assemble_von_mises_load(fsb_mesh* mesh, fsb_vec* u, double mu, double lambda, fsb_vec* b);
+/* Newton terms of the radiation boundary flux m (Ta^4 - T^4) over the given exterior facets
+ * (ScalarTransportSolver.py:334-359 F -= radiation_flux(T)*Tq*ds, :361-374): A += int 4 m T^3 u v ds (A may be NULL),
+ * r += rscale * int m (T^4 - Ta^4) v ds (r may be NULL).  Degree-1 spaces. */
+int fsb_assemble_facet_radiation(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec* T, int64_t nf, const int32_t* fverts,
+                                 double m, double T_ambient, double rscale);
 
 /* ---- DirichletBC.apply / assemble_system ------------------------------------------------------ */
 /* symmetric=0: zero row, unit diagonal, b=g (bc.apply(A,b), SolverBase.py:598-602, 608);

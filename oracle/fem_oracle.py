@@ -402,6 +402,124 @@ def bicgstab_jacobi(A, b, x0=None, rtol=1e-12, atol=0.0, maxit=10000):
     return x, it, rn / bnorm if bnorm > 0 else rn
 
 
+# --------------------------------------------------------------------------- thermal stress, von Mises, radiation
+
+
+def thermal_load(coords, cells, beta, T, T_ref):
+    """b[(a,i)] = int beta (T_h - T_ref) d(phi_a)/dx_i dx: the load of F -= inner(stress_t, grad(v))*dx with
+    stress_t = E/(1-2nu) * tec * (T - T_ref) * I  (LinearElasticitySolver.py:78-85, 232-238).  T: number or
+    nodal array (P1 interpolant, integrated exactly: |T| * mean of the vertex values)."""
+    vol, G = p1_geometry(coords, cells)
+    nv, d = coords.shape
+    Tn = np.broadcast_to(np.asarray(T, dtype=np.float64), (nv,))
+    dT = (Tn[cells] - T_ref).mean(axis=1)
+    be = (beta * vol * dT)[:, None, None] * G                 # [nc, nl, d]
+    b = np.zeros((nv, d))
+    for i in range(d):
+        np.add.at(b[:, i], cells.ravel(), be[:, :, i].ravel())
+    return b.reshape(-1)
+
+
+def von_mises_cells(coords, cells, u, mu, lmbda):
+    """sqrt(3/2 s:s), s = sigma - (1/3) tr(sigma) I per cell for a P1 displacement (LinearElasticitySolver.py:71-73;
+    the 1/3 holds in 2D as well, as written)."""
+    vol, G = p1_geometry(coords, cells)
+    d = coords.shape[1]
+    U = np.asarray(u, dtype=np.float64).reshape(-1, d)[cells]          # [nc, nl, d]
+    H = np.einsum("cai,cak->cik", U, G)                                # grad u
+    eps = 0.5 * (H + np.transpose(H, (0, 2, 1)))
+    sig = 2 * mu * eps + lmbda * np.trace(H, axis1=1, axis2=2)[:, None, None] * np.eye(d)
+    s = sig - np.trace(sig, axis1=1, axis2=2)[:, None, None] / 3.0 * np.eye(d)
+    return np.sqrt(1.5 * np.einsum("cij,cij->c", s, s))
+
+
+def von_mises_projection(coords, cells, u, mu, lmbda):
+    """project(von_Mises, FunctionSpace(mesh, 'P', 1)) (LinearElasticitySolver.py:75-76): M p = int vm phi_a."""
+    nv = coords.shape[0]
+    vol, _ = p1_geometry(coords, cells)
+    vm = von_mises_cells(coords, cells, u, mu, lmbda)
+    nl = cells.shape[1]
+    b = np.zeros(nv)
+    np.add.at(b, cells.ravel(), np.repeat(vm * vol / nl, nl))
+    M = assemble_matrix(cells, local_mass(coords, cells, 1.0), nv)
+    return spla.spsolve(M.tocsc(), b)
+
+
+def _facet_monomial_integral(alpha, fd):
+    """(1/|F|) int_F prod l_a^alpha_a ds on a simplex of dimension fd."""
+    num = math.factorial(fd)
+    for k in alpha:
+        num *= math.factorial(k)
+    return num / math.factorial(fd + sum(alpha))
+
+
+def radiation_terms(coords, fverts, T, m, T_ambient):
+    """Newton terms of the boundary flux m (Ta^4 - T^4) (ScalarTransportSolver.py:334-359, 361-374), T_h linear on each
+    facet, integrated EXACTLY by expanding the polynomials in barycentric monomials:
+    J[f,a,b] = int 4 m T_h^3 l_a l_b ds,  r[f,a] = int m (T_h^4 - Ta^4) l_a ds."""
+    import itertools
+    meas = facet_measure(coords, fverts)
+    nf, d = fverts.shape
+    fd = d - 1
+    t = np.asarray(T, dtype=np.float64)[fverts]                  # [nf, d]
+    J = np.zeros((nf, d, d))
+    r = np.zeros((nf, d))
+
+    def power_terms(p):
+        """(sum_a t_a l_a)^p as a list of (alpha, coefficient[nf])."""
+        out = []
+        for combo in itertools.product(range(d), repeat=p):
+            alpha = [0] * d
+            c = np.ones(nf)
+            for a in combo:
+                alpha[a] += 1
+                c = c * t[:, a]
+            out.append((alpha, c))
+        return out
+    T3, T4 = power_terms(3), power_terms(4)
+    for a in range(d):
+        for alpha, c in T4:
+            al = list(alpha); al[a] += 1
+            r[:, a] += m * c * _facet_monomial_integral(al, fd)
+        r[:, a] -= m * T_ambient ** 4 * _facet_monomial_integral([1 if k == a else 0 for k in range(d)], fd)
+        for b in range(d):
+            for alpha, c in T3:
+                al = list(alpha); al[a] += 1; al[b] += 1
+                J[:, a, b] += 4.0 * m * c * _facet_monomial_integral(al, fd)
+    return meas[:, None, None] * J, meas[:, None] * r
+
+
+def solve_radiation_newton(coords, cells, k, dirichlet, rad_fverts, m, T_ambient, T0, neumann=(), source=None,
+                           rtol=1e-12, maxit=50):
+    """Steady heat conduction with the radiation boundary term on rad_fverts, solved by Newton's method as the
+    reference's NonlinearVariationalSolver does (SolverBase.py:615-626): F(T) = K T - b + R(T), J = K + dR/dT,
+    Dirichlet rows T = g.  Direct linear solves.  -> (T, newton iterations)."""
+    nv = coords.shape[0]
+    K = assemble_matrix(cells, local_laplace(coords, cells, k), nv)
+    b = np.zeros(nv)
+    if source is not None:
+        b += assemble_source(coords, cells, source)
+    for fv, g in neumann:
+        b += assemble_facet_load(coords, fv, g, nv)
+    dofs = np.concatenate([np.asarray(d[0]) for d in dirichlet])
+    vals = np.concatenate([np.broadcast_to(np.asarray(d[1], dtype=np.float64), np.asarray(d[0]).shape) for d in dirichlet])
+    T = np.full(nv, float(T0)) if np.isscalar(T0) else np.array(T0, dtype=np.float64)
+    T[dofs] = vals
+    r0 = None
+    for it in range(maxit):
+        Jf, rf = radiation_terms(coords, rad_fverts, T, m, T_ambient)
+        A = (K + _scatter(rad_fverts, Jf, nv)).tocsr()
+        res = K @ T - b
+        np.add.at(res, rad_fverts.ravel(), rf.ravel())
+        A, rhs = apply_dirichlet(A, -res, dofs, np.zeros(dofs.size), symmetric=True)
+        nrm = np.linalg.norm(rhs)
+        r0 = nrm if r0 is None else r0
+        if nrm <= rtol * max(r0, 1e-300):
+            return T, it
+        T = T + solve_direct(A, rhs)
+    return T, maxit
+
+
 # --------------------------------------------------------------------------- whole-problem restatements
 
 

@@ -193,3 +193,64 @@ def local_facet_mass(coords, fverts, h=1.0):
 
 def interpolate(fn, node_coords):
     return fn(node_coords)
+
+
+# --------------------------------------------------------------------------- thermal stress, von Mises
+def thermal_load(coords, cells, cell_nodes, nnodes, beta, T, T_ref):
+    """b[(a,i)] = int beta (T_h - T_ref) d(phi_a)/dx_i dx with T_h the P2 interpolant of the nodal values (or a
+    constant): |T| sum_j dT_j sum_e S[j,a,e] G_e[i]  (LinearElasticitySolver.py:78-85, 232-238)."""
+    vol, G = fo.p1_geometry(coords, cells)
+    d = coords.shape[1]
+    _, _, S, _ = reference_tensors(d)
+    Tn = np.broadcast_to(np.asarray(T, dtype=np.float64), (nnodes,))
+    dT = Tn[cell_nodes] - T_ref                                    # [nc, nn]
+    be = beta * vol[:, None, None] * np.einsum("cj,jae,cei->cai", dT, S, G)
+    b = np.zeros((nnodes, d))
+    for i in range(d):
+        np.add.at(b[:, i], cell_nodes.ravel(), be[:, :, i].ravel())
+    return b.reshape(-1)
+
+
+def _collapsed_rule(d, n):
+    """Collapsed Gauss-Legendre rule on the reference simplex: barycentric points [np, d+1], weights summing to 1."""
+    x, w = np.polynomial.legendre.leggauss(n)
+    x, w = 0.5 * (x + 1.0), 0.5 * w
+    pts, wts = [], []
+    if d == 2:
+        for i in range(n):
+            for j in range(n):
+                X, Y = x[i], x[j] * (1 - x[i])
+                pts.append((1 - X - Y, X, Y)); wts.append(2 * w[i] * w[j] * (1 - x[i]))
+    else:
+        for i in range(n):
+            for j in range(n):
+                for k in range(n):
+                    X, Y, Z = x[i], x[j] * (1 - x[i]), x[k] * (1 - x[i]) * (1 - x[j])
+                    pts.append((1 - X - Y - Z, X, Y, Z)); wts.append(6 * w[i] * w[j] * w[k] * (1 - x[i]) ** 2 * (1 - x[j]))
+    return np.array(pts), np.array(wts)
+
+
+def von_mises_load(coords, cells, cell_nodes, u, mu, lmbda, n=4):
+    """b_a = int vm(u_h) lambda_a dx over the vertices, u_h degree 2; the integrand is not polynomial, so the value
+    depends on the rule: a collapsed Gauss rule with n = 4 points per axis (degree 5, what UFL would estimate)."""
+    vol, G = fo.p1_geometry(coords, cells)
+    d = coords.shape[1]
+    _, dphi = _basis(d)
+    nn = len(dphi)
+    U = np.asarray(u, dtype=np.float64).reshape(-1, d)[cell_nodes]      # [nc, nn, d]
+    pts, wts = _collapsed_rule(d, n)
+    b = np.zeros(coords.shape[0])
+    for l, w in zip(pts, wts):
+        D = np.zeros((nn, d + 1))
+        for j in range(nn):
+            for e in range(d + 1):
+                D[j, e] = sum(c * np.prod([l[a] ** k for a, k in enumerate(al)]) for al, c in dphi[j][e].items()) if dphi[j][e] else 0.0
+        gphi = np.einsum("je,cek->cjk", D, G)                            # grad phi_j per cell
+        H = np.einsum("cji,cjk->cik", U, gphi)
+        eps = 0.5 * (H + np.transpose(H, (0, 2, 1)))
+        sig = 2 * mu * eps + lmbda * np.trace(H, axis1=1, axis2=2)[:, None, None] * np.eye(d)
+        s = sig - np.trace(sig, axis1=1, axis2=2)[:, None, None] / 3.0 * np.eye(d)
+        vm = np.sqrt(1.5 * np.einsum("cij,cij->c", s, s))
+        for a in range(d + 1):
+            np.add.at(b, cells[:, a], w * vol * vm * l[a])
+    return b

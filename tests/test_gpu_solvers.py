@@ -342,6 +342,6 @@ def test_unsupported_features_raise_solver_error():
         ScalarTransportSolver.ScalarTransportSolver("not a dict")
     bcs2 = {"hot": {'boundary': top, 'boundary_id': 1, 'type': 'Dirichlet', 'value': 1.0}}
     settings, _ = heat_settings(bcs2, 4, 4)
-    settings['radiation_settings'] = {'ambient_temperature': 280, 'emissivity': 0.9}
+    settings['material']['conductivity'] = lambda T: (T - 300) / 300 * 0.6         # nonlinear material (test_heat_transfer.py:56)
     with pytest.raises(SolverBase.SolverError):
         ScalarTransportSolver.ScalarTransportSolver(settings).solve()

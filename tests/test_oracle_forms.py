@@ -1,0 +1,207 @@
+"""Known-answer tests that pin the oracle's restatement of thermal stress, the von Mises projection, the radiation
+boundary term with its Newton solve, and point sources (the reference asserts no numbers for them; these are
+closed forms), plus the host-side pieces around them (PointSource weights, .vtu/.pvd writer).  CPU only."""
+import os
+import xml.etree.ElementTree as ET
+
+import numpy as np
+import pytest
+from scipy.optimize import brentq
+
+from oracle import fem_oracle as fo
+from oracle import fem_oracle_p2 as fp
+
+
+def jitter(c, n, seed=0, amp=0.2):
+    rng = np.random.default_rng(seed)
+    return c + amp / n * (rng.random(c.shape) * 2 - 1)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_thermal_load_divergence_theorem(dim):
+    """sum_a x_a[i] b[(a,i)] = beta int (T - T_ref) dx (take v = x_i e_i, div v = 1), and a uniform temperature
+    loads only the boundary: the entries of every interior node vanish."""
+    n = 4
+    c, t = fo.unit_square_mesh(n, n) if dim == 2 else fo.unit_cube_mesh(n, n, n)
+    interior = np.all((c > 0) & (c < 1), axis=1)
+    cj = jitter(c, n)
+    cj[~interior] = c[~interior]
+    beta = 3.0
+    b = fo.thermal_load(cj, t, beta, 343.0, 293.0).reshape(-1, dim)
+    assert np.abs(b[interior]).max() < 1e-12 * beta * 50
+    assert np.allclose((cj * b).sum(axis=0), beta * 50.0, rtol=1e-12)
+    T = 293.0 + 100 * cj[:, 1]
+    b = fo.thermal_load(cj, t, beta, T, 293.0).reshape(-1, dim)
+    vol, _ = fo.p1_geometry(cj, t)
+    assert np.allclose((cj * b).sum(axis=0), beta * np.sum(vol * (T[t] - 293).mean(axis=1)), rtol=1e-12)
+    # degree 2: quadratic temperature, integrated exactly
+    cn, xn, _ = fp.p2_dofmap(cj, t)
+    T2 = 293.0 + 100 * xn[:, 1] ** 2
+    b2 = fp.thermal_load(cj, t, cn, xn.shape[0], beta, T2, 293.0).reshape(-1, dim)
+    _, M, _, _ = fp.reference_tensors(dim)
+    integral = beta * float(np.sum(vol[:, None] * np.einsum("ij,cj->ci", M, (T2 - 293.0)[cn])))
+    assert np.allclose((xn * b2).sum(axis=0), integral, rtol=1e-11)
+    # the P2 load of a uniform temperature agrees with the P1 one in total force on any node patch (here: all)
+    b2c = fp.thermal_load(cj, t, cn, xn.shape[0], beta, 343.0, 293.0).reshape(-1, dim)
+    assert np.allclose((xn * b2c).sum(axis=0), beta * 50.0, rtol=1e-12)
+
+
+def test_free_thermal_expansion_is_stress_free():
+    """A body heated uniformly and held only against rigid motion expands by eps = beta/(3 lambda + 2 mu) dT without
+    stress: u = eps x is the exact discrete solution (it is linear), and its von Mises stress is zero."""
+    n = 3
+    c, t = fo.unit_cube_mesh(n, n, n)
+    c = jitter(c, n, 3)
+    nv = c.shape[0]
+    E, nu, tec = 2e11, 0.27, 2e-6
+    mu, lam = fo.lame(E, nu)
+    beta = E / (1 - 2 * nu) * tec
+    A = fo.assemble_matrix(t, fo.local_elasticity(c, t, mu, lam), nv, 3)
+    b = fo.thermal_load(c, t, beta, 343.0, 293.0)
+    eps = beta * 50.0 / (3 * lam + 2 * mu)
+    assert abs(eps - tec * 50.0) < 1e-18                        # E/(1-2nu) = 3 lambda + 2 mu
+    uex = (eps * c).ravel()
+    assert np.abs(A @ uex - b).max() < 1e-9 * np.abs(b).max()
+    vm = fo.von_mises_cells(c, t, uex, mu, lam) - 0.0
+    sig_t = beta * 50.0
+    # sigma(u) = (3 lambda + 2 mu) eps I is hydrostatic: no deviator
+    assert vm.max() < 1e-9 * sig_t
+
+
+def test_von_mises_uniaxial_tension_and_projection():
+    """Uniaxial stress: u = eps (x, -nu y, -nu z) gives sigma = diag(E eps, 0, 0) and von Mises = E eps exactly;
+    the P1 projection of a constant is that constant."""
+    c, t = fo.unit_cube_mesh(3, 2, 2)
+    c = jitter(c, 3, 4)
+    E, nu, eps = 2e11, 0.27, 1e-4
+    mu, lam = fo.lame(E, nu)
+    u = eps * np.stack([c[:, 0], -nu * c[:, 1], -nu * c[:, 2]], axis=1)
+    vm = fo.von_mises_cells(c, t, u, mu, lam)
+    assert np.allclose(vm, E * eps, rtol=1e-11)
+    assert np.allclose(fo.von_mises_projection(c, t, u, mu, lam), E * eps, rtol=1e-10)
+    cn, xn, _ = fp.p2_dofmap(c, t)
+    u2 = eps * np.stack([xn[:, 0], -nu * xn[:, 1], -nu * xn[:, 2]], axis=1)
+    vol, _ = fo.p1_geometry(c, t)
+    assert np.allclose(fp.von_mises_load(c, t, cn, u2, mu, lam).sum(), E * eps * vol.sum(), rtol=1e-11)
+    # pure shear in 2D with the reference's 1/3 (not 1/2) deviator: sigma_xy = mu g, vm = sqrt(3) mu g
+    c2, t2 = fo.unit_square_mesh(3, 3)
+    g = 1e-3
+    us = np.stack([g * c2[:, 1], np.zeros(c2.shape[0])], axis=1)
+    assert np.allclose(fo.von_mises_cells(c2, t2, us, mu, lam), np.sqrt(3.0) * mu * g, rtol=1e-12)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_radiation_terms_exact_integration_and_jacobian(dim):
+    n = 3
+    c, t = fo.unit_square_mesh(n, n) if dim == 2 else fo.unit_cube_mesh(n, n, n)
+    c = jitter(c, n, 7)
+    fv, _, _ = fo.exterior_facets(t)
+    T = 300 + 50 * c[:, -1] + 10 * c[:, 0] ** 2
+    m, Ta = 0.9 * 5.670367e-8, 280.0
+    J, r = fo.radiation_terms(c, fv, T, m, Ta)
+    # against a high-order Gauss rule on the facets
+    if dim == 3:
+        pts, w = fp._collapsed_rule(2, 6)
+    else:
+        x, w = np.polynomial.legendre.leggauss(6)
+        pts, w = np.stack([0.5 * (1 - x), 0.5 * (1 + x)], axis=1), 0.5 * w
+    meas = fo.facet_measure(c, fv)
+    Tq = T[fv] @ pts.T
+    rq = m * np.einsum("fp,p,pa->fa", Tq ** 4 - Ta ** 4, w, pts) * meas[:, None]
+    Jq = 4 * m * np.einsum("fp,p,pa,pb->fab", Tq ** 3, w, pts, pts) * meas[:, None, None]
+    assert np.abs(r - rq).max() < 1e-13 * np.abs(r).max() and np.abs(J - Jq).max() < 1e-13 * np.abs(J).max()
+    # total radiated power of an isothermal body: m (T^4 - Ta^4) * area
+    _, r1 = fo.radiation_terms(c, fv, np.full(c.shape[0], 350.0), m, Ta)
+    assert np.allclose(r1.sum(), m * (350.0 ** 4 - Ta ** 4) * meas.sum(), rtol=1e-13)
+
+
+def test_radiation_one_dimensional_balance_known_answer():
+    """Bar heated to 360 K at y = 1 that radiates to 280 K from y = 0 only: the profile is linear (nodally exact for
+    P1) and the end temperature solves k (360 - Tb) = m (Tb^4 - Ta^4).  Newton converges quadratically."""
+    n = 6
+    c, t = fo.unit_square_mesh(n, n)
+    fv, _, _ = fo.exterior_facets(t)
+    bottom = fv[np.all(c[fv][:, :, 1] == 0, axis=1)]
+    top = np.nonzero(c[:, 1] == 1)[0]
+    k, m, Ta = 0.6, 0.9 * 5.670367e-8, 280.0
+    T, its = fo.solve_radiation_newton(c, t, k, [(top, 360.0)], bottom, m, Ta, 300.0)
+    Tb = brentq(lambda x: k * (360.0 - x) - m * (x ** 4 - Ta ** 4), 200.0, 360.0, xtol=1e-13)
+    assert np.abs(T - (Tb + (360.0 - Tb) * c[:, 1])).max() < 1e-9
+    assert its <= 6
+
+
+def test_point_source_weights_and_vtu_writer(tmp_path):
+    from fenicssolver_b200 import SolverBase as sb
+    from fenicssolver_b200.dolfin_compat import FunctionSpace, Point, PointSource, UnitCubeMesh, UnitSquareMesh
+    mesh = UnitSquareMesh(4, 4)
+    for degree in (1, 2):
+        V = FunctionSpace(mesh, "CG", degree)
+        nodes, w = PointSource(V, Point(0.3, 0.6), 2.5).entries()
+        assert abs(w.sum() - 2.5) < 1e-14                       # partition of unity
+        x = V.node_coordinates()[nodes]
+        if degree == 1:
+            assert np.allclose((w[:, None] * x).sum(axis=0), 2.5 * np.array([0.3, 0.6]))     # linear reproduction
+        else:
+            assert np.allclose((w * x[:, 0] * x[:, 1]).sum(), 2.5 * 0.18)                   # quadratic reproduction
+    with pytest.raises(sb.SolverError):
+        mesh.locate_point(Point(1.5, 0.5))
+    m3 = UnitCubeMesh(2, 2, 2)
+    vals = np.arange(27.0)
+    p = os.path.join(str(tmp_path), "T.vtu")
+    sb.write_vtu(p, m3, vals, "temperature")
+    piece = ET.parse(p).getroot().find("./UnstructuredGrid/Piece")
+    assert piece.attrib == {"NumberOfPoints": "27", "NumberOfCells": "48"}
+    conn = np.array(piece.find("./Cells/DataArray[@Name='connectivity']").text.split(), dtype=int).reshape(-1, 4)
+    assert np.array_equal(conn, m3.cells())
+    assert set(piece.find("./Cells/DataArray[@Name='types']").text.split()) == {"10"}
+    got = np.array(piece.find("./PointData/DataArray").text.split(), dtype=float)
+    assert np.array_equal(got, vals)
+    sb.write_pvd(os.path.join(str(tmp_path), "T.pvd"), [(0.0, "T000000.vtu"), (0.5, "T000001.vtu")])
+    ds = ET.parse(os.path.join(str(tmp_path), "T.pvd")).getroot().findall("./Collection/DataSet")
+    assert [d.attrib["file"] for d in ds] == ["T000000.vtu", "T000001.vtu"] and ds[1].attrib["timestep"] == "0.5"
+
+
+def test_forms_carry_thermal_stress_radiation_and_point_sources():
+    """Host-side form generation (no device call): LinearElasticitySolver.py:230-238, ScalarTransportSolver.py:334-374."""
+    import copy
+    from fenicssolver_b200 import LinearElasticitySolver, ScalarTransportSolver, SolverBase
+    from fenicssolver_b200.dolfin_compat import (AutoSubDomain, BoxMesh, Constant, Expression, FunctionSpace, Point, UnitSquareMesh,
+                                                 VectorFunctionSpace, near)
+    quiet = {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0}
+    mesh = BoxMesh(Point(0, 0, 0), Point(10, 1, 1), 4, 2, 2)
+    s = copy.deepcopy(SolverBase.default_case_settings)
+    s.update({'material': {'elastic_modulus': 2e11, 'poisson_ratio': 0.27, 'density': 7800, 'thermal_expansion_coefficient': 2e-6},
+              'function_space': VectorFunctionSpace(mesh, "Lagrange", 2), 'report_settings': quiet,
+              'boundary_conditions': {'fixed': {'boundary': AutoSubDomain(lambda x: near(x[0], 0.0)), 'boundary_id': 1, 'type': 'Dirichlet',
+                                                'value': Constant((0, 0, 0))}},
+              'temperature_distribution': Expression("343", degree=2)})
+    s['solver_settings']['reference_values'] = {'temperature': 293}
+    solver = LinearElasticitySolver.LinearElasticitySolver(s)
+    solver.init_solver()
+    solver.current_step = 0
+    F, bcs = solver.generate_form(0, None, None, solver.w_current, solver.w_prev)
+    beta, T, Tref = F.thermal
+    assert abs(beta - 2e11 / (1 - 0.54) * 2e-6) < 1e-6 and Tref == 293.0
+    assert T.shape == (solver.function_space.num_nodes(),) and np.all(T == 343.0)
+    s['temperature_distribution'] = None
+    solver = LinearElasticitySolver.LinearElasticitySolver(s)
+    solver.init_solver()
+    solver.current_step = 0
+    assert solver.generate_form(0, None, None, solver.w_current, solver.w_prev)[0].thermal is None
+
+    Q = FunctionSpace(UnitSquareMesh(4, 4), "CG", 1)
+    hs = {'solver_name': 'ScalarTransportSolver', 'scalar_name': 'temperature', 'mesh': None, 'function_space': Q,
+          'boundary_conditions': {'hot': {'boundary': AutoSubDomain(lambda x: near(x[1], 1.0)), 'boundary_id': 1, 'type': 'Dirichlet', 'value': 360}},
+          'body_source': None, 'initial_values': {'temperature': 300}, 'report_settings': quiet,
+          'material': {'density': 1000, 'specific_heat_capacity': 4200, 'thermal_conductivity': 0.1},
+          'solver_settings': {'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.1, 'ending_time': 1},
+                              'reference_values': {'temperature': 300}, 'solver_parameters': {}},
+          'radiation_settings': {'emissivity': 0.5}, 'point_source': [((0.3, 0.3), 2.0)]}
+    hsolver = ScalarTransportSolver.ScalarTransportSolver(hs)
+    hsolver.init_solver()
+    hsolver.current_step = 0
+    F, bcs = hsolver.generate_form(0, None, None, hsolver.w_current, hsolver.w_prev)
+    assert hsolver.nonlinear and F.radiation == (0.5 * 5.670367e-8, 300.0)       # ambient falls back to the reference value
+    hsolver.material['emissivity'] = 0.9                                        # material wins over radiation_settings
+    assert hsolver.radiation_coefficients()[0] == 0.9 * 5.670367e-8
+    assert len(F.point_sources) == 1 and F.point_sources[0].magnitude == 2.0
