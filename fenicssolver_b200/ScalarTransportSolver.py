@@ -46,6 +46,7 @@ class ScalarForm:
         self.T_prev = None
         self.radiation = None            # (m = emissivity * Stefan-Boltzmann, T_ambient)
         self.point_sources = []          # PointSource objects
+        self.conductivity_fn = None      # k(T) callable: the stiffness term moves into add_newton_terms
 
     def _k(self):
         k = self.conductivity
@@ -98,7 +99,7 @@ class ScalarForm:
                 raise SolverError('point sources are not implemented for distributed runs')
             b.add_entries(nodes, w)
         symmetric = vel is None and (ktensor is None or np.allclose(ktensor, ktensor.T, rtol=0, atol=0))
-        return b, symmetric
+        return b, symmetric and self.conductivity_fn is None       # the k'(T) Jacobian term is not symmetric
 
     def add_newton_terms(self, space, x, r):
         """Nonlinear part at the iterate x: space.A += dR/dT(x), r -= R(x) (r holds b - A_lin x)."""
@@ -106,6 +107,28 @@ class ScalarForm:
             m, Ta = self.radiation
             fv, _ = space.local_facets(*self.solver.mesh.exterior_facets()[:2])
             _lib.assemble_facet_radiation(space.dmesh, space.A, r, x, fv, m, Ta, rscale=-1.0)
+        if self.conductivity_fn is not None:
+            Th = x.numpy()
+            k, dk = nodal_function_and_derivative(self.conductivity_fn, Th)
+            _lib.assemble_scalar_nonlinear_k(space.dmesh, space.A, r, x, _lib.DeviceVector.from_numpy(space.ctx, k),
+                                             _lib.DeviceVector.from_numpy(space.ctx, dk), rscale=-1.0)
+
+
+def nodal_function_and_derivative(fn, T):
+    """k(T_a) and k'(T_a) at the nodal values.  Central differences, replaced by the complex-step derivative (exact to
+    rounding for the arithmetic expressions material lambdas are made of) whenever the function accepts complex input
+    and the two agree; a non-analytic function (abs, where, ...) keeps the central differences."""
+    T = np.asarray(T, dtype=np.float64)
+    k = np.broadcast_to(np.asarray(fn(T), dtype=np.float64), T.shape).copy()
+    h = 1e-6 * np.maximum(np.abs(T), 1.0)
+    dk = np.broadcast_to((np.asarray(fn(T + h), dtype=np.float64) - np.asarray(fn(T - h), dtype=np.float64)) / (2 * h), T.shape)
+    try:
+        cs = np.imag(np.broadcast_to(np.asarray(fn(T + 1e-30j)), T.shape)) / 1e-30
+        if np.all(np.isfinite(cs)) and np.allclose(cs, dk, rtol=1e-5, atol=1e-7 * max(float(np.abs(dk).max()), 1e-300)):
+            dk = cs
+    except (TypeError, ValueError):
+        pass
+    return k, np.ascontiguousarray(dk, dtype=np.float64)
 
 
 class ScalarTransportSolver(SolverBase):
@@ -122,13 +145,14 @@ class ScalarTransportSolver(SolverBase):
         self.nonlinear_material = False
         for v in self.material.values():
             if callable(v) and not isinstance(v, Constant):
-                self.nonlinear = True
+                self.nonlinear = True            # as the reference does at construction (:60-66)
 
     def _material_number(self, c, T):
         from inspect import isfunction
         if isfunction(c):
+            # a function of the unknown (:77-78): evaluated at nodal values when T is an array, else returned as is
             self.nonlinear_material = True
-            return c(T)
+            return c(T) if isinstance(T, np.ndarray) else c
         return self.get_material_value(c)
 
     def capacity(self, T=None):
@@ -237,10 +261,18 @@ class ScalarTransportSolver(SolverBase):
         F = ScalarForm(self)
         conductivity = self.conductivity(T)
         capacity = self.capacity(T)
-        if self.nonlinear_material or any(callable(v) and not isinstance(v, Constant) for v in self.material.values()):
-            raise SolverError('nonlinear material is outside the device hot path')
-        if isinstance(conductivity, (Function,)) or callable(conductivity):
-            raise SolverError('conductivity must be a number or a constant tensor on the device path')
+        if callable(capacity):
+            raise SolverError('nonlinear capacity is not supported (the reference says so too, :291)')
+        if callable(conductivity) and not isinstance(conductivity, Constant):
+            # k(T): Newton on the device with k_h the P1 interpolant of the nodal values k(T_a)
+            if self.function_space.degree != 1:
+                raise SolverError('temperature-dependent conductivity is implemented for degree-1 spaces')
+            if self.transient_settings['transient']:
+                raise SolverError('temperature-dependent conductivity is implemented for steady problems')
+            self.nonlinear = True
+            F.conductivity_fn, conductivity = conductivity, 0.0
+        elif isinstance(conductivity, (Function,)):
+            raise SolverError('conductivity must be a number, a constant tensor or a function of T on the device path')
         F.conductivity, F.capacity = conductivity, capacity
 
         if not hasattr(self, 'convective_velocity'):

@@ -70,6 +70,7 @@ SIGNATURES = {
     "fsb_assemble_thermal_load": (C.c_int, [c_vp, c_vp, c_dbl, c_vp, c_dbl, c_dbl, c_dbl]),
     "fsb_assemble_von_mises_load": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, c_vp]),
     "fsb_assemble_facet_radiation": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl]),
+    "fsb_assemble_scalar_nonlinear_k": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl]),
     "fsb_apply_dirichlet": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32]),
     "fsb_spmv": (C.c_int, [c_vp, c_vp, c_vp]),
     "fsb_dot": (C.c_int, [c_vp, c_vp, P(c_dbl)]),
@@ -407,3 +408,9 @@ def assemble_facet_radiation(mesh, A, r, T, fverts, m, T_ambient, rscale=1.0):
     fv = _np(fverts, np.int32)
     mesh.ctx.check(mesh.ctx.lib.fsb_assemble_facet_radiation(mesh.h, A.h if A is not None else None, r.h if r is not None else None,
                                                              T.h, fv.shape[0], _ptr(fv), float(m), float(T_ambient), float(rscale)))
+
+
+def assemble_scalar_nonlinear_k(mesh, A, r, T, k, dk, scale=1.0, rscale=1.0):
+    """Newton terms of int k(T) grad T . grad v: A += Jacobian, r += rscale * residual (A or r may be None)."""
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_scalar_nonlinear_k(mesh.h, A.h if A is not None else None, r.h if r is not None else None,
+                                                                T.h, k.h, dk.h, float(scale), float(rscale)))

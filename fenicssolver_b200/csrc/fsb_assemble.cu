@@ -395,6 +395,61 @@ __global__ void k_facet_radiation(int64_t nf, const int32_t* __restrict__ fverts
   }
 }
 
+// Temperature-dependent conductivity k(T) (ScalarTransportSolver.py:228-233, 284-285 with `conductivity` a function of T;
+// examples/test_heat_transfer.py:53-56): k_h is the P1 interpolant of the nodal values k(T_a), so int k_h = |T| mean k_a.
+//   r_a  += rscale * w |T| kbar (G_a . grad T_h)
+//   A_ab += w |T| ( kbar G_a.G_b + k'(T_b)/(D+1) (G_a . grad T_h) )        (the Gateaux derivative, :352-353)
+template <int D>
+__global__ void __launch_bounds__(128)
+k_scalar_nonlinear_k(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz,
+                     const double* __restrict__ T, const double* __restrict__ kn, const double* __restrict__ dkn, double w,
+                     double rscale, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                     double* __restrict__ vals, const uint8_t* __restrict__ posmap, double* __restrict__ r) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    double gT[D], kbar = 0.0, dk[NL];
+#pragma unroll
+    for (int i = 0; i < D; ++i) gT[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NL; ++a) {
+      const double Ta = __ldg(T + v[a]);
+      kbar += __ldg(kn + v[a]);
+      dk[a] = __ldg(dkn + v[a]) / (double)NL;
+#pragma unroll
+      for (int i = 0; i < D; ++i) gT[i] += Ta * g.G[a][i];
+    }
+    kbar /= (double)NL;
+    const double wv = w * g.vol;
+    double flux[NL];
+#pragma unroll
+    for (int a = 0; a < NL; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) s += g.G[a][i] * gT[i];
+      flux[a] = s;
+      if (r) atomicAdd(r + v[a], rscale * wv * kbar * s);
+    }
+    if (vals) {
+      int64_t base[NL];
+      int pos[NL][NL];
+      entry_positions<D>(posmap, c, v, row_ptr, col_idx, base, pos);
+#pragma unroll
+      for (int a = 0; a < NL; ++a)
+#pragma unroll
+        for (int b = 0; b < NL; ++b) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) s += g.G[a][i] * g.G[b][i];
+          add_nz(vals + base[a] + pos[a][b], wv * (kbar * s + dk[b] * flux[a]));
+        }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ Dirichlet
 __global__ void k_bc_scatter(int64_t nbc, const int64_t* __restrict__ dofs, const double* __restrict__ g,
                              uint8_t* __restrict__ flag, double* __restrict__ val, double* __restrict__ x) {
@@ -692,6 +747,26 @@ extern "C" int fsb_assemble_facet_radiation(fsb_mesh* mesh, fsb_mat* A, fsb_vec*
                                                         A ? A->col_idx : nullptr, A ? A->vals : nullptr, r ? r->d : nullptr);
   FSB_LAUNCH_CHECK(ctx);
   FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_scalar_nonlinear_k(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec* T, fsb_vec* k, fsb_vec* dk,
+                                               double scale, double rscale) {
+  if (!mesh || !T || !k || !dk || (!A && !r)) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (mesh->degree != 1) FSB_FAIL(ctx, FSB_ERR_ARG, "temperature-dependent conductivity is implemented for degree-1 spaces");
+  const int64_t n = mesh->nnodes;
+  if (T->n != n || k->n != n || dk->n != n || (r && r->n != n) || (A && (A->bs != 1 || A->nbrows != n)))
+    FSB_FAIL(ctx, FSB_ERR_ARG, "nonlinear conductivity needs the scalar matrix / nodal vectors of this mesh");
+  const uint8_t* pm = (A && ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3)
+    k_scalar_nonlinear_k<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, T->d, k->d, dk->d, scale, rscale,
+                                                           A ? A->row_ptr : nullptr, A ? A->col_idx : nullptr, A ? A->vals : nullptr, pm, r ? r->d : nullptr);
+  else
+    k_scalar_nonlinear_k<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, T->d, k->d, dk->d, scale, rscale,
+                                                           A ? A->row_ptr : nullptr, A ? A->col_idx : nullptr, A ? A->vals : nullptr, pm, r ? r->d : nullptr);
+  FSB_LAUNCH_CHECK(ctx);
   return FSB_OK;
 }
 

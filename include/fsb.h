@@ -164,6 +164,12 @@ int fsb_assemble_von_mises_load(fsb_mesh* mesh, fsb_vec* u, double mu, double la
 int fsb_assemble_facet_radiation(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec* T, int64_t nf, const int32_t* fverts,
                                  double m, double T_ambient, double rscale);
 
+/* Conductivity as a function of the unknown, k(T) (ScalarTransportSolver.py:228-233; examples/test_heat_transfer.py:53-56),
+ * Newton terms at the iterate T with k, dk the nodal values k(T_a), k'(T_a) (k_h = their P1 interpolant):
+ * r += rscale * scale * int k_h grad T . grad v,  A += scale * int (k_h grad u + k'_h u grad T) . grad v.  Degree 1. */
+int fsb_assemble_scalar_nonlinear_k(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec* T, fsb_vec* k, fsb_vec* dk,
+                                    double scale, double rscale);
+
 /* ---- DirichletBC.apply / assemble_system ------------------------------------------------------ */
 /* symmetric=0: zero row, unit diagonal, b=g (bc.apply(A,b), SolverBase.py:598-602, 608);
  * symmetric=1: additionally b -= A[:,bc] g and zero the column (assemble_system, SolverBase.py:644).

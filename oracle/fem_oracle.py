@@ -520,6 +520,48 @@ def solve_radiation_newton(coords, cells, k, dirichlet, rad_fverts, m, T_ambient
     return T, maxit
 
 
+def nonlinear_k_terms(coords, cells, T, kfun, dkfun):
+    """Residual and Jacobian of int k(T) grad T . grad q with k_h the P1 interpolant of the nodal values k(T_a)
+    (ScalarTransportSolver.py:228-233, 284-285, 352-353): R_a = sum |T| kbar G_a.grad T,
+    J_ab = sum |T| (kbar G_a.G_b + k'(T_b)/(d+1) G_a.grad T)."""
+    vol, G = p1_geometry(coords, cells)
+    nv = coords.shape[0]
+    nl = cells.shape[1]
+    Tc = np.asarray(T, dtype=np.float64)[cells]
+    kbar = kfun(Tc).mean(axis=1)
+    gT = np.einsum("ca,cai->ci", Tc, G)
+    flux = np.einsum("cai,ci->ca", G, gT)
+    Re = (vol * kbar)[:, None] * flux
+    Je = vol[:, None, None] * (kbar[:, None, None] * np.einsum("cai,cbi->cab", G, G)
+                                + flux[:, :, None] * (dkfun(Tc) / nl)[:, None, :])
+    R = np.zeros(nv)
+    np.add.at(R, cells.ravel(), Re.ravel())
+    return _scatter(cells, Je, nv), R
+
+
+def solve_nonlinear_k_newton(coords, cells, kfun, dkfun, dirichlet, T0, neumann=(), rtol=1e-12, maxit=50):
+    """Steady conduction with temperature-dependent conductivity by Newton's method (the reference's
+    NonlinearVariationalSolver path, SolverBase.py:615-626).  -> (T, iterations)."""
+    nv = coords.shape[0]
+    b = np.zeros(nv)
+    for fv, g in neumann:
+        b += assemble_facet_load(coords, fv, g, nv)
+    dofs = np.concatenate([np.asarray(d[0]) for d in dirichlet])
+    vals = np.concatenate([np.broadcast_to(np.asarray(d[1], dtype=np.float64), np.asarray(d[0]).shape) for d in dirichlet])
+    T = np.full(nv, float(T0))
+    T[dofs] = vals
+    r0 = None
+    for it in range(maxit):
+        J, R = nonlinear_k_terms(coords, cells, T, kfun, dkfun)
+        A, rhs = apply_dirichlet(J.tocsr(), b - R, dofs, np.zeros(dofs.size), symmetric=False)
+        nrm = np.linalg.norm(rhs)
+        r0 = nrm if r0 is None else r0
+        if nrm <= rtol * max(r0, 1e-300):
+            return T, it
+        T = T + solve_direct(A, rhs)
+    return T, maxit
+
+
 # --------------------------------------------------------------------------- whole-problem restatements
 
 

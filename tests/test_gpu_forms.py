@@ -416,3 +416,43 @@ def test_linear_elasticity_transient_dynamic_stress(tmp_path):
     assert int(piece.attrib["NumberOfPoints"]) == c.shape[0] and int(piece.attrib["NumberOfCells"]) == t.shape[0]
     arr = np.array(piece.find("./PointData/DataArray").text.split(), dtype=np.float64).reshape(-1, 3)
     assert np.abs(arr - u.values).max() <= 1e-14 * np.abs(u.values).max()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_nonlinear_conductivity_terms(ctx, dim):
+    c, t = small_mesh(dim)
+    nv = c.shape[0]
+    rng = np.random.default_rng(3)
+    T = 300 + 60 * rng.random(nv)
+    kf, dkf = (lambda x: 0.6 * (1 + 0.02 * (x - 300.0)) + 1e-5 * x ** 2), (lambda x: 0.6 * 0.02 + 2e-5 * x)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    r = _lib.DeviceVector(ctx, nv)
+    V = lambda a: _lib.DeviceVector.from_numpy(ctx, a)       # noqa: E731
+    _lib.assemble_scalar_nonlinear_k(m, A, r, V(T), V(kf(T)), V(dkf(T)), rscale=-1.0)
+    J, R = fo.nonlinear_k_terms(c, t, T, kf, dkf)
+    close(r.numpy(), -R, 1e-12)
+    _, _, va = A.download_csr()
+    close(va, fo.conform(J, *fo.csr_pattern(t, nv)).data, 1e-12)
+
+
+def test_nonlinear_conductivity_example_matches_oracle_newton():
+    """examples/test_heat_transfer.py:53-56 with `nonlinear = True`: conductivity = lambda T: (T-T_ambient)/T_ambient * 0.6,
+    shifted so that k stays positive on [300, 360]."""
+    n = 16
+    settings, mesh = radiation_settings(n)
+    del settings['radiation_settings']
+    kfun = lambda T: (0.2 + (T - 300) / 300) * 0.6       # noqa: E731
+    solver = ScalarTransportSolver.ScalarTransportSolver(settings)
+    solver.material['conductivity'] = kfun
+    T = solver.solve()
+    info = solver.solve_info
+    assert info['converged'] == 1 and info['newton_iterations'] <= 10
+    c, t = fo.unit_square_mesh(n, n)
+    tp, bt = np.nonzero(c[:, 1] == 1)[0], np.nonzero(c[:, 1] == 0)[0]
+    To, _ = fo.solve_nonlinear_k_newton(c, t, kfun, lambda T: 0.6 / 300 + 0 * T, [(tp, 360.0), (bt, 300.0)], 300.0)
+    assert fo.relative_l2(T.values, To) < TOL
+    # Kirchhoff profile (second-order accurate)
+    q = c[:, 1] * (0.12 * 60 + 0.001 * 3600)
+    s = (-0.12 + np.sqrt(0.12 ** 2 + 2 * 0.002 * q)) / 0.002
+    assert np.abs(T.values - 300 - s).max() < 0.2

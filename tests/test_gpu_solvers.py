@@ -342,6 +342,6 @@ def test_unsupported_features_raise_solver_error():
         ScalarTransportSolver.ScalarTransportSolver("not a dict")
     bcs2 = {"hot": {'boundary': top, 'boundary_id': 1, 'type': 'Dirichlet', 'value': 1.0}}
     settings, _ = heat_settings(bcs2, 4, 4)
-    settings['material']['conductivity'] = lambda T: (T - 300) / 300 * 0.6         # nonlinear material (test_heat_transfer.py:56)
+    settings['material']['capacity'] = lambda T: 4.2e6 * (1 + 1e-3 * T)            # nonlinear capacity: unsupported in the reference too
     with pytest.raises(SolverBase.SolverError):
         ScalarTransportSolver.ScalarTransportSolver(settings).solve()

@@ -205,3 +205,35 @@ def test_forms_carry_thermal_stress_radiation_and_point_sources():
     hsolver.material['emissivity'] = 0.9                                        # material wins over radiation_settings
     assert hsolver.radiation_coefficients()[0] == 0.9 * 5.670367e-8
     assert len(F.point_sources) == 1 and F.point_sources[0].magnitude == 2.0
+
+
+def test_nonlinear_conductivity_kirchhoff_known_answer():
+    """k(T) = k0 (1 + beta (T - 300)) between T = 360 at y = 1 and T = 300 at y = 0: the Kirchhoff variable
+    theta = int k dT is linear in y, so T(y) solves k0 (s + beta s^2 / 2) = y * k0 (60 + beta 60^2 / 2), s = T - 300.
+    The P1 solution (k interpolated at the nodes) converges to it at second order; the Jacobian is the derivative
+    of the residual."""
+    k0, beta = 0.6, 0.02
+    kf, dkf = (lambda T: k0 * (1 + beta * (T - 300.0))), (lambda T: k0 * beta + 0 * T)
+    errs = []
+    for n in (4, 8, 16):
+        c, t = fo.unit_square_mesh(n, n)
+        top, bot = np.nonzero(c[:, 1] == 1)[0], np.nonzero(c[:, 1] == 0)[0]
+        T, its = fo.solve_nonlinear_k_newton(c, t, kf, dkf, [(top, 360.0), (bot, 300.0)], 300.0)
+        q = c[:, 1] * (60 + beta * 1800)
+        s = (-1 + np.sqrt(1 + 2 * beta * q)) / beta
+        errs.append(np.abs(T - 300 - s).max())
+        assert its <= 8
+    assert errs[0] < 0.2 and errs[1] < errs[0] / 3 and errs[2] < errs[1] / 3.5
+    c, t = fo.unit_square_mesh(4, 4)
+    rng = np.random.default_rng(0)
+    T = 300 + 60 * rng.random(c.shape[0])
+    J, R = fo.nonlinear_k_terms(c, t, T, kf, dkf)
+    d = rng.standard_normal(c.shape[0])
+    eps = 1e-4
+    fd = (fo.nonlinear_k_terms(c, t, T + eps * d, kf, dkf)[1] - fo.nonlinear_k_terms(c, t, T - eps * d, kf, dkf)[1]) / (2 * eps)
+    assert np.abs(J @ d - fd).max() < 1e-7 * np.abs(fd).max()
+    from fenicssolver_b200.ScalarTransportSolver import nodal_function_and_derivative
+    k, dk = nodal_function_and_derivative(lambda T: (T - 300) / 300 * 0.6 + 0.1 * T ** 2, T)
+    assert np.allclose(dk, 0.6 / 300 + 0.2 * T, rtol=1e-14) and np.allclose(k, (T - 300) / 300 * 0.6 + 0.1 * T ** 2)
+    k, dk = nodal_function_and_derivative(lambda T: np.where(np.real(T) > 330, 1.0, 0.5) * np.abs(T), T)   # no complex step
+    assert np.allclose(dk, np.where(T > 330, 1.0, 0.5), rtol=1e-6)
