@@ -47,6 +47,7 @@ class ScalarForm:
         self.radiation = None            # (m = emissivity * Stefan-Boltzmann, T_ambient)
         self.point_sources = []          # PointSource objects
         self.conductivity_fn = None      # k(T) callable: the stiffness term moves into add_newton_terms
+        self.supg_pe = None              # Peclet number of the SUPG test function q + tau v.grad q (None: Galerkin)
 
     def _k(self):
         k = self.conductivity
@@ -64,6 +65,7 @@ class ScalarForm:
         vel = None if self.velocity is None else np.asarray(self.velocity, dtype=np.float64)
         adv = c if vel is not None else 0.0
         b = space.scratch_vector('rhs')
+        supg = self.supg_pe if vel is not None else None
         if self.transient:
             A.assemble_scalar(kscale=self.theta * kscale, ktensor=ktensor, mass=c / self.dt, adv=adv, vel=vel)
             tp = self.T_prev.device_vector()
@@ -72,19 +74,30 @@ class ScalarForm:
             elif space.comm.nranks > 1:
                 tp.halo()
             _lib.apply_scalar(space.dmesh, tp, b, kscale=-(1.0 - self.theta) * kscale, ktensor=ktensor, mass=c / self.dt)
+            if supg:
+                _lib.assemble_scalar_supg(space.dmesh, A, vel, supg, mass=c / self.dt, adv=adv)
+                _lib.assemble_scalar_supg(space.dmesh, None, vel, supg, mass=c / self.dt, x=tp, y=b)
         else:
             A.assemble_scalar(kscale=kscale, ktensor=ktensor, adv=adv, vel=vel)
+            if supg:
+                _lib.assemble_scalar_supg(space.dmesh, A, vel, supg, adv=adv)
         for marker, g in self.neumann:
-            fv, _ = space.local_facets(*s.boundary_facets.facets(marker))
+            fv, op = space.local_facets(*s.boundary_facets.facets(marker))
             _lib.assemble_facet_load(space.dmesh, b, fv, g)
+            if supg:
+                _lib.assemble_facet_supg(space.dmesh, None, b, fv, op, vel, supg, g=g)
         for marker, h, Ta in self.robin:
-            fv, _ = space.local_facets(*s.boundary_facets.facets(marker))
+            fv, op = space.local_facets(*s.boundary_facets.facets(marker))
             A.assemble_facet_mass(fv, h)
             _lib.assemble_facet_load(space.dmesh, b, fv, h * Ta)
+            if supg:
+                _lib.assemble_facet_supg(space.dmesh, A, b, fv, op, vel, supg, g=h * Ta, h=h)
         for value, sub_id in self.sources:
             if isinstance(value, np.ndarray):
                 if sub_id is not None:
                     raise SolverError('nodal body source restricted to a subdomain is not implemented')
+                if supg:
+                    raise SolverError('SUPG with a nodal (Expression) body source is not implemented')
                 _lib.assemble_source_nodal(space.dmesh, b, space.vector_from_global(value))
             else:
                 tags = None
@@ -93,6 +106,8 @@ class ScalarForm:
                         raise SolverError('body_source per subdomain needs cell markers (mesh_physical_region.xml)')
                     tags = s.subdomains.array()
                 _lib.assemble_source(space.dmesh, b, float(value), cell_tags=tags, tag=sub_id or 0)
+                if supg:
+                    _lib.assemble_source_supg(space.dmesh, b, float(value), vel, supg, cell_tags=tags, tag=sub_id or 0)
         for ps in self.point_sources:
             nodes, w = ps.entries()
             if space.comm.nranks > 1:
@@ -282,12 +297,19 @@ class ScalarTransportSolver(SolverBase):
                 self.convective_velocity = None
         if self.convective_velocity is not None:
             ads = self.settings.get('advection_settings') or {'stabilization_method': None}
-            if ads.get('stabilization_method'):
-                raise SolverError('advection stabilisation (SPUG/IP) is not implemented on the device path')
             vel = self.translate_value(self.convective_velocity)
             if not (isinstance(vel, np.ndarray) and vel.shape == (self.dimension,)):
                 raise SolverError('convective_velocity must be a constant vector on the device path')
             F.velocity = vel
+            method = ads.get('stabilization_method')
+            if method in ('SPUG', 'SUPG'):               # 'SPUG' is the reference's spelling (:259)
+                # SPUG_method == 2 (:268-270): the test function becomes q + tau v.grad(q) in every integral
+                if self.function_space.degree != 1:
+                    raise SolverError('SUPG is implemented for degree-1 spaces')
+                F.supg_pe = float(ads['Pe'])
+            elif method:
+                raise SolverError('advection stabilisation `{}` is not implemented on the device path (interior penalty '
+                                  'needs interior-facet assembly)'.format(method))
 
         if self.transient_settings['transient']:
             F.transient = True
@@ -311,6 +333,8 @@ class ScalarTransportSolver(SolverBase):
             if self.has_radiation:
                 if self.function_space.degree != 1:
                     raise SolverError('radiation is implemented for degree-1 spaces')
+                if F.supg_pe:
+                    raise SolverError('radiation together with SUPG is not implemented')
                 self.nonlinear = True
                 m_, Ta = self.radiation_coefficients()
                 F.radiation = (m_, Ta)           # F -= radiation_flux(T)*Tq*ds: all exterior facets (:359)

@@ -71,6 +71,9 @@ SIGNATURES = {
     "fsb_assemble_von_mises_load": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, c_vp]),
     "fsb_assemble_facet_radiation": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl]),
     "fsb_assemble_scalar_nonlinear_k": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl]),
+    "fsb_assemble_scalar_supg": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_dbl]),
+    "fsb_assemble_source_supg": (C.c_int, [c_vp, c_vp, c_dbl, c_vp, c_dbl, c_vp, c_i32]),
+    "fsb_assemble_facet_supg": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_dbl]),
     "fsb_apply_dirichlet": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32]),
     "fsb_spmv": (C.c_int, [c_vp, c_vp, c_vp]),
     "fsb_dot": (C.c_int, [c_vp, c_vp, P(c_dbl)]),
@@ -414,3 +417,22 @@ def assemble_scalar_nonlinear_k(mesh, A, r, T, k, dk, scale=1.0, rscale=1.0):
     """Newton terms of int k(T) grad T . grad v: A += Jacobian, r += rscale * residual (A or r may be None)."""
     mesh.ctx.check(mesh.ctx.lib.fsb_assemble_scalar_nonlinear_k(mesh.h, A.h if A is not None else None, r.h if r is not None else None,
                                                                 T.h, k.h, dk.h, float(scale), float(rscale)))
+
+
+# SUPG extra terms (test function q + tau vel.grad q): see include/fsb.h
+def assemble_scalar_supg(mesh, A, vel, pe, mass=0.0, adv=0.0, x=None, y=None):
+    ve = _np(vel, np.float64)
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_scalar_supg(mesh.h, A.h if A is not None else None, x.h if x is not None else None,
+                                                         y.h if y is not None else None, float(mass), float(adv), _ptr(ve), float(pe)))
+
+
+def assemble_source_supg(mesh, b, S, vel, pe, cell_tags=None, tag=0):
+    ve = _np(vel, np.float64)
+    tags = None if cell_tags is None else _np(cell_tags, np.int32)
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_source_supg(mesh.h, b.h, float(S), _ptr(ve), float(pe), _ptr(tags), int(tag)))
+
+
+def assemble_facet_supg(mesh, A, b, fverts, opp, vel, pe, g=0.0, h=0.0):
+    fv, op, ve = _np(fverts, np.int32), _np(opp, np.int32), _np(vel, np.float64)
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_facet_supg(mesh.h, A.h if A is not None else None, b.h if b is not None else None,
+                                                        fv.shape[0], _ptr(fv), _ptr(op), float(g), float(h), _ptr(ve), float(pe)))

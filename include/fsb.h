@@ -170,6 +170,20 @@ int fsb_assemble_facet_radiation(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec
 int fsb_assemble_scalar_nonlinear_k(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec* T, fsb_vec* k, fsb_vec* dk,
                                     double scale, double rscale);
 
+/* SUPG stabilisation (ScalarTransportSolver.py:252-274, method 2): test function Tq = q + tau vel.grad(q),
+ * tau = 0.5 h / (4/(Pe h) + 2 |vel|), h = 2 * cell circumradius.  The three calls add ONLY the extra terms that the
+ * tau vel.grad(q) part of the test function produces (degree 1, constant vel); the Galerkin terms come from the calls above.
+ *   scalar_supg:  A (or y += .. x when A is NULL) gets  int (mass u + adv vel.grad u) tau vel.grad(v)
+ *   source_supg:  b += int S tau vel.grad(v) dx          (cell_tags/tag as in fsb_assemble_source)
+ *   facet_supg:   b += int g tau vel.grad(v) ds,  A += int h u tau vel.grad(v) ds   over facets (vertex lists + opposite
+ *                 vertex, which together name the adjacent cell whose gradient is used)  */
+int fsb_assemble_scalar_supg(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, fsb_vec* y, double mass, double adv,
+                             const double* vel, double pe);
+int fsb_assemble_source_supg(fsb_mesh* mesh, fsb_vec* b, double S, const double* vel, double pe,
+                             const int32_t* cell_tags, int32_t tag);
+int fsb_assemble_facet_supg(fsb_mesh* mesh, fsb_mat* A, fsb_vec* b, int64_t nf, const int32_t* fverts,
+                            const int32_t* opp, double g, double h, const double* vel, double pe);
+
 /* ---- DirichletBC.apply / assemble_system ------------------------------------------------------ */
 /* symmetric=0: zero row, unit diagonal, b=g (bc.apply(A,b), SolverBase.py:598-602, 608);
  * symmetric=1: additionally b -= A[:,bc] g and zero the column (assemble_system, SolverBase.py:644).

@@ -562,6 +562,61 @@ def solve_nonlinear_k_newton(coords, cells, kfun, dkfun, dirichlet, T0, neumann=
     return T, maxit
 
 
+# --------------------------------------------------------------------------- SUPG (ScalarTransportSolver.py:252-274)
+
+
+def circumradius(coords, cells):
+    """Circumradius per cell from the circumcentre (the point equidistant from all vertices): 2 (x_i - x_0).c =
+    |x_i|^2 - |x_0|^2 -- a different route from the edge-length formulas of the CUDA kernel."""
+    X = coords[cells]
+    A = 2.0 * (X[:, 1:, :] - X[:, :1, :])
+    rhs = np.sum(X[:, 1:, :] ** 2, axis=2) - np.sum(X[:, :1, :] ** 2, axis=2)
+    ctr = np.linalg.solve(A, rhs[..., None])[..., 0]
+    return np.linalg.norm(ctr - X[:, 0, :], axis=1)
+
+
+def supg_weights(coords, cells, vel, Pe):
+    """s[c, a] = tau_c (v . G_a): the extra part of the SUPG test function Tq = q + tau v.grad(q) on P1,
+    tau = 0.5 h / (4/(Pe h) + 2 |v|), h = 2 * Circumradius (:256-266)."""
+    vol, G = p1_geometry(coords, cells)
+    vel = np.asarray(vel, dtype=np.float64)
+    h = 2.0 * circumradius(coords, cells)
+    tau = 0.5 * h / (4.0 / (Pe * h) + 2.0 * np.linalg.norm(vel))
+    return tau[:, None] * np.einsum("cai,i->ca", G, vel)
+
+
+def local_supg(coords, cells, vel, Pe, mass=0.0, adv=0.0):
+    """Extra local matrix  s_a int (mass phi_b + adv v.grad phi_b)."""
+    vol, G = p1_geometry(coords, cells)
+    nl = cells.shape[1]
+    s = supg_weights(coords, cells, vel, Pe)
+    col = vol[:, None] * (mass / nl + adv * np.einsum("cbi,i->cb", G, np.asarray(vel, dtype=np.float64)))
+    return s[:, :, None] * col[:, None, :]
+
+
+def supg_source(coords, cells, S, vel, Pe):
+    vol, _ = p1_geometry(coords, cells)
+    b = np.zeros(coords.shape[0])
+    np.add.at(b, cells.ravel(), (S * vol[:, None] * supg_weights(coords, cells, vel, Pe)).ravel())
+    return b
+
+
+def supg_facet_terms(coords, fverts, opp, vel, Pe, g=0.0, h=0.0):
+    """Extra facet terms on the cells (fverts, opp): b_a = g s_a |F| and the matrix h s_a |F|/d over the facet's nodes."""
+    nv = coords.shape[0]
+    cells = np.hstack([fverts, opp[:, None]]).astype(np.int64)
+    s = supg_weights(coords, cells, vel, Pe)
+    meas = facet_measure(coords, fverts)
+    d = fverts.shape[1]
+    b = np.zeros(nv)
+    np.add.at(b, cells.ravel(), (g * s * meas[:, None]).ravel())
+    rows = np.repeat(cells, d, axis=1).ravel()
+    cols = np.tile(fverts, (1, d + 1)).ravel()
+    vals = np.repeat(h * s * meas[:, None] / d, d, axis=1).ravel()
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(nv, nv)).tocsr()
+    return A, b
+
+
 # --------------------------------------------------------------------------- whole-problem restatements
 
 

@@ -456,3 +456,106 @@ def test_nonlinear_conductivity_example_matches_oracle_newton():
     q = c[:, 1] * (0.12 * 60 + 0.001 * 3600)
     s = (-0.12 + np.sqrt(0.12 ** 2 + 2 * 0.002 * q)) / 0.002
     assert np.abs(T.values - 300 - s).max() < 0.2
+
+
+# ----------------------------------------------------------------------------------- SUPG (ScalarTransportSolver.py:252-274)
+@pytest.mark.parametrize("dim", [2, 3])
+def test_supg_extra_terms(ctx, dim):
+    c, t = small_mesh(dim)
+    nv = c.shape[0]
+    vel = np.array([0.7, -0.3, 0.2][:dim])
+    Pe = 5.0
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    _lib.assemble_scalar_supg(m, A, vel, Pe, mass=2.5, adv=1.5)
+    _, _, va = A.download_csr()
+    ref = fo.conform(fo.assemble_matrix(t, fo.local_supg(c, t, vel, Pe, mass=2.5, adv=1.5), nv), *fo.csr_pattern(t, nv))
+    close(va, ref.data)
+    x = np.random.default_rng(1).standard_normal(nv)
+    y = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_scalar_supg(m, None, vel, Pe, mass=2.5, adv=1.5, x=_lib.DeviceVector.from_numpy(ctx, x), y=y)
+    close(y.numpy(), ref @ x, 1e-12)
+    b = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_source_supg(m, b, 4.0, vel, Pe)
+    close(b.numpy(), fo.supg_source(c, t, 4.0, vel, Pe))
+    fv, opp, _ = fo.exterior_facets(t)
+    A.zero()
+    b2 = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_facet_supg(m, A, b2, fv, opp, vel, Pe, g=2.0, h=3.0)
+    Af, bf = fo.supg_facet_terms(c, fv, opp, vel, Pe, g=2.0, h=3.0)
+    close(b2.numpy(), bf, 1e-12)
+    _, _, va = A.download_csr()
+    close(va, fo.conform(Af, *fo.csr_pattern(t, nv)).data, 1e-12)
+
+
+def supg_case(n, transient=None):
+    mesh = UnitSquareMesh(n, n)
+    Q = FunctionSpace(mesh, "CG", 1)
+    bcs = {"hot": {'boundary': top, 'boundary_id': 1, 'type': 'Dirichlet', 'value': Constant(360)},
+           "cold": {'boundary': bottom, 'boundary_id': 2, 'type': 'HTC', 'value': Constant(100), 'ambient': Constant(300)},
+           "left": {'boundary': left, 'boundary_id': 3, 'type': 'heatFlux', 'value': Constant(40.0)},
+           "right": {'boundary': right, 'boundary_id': 4, 'type': 'symmetry', 'value': None}}
+    return {'solver_name': 'ScalarTransportSolver', 'mesh': None, 'function_space': Q, 'periodic_boundary': None, 'fe_degree': 1,
+            'boundary_conditions': bcs, 'body_source': 2000.0, 'initial_values': {'temperature': 300},
+            'material': {'density': 1000, 'specific_heat_capacity': 4200, 'thermal_conductivity': 0.6},
+            'convective_velocity': Constant((0.5e-5, -2e-5)),
+            'advection_settings': {'stabilization_method': 'SPUG', 'Pe': 50.0},
+            'solver_settings': {'transient_settings': transient or {'transient': False, 'starting_time': 0, 'time_step': 0.1, 'ending_time': 1},
+                                'reference_values': {'temperature': 300}, 'solver_parameters': {}},
+            'scalar_name': 'temperature', 'report_settings': QUIET}
+
+
+def supg_oracle_system(n, dt=None, Tn=None):
+    c, t = fo.unit_square_mesh(n, n)
+    nv = c.shape[0]
+    k, cap, vel, Pe = 0.6, 1000 * 4200.0, np.array([0.5e-5, -2e-5]), 50.0
+    fv, opp, _ = fo.exterior_facets(t)
+    mid = c[fv].mean(axis=1)
+    fb, fl = mid[:, 1] == 0, mid[:, 0] == 0
+    K = fo.assemble_matrix(t, fo.local_laplace(c, t, k), nv)
+    C = fo.assemble_matrix(t, fo.local_advection(c, t, vel, cap) + fo.local_supg(c, t, vel, Pe, adv=cap), nv)
+    Ah, bh = fo.supg_facet_terms(c, fv[fb], opp[fb], vel, Pe, g=100.0 * 300.0, h=100.0)
+    _, bl = fo.supg_facet_terms(c, fv[fl], opp[fl], vel, Pe, g=40.0)
+    R = fo._scatter(fv[fb], fo.local_facet_mass(c, fv[fb], 100.0), nv) + Ah
+    loads = (fo.assemble_source(c, t, 2000.0) + fo.supg_source(c, t, 2000.0, vel, Pe) + fo.assemble_facet_load(c, fv[fb], 100.0 * 300.0, nv)
+             + bh + fo.assemble_facet_load(c, fv[fl], 40.0, nv) + bl)
+    tp = np.nonzero(c[:, 1] == 1)[0]
+    if dt is None:
+        A, b = K + C + R, loads
+    else:
+        M = fo.assemble_matrix(t, fo.local_mass(c, t, cap / dt) + fo.local_supg(c, t, vel, Pe, mass=cap / dt), nv)
+        A, b = M + 0.5 * K + C + R, M @ Tn - 0.5 * (K @ Tn) + loads
+    Ab, bb = fo.apply_dirichlet(A.tocsr(), b, tp, np.full(tp.size, 360.0), symmetric=False)
+    return fo.solve_direct(Ab, bb)
+
+
+def test_supg_steady_with_htc_flux_and_source_matches_oracle():
+    """using_convective_velocity + HTC of examples/test_heat_transfer.py:139-160 with advection_settings
+    {'stabilization_method': 'SPUG', 'Pe': ...}: every integral carries the stabilised test function."""
+    n = 16
+    solver = ScalarTransportSolver.ScalarTransportSolver(supg_case(n))
+    T = solver.solve()
+    assert solver.solve_info['converged'] == 1
+    To = supg_oracle_system(n)
+    assert fo.relative_l2(T.values, To) < TOL
+    plain = supg_case(n)
+    plain['advection_settings'] = {'stabilization_method': None}
+    Tg = ScalarTransportSolver.ScalarTransportSolver(plain).solve()
+    assert fo.relative_l2(Tg.values, To) > 1e-6          # the stabilisation does change the discrete answer
+    bad = supg_case(n)
+    bad['advection_settings'] = {'stabilization_method': 'IP', 'alpha': 0.1}
+    with pytest.raises(SolverBase.SolverError):
+        ScalarTransportSolver.ScalarTransportSolver(bad).solve()
+
+
+def test_supg_transient_matches_oracle():
+    n, nsteps = 8, 3
+    dt = 1000 * 4200.0 / (n * n) / 0.6
+    s = supg_case(n, {'transient': True, 'starting_time': 0.0, 'time_step': dt, 'ending_time': dt * (nsteps - 0.5)})
+    solver = ScalarTransportSolver.ScalarTransportSolver(s)
+    T = solver.solve()
+    assert solver.current_step == nsteps
+    Tn = np.full((n + 1) ** 2, 300.0)
+    for _ in range(nsteps):
+        Tn = supg_oracle_system(n, dt, Tn)
+    assert fo.relative_l2(T.values, Tn) < TOL
