@@ -104,7 +104,7 @@ class ScalarForm:
                 if sub_id is not None:
                     if s.subdomains is None:
                         raise SolverError('body_source per subdomain needs cell markers (mesh_physical_region.xml)')
-                    tags = s.subdomains.array()
+                    tags = space.local_cell_tags(s.subdomains.array())
                 _lib.assemble_source(space.dmesh, b, float(value), cell_tags=tags, tag=sub_id or 0)
                 if supg:
                     _lib.assemble_source_supg(space.dmesh, b, float(value), vel, supg, cell_tags=tags, tag=sub_id or 0)

@@ -82,6 +82,7 @@ SIGNATURES = {
     "fsb_dist_unique_id": (C.c_int, [c_vp]),
     "fsb_dist_init": (C.c_int, [c_vp, c_i32, c_i32, c_vp]),
     "fsb_dist_set_slab": (C.c_int, [c_vp, c_i32, c_i32, c_i64]),
+    "fsb_dist_set_halo": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "fsb_dist_halo": (C.c_int, [c_vp]),
     "fsb_dist_allreduce_max": (C.c_int, [c_vp, P(c_dbl)]),
 }
@@ -174,6 +175,11 @@ class Context:
     def dist_set_slab(self, ghost_lo, ghost_hi, owned_planes):
         self.check(self.lib.fsb_dist_set_slab(self.h, ghost_lo, ghost_hi, owned_planes))
 
+    def dist_set_halo(self, n_owned, n_local, neigh_rank, send_ptr, send_idx, recv_off, recv_cnt):
+        nr = _np(neigh_rank, np.int32)
+        sp_, si, ro, rc_ = _np(send_ptr, np.int64), _np(send_idx, np.int64), _np(recv_off, np.int64), _np(recv_cnt, np.int64)
+        self.check(self.lib.fsb_dist_set_halo(self.h, int(n_owned), int(n_local), nr.size, _ptr(nr), _ptr(sp_), _ptr(si), _ptr(ro), _ptr(rc_)))
+
     def allreduce_max(self, value):
         v = c_dbl(value)
         self.check(self.lib.fsb_dist_allreduce_max(self.h, C.byref(v)))
@@ -211,14 +217,16 @@ class DeviceMesh(_Handle):
         return cls(ctx, h)
 
     @classmethod
-    def upload_p2(cls, ctx, coords, cell_nodes, nnodes):
-        """Degree-2 node layout: cell_nodes[nc][6|10] = sorted vertices then edge nodes (UFC order)."""
+    def upload_p2(cls, ctx, coords, cell_nodes, nnodes, nverts=None):
+        """Degree-2 node layout: cell_nodes[nc][6|10] = sorted vertices then edge nodes (UFC order).  `nverts`: how many
+        leading rows of `coords` to upload (default: all; pass nnodes with coordinates for every node when the vertex
+        nodes do not come first, as in a partitioned space)."""
         coords = _np(coords, np.float64)
         cell_nodes = _np(cell_nodes, np.int32)
         gdim = coords.shape[1]
         h = c_vp()
-        ctx.check(ctx.lib.fsb_mesh_upload_p2(ctx.h, gdim, gdim, coords.shape[0], _ptr(coords), cell_nodes.shape[0], _ptr(cell_nodes),
-                                             int(nnodes), C.byref(h)))
+        ctx.check(ctx.lib.fsb_mesh_upload_p2(ctx.h, gdim, gdim, int(nverts) if nverts is not None else coords.shape[0], _ptr(coords),
+                                             cell_nodes.shape[0], _ptr(cell_nodes), int(nnodes), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

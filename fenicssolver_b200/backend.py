@@ -7,7 +7,9 @@ numerical fallback on the host.
 
 Distributed runs (one process per GPU): a box mesh is cut into z-slabs of vertex planes, each rank
 generates its slab plus one ghost plane per neighbour on its own device, assembles without
-communication (owner computes) and solves with halo exchange + all-reduced dot products.
+communication (owner computes) and solves with halo exchange + all-reduced dot products.  Any other
+mesh (file meshes, user arrays) and every degree-2 space is split by recursive coordinate bisection of its nodes
+(partition.NodePartition): owned nodes first, ghosts appended, general send lists for the halo.
 """
 from __future__ import annotations
 
@@ -18,6 +20,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import SolverError
+from .partition import NodePartition, rcb_partition
 
 _contexts = {}
 
@@ -79,15 +82,30 @@ class DeviceSpace:
         self.v_off = 0                                  # global vertex id of local vertex 0
         self.ghost_lo = self.ghost_hi = 0
         nv_global = mesh.num_vertices() if self.degree == 1 else space.num_nodes()
-        if self.degree == 2:
-            if self.comm.nranks > 1:
-                raise SolverError("distributed P2 spaces are not implemented")
+        self.part = None                                # NodePartition of a general (non-slab) distributed space
+        general = self.comm.nranks > 1 and (self.degree == 2 or not mesh.box or getattr(mesh, "force_general_partition", False))
+        if general:
+            # host integer work on the replicated mesh: node partition, local numbering, halo lists
+            fs = space if space is not None else None
+            cell_nodes = mesh.cells() if self.degree == 1 else fs.cell_nodes()
+            node_xyz = mesh.coordinates() if self.degree == 1 else fs.node_coordinates()
+            owner = rcb_partition(node_xyz, self.comm.nranks)
+            self.part = NodePartition(cell_nodes, owner, self.comm.rank, self.comm.nranks)
+            pt = self.part
+            if self.degree == 1:
+                self.dmesh = _lib.DeviceMesh.upload(self.ctx, node_xyz[pt.l2g], np.sort(pt.cell_nodes_local, axis=1))
+            else:
+                # coordinates for every local node, so the vertex nodes of a cell may carry any local id
+                self.dmesh = _lib.DeviceMesh.upload_p2(self.ctx, node_xyz[pt.l2g], pt.cell_nodes_local, pt.n_local, nverts=pt.n_local)
+            if self.ctx.nranks == 1:
+                uid = self.ctx.dist_unique_id() if self.comm.rank == 0 else None
+                uid = self.comm.bootstrap(uid)
+                self.ctx.dist_init(self.comm.rank, self.comm.nranks, uid)
+            self.ctx.dist_set_halo(pt.n_owned, pt.n_local, pt.neighbours, pt.send_ptr, pt.send_idx, pt.recv_off, pt.recv_cnt)
+        elif self.degree == 2:
             # degree-2 node layout: host integer work (edge numbering), then one upload
             self.dmesh = _lib.DeviceMesh.upload_p2(self.ctx, mesh.coordinates(), space.cell_nodes(), space.num_nodes())
         elif self.comm.nranks > 1:
-            if not mesh.box:
-                raise SolverError("distributed runs need a generated box mesh (z-slab partition); "
-                                  "unstructured partitioning is not implemented")
             n = mesh.box["n"]
             nlast = n[-1]
             if nlast + 1 < self.comm.nranks:
@@ -118,8 +136,12 @@ class DeviceSpace:
         _, _, self.nv_local, self.nc_local = self.dmesh.sizes()
         if self.degree == 2:
             self.nv_local = space.num_nodes()           # rows are P2 nodes (vertices + edges)
-        self.own_v0 = self.ghost_lo * getattr(self, "plane", 0)
-        self.own_v1 = self.own_v0 + (self.owned_planes * self.plane if self.comm.nranks > 1 else self.nv_local)
+        if self.part is not None:
+            self.nv_local = self.part.n_local
+            self.own_v0, self.own_v1 = 0, self.part.n_owned
+        else:
+            self.own_v0 = self.ghost_lo * getattr(self, "plane", 0)
+            self.own_v1 = self.own_v0 + (self.owned_planes * self.plane if self.comm.nranks > 1 else self.nv_local)
         self.nv_global = nv_global
         self.ctx.sync()
         self.timings["mesh"] = time.perf_counter() - t0
@@ -142,12 +164,27 @@ class DeviceSpace:
     def local_vertices(self, gverts):
         """Global vertex ids -> local ids, dropping those outside this rank's planes."""
         g = np.asarray(gverts, dtype=np.int64)
+        if self.part is not None:
+            l, ok = self.part.to_local(g)
+            return l[ok]
         l = g - self.v_off
         return l[(l >= 0) & (l < self.nv_local)]
 
     def local_facets(self, fverts, opp=None):
         """Facets (global vertex lists) -> what the facet kernels take: local vertex lists (P1) or the facets'
         P2 node lists (vertices then edges), plus the opposite vertices when given."""
+        if self.part is not None:
+            fn = self.fs.facet_nodes(fverts) if self.degree == 2 else np.asarray(fverts, dtype=np.int64)
+            nfn = fn.shape[1] if fn.ndim == 2 else 0
+            if fn.shape[0] == 0:
+                return np.zeros((0, nfn), dtype=np.int32), (None if opp is None else np.zeros(0, dtype=np.int32))
+            l, ok = self.part.to_local(fn)
+            keep = ok.all(axis=1)
+            if opp is None:
+                return (l[keep] if self.degree == 2 else np.sort(l[keep], axis=1)).astype(np.int32), None
+            lo, oko = self.part.to_local(opp)
+            keep &= oko
+            return (l[keep] if self.degree == 2 else np.sort(l[keep], axis=1)).astype(np.int32), lo[keep].astype(np.int32)
         if self.degree == 2:
             fn = self.fs.facet_nodes(fverts)
             return fn, (None if opp is None else np.asarray(opp, dtype=np.int32))
@@ -163,11 +200,26 @@ class DeviceSpace:
         """Global dof ids/values -> local, dropping those outside this rank's planes."""
         g = np.asarray(gdofs, dtype=np.int64)
         v = np.broadcast_to(np.asarray(gvals, dtype=np.float64), g.shape)
+        if self.part is not None:
+            ln, ok = self.part.to_local(g // self.ncomp)
+            return (ln * self.ncomp + g % self.ncomp)[ok], v[ok]
         l = g - self.v_off * self.ncomp
         keep = (l >= 0) & (l < self.ndof_local)
         return l[keep], v[keep]
 
+    def local_cell_tags(self, tags):
+        """Global per-cell array -> the cells this rank holds."""
+        if self.part is not None:
+            return np.asarray(tags)[self.part.cells_global]
+        if self.comm.nranks > 1:
+            per_layer = self.mesh.num_cells() // self.mesh.box["n"][-1]
+            return np.asarray(tags)[self.v_off // self.plane * per_layer:][:self.nc_local]
+        return tags
+
     def local_coordinates(self):
+        if self.part is not None:
+            xyz = self.mesh.coordinates() if self.degree == 1 else self.fs.node_coordinates()
+            return xyz[self.part.l2g]
         if self.comm.nranks == 1:
             return self.mesh.coordinates()
         return self.mesh.coordinates()[self.v_off:self.v_off + self.nv_local]
@@ -181,6 +233,8 @@ class DeviceSpace:
 
     def vector_from_global(self, values):
         a = np.asarray(values, dtype=np.float64).ravel()
+        if self.part is not None:
+            return _lib.DeviceVector.from_numpy(self.ctx, a.reshape(-1, self.ncomp)[self.part.l2g].ravel())
         lo = self.v_off * self.ncomp
         return _lib.DeviceVector.from_numpy(self.ctx, a[lo:lo + self.ndof_local])
 
@@ -213,6 +267,12 @@ class DeviceSpace:
             return mine
         import torch.distributed as dist
         parts = [None] * self.comm.nranks
+        if self.part is not None:
+            dist.all_gather_object(parts, (self.part.owned, mine))
+            out = np.empty((self.nv_global, self.ncomp))
+            for ids, vals in parts:
+                out[ids] = vals.reshape(-1, self.ncomp)
+            return out.ravel()
         dist.all_gather_object(parts, mine)
         return np.concatenate(parts)
 

@@ -1,4 +1,9 @@
-// K8: z-slab distribution — ghost-plane halo exchange and scalar all-reduce over NCCL (NVLink/NVSwitch).
+// K8: distribution — halo exchange and scalar all-reduce over NCCL (NVLink/NVSwitch).  Two layouts:
+//  * z-slabs of a box mesh: [ghost plane below | owned planes | ghost plane above], neighbours rank-1 / rank+1
+//    (fsb_dist_set_slab; this is the layout the peer-memory CG kernels understand);
+//  * any partition of the nodes (fsb_dist_set_halo): local numbering [owned nodes | ghosts grouped by owner rank],
+//    per-neighbour send lists packed by a gather kernel, received straight into the ghost range (PETSc VecScatter
+//    style; unstructured meshes, degree-2 spaces).
 //
 // NCCL is bound at run time (dlopen "libnccl.so.2": inside a torch process this resolves to the copy
 // torch already loaded) so libfsb.so has no link-time dependency on it; only the handful of entry
@@ -59,6 +64,14 @@ struct fsb_dist {
   int ghost_lo = 0, ghost_hi = 0;
   int64_t owned_planes = 0;
   bool slab_set = false;
+  // general halo plan (fsb_dist_set_halo)
+  bool halo_set = false;
+  int64_t n_owned = 0, n_local = 0;
+  std::vector<int> nb_rank;
+  std::vector<int64_t> send_ptr, recv_off, recv_cnt;     // per neighbour, in nodes
+  int64_t* d_send_idx = nullptr;                          // concatenated send lists (local node ids)
+  double* d_sendbuf = nullptr;
+  size_t sendbuf_cap = 0;                                 // doubles
   // peer memory (CUDA IPC): this rank's CommBuf and every rank's mapping of it
   CommBuf* comm_local = nullptr;
   CommBuf* comm_of[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -115,6 +128,8 @@ void fsb_dist_destroy(fsb_ctx* ctx) {
   for (int r = 0; r < kMaxRanks; ++r)
     if (ctx->dist->comm_of[r] && r != ctx->dist->rank) cudaIpcCloseMemHandle(ctx->dist->comm_of[r]);
   cudaFree(ctx->dist->comm_local);
+  cudaFree(ctx->dist->d_send_idx);
+  cudaFree(ctx->dist->d_sendbuf);
   if (ctx->dist->comm && nccl().ok) nccl().CommDestroy(ctx->dist->comm);
   delete ctx->dist;
   ctx->dist = nullptr;
@@ -233,11 +248,48 @@ extern "C" int fsb_dist_set_slab(fsb_ctx* ctx, int32_t ghost_lo, int32_t ghost_h
   fsb_dist* d = ctx->dist;
   if ((ghost_lo && d->rank == 0) || (ghost_hi && d->rank == d->nranks - 1)) FSB_FAIL(ctx, FSB_ERR_ARG, "ghost plane without a neighbour rank");
   d->ghost_lo = ghost_lo; d->ghost_hi = ghost_hi; d->owned_planes = owned_planes; d->slab_set = true;
+  d->halo_set = false;
+  return FSB_OK;
+}
+
+extern "C" int fsb_dist_set_halo(fsb_ctx* ctx, int64_t n_owned, int64_t n_local, int32_t nneigh, const int32_t* neigh_rank,
+                                 const int64_t* send_ptr, const int64_t* send_idx, const int64_t* recv_off, const int64_t* recv_cnt) {
+  if (!ctx || n_owned < 0 || n_local < n_owned || nneigh < 0 || (nneigh > 0 && (!neigh_rank || !send_ptr || !recv_off || !recv_cnt)))
+    return FSB_ERR_ARG;
+  if (!ctx->dist) FSB_FAIL(ctx, FSB_ERR_STATE, "fsb_dist_init has not been called");
+  fsb_dist* d = ctx->dist;
+  const int64_t nsend = nneigh ? send_ptr[nneigh] : 0;
+  if (nsend > 0 && !send_idx) return FSB_ERR_ARG;
+  for (int i = 0; i < nneigh; ++i) {
+    if (neigh_rank[i] < 0 || neigh_rank[i] >= d->nranks || neigh_rank[i] == d->rank) FSB_FAIL(ctx, FSB_ERR_ARG, "bad neighbour rank");
+    if (send_ptr[i + 1] < send_ptr[i] || recv_off[i] < n_owned || recv_off[i] + recv_cnt[i] > n_local)
+      FSB_FAIL(ctx, FSB_ERR_ARG, "halo lists out of range");
+  }
+  for (int64_t k = 0; k < nsend; ++k)
+    if (send_idx[k] < 0 || send_idx[k] >= n_owned) FSB_FAIL(ctx, FSB_ERR_ARG, "send list entry is not an owned node");
+  d->slab_set = false;
+  d->halo_set = true;
+  d->n_owned = n_owned; d->n_local = n_local;
+  d->nb_rank.assign(neigh_rank, neigh_rank + nneigh);
+  d->send_ptr.assign(send_ptr, send_ptr + (nneigh ? nneigh + 1 : 0));
+  d->recv_off.assign(recv_off, recv_off + nneigh);
+  d->recv_cnt.assign(recv_cnt, recv_cnt + nneigh);
+  cudaFree(d->d_send_idx);
+  d->d_send_idx = nullptr;
+  if (nsend > 0) {
+    FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&d->d_send_idx, sizeof(int64_t) * nsend));
+    FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(d->d_send_idx, send_idx, sizeof(int64_t) * nsend, cudaMemcpyHostToDevice, ctx->stream));
+    FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return FSB_OK;
 }
 
 void fsb_dist_owned_range(fsb_ctx* ctx, int64_t n, int64_t* o0, int64_t* o1) {
   *o0 = 0; *o1 = n;
+  if (fsb_dist_active(ctx) && ctx->dist->halo_set && ctx->dist->n_local > 0) {
+    *o1 = ctx->dist->n_owned * (n / ctx->dist->n_local);      // vectors hold ncomp values per node
+    return;
+  }
   if (!fsb_dist_active(ctx) || !ctx->dist->slab_set) return;
   fsb_dist* d = ctx->dist;
   const int64_t planes = d->ghost_lo + d->owned_planes + d->ghost_hi;
@@ -246,9 +298,44 @@ void fsb_dist_owned_range(fsb_ctx* ctx, int64_t n, int64_t* o0, int64_t* o1) {
   *o1 = *o0 + d->owned_planes * plane;
 }
 
+__global__ void k_pack(const double* __restrict__ v, const int64_t* __restrict__ idx, int64_t nsend, int bs, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nsend * bs; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = v[idx[i / bs] * bs + i % bs];
+}
+
+// general partition: gather the send lists into one buffer, one send + one receive per neighbour; the ghosts of a
+// neighbour are contiguous in the local numbering, so the receive lands in place
+static int halo_general(fsb_ctx* ctx, double* v, int64_t n) {
+  fsb_dist* d = ctx->dist;
+  if (d->n_local <= 0 || n % d->n_local) FSB_FAIL(ctx, FSB_ERR_ARG, "vector length is not a multiple of the local node count");
+  const int bs = (int)(n / d->n_local);
+  const int nn = (int)d->nb_rank.size();
+  if (nn == 0) return FSB_OK;
+  const int64_t nsend = d->send_ptr[nn];
+  if ((size_t)(nsend * bs) > d->sendbuf_cap) {
+    cudaFree(d->d_sendbuf);
+    d->d_sendbuf = nullptr; d->sendbuf_cap = 0;
+    FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&d->d_sendbuf, sizeof(double) * nsend * bs));
+    d->sendbuf_cap = (size_t)(nsend * bs);
+  }
+  if (nsend > 0) {
+    k_pack<<<fsb_grid(nsend * bs, 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(v, d->d_send_idx, nsend, bs, d->d_sendbuf);
+    FSB_LAUNCH_CHECK(ctx);
+  }
+  FSB_CHECK_NCCL(ctx, nccl().GroupStart());
+  for (int i = 0; i < nn; ++i) {
+    const int64_t cnt = d->send_ptr[i + 1] - d->send_ptr[i];
+    if (cnt > 0) FSB_CHECK_NCCL(ctx, nccl().Send(d->d_sendbuf + d->send_ptr[i] * bs, (size_t)(cnt * bs), kNcclFloat64, d->nb_rank[i], d->comm, ctx->stream));
+    if (d->recv_cnt[i] > 0) FSB_CHECK_NCCL(ctx, nccl().Recv(v + d->recv_off[i] * bs, (size_t)(d->recv_cnt[i] * bs), kNcclFloat64, d->nb_rank[i], d->comm, ctx->stream));
+  }
+  FSB_CHECK_NCCL(ctx, nccl().GroupEnd());
+  return FSB_OK;
+}
+
 // v has (ghost_lo + owned + ghost_hi) planes; the plane size follows from n
 static int halo(fsb_ctx* ctx, double* v, int64_t n) {
   fsb_dist* d = ctx->dist;
+  if (d->halo_set) return halo_general(ctx, v, n);
   if (!d->slab_set) FSB_FAIL(ctx, FSB_ERR_STATE, "fsb_dist_set_slab has not been called");
   const int64_t planes = d->ghost_lo + d->owned_planes + d->ghost_hi;
   if (n % planes) FSB_FAIL(ctx, FSB_ERR_ARG, "vector length is not a whole number of planes");

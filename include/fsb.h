@@ -210,6 +210,13 @@ int fsb_dist_init(fsb_ctx* ctx, int32_t rank, int32_t nranks, const void* uid128
  * of owned vertex planes; the plane size follows from each vector's length; neighbours are
  * rank-1 / rank+1. */
 int fsb_dist_set_slab(fsb_ctx* ctx, int32_t ghost_lo, int32_t ghost_hi, int64_t owned_planes);
+/* general node partition (unstructured meshes, degree-2 spaces): vectors are numbered [n_owned owned nodes | ghosts],
+ * the ghosts owned by neighbour i being the contiguous range [recv_off[i], recv_off[i]+recv_cnt[i]); send_idx holds,
+ * per neighbour (send_ptr[i]..send_ptr[i+1]), the owned local nodes that neighbour reads, in the order of its ghost range.
+ * Vectors with ncomp values per node are handled by their length.  Replaces a slab declaration on this ctx (the
+ * peer-memory CG path needs the slab layout; here the Krylov solvers use NCCL send/recv + all-reduce). */
+int fsb_dist_set_halo(fsb_ctx* ctx, int64_t n_owned, int64_t n_local, int32_t nneigh, const int32_t* neigh_rank,
+                      const int64_t* send_ptr, const int64_t* send_idx, const int64_t* recv_off, const int64_t* recv_cnt);
 int fsb_dist_halo(fsb_vec* v);                                  /* refresh ghost planes of v */
 int fsb_dist_allreduce_max(fsb_ctx* ctx, double* value);        /* host scalar, for timing */
 

@@ -20,3 +20,15 @@ def test_two_rank_slab_solve_matches_single_gpu():
                         "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"), "20"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_two_rank_general_partition_matches_single_gpu():
+    """Unstructured mesh, degree-2 elasticity and a transient run on the general node partition (RCB + send-list halo)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29543", os.path.join(ROOT, "tools", "dist_check_general.py"), "10"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "DIST_GENERAL_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

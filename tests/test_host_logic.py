@@ -285,6 +285,37 @@ assert np.array_equal(allv, np.arange(mesh.num_vertices()))
 cells = mesh.cells()
 touch = np.isin(cells, owned).any(axis=1)
 assert cells[touch].min() >= v_off and cells[touch].max() < v_off + nv_local
+# ---- general node partition (unstructured meshes / degree 2): the halo lists drive a real exchange over gloo and the
+# owner-computes SpMV of the locally assembled matrices reproduces the global product on the owned rows
+import torch
+from fenicssolver_b200.partition import NodePartition, rcb_partition
+from oracle import fem_oracle as fo
+c, t = fo.unit_cube_mesh(5, 4, 3)
+rng = np.random.default_rng(0)
+c = c + 0.02 * rng.standard_normal(c.shape)
+part = rcb_partition(c, comm.nranks)
+P = NodePartition(t, part, comm.rank, comm.nranks)
+nv = c.shape[0]
+A = fo.assemble_matrix(t, fo.local_laplace(c, t, 2.0) + fo.local_mass(c, t, 1.0), nv).tocsr()
+xg = rng.standard_normal(nv)
+Aloc = fo.assemble_matrix(np.sort(P.cell_nodes_local, axis=1), fo.local_laplace(c[P.l2g], np.sort(P.cell_nodes_local, axis=1), 2.0)
+                          + fo.local_mass(c[P.l2g], np.sort(P.cell_nodes_local, axis=1), 1.0), P.n_local).tocsr()
+xl = np.zeros(P.n_local)
+xl[:P.n_owned] = xg[P.owned]                       # ghosts unknown until the halo exchange
+reqs, bufs = [], []
+for i, r in enumerate(P.neighbours):
+    sb = torch.from_numpy(xl[P.send_idx[P.send_ptr[i]:P.send_ptr[i + 1]]].copy())
+    rb = torch.empty(int(P.recv_cnt[i]), dtype=torch.float64)
+    reqs += [dist.isend(sb, int(r)), dist.irecv(rb, int(r))]
+    bufs.append((i, rb))
+for q in reqs:
+    q.wait()
+for i, rb in bufs:
+    xl[P.recv_off[i]:P.recv_off[i] + P.recv_cnt[i]] = rb.numpy()
+assert np.array_equal(xl, xg[P.l2g])
+yl = (Aloc @ xl)[:P.n_owned]
+assert np.abs(yl - (A @ xg)[P.owned]).max() < 1e-12
+dist.barrier()
 dist.destroy_process_group()
 print("rank", comm.rank, "ok")
 """
@@ -298,3 +329,41 @@ def test_world_size_two_gloo_partition(tmp_path):
                         "--master-port", "29533", script], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 5])
+@pytest.mark.parametrize("degree", [1, 2])
+def test_node_partition_lists_are_consistent(nranks, degree):
+    """partition.NodePartition for every rank of a jittered mesh: the owned sets tile the nodes, each neighbour pair agrees
+    on the halo lists (what a sends b is b's ghost range from a, same order), local cells contain every cell of every
+    owned node, and RCB is balanced and deterministic."""
+    from fenicssolver_b200.dolfin_compat import FunctionSpace, Mesh
+    from fenicssolver_b200.partition import NodePartition, rcb_partition
+    from oracle import fem_oracle as fo
+    c, t = fo.unit_cube_mesh(4, 3, 5)
+    c = c + 0.03 * np.random.default_rng(1).standard_normal(c.shape)
+    V = FunctionSpace(Mesh(c, t), "CG", degree)
+    cn, xn = V.cell_nodes().astype(np.int64), V.node_coordinates()
+    part = rcb_partition(xn, nranks)
+    assert np.array_equal(part, rcb_partition(xn.copy(), nranks))
+    counts = np.bincount(part, minlength=nranks)
+    assert counts.max() - counts.min() <= 2
+    P = [NodePartition(cn, part, r, nranks) for r in range(nranks)]
+    assert np.array_equal(np.sort(np.concatenate([p.owned for p in P])), np.arange(xn.shape[0]))
+    for a in range(nranks):
+        pa = P[a]
+        assert np.array_equal(pa.l2g[pa.g2l[pa.l2g]], pa.l2g) and pa.n_local == np.unique(pa.l2g).size
+        # every cell touching an owned node is local, with all its nodes
+        touch = np.isin(cn, pa.owned).any(axis=1)
+        assert np.array_equal(np.nonzero(touch)[0], pa.cells_global)
+        assert np.array_equal(pa.l2g[pa.cell_nodes_local], cn[touch])
+        # ghosts are exactly the non-owned nodes of those cells
+        assert np.array_equal(np.sort(pa.ghosts), np.setdiff1d(np.unique(cn[touch]), pa.owned))
+        for i, b in enumerate(pa.neighbours):
+            pb = P[b]
+            j = int(np.nonzero(pb.neighbours == a)[0][0])
+            sent = pa.l2g[pa.send_idx[pa.send_ptr[i]:pa.send_ptr[i + 1]]]
+            got = pb.l2g[pb.recv_off[j]:pb.recv_off[j] + pb.recv_cnt[j]]
+            assert np.array_equal(sent, got)
+            assert np.all(part[sent] == a)
+        assert pa.recv_cnt.sum() == pa.ghosts.size
