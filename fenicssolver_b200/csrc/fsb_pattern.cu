@@ -144,13 +144,20 @@ __global__ void k_v2c_fill(const int32_t* __restrict__ cells, int64_t ncells, in
 static constexpr int kRowCap = 512;      // power of two
 static constexpr int kRowWarps = 8;
 
+// The counting pass (FILL = false) also parks the sorted columns of every row with at most kRowKeep entries in `keep`
+// (stride kRowKeep), so the fill pass only has to copy them; rows longer than that are sorted again by the fill pass
+// (FILL = true, which skips the short rows when `keep` is given).
+static constexpr int kRowKeep = 32;
+
 template <bool FILL>
 __global__ void __launch_bounds__(kRowWarps * 32)
 k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vptr, const int32_t* __restrict__ v2c,
-       int64_t nrows, int32_t* __restrict__ row_len, const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx) {
+       int64_t nrows, int32_t* __restrict__ row_len, const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx,
+       int32_t* __restrict__ keep) {
   __shared__ int32_t s_cand[kRowWarps][kRowCap];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int64_t r = (int64_t)blockIdx.x * kRowWarps + w; r < nrows; r += (int64_t)gridDim.x * kRowWarps) {
+    if (FILL && keep && row_ptr[r + 1] - row_ptr[r] <= kRowKeep) continue;      // copied from `keep` by k_rows_copy
     const int64_t p0 = vptr[r];
     const int m = (int)(vptr[r + 1] - p0) * nl;
     const bool cached = m <= kRowCap;
@@ -178,7 +185,9 @@ k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vp
         const int32_t v = i < m ? s_cand[w][i] : 0x7fffffff;
         const bool first = i < m && (i == 0 || s_cand[w][i - 1] != v);
         const unsigned mask = __ballot_sync(0xffffffffu, first);
-        if (FILL && first) col_idx[row_ptr[r] + count + __popc(mask & ((1u << lane) - 1))] = v;
+        const int slot = count + __popc(mask & ((1u << lane) - 1));
+        if (FILL && first) col_idx[row_ptr[r] + slot] = v;
+        if (!FILL && keep && first && slot < kRowKeep) keep[r * kRowKeep + slot] = v;
         count += __popc(mask);
       }
       if (!FILL && lane == 0) row_len[r] = count;
@@ -217,6 +226,18 @@ k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vp
     __syncwarp();
     if (!FILL && lane == 0) row_len[r] = nfirst;
     __syncwarp();
+  }
+}
+
+// fill pass for the short rows: one thread per kept slot
+__global__ void k_rows_copy(int64_t nrows, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ keep,
+                            int32_t* __restrict__ col_idx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows * kRowKeep; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / kRowKeep;
+    const int k = (int)(i % kRowKeep);
+    const int64_t base = row_ptr[r];
+    const int len = (int)(row_ptr[r + 1] - base);
+    if (len <= kRowKeep && k < len) col_idx[base + k] = keep[i];
   }
 }
 
@@ -274,10 +295,10 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   const int cap = ctx->sm_count * 16;
   fsb_mat* A = new fsb_mat();
   A->ctx = ctx; A->mesh = mesh; A->bs = ncomp; A->nbrows = nv; A->own0 = 0; A->own1 = nv;
-  int32_t *deg = nullptr, *v2c = nullptr, *d_max = nullptr;
+  int32_t *deg = nullptr, *v2c = nullptr, *d_max = nullptr, *keep = nullptr;
   int64_t* vptr = nullptr;
   int rc = FSB_OK;
-  auto cleanup = [&]() { fsb_dfree(ctx, deg); fsb_dfree(ctx, v2c); fsb_dfree(ctx, vptr); fsb_dfree(ctx, d_max); };
+  auto cleanup = [&]() { fsb_dfree(ctx, deg); fsb_dfree(ctx, v2c); fsb_dfree(ctx, vptr); fsb_dfree(ctx, d_max); fsb_dfree(ctx, keep); };
 #define TRY(x) do { rc = (x); if (rc) { cleanup(); fsb_mat_destroy(A); return rc; } } while (0)
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); fsb_mat_destroy(A); return FSB_ERR_CUDA; } } while (0)
   TRY(fsb_dmalloc(ctx, &deg, (size_t)nv + 1));
@@ -293,7 +314,9 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   ctx->launches++; TRYCUDA(cudaGetLastError());
   // row lengths -> row_ptr
   TRY(fsb_dmalloc(ctx, &A->row_ptr, (size_t)nv + 1));
-  k_rows<false><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cell_nodes, nl, vptr, v2c, nv, deg, nullptr, nullptr);
+  // scratch for the sorted short rows (128 B per row); without it the fill pass simply sorts every row again
+  if (fsb_dmalloc(ctx, &keep, (size_t)nv * kRowKeep) != FSB_OK) { keep = nullptr; ctx->err.clear(); }
+  k_rows<false><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cell_nodes, nl, vptr, v2c, nv, deg, nullptr, nullptr, keep);
   ctx->launches++; TRYCUDA(cudaGetLastError());
   TRYCUDA(cudaMemsetAsync(d_max, 0, sizeof(int32_t), ctx->stream));
   k_max_i32<<<fsb_grid(nv, 256, cap), 256, 0, ctx->stream>>>(deg, nv, d_max);
@@ -307,11 +330,18 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   A->nnzb = nnzb;
   A->max_row_len = maxlen;
   TRY(fsb_dmalloc(ctx, &A->col_idx, (size_t)nnzb));
-  k_rows<true><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cell_nodes, nl, vptr, v2c, nv, nullptr, A->row_ptr, A->col_idx);
-  ctx->launches++; TRYCUDA(cudaGetLastError());
+  if (keep) {
+    k_rows_copy<<<fsb_grid(nv * kRowKeep, 256, (int64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(nv, A->row_ptr, keep, A->col_idx);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+  }
+  if (!keep || maxlen > kRowKeep) {
+    k_rows<true><<<fsb_grid(nv, kRowWarps, cap), kRowWarps * 32, 0, ctx->stream>>>(mesh->cell_nodes, nl, vptr, v2c, nv, nullptr, A->row_ptr, A->col_idx, keep);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+  }
   TRYCUDA(cudaStreamSynchronize(ctx->stream));
   fsb_dfree(ctx, v2c); v2c = nullptr;
   fsb_dfree(ctx, vptr); vptr = nullptr;
+  fsb_dfree(ctx, keep); keep = nullptr;
   TRY(fsb_dmalloc(ctx, &A->vals, (size_t)nnzb * ncomp * ncomp));
   TRYCUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * nnzb * ncomp * ncomp + 512, ctx->stream));
   if (maxlen <= 256) {
