@@ -160,6 +160,50 @@ k_rows(const int32_t* __restrict__ cells, int nl, const int64_t* __restrict__ vp
     if (FILL && keep && row_ptr[r + 1] - row_ptr[r] <= kRowKeep) continue;      // copied from `keep` by k_rows_copy
     const int64_t p0 = vptr[r];
     const int m = (int)(vptr[r + 1] - p0) * nl;
+    if (!FILL && keep && m <= 256) {
+      // fast path of the counting pass: every neighbour appears ~6 times among the candidates, so insert them into a
+      // 64-slot shared-memory hash set (32-bit CAS), and if at most kRowKeep distinct columns come out, sort those 32
+      // values inside the warp with shuffles: no 128-element shared-memory sort
+      int32_t* tab = s_cand[w];
+      tab[lane] = -1; tab[lane + 32] = -1;
+      __syncwarp();
+      bool ovf = false;
+      for (int i = lane; i < m; i += 32) {
+        const int32_t v = cells[(int64_t)v2c[p0 + i / nl] * nl + i % nl];
+        unsigned h = ((unsigned)v * 2654435761u) >> 26;
+        for (int probes = 0;; ++probes) {
+          const int32_t old = atomicCAS(&tab[h], -1, v);
+          if (old == -1 || old == v) break;
+          if (probes >= 64) { ovf = true; break; }
+          h = (h + 1) & 63;
+        }
+      }
+      __syncwarp();
+      ovf = __any_sync(0xffffffffu, ovf);
+      const int32_t a0 = tab[lane], a1 = tab[lane + 32];
+      const unsigned m0 = __ballot_sync(0xffffffffu, a0 != -1), m1 = __ballot_sync(0xffffffffu, a1 != -1);
+      const int count = __popc(m0) + __popc(m1);
+      __syncwarp();
+      if (!ovf && count <= kRowKeep) {
+        const unsigned lt = (1u << lane) - 1;
+        if (a0 != -1) tab[64 + __popc(m0 & lt)] = a0;
+        if (a1 != -1) tab[64 + __popc(m0) + __popc(m1 & lt)] = a1;
+        __syncwarp();
+        int32_t v = lane < count ? tab[64 + lane] : 0x7fffffff;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            const int32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? min(v, o) : max(v, o);
+          }
+        if (lane < count) keep[r * kRowKeep + lane] = v;
+        if (lane == 0) row_len[r] = count;
+        __syncwarp();
+        continue;
+      }
+    }
     const bool cached = m <= kRowCap;
     if (cached) {
       // common case: bitonic-sort the candidates in shared memory (padded with INT_MAX to a power of

@@ -16,6 +16,9 @@
 // ------------------------------------------------------------------------------------ vector kernels
 static constexpr int kVecThreads = 256;
 static unsigned vec_grid(fsb_ctx* ctx, int64_t n) { return fsb_grid(n, kVecThreads * 4, std::min<int64_t>(kMaxPartials, (int64_t)ctx->sm_count * 8)); }
+// the two classic-CG vector kernels keep 3 CTAs per SM resident (80 registers: ten 16-byte loads in flight per thread) and
+// stride over the rows, so exactly one resident wave is launched: no partial last wave
+static unsigned vec_grid_wave(fsb_ctx* ctx, int64_t n) { return fsb_grid(n, kVecThreads * 4, std::min<int64_t>(kMaxPartials, (int64_t)ctx->sm_count * 3)); }
 
 __global__ void __launch_bounds__(kVecThreads)
 k_dot(const double* __restrict__ x, const double* __restrict__ y, int64_t n0, int64_t n1, double* partials, double* out, unsigned* counter) {
@@ -100,14 +103,15 @@ __global__ void k_mail_seed(PeerComm pc, int slot, unsigned long long seq, const
 }
 
 // alpha = rz/pq ; x += alpha p ; r -= alpha q ; z = dinv r ; sums rz', rr' -> out[0..2) (or the mailboxes)
-__global__ void __launch_bounds__(kVecThreads)
+template <bool PEER>
+__global__ void __launch_bounds__(kVecThreads, 3)
 k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot, int pq_slot, const double* __restrict__ p,
             const double* __restrict__ q, const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
             double* partials, double* out, unsigned* counter, const int* done, CgPeer cp, int par) {
   __shared__ double red[32];
   if (*done) return;
   double alpha;
-  if (cp.pc.nranks > 1) {
+  if (PEER) {
     double a[2], b[2];
     mail_sum<2>(cp.pc, MAIL_RZ + par, cp.seq, a, red);
     mail_sum<2>(cp.pc, MAIL_PQ + par, cp.seq + 1, b, red);
@@ -130,11 +134,18 @@ k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot
   const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
   if (tid == 0 && a0 > n0) one(n0);
   if (tid == 1 && a0 + 2 * npair < n1) one(n1 - 1);
-  for (int64_t j = tid; j < npair; j += nth) {
-    const int64_t i = a0 + 2 * j;
+  // two 16-byte pairs per thread and trip, all ten loads issued before the first use (bytes in flight, not occupancy,
+  // is what a 7-stream kernel needs to reach the HBM rate)
+  for (int64_t j = tid; j < npair; j += 2 * nth) {
+    const int64_t i = a0 + 2 * j, k = i + 2 * nth;
+    const bool two = j + nth < npair;
+    const double2 zero = make_double2(0.0, 0.0);
     const double2 pv = *reinterpret_cast<const double2*>(p + i), qv = *reinterpret_cast<const double2*>(q + i);
     const double2 dv = *reinterpret_cast<const double2*>(dinv + i);
     double2 xv = *reinterpret_cast<double2*>(x + i), rv = *reinterpret_cast<double2*>(r + i);
+    const double2 pw = two ? *reinterpret_cast<const double2*>(p + k) : zero, qw = two ? *reinterpret_cast<const double2*>(q + k) : zero;
+    const double2 dw = two ? *reinterpret_cast<const double2*>(dinv + k) : zero;
+    double2 xw = two ? *reinterpret_cast<double2*>(x + k) : zero, rw = two ? *reinterpret_cast<double2*>(r + k) : zero;
     xv.x += alpha * pv.x; xv.y += alpha * pv.y;
     rv.x -= alpha * qv.x; rv.y -= alpha * qv.y;
     *reinterpret_cast<double2*>(x + i) = xv;
@@ -142,22 +153,32 @@ k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot
     const double z0 = dv.x * rv.x, z1 = dv.y * rv.y;
     s0 += rv.x * z0 + rv.y * z1;
     s1 += z0 * z0 + z1 * z1;
+    if (two) {
+      xw.x += alpha * pw.x; xw.y += alpha * pw.y;
+      rw.x -= alpha * qw.x; rw.y -= alpha * qw.y;
+      *reinterpret_cast<double2*>(x + k) = xw;
+      *reinterpret_cast<double2*>(r + k) = rw;
+      const double y0 = dw.x * rw.x, y1 = dw.y * rw.y;
+      s0 += rw.x * y0 + rw.y * y1;
+      s1 += y0 * y0 + y1 * y1;
+    }
   }
   double mine[2] = {block_sum(s0, red), block_sum(s1, red)};
-  if (cp.pc.nranks > 1) finish_partials_mail<2>(mine, partials, kMaxPartials, counter, red, cp.pc, MAIL_RZ + (par ^ 1), cp.seq + 1);
+  if (PEER) finish_partials_mail<2>(mine, partials, kMaxPartials, counter, red, cp.pc, MAIL_RZ + (par ^ 1), cp.seq + 1);
   else finish_partials<2>(mine, partials, kMaxPartials, out, counter, red);
 }
 
 // beta = rz'/rz ; p = dinv r + beta p ; block 0 / thread 0 advances the iteration state.  Distributed: the
 // boundary planes of the new p are also stored into the neighbours' ghost planes (peer memory) and the
 // last CTA raises the neighbours' halo flags.
-__global__ void __launch_bounds__(kVecThreads)
+template <bool PEER>
+__global__ void __launch_bounds__(kVecThreads, 3)
 k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int rz_new, int rr_new, int pq_slot,
              const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ p, double rtol, double atol,
              int maxit, int* state, CgPeer cp, int par, unsigned* counter) {
   __shared__ double red[8];
   if (state[0]) return;
-  const bool peer = cp.pc.nranks > 1;
+  constexpr bool peer = PEER;
   double rzn, rzo, rr_v, pq_v;
   if (peer) {
     double a[2], b[2], c[2];
@@ -179,14 +200,24 @@ k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int 
   const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
   if (tid == 0 && a0 > n0) { const double v = dinv[n0] * r[n0] + beta * p[n0]; p[n0] = v; if (peer) push(n0, v); }
   if (tid == 1 && a0 + 2 * npair < n1) { const double v = dinv[n1 - 1] * r[n1 - 1] + beta * p[n1 - 1]; p[n1 - 1] = v; if (peer) push(n1 - 1, v); }
-  for (int64_t j = tid; j < npair; j += nth) {
-    const int64_t i = a0 + 2 * j;
+  for (int64_t j = tid; j < npair; j += 2 * nth) {
+    const int64_t i = a0 + 2 * j, k = i + 2 * nth;
+    const bool two = j + nth < npair;
+    const double2 zero = make_double2(0.0, 0.0);
     const double2 dv = *reinterpret_cast<const double2*>(dinv + i), rv = *reinterpret_cast<const double2*>(r + i);
     double2 pv = *reinterpret_cast<double2*>(p + i);
+    const double2 dw = two ? *reinterpret_cast<const double2*>(dinv + k) : zero, rw = two ? *reinterpret_cast<const double2*>(r + k) : zero;
+    double2 pw = two ? *reinterpret_cast<double2*>(p + k) : zero;
     pv.x = dv.x * rv.x + beta * pv.x;
     pv.y = dv.y * rv.y + beta * pv.y;
     *reinterpret_cast<double2*>(p + i) = pv;
     if (peer) { push(i, pv.x); push(i + 1, pv.y); }
+    if (two) {
+      pw.x = dw.x * rw.x + beta * pw.x;
+      pw.y = dw.y * rw.y + beta * pw.y;
+      *reinterpret_cast<double2*>(p + k) = pw;
+      if (peer) { push(k, pw.x); push(k + 1, pw.y); }
+    }
   }
   if (peer) {
     __threadfence_system();           // this CTA's peer stores are visible system-wide before it counts itself done
@@ -559,7 +590,7 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   }
   double* scal = ctx->d_scalars;
   int* state = ctx->d_state;
-  const unsigned vg = vec_grid(ctx, n1 - n0);
+  const unsigned vg = vec_grid(ctx, n1 - n0), vgw = vec_grid_wave(ctx, n1 - n0);
   SpmvTimer timer;
 
   FSB_CHECK_CUDA(ctx, cudaMemsetAsync(state, 0, sizeof(int) * 8, ctx->stream));
@@ -611,10 +642,12 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
         }
         if (ctx->profile) cudaEventRecord(timer.next(slot), ctx->stream);
         if (dist && !p2p && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + pq, 1))) return rc;
-        k_cg_update<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, pq, p, q, dinv, x->d, r, ctx->d_partials, scal + rzn, ctx->d_counters + 2, state, cp, par);
+        if (p2p) k_cg_update<true><<<vgw, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, pq, p, q, dinv, x->d, r, ctx->d_partials, scal + rzn, ctx->d_counters + 2, state, cp, par);
+        else k_cg_update<false><<<vgw, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, pq, p, q, dinv, x->d, r, ctx->d_partials, scal + rzn, ctx->d_counters + 2, state, cp, par);
         FSB_LAUNCH_CHECK(ctx);
         if (dist && !p2p && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + rzn, 2))) return rc;
-        k_cg_pupdate<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, rzn, rrn, pq, r, dinv, p, rtol, atol, maxit, state, cp, par, ctx->d_counters + 4);
+        if (p2p) k_cg_pupdate<true><<<vgw, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, rzn, rrn, pq, r, dinv, p, rtol, atol, maxit, state, cp, par, ctx->d_counters + 4);
+        else k_cg_pupdate<false><<<vgw, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rz, rzn, rrn, pq, r, dinv, p, rtol, atol, maxit, state, cp, par, ctx->d_counters + 4);
         FSB_LAUNCH_CHECK(ctx);
       }
       launched += batch;
