@@ -70,14 +70,16 @@ k_cg_init(int64_t n0, int64_t n1, const double* __restrict__ b, const double* __
   finish_partials<3>(mine, partials, kMaxPartials, out, counter, red);
 }
 
-__global__ void k_check0(const double* __restrict__ scal, int rr_slot, int bb_slot, double rtol, double atol, int maxit, int* state, double* final_rr) {
+// `restart`: keep the iteration count of the run being restarted (BiCGStab after a breakdown)
+__global__ void k_check0(const double* __restrict__ scal, int rr_slot, int bb_slot, double rtol, double atol, int maxit, int* state, double* final_rr,
+                         int restart = 0) {
   const double rr = scal[rr_slot], bb = scal[bb_slot];
   const double tol2 = fmax(rtol * rtol * bb, atol * atol);
-  state[1] = 0;
+  if (!restart) state[1] = 0;
   *final_rr = rr;
   if (rr <= tol2) { state[0] = 1; state[2] = 1; }
   else if (!(rr == rr)) { state[0] = 1; state[2] = -1; }
-  else if (maxit <= 0) { state[0] = 1; state[2] = 0; }
+  else if (maxit <= state[1]) { state[0] = 1; state[2] = 0; }
   else { state[0] = 0; state[2] = 0; }
 }
 
@@ -740,15 +742,30 @@ k_bcg_s(int64_t n0, int64_t n1, const double* __restrict__ scal, int rho_cur, co
   finish_partials<1>(mine, partials, kMaxPartials, out, counter, red);
 }
 
-__device__ __forceinline__ void bcg_advance(double* __restrict__ scal, int rr_new, double rho_new, double rtol, double atol, int maxit,
+// the recurrence scalars of one iteration; `ok` is false when any of them is zero or not finite, and then the
+// iteration leaves x untouched (a breakdown is reported and the host restarts from x)
+struct BcgScalars { double alpha, omega, rho_new, beta; bool ok; };
+__device__ __forceinline__ BcgScalars bcg_scalars(const double* __restrict__ scal, int rho_cur) {
+  BcgScalars c;
+  const double rho = scal[rho_cur];
+  c.alpha = rho / scal[S_RV];
+  c.omega = scal[S_TS] / scal[S_TT];
+  c.rho_new = scal[S_RS] - c.omega * scal[S_RT];
+  c.beta = (c.rho_new / rho) * (c.alpha / c.omega);
+  c.ok = isfinite(c.alpha) && isfinite(c.omega) && isfinite(c.beta) && isfinite(c.rho_new) && c.omega != 0.0;
+  return c;
+}
+
+__device__ __forceinline__ void bcg_advance(double* __restrict__ scal, int rr_new, double rho_new, bool ok, double rtol, double atol, int maxit,
                                             int* state) {
-  const double rr = scal[rr_new], bb = scal[S_BBB], tt = scal[S_TT], rv = scal[S_RV];
+  const double rr = scal[rr_new], bb = scal[S_BBB];
   const double tol2 = fmax(rtol * rtol * bb, atol * atol);
   const int it = state[1] + 1;
   state[1] = it;
+  if (!ok) { state[2] = -1; state[0] = 1; return; }          // x was not updated: S_FINAL_RR keeps the last valid norm
   scal[S_FINAL_RR] = rr;
   if (rr <= tol2) { state[2] = 1; state[0] = 1; }
-  else if (!(rr == rr) || rho_new == 0.0 || tt == 0.0 || rv == 0.0 || !(rho_new == rho_new)) { state[2] = -1; state[0] = 1; }
+  else if (!(rr == rr) || rho_new == 0.0) { state[2] = -1; state[0] = 1; }
   else if (it >= maxit) { state[2] = 0; state[0] = 1; }
 }
 
@@ -760,14 +777,11 @@ k_bcg_xp(int64_t n0, int64_t n1, double* __restrict__ scal, int rho_cur, int rho
          double rtol, double atol, int maxit, int* state, int advance) {
   __shared__ double red[32];
   if (state[0]) return;
-  const double rho = scal[rho_cur];
-  const double alpha = rho / scal[S_RV];
-  const double omega = scal[S_TS] / scal[S_TT];
-  const double rho_new = scal[S_RS] - omega * scal[S_RT];
-  const double beta = (rho_new / rho) * (alpha / omega);
+  const BcgScalars c = bcg_scalars(scal, rho_cur);
+  const double alpha = c.alpha, omega = c.omega, rho_new = c.rho_new, beta = c.beta;
   if (blockIdx.x == 0 && threadIdx.x == 0) scal[rho_next] = rho_new;
   double s0 = 0;
-  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n1; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = n0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c.ok && i < n1; i += (int64_t)gridDim.x * blockDim.x) {
     const double di = dinv[i], shi = sh[i];
     x[i] += alpha * ph[i] + omega * shi;
     const double ri = r[i] - omega * t[i];
@@ -780,12 +794,13 @@ k_bcg_xp(int64_t n0, int64_t n1, double* __restrict__ scal, int rho_cur, int rho
   }
   double mine[1] = {block_sum(s0, red)};
   const bool last = finish_partials_last<1>(mine, partials, kMaxPartials, scal + rr_new, counter, red);
-  if (advance && last && threadIdx.x == 0) bcg_advance(scal, rr_new, rho_new, rtol, atol, maxit, state);
+  if (advance && last && threadIdx.x == 0) bcg_advance(scal, rr_new, rho_new, c.ok, rtol, atol, maxit, state);
 }
 
-__global__ void k_bcg_check(double* __restrict__ scal, int rho_new, int rr_new, double rtol, double atol, int maxit, int* state) {
+__global__ void k_bcg_check(double* __restrict__ scal, int rho_cur, int rho_new, int rr_new, double rtol, double atol, int maxit, int* state) {
   if (state[0]) return;
-  bcg_advance(scal, rr_new, scal[rho_new], rtol, atol, maxit, state);
+  const BcgScalars c = bcg_scalars(scal, rho_cur);
+  bcg_advance(scal, rr_new, scal[rho_new], c.ok, rtol, atol, maxit, state);
 }
 
 extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit,
@@ -821,44 +836,61 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   if (A->bs == 1) DINV_LAUNCH(1); else if (A->bs == 2) DINV_LAUNCH(2); else DINV_LAUNCH(3);
 #undef DINV_LAUNCH
   FSB_LAUNCH_CHECK(ctx);
-  if (dist && (rc = fsb_dist_halo_raw(ctx, x->d, n))) return rc;
-  if ((rc = fsb_launch_spmv(S, x->d, v, nullptr, 0, nullptr, nullptr))) return rc;
-  k_bcg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, v, dinv, r, rhat, p, ph, ctx->d_partials, scal + S_RHO0, ctx->d_counters + 1);
-  FSB_LAUNCH_CHECK(ctx);
-  if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RHO0, 3))) return rc;
-  k_check0<<<1, 1, 0, ctx->stream>>>(scal, S_RRB0, S_BBB, rtol, atol, maxit, state, scal + S_FINAL_RR);
-  FSB_LAUNCH_CHECK(ctx);
-
-  int first, rest;
-  batch_plan(ctx, A->last_iters, &first, &rest);
-  int launched = 0;
+  // (re)start from x: r = b - A x, rhat = p = r.  A breakdown (a recurrence scalar hits zero or stops being finite:
+  // with rho carried by recurrence that happens once the residual is down at rounding level, or on tiny systems
+  // that are solved exactly half-way through an iteration) leaves x at its last valid value, so the standard
+  // remedy applies: restart the recurrences from the true residual, a few times at most.
+  int launched = 0, restarts = 0;
   bool finished = false;
   while (!finished) {
-    const int batch = launched == 0 ? first : rest;
-    for (int k = 0; k < batch; ++k) {
-      const int par = (launched + k) & 1;
-      const int rho = par ? S_RHO1 : S_RHO0, rhon = par ? S_RHO0 : S_RHO1, rrn = par ? S_RRB0 : S_RRB1;
-      if (dist && (rc = fsb_dist_halo_raw(ctx, ph, n))) return rc;
-      if ((rc = fsb_launch_spmv(S, ph, v, rhat, 0, scal + S_RV, state))) return rc;
-      if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RV, 1))) return rc;
-      k_bcg_s<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, v, rhat, dinv, r, sh, ctx->d_partials, scal + S_RS, ctx->d_counters + 5, state);
-      FSB_LAUNCH_CHECK(ctx);
-      if (dist && (rc = fsb_dist_halo_raw(ctx, sh, n))) return rc;
-      if ((rc = fsb_launch_spmv(S, sh, t, r, 1, scal + S_TS, state, nullptr, rhat))) return rc;
-      if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_TS, 4))) return rc;        // t.s, t.t, rhat.t, rhat.s
-      k_bcg_xp<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, rhon, rrn, sh, t, v, dinv, x->d, r, p, ph, ctx->d_partials,
-                                                    ctx->d_counters + 2, rtol, atol, maxit, state, dist ? 0 : 1);
-      FSB_LAUNCH_CHECK(ctx);
-      if (dist) {
-        if ((rc = fsb_dist_allreduce_sum_dev(ctx, scal + rrn, 1))) return rc;
-        k_bcg_check<<<1, 1, 0, ctx->stream>>>(scal, rhon, rrn, rtol, atol, maxit, state);
+    if (dist && (rc = fsb_dist_halo_raw(ctx, x->d, n))) return rc;
+    if ((rc = fsb_launch_spmv(S, x->d, v, nullptr, 0, nullptr, nullptr))) return rc;
+    k_bcg_init<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, b->d, v, dinv, r, rhat, p, ph, ctx->d_partials, scal + S_RHO0, ctx->d_counters + 1);
+    FSB_LAUNCH_CHECK(ctx);
+    if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RHO0, 3))) return rc;
+    k_check0<<<1, 1, 0, ctx->stream>>>(scal, S_RRB0, S_BBB, rtol, atol, maxit, state, scal + S_FINAL_RR, restarts > 0);
+    FSB_LAUNCH_CHECK(ctx);
+
+    int first, rest;
+    batch_plan(ctx, A->last_iters, &first, &rest);
+    const int base = launched;
+    bool stopped = false;
+    while (!stopped) {
+      const int batch = launched == base ? first : rest;
+      for (int k = 0; k < batch; ++k) {
+        const int par = (launched - base + k) & 1;
+        const int rho = par ? S_RHO1 : S_RHO0, rhon = par ? S_RHO0 : S_RHO1, rrn = par ? S_RRB0 : S_RRB1;
+        if (dist && (rc = fsb_dist_halo_raw(ctx, ph, n))) return rc;
+        if ((rc = fsb_launch_spmv(S, ph, v, rhat, 0, scal + S_RV, state))) return rc;
+        if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RV, 1))) return rc;
+        k_bcg_s<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, v, rhat, dinv, r, sh, ctx->d_partials, scal + S_RS, ctx->d_counters + 5, state);
         FSB_LAUNCH_CHECK(ctx);
+        if (dist && (rc = fsb_dist_halo_raw(ctx, sh, n))) return rc;
+        if ((rc = fsb_launch_spmv(S, sh, t, r, 1, scal + S_TS, state, nullptr, rhat))) return rc;
+        if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_TS, 4))) return rc;        // t.s, t.t, rhat.t, rhat.s
+        k_bcg_xp<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, rhon, rrn, sh, t, v, dinv, x->d, r, p, ph, ctx->d_partials,
+                                                      ctx->d_counters + 2, rtol, atol, maxit, state, dist ? 0 : 1);
+        FSB_LAUNCH_CHECK(ctx);
+        if (dist) {
+          if ((rc = fsb_dist_allreduce_sum_dev(ctx, scal + rrn, 1))) return rc;
+          k_bcg_check<<<1, 1, 0, ctx->stream>>>(scal, rho, rhon, rrn, rtol, atol, maxit, state);
+          FSB_LAUNCH_CHECK(ctx);
+        }
       }
+      launched += batch;
+      FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, state, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (ctx->h_state[0] || launched >= maxit) stopped = true;
     }
-    launched += batch;
-    FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, state, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_state[0] || launched >= maxit) finished = true;
+    // outcome -1 with iterations to spare: restart (state[1] keeps counting across restarts)
+    if (ctx->h_state[0] && ctx->h_state[2] == -1 && restarts < 4 && ctx->h_state[1] < maxit) {
+      ++restarts;
+      static const bool trace = getenv("FSB_SOLVE_TRACE") != nullptr;
+      if (trace) fprintf(stderr, "libfsb: BiCGStab restart %d after %d iterations\n", restarts, ctx->h_state[1]);
+      FSB_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned) * 16, ctx->stream));
+      continue;
+    }
+    finished = true;
   }
   FSB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
   rc = read_outcome(ctx, S_FINAL_RR, S_BBB, info);
@@ -867,6 +899,9 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   info->solve_ms = ms;
+  // restarts exhausted with a valid iterate: the recurrences stall at rounding level; report "not converged" with the
+  // last valid residual norm instead of an error (x is the best iterate).  Non-finite data still raises.
+  if (info->converged < 0 && restarts >= 4 && std::isfinite(info->rnorm) && info->rnorm > 0.0) info->converged = 0;
   if (info->converged < 0) FSB_FAIL(ctx, FSB_ERR_BREAKDOWN, "BiCGStab breakdown (zero or non-finite recurrence scalar)");
   return FSB_OK;
 }
