@@ -439,7 +439,7 @@ class SolverBase():
             rtol, maxit = min(rtol, PARITY_RTOL), max(maxit, PARITY_MAXIT)
         return {'rtol': rtol, 'atol': float(sp.get('absolute_tolerance', 0.0)), 'maxit': maxit,
                 'method': sp.get('linear_solver'), 'precond': sp.get('preconditioner', 'jacobi'),
-                'drop_zeros': bool(sp.get('drop_zeros', False))}
+                'drop_zeros': bool(sp.get('drop_zeros', False)), 'mg_sweeps': sp.get('mg_sweeps', 2)}
 
     def solve_linear_problem(self, F, u, Dirichlet_bcs):
         """assemble A and b, apply the Dirichlet conditions, solve (SolverBase.py:592-613).  F is the
@@ -461,7 +461,17 @@ class SolverBase():
         # 'drop_zeros': the Krylov SpMVs skip the entries that are exactly zero after assembly (same solution;
         # the assembled pattern, which is the parity object, keeps them as dolfin/PETSc do)
         space.ctx.set_option("drop_zeros", int(kp['drop_zeros']))
-        info = space.solve(b, x, method=method, rtol=kp['rtol'], atol=kp['atol'], maxit=kp['maxit'], precond=kp['precond'])
+        if kp['precond'] in ('gmg', 'amg', 'petsc_amg') and method == 'cg':
+            # CG preconditioned by geometric multigrid on the nested box meshes: what solve_amg's CG + GAMG is for the
+            # reference (SolverBase.py:643-672); the coarse levels are assembled from the same settings
+            mg = self.multigrid_hierarchy(space)
+            self.timings['mg_setup'] = time.perf_counter() - t0
+            info = mg.solve(b, x, rtol=kp['rtol'], atol=kp['atol'], maxit=kp['maxit'], nu=int(kp.get('mg_sweeps', 2)))
+            info['mg_levels'] = len(mg.matrices)
+        else:
+            if kp['precond'] in ('gmg', 'amg', 'petsc_amg'):
+                raise SolverError('the multigrid preconditioner needs a symmetric problem (CG)')
+            info = space.solve(b, x, method=method, rtol=kp['rtol'], atol=kp['atol'], maxit=kp['maxit'], precond=kp['precond'])
         self.timings['solve'] = time.perf_counter() - t0
         self.solve_info = info
         if info['converged'] != 1:
@@ -472,6 +482,46 @@ class SolverBase():
         elif not self.parallel:
             u.set_device(x)
         return u
+
+    def multigrid_hierarchy(self, space):
+        """Level matrices for the multigrid preconditioner: the fine one is space.A as just assembled; every coarser
+        box (cell counts halved while they stay even and >= 4) gets a shallow copy of this solver that marks its
+        own boundary facets with the same predicates and assembles the same form there.  The level spaces (meshes,
+        patterns) are kept across steps; the values are re-assembled because a transient run changes them."""
+        import copy as _copy
+        from . import _lib as L
+        mesh = self.mesh
+        if not getattr(mesh, 'box', None) or self.parallel or self.function_space.degree != 1:
+            raise SolverError("preconditioner 'gmg' needs a generated box mesh (UnitCubeMesh/BoxMesh/...), degree 1, one GPU")
+        n = [int(k) for k in mesh.box['n']]
+        sizes = [n]
+        while all(k % 2 == 0 and k >= 4 for k in sizes[-1]):
+            sizes.append([k // 2 for k in sizes[-1]])
+        levels = self.__dict__.setdefault('_mg_levels', {})
+        mats = [space.A]
+        for nl in sizes[1:]:
+            key = tuple(nl)
+            c = levels.get(key)
+            if c is None:
+                c = _copy.copy(self)
+                c.mesh = Mesh(box={'n': tuple(nl), 'p0': mesh.box['p0'], 'p1': mesh.box['p1']})
+                c.subdomains = None
+                c.generate_boundary_facets()
+                ncomp = self.function_space.ncomp
+                c.function_space = FunctionSpace(c.mesh, 'CG', 1) if ncomp == 1 else VectorFunctionSpace(c.mesh, 'CG', 1)
+                c._space = DeviceSpace(c.mesh, ncomp, ctx=space.ctx, space=c.function_space)
+                c.timings = {}
+                c.__dict__.pop('_mg_levels', None)
+                levels[key] = c
+            zero = Function(c.function_space)
+            Fc, bcs_c = c.generate_form(self.current_step, None, None, zero, zero)
+            bc_, _sym = Fc.assemble(c._space)
+            dofs, vals = collect_dirichlet(bcs_c, c.function_space)
+            c._space.apply_dirichlet(bc_, dofs, np.zeros(len(dofs)), symmetric=True)
+            mats.append(c._space.A)
+        mg = L.Multigrid(space.ctx, mats, sizes, mesh.tdim)
+        self._mg = mg
+        return mg
 
     def local_result(self):
         """This rank's owned part of the last solution (host copy); with gather_result=False this is the

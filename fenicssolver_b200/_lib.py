@@ -79,6 +79,11 @@ SIGNATURES = {
     "fsb_dot": (C.c_int, [c_vp, c_vp, P(c_dbl)]),
     "fsb_solve_cg": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
     "fsb_solve_bicgstab": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
+    "fsb_mg_create": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, P(c_vp)]),
+    "fsb_mg_omega": (C.c_int, [c_vp, c_i32, P(c_dbl)]),
+    "fsb_mg_apply": (C.c_int, [c_vp, c_vp, c_vp, c_i32]),
+    "fsb_solve_cg_mg": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
+    "fsb_mg_destroy": (None, [c_vp]),
     "fsb_dist_unique_id": (C.c_int, [c_vp]),
     "fsb_dist_init": (C.c_int, [c_vp, c_i32, c_i32, c_vp]),
     "fsb_dist_set_slab": (C.c_int, [c_vp, c_i32, c_i32, c_i64]),
@@ -370,6 +375,35 @@ class DeviceMatrix(_Handle):
         fn = {"cg": self.ctx.lib.fsb_solve_cg, "bicgstab": self.ctx.lib.fsb_solve_bicgstab}[method]
         pc = {"none": 0, None: 0, "jacobi": 1}[precond]
         self.ctx.check(fn(self.h, b.h, x.h, float(rtol), float(atol), int(maxit), pc, C.byref(info)))
+        return {"iterations": info.iterations, "converged": info.converged, "rnorm": info.rnorm, "bnorm": info.bnorm,
+                "solve_ms": info.solve_ms, "spmv_ms": info.spmv_ms, "operand_nnzb": info.operand_nnzb}
+
+
+class Multigrid(_Handle):
+    """Geometric multigrid hierarchy over assembled level matrices (fine first) on nested box meshes."""
+    _destroy = "fsb_mg_destroy"
+
+    def __init__(self, ctx, matrices, ncells, tdim):
+        self.matrices = list(matrices)              # keep the level matrices alive
+        arr = (c_vp * len(matrices))(*[m.h for m in matrices])
+        nc = np.zeros((len(matrices), 3), dtype=np.int32)
+        for l, n in enumerate(ncells):
+            nc[l, :len(n)] = n
+        h = c_vp()
+        ctx.check(ctx.lib.fsb_mg_create(ctx.h, len(matrices), arr, _ptr(nc), int(tdim), C.byref(h)))
+        super().__init__(ctx, h)
+
+    def apply(self, r, z, nu=2):
+        self.ctx.check(self.ctx.lib.fsb_mg_apply(self.h, r.h, z.h, int(nu)))
+
+    def omega(self, level):
+        w = c_dbl()
+        self.ctx.check(self.ctx.lib.fsb_mg_omega(self.h, int(level), C.byref(w)))
+        return w.value
+
+    def solve(self, b, x, rtol=1e-12, atol=0.0, maxit=1000, nu=2):
+        info = SolveInfo()
+        self.ctx.check(self.ctx.lib.fsb_solve_cg_mg(self.h, b.h, x.h, float(rtol), float(atol), int(maxit), int(nu), C.byref(info)))
         return {"iterations": info.iterations, "converged": info.converged, "rnorm": info.rnorm, "bnorm": info.bnorm,
                 "solve_ms": info.solve_ms, "spmv_ms": info.spmv_ms, "operand_nnzb": info.operand_nnzb}
 

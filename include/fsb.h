@@ -33,6 +33,7 @@ extern "C" {
 typedef struct fsb_ctx fsb_ctx;
 typedef struct fsb_mesh fsb_mesh;
 typedef struct fsb_mat fsb_mat;
+typedef struct fsb_mg fsb_mg;     /* geometric multigrid hierarchy (box meshes) */
 typedef struct fsb_vec fsb_vec;
 
 typedef enum {
@@ -201,6 +202,20 @@ int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, i
                  int32_t precond, fsb_solve_info* info);
 int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit,
                        int32_t precond, fsb_solve_info* info);
+
+/* ---- multigrid-preconditioned CG: the reference's 3-D elasticity path is CG + PETSc GAMG (SolverBase.py:643-672 solve_amg) --
+ * Geometric multigrid on generated box meshes, whose triangulation is nested under halving the cell counts: level 0 is
+ * the fine matrix, A[l] the same form assembled (and Dirichlet-eliminated with fsb_apply_dirichlet, so constrained dofs
+ * are known) on the box with ncells[l][0..2] = ncells[l-1]/2 cells per axis.  The matrices stay owned by the caller and must
+ * outlive the hierarchy.  P1 interpolation along the coarse edges / its transpose, damped-Jacobi smoothing (damping from a
+ * power-iteration estimate per level), V(nu,nu) cycle as the preconditioner of CG; convergence test as fsb_solve_cg.
+ * Single GPU. */
+int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells /*[nlevels][3]*/, int32_t tdim, fsb_mg** mg);
+int fsb_mg_omega(fsb_mg* mg, int32_t level, double* omega);      /* the Jacobi damping chosen for a level */
+int fsb_mg_apply(fsb_mg* mg, fsb_vec* r, fsb_vec* z, int32_t nu);  /* z = one V(nu,nu) cycle applied to r (zero start) */
+int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit, int32_t nu,
+                    fsb_solve_info* info);
+void fsb_mg_destroy(fsb_mg* mg);
 
 /* ---- distributed: mesh partition + PETSc VecScatter/MPI_Allreduce (SolverBase.py:102-118, 634) -- */
 #define FSB_NCCL_UID_BYTES 128

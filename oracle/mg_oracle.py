@@ -1,0 +1,44 @@
+"""CPU restatement of the geometric multigrid V-cycle of csrc/fsb_mg.cu.  TEST INFRASTRUCTURE ONLY (see fem_oracle.py).
+
+The reference reaches multigrid through PETSc GAMG (SolverBase.py:643-672, solve_amg); an algebraic hierarchy cannot be
+reproduced without PETSc, so what is pinned here is the library's own geometric scheme: nestedness of dolfin's box meshes
+and Galerkin = re-discretisation (tests/test_oracle_forms.py), and this V-cycle, which the CUDA path must match to
+rounding when given the same level matrices and dampings."""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def prolongation(ncells_fine, ncomp=1):
+    """P1 interpolation from the box with ncells/2 cells per axis: fine vertex 2C + d is the coarse vertex C (d = 0) or the
+    midpoint of the coarse edge (C, C + d)."""
+    nf = list(ncells_fine) + [0] * (3 - len(ncells_fine))
+    df = [k + 1 for k in nf]
+    dc = [k // 2 + 1 for k in nf]
+    f = np.arange(df[0] * df[1] * df[2])
+    i, j, k = f % df[0], (f // df[0]) % df[1], f // (df[0] * df[1])
+    di, dj, dk = i & 1, j & 1, k & 1
+    c0 = (i >> 1) + dc[0] * ((j >> 1) + dc[1] * (k >> 1))
+    c1 = ((i >> 1) + di) + dc[0] * (((j >> 1) + dj) + dc[1] * ((k >> 1) + dk))
+    P = sp.coo_matrix((np.full(2 * f.size, 0.5), (np.concatenate([f, f]), np.concatenate([c0, c1]))),
+                      shape=(f.size, dc[0] * dc[1] * dc[2])).tocsr()          # d = 0: the two halves add up to 1
+    return sp.kron(P, sp.identity(ncomp)).tocsr() if ncomp > 1 else P
+
+
+def vcycle(levels, transfers, b, nu=2, coarse_sweeps=24, l=0):
+    """levels[l] = dict(A, dinv, omega, bc mask); transfers[l] = P from level l+1 to l.  Zero initial guess."""
+    L = levels[l]
+
+    def smooth(x, rhs, sweeps, zero):
+        for s in range(sweeps):
+            x = L['omega'] * L['dinv'] * rhs if (s == 0 and zero) else x + L['omega'] * L['dinv'] * (rhs - L['A'] @ x)
+        return x
+    if l == len(levels) - 1:
+        return smooth(None, b, coarse_sweeps, True)
+    x = smooth(None, b, nu, True)
+    bc = transfers[l].T @ (b - L['A'] @ x)
+    bc[levels[l + 1]['bc']] = 0.0
+    corr = transfers[l] @ vcycle(levels, transfers, bc, nu, coarse_sweeps, l + 1)
+    corr[L['bc']] = 0.0
+    return smooth(x + corr, b, nu, False)

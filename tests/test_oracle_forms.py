@@ -285,3 +285,47 @@ def test_supg_weights_consistency_and_monotone_profile(dim):
         tv = [np.abs(np.diff(s_.reshape(n + 1, n + 1)[:, 5])).sum() for s_ in sols]      # total variation along the flow
         assert sols[0].min() < -1.5 and tv[0] > 7
         assert sols[1].min() > -0.35 and sols[1].max() < 1 + 1e-10 and tv[1] < 1.3
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_box_meshes_are_nested_and_rediscretisation_is_galerkin(dim):
+    """What the geometric multigrid preconditioner (csrc/fsb_mg.cu) rests on: dolfin's box triangulation with n/2 cells per
+    axis is nested in the one with n cells, the fine vertex 2C + d being the midpoint of the coarse edge (C, C + d).  So
+    the prolongation built from that rule reproduces P1 functions of the coarse mesh exactly, and the coarse stiffness,
+    mass and elasticity matrices equal P^T A_fine P."""
+    import scipy.sparse as sp
+    n = (4, 6, 2)[:dim]
+    nc = tuple(k // 2 for k in n)
+    p1 = (1.0, 1.5, 0.5)[:dim]
+    if dim == 2:
+        cf, tf = fo.rectangle_mesh(0, 0, p1[0], p1[1], *n)
+        cc, tc = fo.rectangle_mesh(0, 0, p1[0], p1[1], *nc)
+    else:
+        cf, tf = fo.box_mesh((0, 0, 0), p1, *n)
+        cc, tc = fo.box_mesh((0, 0, 0), p1, *nc)
+    dims_f = [k + 1 for k in n] + [1] * (3 - dim)
+    dims_c = [k + 1 for k in nc] + [1] * (3 - dim)
+    rows, cols, vals = [], [], []
+    for f in range(cf.shape[0]):
+        i, j, k = f % dims_f[0], (f // dims_f[0]) % dims_f[1], f // (dims_f[0] * dims_f[1])
+        d = (i & 1, j & 1, k & 1)
+        c0 = (i >> 1) + dims_c[0] * ((j >> 1) + dims_c[1] * (k >> 1))
+        c1 = ((i >> 1) + d[0]) + dims_c[0] * (((j >> 1) + d[1]) + dims_c[1] * ((k >> 1) + d[2]))
+        if d == (0, 0, 0):
+            rows += [f]; cols += [c0]; vals += [1.0]
+        else:
+            rows += [f, f]; cols += [c0, c1]; vals += [0.5, 0.5]
+    P = sp.csr_matrix((vals, (rows, cols)), shape=(cf.shape[0], cc.shape[0]))
+    assert np.abs(P @ cc - cf).max() < 1e-15                     # coordinates are P1: interpolation reproduces them
+    # every fine cell lies inside ONE coarse cell's vertex hull in the sense that matters: Galerkin = rediscretisation
+    for local in (lambda c, t: fo.local_laplace(c, t, 2.0), lambda c, t: fo.local_mass(c, t, 3.0)):
+        Af = fo.assemble_matrix(tf, local(cf, tf), cf.shape[0])
+        Ac = fo.assemble_matrix(tc, local(cc, tc), cc.shape[0])
+        G = (P.T @ Af @ P).toarray()
+        assert np.abs(G - Ac.toarray()).max() < 1e-12 * np.abs(Ac.toarray()).max()
+    mu, lam = fo.lame(2e11, 0.27)
+    Pv = sp.kron(P, sp.identity(dim)).tocsr()
+    Af = fo.assemble_matrix(tf, fo.local_elasticity(cf, tf, mu, lam), cf.shape[0], dim)
+    Ac = fo.assemble_matrix(tc, fo.local_elasticity(cc, tc, mu, lam), cc.shape[0], dim)
+    G = (Pv.T @ Af @ Pv).toarray()
+    assert np.abs(G - Ac.toarray()).max() < 1e-11 * np.abs(Ac.toarray()).max()
