@@ -519,7 +519,13 @@ class SolverBase():
             dofs, vals = collect_dirichlet(bcs_c, c.function_space)
             c._space.apply_dirichlet(bc_, dofs, np.zeros(len(dofs)), symmetric=True)
             mats.append(c._space.A)
-        mg = L.Multigrid(space.ctx, mats, sizes, mesh.tdim)
+        # the dampings depend on the operator only through lambda_max(D^-1 A) per level, which a re-assembly of the same
+        # form on the same meshes (the next time step) does not change: reuse them, estimate once
+        prev = self.__dict__.get('_mg_omega')
+        reuse = prev if (prev is not None and prev[0] == [tuple(k) for k in sizes]
+                         and self.solver_settings.get('solver_parameters', {}).get('mg_reuse_damping', True)) else None
+        mg = L.Multigrid(space.ctx, mats, sizes, mesh.tdim, omega=None if reuse is None else reuse[1])
+        self._mg_omega = ([tuple(k) for k in sizes], [mg.omega(l) for l in range(len(mats))])
         self._mg = mg
         return mg
 
@@ -529,9 +535,28 @@ class SolverBase():
         return self.device_space().owned_values(self._last_x)
 
     def solve_amg(self, F, u, bcs):
-        """The reference's 3D elasticity path (assemble_system + CG/GAMG, SolverBase.py:643-672).  Here:
-        symmetric elimination + Jacobi-CG on the 3x3 block matrix, converged to the parity tolerance."""
-        return self.solve_linear_problem(F, u, bcs)
+        """The reference's 3D elasticity path: assemble_system + CG preconditioned by PETSc GAMG (SolverBase.py:643-672).
+        Here: symmetric elimination + CG on the 3x3 block matrix, preconditioned by geometric multigrid when the mesh is a
+        generated box with at least one coarser level (single GPU, degree 1) and the user named no preconditioner;
+        Jacobi otherwise.  Converged to the parity tolerance either way (the reference stops at dolfin's default 1e-6)."""
+        sp = self.solver_settings.setdefault('solver_parameters', {})
+        auto = 'preconditioner' not in sp
+        if auto and self._multigrid_levels() >= 2:
+            sp['preconditioner'] = 'gmg'
+        try:
+            return self.solve_linear_problem(F, u, bcs)
+        finally:
+            if auto:
+                sp.pop('preconditioner', None)
+
+    def _multigrid_levels(self):
+        mesh = self.mesh
+        if not getattr(mesh, 'box', None) or self.parallel or self.function_space.degree != 1:
+            return 0
+        n, levels = [int(k) for k in mesh.box['n']], 1
+        while all(k % 2 == 0 and k >= 4 for k in n):
+            n, levels = [k // 2 for k in n], levels + 1
+        return levels
 
     def solve_nonlinear_problem(self, F, u_current, Dirichlet_bcs, J):
         """Newton's method on the device (NonlinearVariationalSolver, SolverBase.py:615-626).  Each iteration

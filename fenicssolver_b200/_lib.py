@@ -79,7 +79,7 @@ SIGNATURES = {
     "fsb_dot": (C.c_int, [c_vp, c_vp, P(c_dbl)]),
     "fsb_solve_cg": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
     "fsb_solve_bicgstab": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
-    "fsb_mg_create": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, P(c_vp)]),
+    "fsb_mg_create": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, P(c_vp)]),
     "fsb_mg_omega": (C.c_int, [c_vp, c_i32, P(c_dbl)]),
     "fsb_mg_apply": (C.c_int, [c_vp, c_vp, c_vp, c_i32]),
     "fsb_solve_cg_mg": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
@@ -383,14 +383,16 @@ class Multigrid(_Handle):
     """Geometric multigrid hierarchy over assembled level matrices (fine first) on nested box meshes."""
     _destroy = "fsb_mg_destroy"
 
-    def __init__(self, ctx, matrices, ncells, tdim):
+    def __init__(self, ctx, matrices, ncells, tdim, omega=None):
+        """`omega`: per-level dampings from an earlier hierarchy on the same levels (skips the eigenvalue estimates)."""
         self.matrices = list(matrices)              # keep the level matrices alive
         arr = (c_vp * len(matrices))(*[m.h for m in matrices])
         nc = np.zeros((len(matrices), 3), dtype=np.int32)
         for l, n in enumerate(ncells):
             nc[l, :len(n)] = n
         h = c_vp()
-        ctx.check(ctx.lib.fsb_mg_create(ctx.h, len(matrices), arr, _ptr(nc), int(tdim), C.byref(h)))
+        om = None if omega is None else _np(omega, np.float64)
+        ctx.check(ctx.lib.fsb_mg_create(ctx.h, len(matrices), arr, _ptr(nc), int(tdim), _ptr(om), C.byref(h)))
         super().__init__(ctx, h)
 
     def apply(self, r, z, nu=2):

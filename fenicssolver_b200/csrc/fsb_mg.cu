@@ -255,7 +255,8 @@ extern "C" void fsb_mg_destroy(fsb_mg* mg) {
   delete mg;
 }
 
-extern "C" int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells, int32_t tdim, fsb_mg** out) {
+extern "C" int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells, int32_t tdim, const double* omega,
+                             fsb_mg** out) {
   if (!ctx || !A || !ncells || !out || nlevels < 1 || (tdim != 2 && tdim != 3)) return FSB_ERR_ARG;
   if (fsb_dist_active(ctx)) FSB_FAIL(ctx, FSB_ERR_STATE, "the multigrid preconditioner is single-GPU");
   fsb_mg* mg = new fsb_mg();
@@ -279,7 +280,8 @@ extern "C" int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const i
       break;
     k_mg_dinv<<<mg_grid(ctx, L.n), 256, 0, ctx->stream>>>(L.n, mg->bs, L.A->row_ptr, L.A->col_idx, L.A->vals, L.dinv);
     ctx->launches++;
-    if ((rc = mg_estimate_omega(mg, L))) break;
+    if (omega && omega[l] > 0.0) L.omega = omega[l];
+    else if ((rc = mg_estimate_omega(mg, L))) break;
   }
   const int64_t n0 = mg->lv[0].n;
   if (!rc) rc = fsb_dmalloc(ctx, &mg->p, (size_t)n0);

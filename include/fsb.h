@@ -210,7 +210,8 @@ int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double a
  * outlive the hierarchy.  P1 interpolation along the coarse edges / its transpose, damped-Jacobi smoothing (damping from a
  * power-iteration estimate per level), V(nu,nu) cycle as the preconditioner of CG; convergence test as fsb_solve_cg.
  * Single GPU. */
-int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells /*[nlevels][3]*/, int32_t tdim, fsb_mg** mg);
+int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells /*[nlevels][3]*/, int32_t tdim,
+                  const double* omega /* per-level Jacobi dampings to reuse (entries <= 0 or NULL: estimate) */, fsb_mg** mg);
 int fsb_mg_omega(fsb_mg* mg, int32_t level, double* omega);      /* the Jacobi damping chosen for a level */
 int fsb_mg_apply(fsb_mg* mg, fsb_vec* r, fsb_vec* z, int32_t nu);  /* z = one V(nu,nu) cycle applied to r (zero start) */
 int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit, int32_t nu,

@@ -165,3 +165,29 @@ def test_gmg_needs_a_box_mesh_and_a_symmetric_problem():
     s['convective_velocity'] = (0.0, 0.0, 1e-3)
     with pytest.raises(SolverBase.SolverError):
         ScalarTransportSolver.ScalarTransportSolver(s).solve()
+
+
+def test_solve_amg_defaults_to_multigrid_on_even_boxes():
+    """LinearElasticitySolver.solve_form -> solve_amg (3-D): multigrid-preconditioned CG when the box can be coarsened and
+    no preconditioner was named, Jacobi-CG otherwise; the settings dict is left as the user wrote it."""
+    def settings(n):
+        s = copy.deepcopy(SolverBase.default_case_settings)
+        s.update({'mesh': BoxMesh(Point(0, 0, 0), Point(4, 1, 1), *n), 'material': {'elastic_modulus': 2e11, 'poisson_ratio': 0.27, 'density': 7800},
+                  'boundary_conditions': {'clamp': {'boundary': AutoSubDomain(lambda x: near(x[0], 0.0)), 'boundary_id': 1, 'type': 'Dirichlet',
+                                                    'value': Constant((0, 0, 0))}},
+                  'body_source': (0.0, 0.0, -7800 * 9.81), 'report_settings': QUIET})
+        s['solver_settings'] = dict(s['solver_settings'], solver_parameters={})
+        return s
+    even = LinearElasticitySolver.LinearElasticitySolver(settings((16, 4, 4)))
+    even.solve()
+    assert even.solve_info.get('mg_levels') == 2 and even.solve_info['converged'] == 1
+    assert 'preconditioner' not in even.solver_settings['solver_parameters']
+    odd = LinearElasticitySolver.LinearElasticitySolver(settings((15, 3, 3)))
+    odd.solve()
+    assert 'mg_levels' not in odd.solve_info and odd.solve_info['converged'] == 1
+    named = settings((16, 4, 4))
+    named['solver_settings']['solver_parameters']['preconditioner'] = 'jacobi'
+    jac = LinearElasticitySolver.LinearElasticitySolver(named)
+    uj = jac.solve()
+    assert 'mg_levels' not in jac.solve_info
+    assert fo.relative_l2(even.result.vector().get_local(), uj.vector().get_local()) < 1e-8

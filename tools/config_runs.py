@@ -15,6 +15,7 @@ from fenicssolver_b200.dolfin_compat import near  # noqa: E402
 QUIET = {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0, 'plotting_interactive': False}
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 NSTEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+PRECOND = os.environ.get("FSB_PRECOND", "jacobi")        # 'gmg': CG preconditioned by geometric multigrid (C3)
 
 
 def c3():
@@ -23,7 +24,7 @@ def c3():
          'boundary_conditions': {'clamp': {'boundary': lambda x: near(x[0], 0.0), 'boundary_id': 1, 'type': 'Dirichlet', 'value': (0, 0, 0)}},
          'body_source': (0.0, 0.0, -7800 * 9.81), 'initial_values': {},
          'solver_settings': {'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.01, 'ending_time': 0.03},
-                             'reference_values': {}, 'solver_parameters': {}},
+                             'reference_values': {}, 'solver_parameters': {'preconditioner': PRECOND}},
          'report_settings': QUIET}
     solver = LinearElasticitySolver.LinearElasticitySolver(s)
     solver.device_space().ctx.set_option("profile", 1)
@@ -35,10 +36,10 @@ def c3():
     sizes = solver.device_space().A.sizes()
     bytes_spmv = sizes["nnzb"] * 76 + sizes["nrows"] // 3 * 56
     it = max(info["iterations"], 1)
-    print(json.dumps({"config": "C3 elasticity cantilever %d^3 P1, %d DoF, Jacobi-CG rtol 1e-12 (reference load sign)" % (N, sizes["nrows"]),
+    print(json.dumps({"config": "C3 elasticity cantilever %d^3 P1, %d DoF, %s-CG rtol 1e-12 (reference load sign)" % (N, sizes["nrows"], PRECOND),
                       "iterations": info["iterations"], "converged": info["converged"], "wall_s": dt,
                       "timings": solver.timings, "solve_ms": info["solve_ms"], "ms_per_iteration": info["solve_ms"] / it,
-                      "spmv_ms": info["spmv_ms"] / it, "spmv_GBps": bytes_spmv / (info["spmv_ms"] / it * 1e-3) / 1e9,
+                      "spmv_ms": info["spmv_ms"] / it, "spmv_GBps": (bytes_spmv / (info["spmv_ms"] / it * 1e-3) / 1e9) if info["spmv_ms"] else None,
                       "Mdof_per_s": sizes["nrows"] / (solver.timings["assemble"] + solver.timings["solve"]) / 1e6,
                       "tip_displacement": tip.tolist()}), flush=True)
 
