@@ -559,3 +559,55 @@ def test_supg_transient_matches_oracle():
     for _ in range(nsteps):
         Tn = supg_oracle_system(n, dt, Tn)
     assert fo.relative_l2(T.values, Tn) < TOL
+
+
+def test_new_entry_points_empty_inputs_and_errors(ctx):
+    """Empty lists are no-ops, wrong sizes / degrees / parameters come back as SolverError with a message."""
+    c, t = small_mesh(3)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    b, T = _lib.DeviceVector(ctx, nv), _lib.DeviceVector(ctx, nv)
+    b3 = _lib.DeviceVector(ctx, 3 * nv)
+    empty_f = np.zeros((0, 3), dtype=np.int32)
+    _lib.assemble_facet_radiation(m, A, b, T, empty_f, 5e-8, 300.0)                       # nf = 0
+    _lib.assemble_facet_supg(m, A, b, empty_f, np.zeros(0, dtype=np.int32), [1.0, 0, 0], 10.0, g=1.0, h=1.0)
+    b.add_entries(np.zeros(0, dtype=np.int64), np.zeros(0))
+    assert np.all(b.numpy() == 0.0) and np.all(A.download_csr()[2] == 0.0)
+    with pytest.raises(_lib.SolverError):
+        b.add_entries([nv], [1.0])                                                       # index out of range
+    with pytest.raises(_lib.SolverError):
+        _lib.assemble_thermal_load(m, b, 1.0, T_const=1.0)                               # rhs must have ncomp == dim
+    with pytest.raises(_lib.SolverError):
+        _lib.assemble_thermal_load(m, b3, 1.0, T=b3)                                     # temperature must be nodal scalar
+    with pytest.raises(_lib.SolverError):
+        _lib.assemble_von_mises_load(m, b, 1.0, 1.0, b)                                  # displacement size
+    with pytest.raises(_lib.SolverError):
+        _lib.assemble_scalar_supg(m, A, [1.0, 0, 0], 0.0, adv=1.0)                       # Peclet must be positive
+    with pytest.raises(_lib.SolverError):
+        _lib.assemble_scalar_nonlinear_k(m, A, b, T, b3, T)                              # nodal vector sizes
+    cn, xn, _ = fp.p2_dofmap(c, t)
+    m2 = _lib.DeviceMesh.upload_p2(ctx, c, cn, xn.shape[0])
+    A2 = _lib.DeviceMatrix.create(m2, 1)
+    v2 = _lib.DeviceVector(ctx, xn.shape[0])
+    fv, _, _ = fo.exterior_facets(t)
+    with pytest.raises(_lib.SolverError):
+        _lib.assemble_facet_radiation(m2, A2, v2, v2, fv, 5e-8, 300.0)                   # degree-1 only
+    with pytest.raises(_lib.SolverError):
+        _lib.assemble_scalar_supg(m2, A2, [1.0, 0, 0], 5.0, adv=1.0)
+    with pytest.raises(_lib.SolverError):
+        ctx.dist_set_halo(1, 2, [1], [0, 1], [0], [1], [1])                              # no fsb_dist_init
+    with pytest.raises(_lib.SolverError):
+        _lib.Multigrid(ctx, [A], [(3, 4, 3)], 3)                                         # matrix does not match the box
+    # a single-level hierarchy is legal: the "V-cycle" is the coarse smoother
+    mb = _lib.DeviceMesh.box(ctx, (2, 2, 2), (0, 0, 0), (1, 1, 1))
+    Ab = _lib.DeviceMatrix.create(mb, 1)
+    Ab.assemble_scalar(kscale=1.0, mass=1.0)
+    mg = _lib.Multigrid(ctx, [Ab], [(2, 2, 2)], 3)
+    rhs, x = _lib.DeviceVector(ctx, 27), _lib.DeviceVector(ctx, 27)
+    rhs.fill(1.0)
+    info = mg.solve(rhs, x, rtol=1e-12, maxit=200)
+    assert info["converged"] == 1
+    rp, ci, va = Ab.download_csr()
+    M = sp.csr_matrix((va, ci.astype(np.int64), rp), shape=(27, 27))
+    assert np.abs(M @ x.numpy() - 1.0).max() < 1e-9
