@@ -44,7 +44,7 @@ class ElasticityForm:
             fv, _ = space.local_facets(*s.boundary_facets.facets(marker))
             _lib.assemble_facet_load(space.dmesh, b, fv, t, ncomp=dim, scale=self.load_sign)
         for marker, p in self.pressures:
-            fv, op = space.local_facets(*s.boundary_facets.facets(marker))
+            fv, op = space.local_facets(*(s.mesh.exterior_facets()[:2] if marker is None else s.boundary_facets.facets(marker)))
             _lib.assemble_facet_load(space.dmesh, b, fv, p, ncomp=dim, scale=self.load_sign, opp=op, normal=True)
         for f in self.body_forces:
             if isinstance(f, np.ndarray) and f.shape == (dim,):
@@ -137,7 +137,11 @@ class LinearElasticitySolver(SolverBase):
         if 'point_source' in self.settings and self.settings['point_source']:
             raise SolverError('point_source is not implemented (and reads surface_source in the reference, :105-108)')
         if 'surface_source' in self.settings and self.settings['surface_source']:
-            raise SolverError('surface_source on all boundaries is not implemented on the device path')
+            # dot(mesh_normal*gS, v)*ds over the whole exterior surface (:110-115); a given 'direction' is read but never
+            # used by the reference (the branch adds nothing), which is reproduced
+            ss = self.settings['surface_source']
+            if not ss.get('direction'):
+                F.pressures.append((None, float(self.translate_value(self.get_flux(u, ss['value'])))))
 
         for name, bc_settings in self.boundary_conditions.items():
             i = bc_settings['boundary_id']

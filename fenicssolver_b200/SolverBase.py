@@ -565,28 +565,26 @@ class SolverBase():
         from the start).  Stops on ||F|| <= newton_rtol * ||F_0|| (default 1e-11; dolfin's own default is 1e-9) or
         newton_atol.  `J` is unused: the forms know their own derivative."""
         space = self.device_space()
-        if space.comm.nranks > 1:
-            raise SolverError('the Newton solver is not implemented for distributed runs')
+        dist = space.comm.nranks > 1
         kp = self.krylov_parameters()
         sp = self.solver_settings.get('solver_parameters') or {}
         n_rtol, n_atol = float(sp.get('newton_relative_tolerance', 1e-11)), float(sp.get('newton_absolute_tolerance', 1e-14))
         n_maxit = int(sp.get('newton_maximum_iterations', 50))
         dofs, vals = collect_dirichlet(Dirichlet_bcs, self.function_space)
-        ldofs, lvals = space.local_dofs(dofs, vals)
-        xh = u_current.array().copy()
-        xh[ldofs] = lvals
-        x = space.vector_from_global(xh)
+        xg = u_current.array().copy()                         # global nodal values; every rank imposes the same Dirichlet data
+        xg[dofs] = np.broadcast_to(vals, np.shape(dofs))
+        x = space.vector_from_global(xg)                      # local part (owned + ghosts)
         y, dx = space.scratch_vector('newton_y'), space.scratch_vector('newton_dx')
         t0 = time.perf_counter()
         r0, history, lin_iters = None, [], 0
         for it in range(n_maxit + 1):
             b, symmetric_form = F.assemble(space)                 # linear part: space.A, b
-            space.A.spmv(x, y)
+            space.A.spmv(x, y)                                    # refreshes the ghosts of x first when distributed
             b.axpy(-1.0, y)                                       # b <- b - A_lin x
             F.add_newton_terms(space, x, b)                       # A += dR/dx, b -= R(x)
             method = kp['method'] or ('cg' if symmetric_form else 'bicgstab')
             space.apply_dirichlet(b, dofs, np.zeros(len(dofs)), symmetric=(method == 'cg'))
-            rn = float(np.sqrt(b.dot(b)))
+            rn = float(np.sqrt(b.dot(b)))                         # owned rows, all-reduced
             history.append(rn)
             r0 = rn if r0 is None else r0
             if rn <= max(n_rtol * r0, n_atol) or it == n_maxit:
@@ -597,6 +595,8 @@ class SolverBase():
             if info['converged'] != 1:
                 self.logger.warning("%s did not converge inside Newton iteration %d: %s", method, it, info)
             x.axpy(1.0, dx)
+            if dist:
+                x.halo()                                          # the update is only valid on the owned rows
         self.timings['solve'] = time.perf_counter() - t0
         converged = history[-1] <= max(n_rtol * r0, n_atol)
         self.solve_info = {'iterations': lin_iters, 'converged': int(converged), 'newton_iterations': len(history) - 1,
@@ -605,7 +605,10 @@ class SolverBase():
         if not converged:
             self.logger.warning("Newton did not converge: residuals %s", history)
         self._last_x = x
-        u_current.set_device(x)
+        if dist and self.solver_settings.get('gather_result', True):
+            u_current.assign_array(space.gather_global(x))
+        elif not dist:
+            u_current.set_device(x)
         return u_current
 
 

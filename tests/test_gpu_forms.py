@@ -598,7 +598,7 @@ def test_new_entry_points_empty_inputs_and_errors(ctx):
     with pytest.raises(_lib.SolverError):
         ctx.dist_set_halo(1, 2, [1], [0, 1], [0], [1], [1])                              # no fsb_dist_init
     with pytest.raises(_lib.SolverError):
-        _lib.Multigrid(ctx, [A], [(3, 4, 3)], 3)                                         # matrix does not match the box
+        _lib.Multigrid(ctx, [A], [(3, 3, 3)], 3)                                         # matrix does not match the box
     # a single-level hierarchy is legal: the "V-cycle" is the coarse smoother
     mb = _lib.DeviceMesh.box(ctx, (2, 2, 2), (0, 0, 0), (1, 1, 1))
     Ab = _lib.DeviceMatrix.create(mb, 1)
@@ -611,3 +611,25 @@ def test_new_entry_points_empty_inputs_and_errors(ctx):
     rp, ci, va = Ab.download_csr()
     M = sp.csr_matrix((va, ci.astype(np.int64), rp), shape=(27, 27))
     assert np.abs(M @ x.numpy() - 1.0).max() < 1e-9
+
+
+def test_elasticity_surface_source_is_a_normal_load_on_the_whole_surface():
+    """settings['surface_source'] = {'value': p} (LinearElasticitySolver.py:110-115): dot(mesh_normal*p, v)*ds over every
+    exterior facet, with the reference's load sign."""
+    n = (6, 3, 3)
+    s, mesh = elasticity_settings(1, n, False, False, False)
+    s['surface_source'] = {'value': 2.5e6, 'direction': None}
+    solver = LinearElasticitySolver.LinearElasticitySolver(s)
+    u = solver.solve()
+    c, t = fo.box_mesh((0, 0, 0), (xmax, 1, 1), *n)
+    nv = c.shape[0]
+    mu, lam = fo.lame(2e11, 0.27)
+    A = fo.assemble_matrix(t, fo.local_elasticity(c, t, mu, lam), nv, 3)
+    fv, opp, _ = fo.exterior_facets(t)
+    meas, nrm = fo.facet_measure(c, fv, opp)
+    b = -fo.assemble_facet_load(c, fv, 2.5e6 * nrm, nv, 3)
+    lv, rv = np.nonzero(c[:, 0] == 0)[0], np.nonzero(c[:, 0] == xmax)[0]
+    dofs = np.concatenate([lv * 3, (rv[:, None] * 3 + np.arange(3)).ravel()])
+    vals = np.concatenate([np.zeros(lv.size), np.tile([0, 0, 1e-3], rv.size)])
+    Ab, bb = fo.apply_dirichlet(A, b, dofs, vals, symmetric=True)
+    assert fo.relative_l2(u.vector().get_local(), fo.solve_direct(Ab, bb)) < 1e-9

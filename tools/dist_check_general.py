@@ -2,7 +2,8 @@
 owned-first local numbering, send-list halo) compared on rank 0 with single-GPU solves of the same problems:
  A  heat with flux + HTC + source on an unstructured (jittered, user-array) tetrahedral mesh, Jacobi-CG
  B  the reference's elasticity example on its own degree-2 space (P2 nodes partitioned), Jacobi-CG on 3x3 blocks
- C  transient advection-diffusion on the unstructured mesh (BiCGStab, T_prev halo every step)."""
+ C  transient advection-diffusion on the unstructured mesh (BiCGStab, T_prev halo every step)
+ D  radiation boundary on the unstructured mesh: Newton iterations with distributed residuals and updates."""
 import copy
 import os
 import sys
@@ -14,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 QUIET = {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0, 'plotting_interactive': False}
 
 
-def heat_case(mesh, distributed, transient=False):
+def heat_case(mesh, distributed, transient=False, radiation=False):
     from fenicssolver_b200.dolfin_compat import near
     k, rho, cp = 0.6, 1000.0, 4200.0
     n = 10
@@ -32,6 +33,8 @@ def heat_case(mesh, distributed, transient=False):
          'report_settings': QUIET}
     if transient:
         s['convective_velocity'] = (0.0, 1e-6, 2e-6)
+    if radiation:
+        s['radiation_settings'] = {'ambient_temperature': 280.0, 'emissivity': 0.9}      # Newton, all exterior facets
     return s
 
 
@@ -74,7 +77,8 @@ def main():
 
     cases = [("A heat/unstructured", ScalarTransportSolver.ScalarTransportSolver, lambda d: heat_case(mesh, d), 1),
              ("B elasticity/P2", LinearElasticitySolver.LinearElasticitySolver, elasticity_case, 3),
-             ("C transient/unstructured", ScalarTransportSolver.ScalarTransportSolver, lambda d: heat_case(mesh, d, True), 1)]
+             ("C transient/unstructured", ScalarTransportSolver.ScalarTransportSolver, lambda d: heat_case(mesh, d, True), 1),
+             ("D radiation-Newton/unstructured", ScalarTransportSolver.ScalarTransportSolver, lambda d: heat_case(mesh, d, radiation=True), 1)]
     for name, cls, make, ncomp in cases:
         sv = cls(make(True))
         xd = sv.solve().vector().get_local()
