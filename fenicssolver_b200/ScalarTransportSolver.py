@@ -39,7 +39,7 @@ class ScalarForm:
         self.transient = False
         self.dt = None
         self.theta = 0.5
-        self.velocity = None             # constant vector
+        self.velocity = None             # constant vector, or nodal field [nverts, dim] (P1 interpolant)
         self.neumann = []                # (marker id, constant g)
         self.robin = []                  # (marker id, h, T_ambient)
         self.sources = []                # (value (number | nodal array), subdomain id | None)
@@ -63,6 +63,14 @@ class ScalarForm:
         kscale, ktensor = self._k()
         c = float(self.capacity)
         vel = None if self.velocity is None else np.asarray(self.velocity, dtype=np.float64)
+        vel_field = None
+        if vel is not None and vel.ndim == 2:
+            # a velocity FIELD: the convection matrix comes from its own kernel, nothing else sees the velocity
+            if self.supg_pe:
+                raise SolverError('SUPG with a velocity field is not implemented (constant velocity only)')
+            if space.comm.nranks > 1:
+                raise SolverError('a velocity field is implemented for single-GPU runs')
+            vel_field, vel = _lib.DeviceVector.from_numpy(space.ctx, vel.ravel()), None
         adv = c if vel is not None else 0.0
         b = space.scratch_vector('rhs')
         supg = self.supg_pe if vel is not None else None
@@ -81,6 +89,8 @@ class ScalarForm:
             A.assemble_scalar(kscale=kscale, ktensor=ktensor, adv=adv, vel=vel)
             if supg:
                 _lib.assemble_scalar_supg(space.dmesh, A, vel, supg, adv=adv)
+        if vel_field is not None:
+            _lib.assemble_advection_nodal(space.dmesh, A, vel_field, scale=c)      # fully implicit, like the constant case (:311)
         for marker, g in self.neumann:
             fv, op = space.local_facets(*s.boundary_facets.facets(marker))
             _lib.assemble_facet_load(space.dmesh, b, fv, g)
@@ -113,7 +123,7 @@ class ScalarForm:
             if space.comm.nranks > 1:
                 raise SolverError('point sources are not implemented for distributed runs')
             b.add_entries(nodes, w)
-        symmetric = vel is None and (ktensor is None or np.allclose(ktensor, ktensor.T, rtol=0, atol=0))
+        symmetric = vel is None and vel_field is None and (ktensor is None or np.allclose(ktensor, ktensor.T, rtol=0, atol=0))
         return b, symmetric and self.conductivity_fn is None       # the k'(T) Jacobian term is not symmetric
 
     def add_newton_terms(self, space, x, r):
@@ -298,8 +308,13 @@ class ScalarTransportSolver(SolverBase):
         if self.convective_velocity is not None:
             ads = self.settings.get('advection_settings') or {'stabilization_method': None}
             vel = self.translate_value(self.convective_velocity)
-            if not (isinstance(vel, np.ndarray) and vel.shape == (self.dimension,)):
-                raise SolverError('convective_velocity must be a constant vector on the device path')
+            nv = self.mesh.num_vertices()
+            if isinstance(vel, np.ndarray) and vel.shape == (self.dimension,):
+                pass                                           # Constant((vx, vy[, vz]))
+            elif isinstance(vel, np.ndarray) and vel.size == nv * self.dimension and self.function_space.degree == 1:
+                vel = vel.reshape(nv, self.dimension)          # Expression / Function / nodal array: P1 interpolant of the field
+            else:
+                raise SolverError('convective_velocity must be a constant vector or a field with dim values per vertex (degree 1)')
             F.velocity = vel
             method = ads.get('stabilization_method')
             if method in ('SPUG', 'SUPG'):               # 'SPUG' is the reference's spelling (:259)

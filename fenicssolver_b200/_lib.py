@@ -71,6 +71,7 @@ SIGNATURES = {
     "fsb_assemble_von_mises_load": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl, c_vp]),
     "fsb_assemble_facet_radiation": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_dbl, c_dbl, c_dbl]),
     "fsb_assemble_scalar_nonlinear_k": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl]),
+    "fsb_assemble_advection_nodal": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl]),
     "fsb_assemble_scalar_supg": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_dbl]),
     "fsb_assemble_source_supg": (C.c_int, [c_vp, c_vp, c_dbl, c_vp, c_dbl, c_vp, c_i32]),
     "fsb_assemble_facet_supg": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_dbl]),
@@ -480,3 +481,9 @@ def assemble_facet_supg(mesh, A, b, fverts, opp, vel, pe, g=0.0, h=0.0):
     fv, op, ve = _np(fverts, np.int32), _np(opp, np.int32), _np(vel, np.float64)
     mesh.ctx.check(mesh.ctx.lib.fsb_assemble_facet_supg(mesh.h, A.h if A is not None else None, b.h if b is not None else None,
                                                         fv.shape[0], _ptr(fv), _ptr(op), float(g), float(h), _ptr(ve), float(pe)))
+
+
+def assemble_advection_nodal(mesh, A, vel, scale=1.0, x=None, y=None):
+    """A += scale * int (v_h.grad u) v dx with v_h the P1 interpolant of the nodal velocity DeviceVector `vel` (or y += .. x)."""
+    mesh.ctx.check(mesh.ctx.lib.fsb_assemble_advection_nodal(mesh.h, A.h if A is not None else None, x.h if x is not None else None,
+                                                             y.h if y is not None else None, vel.h, float(scale)))

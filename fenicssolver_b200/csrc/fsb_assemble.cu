@@ -347,6 +347,61 @@ k_scalar_nonlinear_k(int64_t ncells, const int32_t* __restrict__ cells, const do
   }
 }
 
+// Convection by a velocity FIELD (ScalarTransportSolver.py:130-139 get_convective_velocity_function, :311): v_h is the P1
+// interpolant of the nodal velocities, so int (v_h . grad phi_b) phi_a = |T|/((D+1)(D+2)) sum_c (1 + delta_ac) v_c . G_b.
+//   A_ab += w * that            or (ACTION)   y_a += w * sum_b (...) x_b
+template <int D, bool ACTION>
+__global__ void __launch_bounds__(128)
+k_advection_nodal(int64_t ncells, const int32_t* __restrict__ cells, const double* __restrict__ xyz, const double* __restrict__ vel,
+                  double w, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx, double* __restrict__ vals,
+                  const uint8_t* __restrict__ posmap, const double* __restrict__ x, double* __restrict__ y) {
+  constexpr int NL = D + 1;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+    int v[NL];
+    load_cell<D>(cells, c, v);
+    Geo<D> g;
+    p1_geometry<D>(xyz, v, g);
+    double vn[NL][D], vs[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) vs[i] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int i = 0; i < D; ++i) { vn[a][i] = __ldg(vel + (int64_t)v[a] * D + i); vs[i] += vn[a][i]; }
+    const double f = w * g.vol / (double)(NL * (NL + 1));
+    double Ce[NL][NL];
+#pragma unroll
+    for (int a = 0; a < NL; ++a)
+#pragma unroll
+      for (int b = 0; b < NL; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) s += (vs[i] + vn[a][i]) * g.G[b][i];
+        Ce[a][b] = f * s;
+      }
+    if (ACTION) {
+      double xl[NL];
+#pragma unroll
+      for (int b = 0; b < NL; ++b) xl[b] = __ldg(x + v[b]);
+#pragma unroll
+      for (int a = 0; a < NL; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < NL; ++b) s += Ce[a][b] * xl[b];
+        atomicAdd(y + v[a], s);
+      }
+    } else {
+      int64_t base[NL];
+      int pos[NL][NL];
+      entry_positions<D>(posmap, c, v, row_ptr, col_idx, base, pos);
+#pragma unroll
+      for (int a = 0; a < NL; ++a)
+#pragma unroll
+        for (int b = 0; b < NL; ++b) add_nz(vals + base[a] + pos[a][b], Ce[a][b]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ Dirichlet
 __global__ void k_bc_scatter(int64_t nbc, const int64_t* __restrict__ dofs, const double* __restrict__ g,
                              uint8_t* __restrict__ flag, double* __restrict__ val, double* __restrict__ x) {
@@ -663,6 +718,27 @@ extern "C" int fsb_assemble_scalar_nonlinear_k(fsb_mesh* mesh, fsb_mat* A, fsb_v
   else
     k_scalar_nonlinear_k<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, T->d, k->d, dk->d, scale, rscale,
                                                            A ? A->row_ptr : nullptr, A ? A->col_idx : nullptr, A ? A->vals : nullptr, pm, r ? r->d : nullptr);
+  FSB_LAUNCH_CHECK(ctx);
+  return FSB_OK;
+}
+
+extern "C" int fsb_assemble_advection_nodal(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, fsb_vec* y, fsb_vec* vel, double scale) {
+  if (!mesh || !vel || (!A && (!x || !y))) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  if (mesh->degree != 1) FSB_FAIL(ctx, FSB_ERR_ARG, "a nodal velocity field is implemented for degree-1 spaces");
+  const int64_t n = mesh->nnodes;
+  if (vel->n != n * mesh->tdim) FSB_FAIL(ctx, FSB_ERR_ARG, "the velocity field needs dim values per vertex");
+  if (A && (A->bs != 1 || A->nbrows != n)) FSB_FAIL(ctx, FSB_ERR_ARG, "matrix does not belong to a scalar P1 space on this mesh");
+  if (!A && (x->n != n || y->n != n || x == y)) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the mesh");
+  const uint8_t* pm = (A && ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
+  if (mesh->tdim == 3) {
+    if (A) k_advection_nodal<3, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, vel->d, scale, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);
+    else k_advection_nodal<3, true><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, vel->d, scale, nullptr, nullptr, nullptr, nullptr, x->d, y->d);
+  } else {
+    if (A) k_advection_nodal<2, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, vel->d, scale, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);
+    else k_advection_nodal<2, true><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, vel->d, scale, nullptr, nullptr, nullptr, nullptr, x->d, y->d);
+  }
   FSB_LAUNCH_CHECK(ctx);
   return FSB_OK;
 }

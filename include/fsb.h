@@ -171,6 +171,10 @@ int fsb_assemble_facet_radiation(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec
 int fsb_assemble_scalar_nonlinear_k(fsb_mesh* mesh, fsb_mat* A, fsb_vec* r, fsb_vec* T, fsb_vec* k, fsb_vec* dk,
                                     double scale, double rscale);
 
+/* Convection by a velocity field given at the vertices (dim values per vertex, P1 interpolant v_h; the reference interpolates
+ * Expression velocities into a Lagrange space, ScalarTransportSolver.py:130-139): A += scale * int (v_h.grad u) v dx, or
+ * y += (that) x when A is NULL.  Degree 1. */
+int fsb_assemble_advection_nodal(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, fsb_vec* y, fsb_vec* vel, double scale);
 /* SUPG stabilisation (ScalarTransportSolver.py:252-274, method 2): test function Tq = q + tau vel.grad(q),
  * tau = 0.5 h / (4/(Pe h) + 2 |vel|), h = 2 * cell circumradius.  The three calls add ONLY the extra terms that the
  * tau vel.grad(q) part of the test function produces (degree 1, constant vel); the Galerkin terms come from the calls above.

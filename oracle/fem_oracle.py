@@ -241,6 +241,16 @@ def local_advection(coords, cells, vel, c=1.0):
     return (c * vol)[:, None, None] * np.einsum("caj,cbj->cab", w, G)
 
 
+def local_advection_nodal(coords, cells, vel_nodes, c=1.0):
+    """C_e[a,b] = c int (v_h . grad phi_b) phi_a with v_h the P1 interpolant of the nodal velocities
+    (ScalarTransportSolver.py:130-139, 311): c |T|/((d+1)(d+2)) sum_k (1 + delta_ak) v_k . G_b."""
+    vol, G = p1_geometry(coords, cells)
+    nl = cells.shape[1]
+    V = np.asarray(vel_nodes, dtype=np.float64).reshape(coords.shape[0], -1)[cells]      # [nc, nl, d]
+    wsum = V.sum(axis=1)[:, None, :] + V                                                  # sum_k (1 + delta_ak) v_k
+    return (c * vol / (nl * (nl + 1)))[:, None, None] * np.einsum("cai,cbi->cab", wsum, G)
+
+
 def local_elasticity(coords, cells, mu, lmbda):
     """K_e[(a,i),(b,j)] = |T| ( mu (G_a.G_b d_ij + G_a[j] G_b[i]) + lambda G_a[i] G_b[j] )
     from inner(sigma(u), grad(v)) dx, sigma = 2 mu sym(grad u) + lambda div(u) I

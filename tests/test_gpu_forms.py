@@ -633,3 +633,51 @@ def test_elasticity_surface_source_is_a_normal_load_on_the_whole_surface():
     vals = np.concatenate([np.zeros(lv.size), np.tile([0, 0, 1e-3], rv.size)])
     Ab, bb = fo.apply_dirichlet(A, b, dofs, vals, symmetric=True)
     assert fo.relative_l2(u.vector().get_local(), fo.solve_direct(Ab, bb)) < 1e-9
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_advection_by_a_velocity_field(ctx, dim):
+    """fsb_assemble_advection_nodal against the oracle (matrix and matrix-free action), then through the solver with an
+    Expression velocity (a rotating flow), ScalarTransportSolver.py:130-139."""
+    c, t = small_mesh(dim)
+    nv = c.shape[0]
+    vel = np.stack([-c[:, 1], c[:, 0]] + ([0.3 * c[:, 2] + c[:, 0]] if dim == 3 else []), axis=1)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 1)
+    vd = _lib.DeviceVector.from_numpy(ctx, vel.ravel())
+    _lib.assemble_advection_nodal(m, A, vd, scale=2.5)
+    ref = fo.conform(fo.assemble_matrix(t, fo.local_advection_nodal(c, t, vel, 2.5), nv), *fo.csr_pattern(t, nv))
+    _, _, va = A.download_csr()
+    close(va, ref.data)
+    x = np.random.default_rng(4).standard_normal(nv)
+    y = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_advection_nodal(m, None, vd, scale=2.5, x=_lib.DeviceVector.from_numpy(ctx, x), y=y)
+    close(y.numpy(), ref @ x, 1e-12)
+    # a constant field reproduces the constant-velocity kernel
+    A.zero()
+    _lib.assemble_advection_nodal(m, A, _lib.DeviceVector.from_numpy(ctx, np.tile([0.4, -0.7, 0.2][:dim], nv)), scale=1.0)
+    B = _lib.DeviceMatrix.create(m, 1)
+    B.assemble_scalar(kscale=0.0, adv=1.0, vel=np.array([0.4, -0.7, 0.2][:dim]))
+    close(A.download_csr()[2], B.download_csr()[2], 1e-12)
+
+
+def test_rotating_flow_expression_velocity_matches_oracle():
+    n = 16
+    settings, mesh = radiation_settings(n)
+    del settings['radiation_settings']
+    settings['convective_velocity'] = Expression(("-w*(x[1]-0.5)", "w*(x[0]-0.5)"), w=2e-6, degree=1)
+    solver = ScalarTransportSolver.ScalarTransportSolver(settings)
+    solver.material['conductivity'] = 0.6
+    T = solver.solve()
+    assert solver.solve_info['converged'] == 1
+    c, t = fo.unit_square_mesh(n, n)
+    nv = c.shape[0]
+    vel = np.stack([-2e-6 * (c[:, 1] - 0.5), 2e-6 * (c[:, 0] - 0.5)], axis=1)
+    cap = 1000 * 4200.0
+    A = fo.assemble_matrix(t, fo.local_laplace(c, t, 0.6) + fo.local_advection_nodal(c, t, vel, cap), nv)
+    tp, bt = np.nonzero(c[:, 1] == 1)[0], np.nonzero(c[:, 1] == 0)[0]
+    Ab, bb = fo.apply_dirichlet(fo.conform(A, *fo.csr_pattern(t, nv)), np.zeros(nv), np.concatenate([tp, bt]),
+                                np.concatenate([np.full(tp.size, 360.0), np.full(bt.size, 300.0)]), symmetric=False)
+    To = fo.solve_direct(Ab, bb)
+    assert fo.relative_l2(T.values, To) < TOL
+    assert np.abs(To - (300 + 60 * c[:, 1])).max() > 1.0         # the swirl does bend the isotherms
