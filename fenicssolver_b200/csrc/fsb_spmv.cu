@@ -330,12 +330,18 @@ __global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, i
 // with 2 lanes x 8 slots per row: they get one lane per row (tools/spmv_short_rows.py on the squeezed C2
 // operand: 256 rows x 1 lane x 2 stages 6 265 GB/s, x 2 lanes 3 062 GB/s; deeper pipelines lose the second CTA).
 static bool spmv_short_rows(const fsb_mat* A) { return A->bs == 1 && A->avg_row > 0.0 && A->avg_row <= 8.5; }
+// Long rows (degree-2 spaces: ~28 blocks per row on average, up to ~90): a tile of 256 / 192 scalar rows no longer fits a
+// stage (3x3 blocks fell back to the plain kernel) and 2 lanes per row leave most of a row's gathers serial.  Half the rows
+// per tile and 4 lanes per row (tools/spmv_long_rows.py, P2 on 48^3: CSR 2 564 -> 3 348 GB/s, 3x3 BSR 3 481 -> 4 186 GB/s).
+static bool spmv_long_rows(const fsb_mat* A) { return A->avg_row > 20.0; }
 static int spmv_rows(fsb_ctx* ctx, const fsb_mat* A) {
   const int big = A->bs == 3 ? 192 : 256;
-  const int opt = ctx->spmv_rows ? ctx->spmv_rows : 256;
+  const int opt = ctx->spmv_rows ? ctx->spmv_rows : (spmv_long_rows(A) ? 128 : 256);
   return opt == 128 ? big / 2 : (opt == 512 && A->bs == 1 ? 512 : big);
 }
-static int spmv_lpr(fsb_ctx* ctx, const fsb_mat* A) { return ctx->spmv_lpr ? ctx->spmv_lpr : (spmv_short_rows(A) ? 1 : 2); }
+static int spmv_lpr(fsb_ctx* ctx, const fsb_mat* A) {
+  return ctx->spmv_lpr ? ctx->spmv_lpr : (spmv_short_rows(A) ? 1 : (spmv_long_rows(A) && A->bs != 2 ? 4 : 2));      // 2x2 blocks: 2 lanes only
+}
 static int spmv_stages(fsb_ctx* ctx, const fsb_mat* A) { return ctx->spmv_stages ? ctx->spmv_stages : (A->bs == 3 ? 3 : 2); }
 static constexpr size_t kSmemBudget = 200 * 1024;
 
