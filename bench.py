@@ -131,7 +131,7 @@ def cpu_heat(N, iters_full, sample_iters, steps=1, warmup=0):
     sample: the whole assembly + Dirichlet, then `sample_iters` CG iterations; the solve time is scaled to
     the `iters_full` iterations the full solve needs (same recurrence => same count)."""
     from oracle import c_oracle as co
-    cores = co.num_threads()
+    cores = co.use_all_cores()          # not OMP_NUM_THREADS: torchrun exports 1 into every rank
     h = co.HeatCube(N)
     times = []
     for s in range(warmup + steps):

@@ -37,6 +37,7 @@ SIGNATURES = {
     "fsb_set_option": (C.c_int, [c_vp, C.c_char_p, c_i64]),
     "fsb_launch_count": (c_i64, [c_vp]),
     "fsb_mesh_upload": (C.c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, P(c_vp)]),
+    "fsb_mesh_upload_part": (C.c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_i64, P(c_vp)]),
     "fsb_mesh_box": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, P(c_vp)]),
     "fsb_mesh_upload_p2": (C.c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_i64, P(c_vp)]),
     "fsb_mesh_sizes": (C.c_int, [c_vp, P(c_i32), P(c_i32), P(c_i64), P(c_i64)]),
@@ -214,12 +215,15 @@ class DeviceMesh(_Handle):
     _destroy = "fsb_mesh_destroy"
 
     @classmethod
-    def upload(cls, ctx, coords, cells):
+    def upload(cls, ctx, coords, cells, vertex_offset=0):
+        """`vertex_offset`: `cells` holds global ids of a mesh whose vertices [offset, offset + len(coords)) are `coords` (a slab of
+        a larger mesh, passed as slices of the global arrays); the ids are made local on the device."""
         coords = _np(coords, np.float64)
         cells = _np(cells, np.int32)
         h = c_vp()
         gdim, tdim = coords.shape[1], cells.shape[1] - 1
-        ctx.check(ctx.lib.fsb_mesh_upload(ctx.h, gdim, tdim, coords.shape[0], _ptr(coords), cells.shape[0], _ptr(cells), C.byref(h)))
+        ctx.check(ctx.lib.fsb_mesh_upload_part(ctx.h, gdim, tdim, coords.shape[0], _ptr(coords), cells.shape[0], _ptr(cells),
+                                               int(vertex_offset), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

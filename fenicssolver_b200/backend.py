@@ -121,7 +121,7 @@ class DeviceSpace:
                 per_layer = mesh.num_cells() // nlast
                 nvl = (layer1 - layer0 + 1) * self.plane
                 self.dmesh = _lib.DeviceMesh.upload(self.ctx, mesh.coordinates()[self.v_off:self.v_off + nvl],
-                                                    mesh.cells()[per_layer * layer0:per_layer * layer1] - self.v_off)
+                                                    mesh.cells()[per_layer * layer0:per_layer * layer1], vertex_offset=self.v_off)
             else:
                 self.dmesh = _lib.DeviceMesh.box(self.ctx, n, mesh.box["p0"], mesh.box["p1"], layer0, layer1)
             if self.ctx.nranks == 1:

@@ -220,8 +220,17 @@ extern "C" void fsb_vec_destroy(fsb_vec* v) {
 }
 
 // ------------------------------------------------------------------------------------ meshes
+__global__ void k_shift_i32(int32_t* __restrict__ p, int64_t n, int32_t delta) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] += delta;
+}
+
 extern "C" int fsb_mesh_upload(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz,
                                int64_t ncells, const int32_t* cells, fsb_mesh** out) {
+  return fsb_mesh_upload_part(ctx, gdim, tdim, nverts, xyz, ncells, cells, 0, out);
+}
+
+extern "C" int fsb_mesh_upload_part(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz,
+                                    int64_t ncells, const int32_t* cells, int64_t vertex_offset, fsb_mesh** out) {
   if (!ctx || !out || !xyz || !cells) return FSB_ERR_ARG;
   if (gdim != tdim || (tdim != 2 && tdim != 3)) FSB_FAIL(ctx, FSB_ERR_ARG, "only gdim==tdim in {2,3} is supported");
   if (nverts <= 0 || ncells <= 0 || nverts > 0x7fffffffll) FSB_FAIL(ctx, FSB_ERR_ARG, "bad mesh sizes");
@@ -231,6 +240,10 @@ extern "C" int fsb_mesh_upload(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t
   if (rc) { fsb_mesh_destroy(m); return rc; }
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->xyz, xyz, sizeof(double) * nverts * gdim, cudaMemcpyHostToDevice, ctx->stream));
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(m->cells, cells, sizeof(int32_t) * ncells * (tdim + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (vertex_offset) {      // the caller passed a slice of a global cell table: renumber on the device, not on the host
+    k_shift_i32<<<fsb_grid(ncells * (tdim + 1), 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(m->cells, ncells * (tdim + 1), (int32_t)-vertex_offset);
+    ctx->launches++;
+  }
   FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   m->degree = 1; m->nl = m->tdim + 1; m->nnodes = m->nverts; m->cell_nodes = m->cells;
   *out = m;

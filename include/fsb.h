@@ -77,6 +77,11 @@ int64_t fsb_launch_count(fsb_ctx* ctx);   /* kernels launched by this library on
 /* Mesh(filename) (SolverBase.py:224): host arrays; cells[ncells][tdim+1] sorted ascending per cell. */
 int fsb_mesh_upload(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz,
                     int64_t ncells, const int32_t* cells, fsb_mesh** mesh);
+/* The same for a contiguous part of a larger mesh (a z-slab of a host box mesh in a distributed run): `cells` holds GLOBAL vertex
+ * ids, `xyz` the coordinates of the vertices [vertex_offset, vertex_offset + nverts); ids are shifted to local on the device,
+ * so the caller can pass slices of its (pinned) global arrays without a host pass over them. */
+int fsb_mesh_upload_part(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts, const double* xyz,
+                         int64_t ncells, const int32_t* cells, int64_t vertex_offset, fsb_mesh** mesh);
 /* UnitSquareMesh/RectangleMesh (tdim 2, diagonal "right") and UnitCubeMesh/BoxMesh (tdim 3)
  * generated on the device in dolfin's layout (examples/test_heat_transfer.py:34,
  * examples/test_linear_elasticity.py:42).  layer0/layer1 select the cell layers [layer0,layer1)

@@ -58,6 +58,14 @@ def num_threads():
     return load().fo_num_threads()
 
 
+def use_all_cores():
+    """Use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1 in every rank)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().fo_set_num_threads(int(n))
+    return num_threads()
+
+
 def box_mesh(n, p0=(0, 0, 0), p1=(1, 1, 1)):
     lib = load()
     n_ = np.asarray(n, dtype=np.int32)

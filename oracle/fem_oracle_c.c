@@ -30,6 +30,16 @@ int fo_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1 into every rank; the CPU baseline is meant to use every host core it
+ * is allowed to run on, so the caller sets the count explicitly (bench.py passes the size of the affinity mask) */
+void fo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static const int HEX_TETS[6][4] = {{0, 1, 3, 7}, {0, 1, 5, 7}, {0, 4, 5, 7}, {0, 2, 3, 7}, {0, 4, 6, 7}, {0, 2, 6, 7}};
 
 /* coords[nverts][3], cells[ncells][4] (sorted per cell) in the dolfin BoxMesh layout */
