@@ -86,9 +86,8 @@ class DeviceSpace:
         general = self.comm.nranks > 1 and (self.degree == 2 or not mesh.box or getattr(mesh, "force_general_partition", False))
         if general:
             # host integer work on the replicated mesh: node partition, local numbering, halo lists
-            fs = space if space is not None else None
-            cell_nodes = mesh.cells() if self.degree == 1 else fs.cell_nodes()
-            node_xyz = mesh.coordinates() if self.degree == 1 else fs.node_coordinates()
+            cell_nodes = mesh.cells() if self.degree == 1 else space.cell_nodes()
+            node_xyz = mesh.coordinates() if self.degree == 1 else space.node_coordinates()
             owner = rcb_partition(node_xyz, self.comm.nranks)
             self.part = NodePartition(cell_nodes, owner, self.comm.rank, self.comm.nranks)
             pt = self.part
