@@ -17,13 +17,11 @@ Inputs are larger than L2 (CSR 3 GB, vectors 136 MB each at 256^3), so no explic
 from __future__ import annotations
 
 import argparse
-import copy
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np

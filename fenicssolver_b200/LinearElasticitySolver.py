@@ -15,8 +15,6 @@ Out of scope: elastodynamics, modal analysis -> SolverError.
 """
 from __future__ import annotations
 
-import numbers
-
 import numpy as np
 
 from . import _lib

@@ -12,8 +12,6 @@ detection, SubDomain.mark.
 from __future__ import annotations
 
 import math
-import numbers
-import os
 import re
 
 import numpy as np

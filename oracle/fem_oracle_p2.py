@@ -18,12 +18,10 @@ coordinates) with reference tensors integrated EXACTLY with the monomial formula
 """
 from __future__ import annotations
 
-import itertools
 import math
 from functools import lru_cache
 
 import numpy as np
-import scipy.sparse as sp
 
 from . import fem_oracle as fo
 
