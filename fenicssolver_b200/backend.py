@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import os
 import time
+import weakref
 
 import numpy as np
 
@@ -100,7 +101,7 @@ class DeviceSpace:
                 uid = self.ctx.dist_unique_id() if self.comm.rank == 0 else None
                 uid = self.comm.bootstrap(uid)
                 self.ctx.dist_init(self.comm.rank, self.comm.nranks, uid)
-            self.ctx.dist_set_halo(pt.n_owned, pt.n_local, pt.neighbours, pt.send_ptr, pt.send_idx, pt.recv_off, pt.recv_cnt)
+            self.activate(force=True)
         elif self.degree == 2:
             # degree-2 node layout: host integer work (edge numbering), then one upload
             self.dmesh = _lib.DeviceMesh.upload_p2(self.ctx, mesh.coordinates(), space.cell_nodes(), space.num_nodes())
@@ -127,7 +128,7 @@ class DeviceSpace:
                 uid = self.ctx.dist_unique_id() if self.comm.rank == 0 else None
                 uid = self.comm.bootstrap(uid)
                 self.ctx.dist_init(self.comm.rank, self.comm.nranks, uid)
-            self.ctx.dist_set_slab(self.ghost_lo, self.ghost_hi, self.owned_planes)
+            self.activate(force=True)
         elif mesh.box and not getattr(mesh, "force_upload", False):
             self.dmesh = _lib.DeviceMesh.box(self.ctx, mesh.box["n"], mesh.box["p0"], mesh.box["p1"])
         else:
@@ -150,6 +151,19 @@ class DeviceSpace:
             self.A.set_owned_rows(self.own_v0, self.own_v1)
         self.ctx.sync()
         self.timings["symbolic"] = time.perf_counter() - t0
+
+    def activate(self, force=False):
+        """The halo layout (slab or send lists) is state of the context: declare this space's layout if another
+        distributed space on the same context was the last one to do so."""
+        owner = getattr(self.ctx, "_layout_owner", None)
+        if self.comm.nranks == 1 or (not force and owner is not None and owner() is self):
+            return
+        if self.part is not None:
+            pt = self.part
+            self.ctx.dist_set_halo(pt.n_owned, pt.n_local, pt.neighbours, pt.send_ptr, pt.send_idx, pt.recv_off, pt.recv_cnt)
+        else:
+            self.ctx.dist_set_slab(self.ghost_lo, self.ghost_hi, self.owned_planes)
+        self.ctx._layout_owner = weakref.ref(self)       # weak: the context must not keep a released space alive
 
     # ---- index helpers ----------------------------------------------------------------------------
     @property
@@ -277,9 +291,11 @@ class DeviceSpace:
 
     # ---- Dirichlet + solve ------------------------------------------------------------------------
     def apply_dirichlet(self, b, gdofs, gvals, symmetric, x=None):
+        self.activate()
         d, v = self.local_dofs(gdofs, gvals)
         self.A.apply_dirichlet(b, d, v, symmetric=symmetric, x=x)
 
     def solve(self, b, x, method="cg", rtol=1e-12, atol=0.0, maxit=100000, precond="jacobi"):
+        self.activate()
         info = self.A.solve(b, x, method=method, rtol=rtol, atol=atol, maxit=maxit, precond=precond)
         return info
