@@ -141,6 +141,21 @@ __global__ void k_mg_dot(int64_t n, const double* __restrict__ x, const double* 
   s = block_sum(s, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
+// x += a p ; r -= a q ; per-CTA partial of |D^-1 r|^2 (finished by k_mg_dot_final)
+__global__ void k_mg_update(int64_t n, double a, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+                            double* __restrict__ x, double* __restrict__ r, double* __restrict__ partials) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += a * p[i];
+    const double ri = r[i] - a * q[i];
+    r[i] = ri;
+    const double zi = dinv[i] * ri;
+    s += zi * zi;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
 __global__ void k_mg_dot_final(int nparts, const double* __restrict__ partials, double* __restrict__ out) {
   __shared__ double red[32];
   double s = 0.0;
@@ -299,20 +314,20 @@ extern "C" int fsb_mg_omega(fsb_mg* mg, int32_t level, double* omega) {
   return FSB_OK;
 }
 
-// z = V(r) on the fine level (r is copied into the level's right-hand side)
+// z = V(r) on the fine level: the cycle reads r as the level's right-hand side and builds the iterate directly in z
 static int mg_apply(fsb_mg* mg, const double* r, double* z) {
-  fsb_ctx* ctx = mg->ctx;
   Level& L = mg->lv[0];
-  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(L.b, r, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, ctx->stream));
-  int rc = mg_vcycle(mg, 0);
-  if (rc) return rc;
-  FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(z, L.x, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, ctx->stream));
-  return FSB_OK;
+  double *b0 = L.b, *x0 = L.x;
+  L.b = const_cast<double*>(r);      // never written by the cycle
+  L.x = z;
+  const int rc = mg_vcycle(mg, 0);
+  L.b = b0; L.x = x0;
+  return rc;
 }
 
 extern "C" int fsb_mg_apply(fsb_mg* mg, fsb_vec* r, fsb_vec* z, int32_t nu) {
   if (!mg || !r || !z) return FSB_ERR_ARG;
-  if (r->n != mg->lv[0].n || z->n != r->n) FSB_FAIL(mg->ctx, FSB_ERR_ARG, "vector sizes do not match the fine level");
+  if (r->n != mg->lv[0].n || z->n != r->n || r == z) FSB_FAIL(mg->ctx, FSB_ERR_ARG, "vector sizes do not match the fine level");
   mg->nu = nu > 0 ? nu : 2;
   return mg_apply(mg, r->d, z->d);
 }
@@ -351,16 +366,22 @@ extern "C" int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, 
     FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     if ((rc = mg_dot(mg, n, r, z, nullptr, &rz))) return rc;
     while (it < maxit) {
-      if ((rc = mg_spmv(L, p, q))) return rc;
-      if ((rc = mg_dot(mg, n, p, q, nullptr, &pq))) return rc;
+      // q = A p with p.q fused into the SpMV (no separate pass over p and q)
+      if ((rc = fsb_launch_spmv(L.A, p, q, p, 0, ctx->d_scalars + 50, nullptr))) return rc;
+      FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(&pq, ctx->d_scalars + 50, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       if (!(pq == pq) || pq == 0.0 || !(rz == rz)) { outcome = -1; break; }
       const double alpha = rz / pq;
-      k_mg_axpy<<<g, 256, 0, ctx->stream>>>(n, alpha, p, x->d);
-      FSB_LAUNCH_CHECK(ctx);
-      k_mg_axpy<<<g, 256, 0, ctx->stream>>>(n, -alpha, q, r);
-      FSB_LAUNCH_CHECK(ctx);
+      {
+        const unsigned gp = std::min<unsigned>(g, kMaxPartials);
+        k_mg_update<<<gp, 256, 0, ctx->stream>>>(n, alpha, p, q, L.dinv, x->d, r, ctx->d_partials);
+        FSB_LAUNCH_CHECK(ctx);
+        k_mg_dot_final<<<1, 256, 0, ctx->stream>>>((int)gp, ctx->d_partials, ctx->d_scalars + 48);
+        FSB_LAUNCH_CHECK(ctx);
+        FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(&rr, ctx->d_scalars + 48, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      }
       ++it;
-      if ((rc = mg_dot(mg, n, r, r, L.dinv, &rr))) return rc;
       if (rr <= tol2) { outcome = 1; break; }
       if (!(rr == rr)) { outcome = -1; break; }
       if ((rc = mg_apply(mg, r, z))) return rc;
