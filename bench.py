@@ -363,7 +363,7 @@ def main():
                    "iterations": ginfos[-1]["iterations"], "converged": ginfos[-1]["converged"], "levels": len(mgh.matrices),
                    "solve_ms": float(np.mean([i["solve_ms"] for i in ginfos])),
                    "rel_l2_vs_exact": float(np.sqrt(np.sum((xs3 - exact) ** 2) / np.sum(exact ** 2))),
-                   "what": "same timed step with solver_parameters['preconditioner'] = 'gmg': V(2,2) damped-Jacobi cycles on the nested box "
+                   "what": "same timed step with solver_parameters['preconditioner'] = 'gmg': V(2,2) Chebyshev-smoothed cycles on the nested box "
                            "meshes, coarse levels re-assembled every step; same rtol and norm"}
             del mgh
         except Exception as ex:          # a reported extra, never a reason to lose the bench line

@@ -26,19 +26,41 @@ def prolongation(ncells_fine, ncomp=1):
     return sp.kron(P, sp.identity(ncomp)).tocsr() if ncomp > 1 else P
 
 
-def vcycle(levels, transfers, b, nu=2, coarse_sweeps=24, l=0):
-    """levels[l] = dict(A, dinv, omega, bc mask); transfers[l] = P from level l+1 to l.  Zero initial guess."""
-    L = levels[l]
+CHEB_RATIO = 10.0
 
-    def smooth(x, rhs, sweeps, zero):
-        for s in range(sweeps):
-            x = L['omega'] * L['dinv'] * rhs if (s == 0 and zero) else x + L['omega'] * L['dinv'] * (rhs - L['A'] @ x)
-        return x
+
+def chebyshev(L, x, rhs, deg, zero):
+    """Chebyshev iteration of degree `deg` for D^-1 A on [lmax / CHEB_RATIO, lmax], lmax = 4 / (3 omega)."""
+    lmax = 4.0 / (3.0 * L['omega'])
+    lmin = lmax / CHEB_RATIO
+    theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+    sigma = theta / delta
+    rho0 = 1.0 / sigma
+    d = None
+    for k in range(deg):
+        r = rhs if (k == 0 and zero) else rhs - L['A'] @ x
+        if k == 0:
+            d = L['dinv'] * r / theta
+        else:
+            rho1 = 1.0 / (2.0 * sigma - rho0)
+            d = rho1 * rho0 * d + (2.0 * rho1 / delta) * L['dinv'] * r
+            rho0 = rho1
+        x = d.copy() if (k == 0 and zero) else x + d
+    return x
+
+
+def vcycle(levels, transfers, b, nu=2, coarse_sweeps=24, l=0):
+    """levels[l] = dict(A, dinv, omega, bc mask); transfers[l] = P from level l+1 to l.  Zero initial guess; Chebyshev
+    smoothing of degree nu before and after the coarse correction, damped Jacobi on the coarsest level."""
+    L = levels[l]
     if l == len(levels) - 1:
-        return smooth(None, b, coarse_sweeps, True)
-    x = smooth(None, b, nu, True)
+        x = None
+        for s in range(coarse_sweeps):
+            x = L['omega'] * L['dinv'] * b if s == 0 else x + L['omega'] * L['dinv'] * (b - L['A'] @ x)
+        return x
+    x = chebyshev(L, None, b, nu, True)
     bc = transfers[l].T @ (b - L['A'] @ x)
     bc[levels[l + 1]['bc']] = 0.0
     corr = transfers[l] @ vcycle(levels, transfers, bc, nu, coarse_sweeps, l + 1)
     corr[L['bc']] = 0.0
-    return smooth(x + corr, b, nu, False)
+    return chebyshev(L, x + corr, b, nu, False)
