@@ -216,12 +216,15 @@ int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double a
  * Geometric multigrid on generated box meshes, whose triangulation is nested under halving the cell counts: level 0 is
  * the fine matrix, A[l] the same form assembled (and Dirichlet-eliminated with fsb_apply_dirichlet, so constrained dofs
  * are known) on the box with ncells[l][0..2] = ncells[l-1]/2 cells per axis.  The matrices stay owned by the caller and must
- * outlive the hierarchy.  P1 interpolation along the coarse edges / its transpose, damped-Jacobi smoothing (damping from a
- * power-iteration estimate per level), V(nu,nu) cycle as the preconditioner of CG; convergence test as fsb_solve_cg.
+ * outlive the hierarchy.  P1 interpolation along the coarse edges / its transpose, Chebyshev smoothing of degree nu on D^-1 A
+ * over [lambda_max/10, lambda_max] (lambda_max from a power iteration capped by the Gershgorin bound, per level; reported
+ * through fsb_mg_omega as omega = 4/(3 lambda_max)), damped Jacobi on the coarsest level, V(nu,nu) cycle as the
+ * preconditioner of CG; convergence test as fsb_solve_cg.
  * Single GPU. */
 int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells /*[nlevels][3]*/, int32_t tdim,
-                  const double* omega /* per-level Jacobi dampings to reuse (entries <= 0 or NULL: estimate) */, fsb_mg** mg);
-int fsb_mg_omega(fsb_mg* mg, int32_t level, double* omega);      /* the Jacobi damping chosen for a level */
+                  const double* omega /* per-level values to reuse from an earlier hierarchy (entries <= 0 or NULL: estimate) */,
+                  fsb_mg** mg);
+int fsb_mg_omega(fsb_mg* mg, int32_t level, double* omega);      /* 4 / (3 lambda_max estimate) of a level */
 int fsb_mg_apply(fsb_mg* mg, fsb_vec* r, fsb_vec* z, int32_t nu);  /* z = one V(nu,nu) cycle applied to r (zero start) */
 int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit, int32_t nu,
                     fsb_solve_info* info);
