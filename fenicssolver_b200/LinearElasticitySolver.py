@@ -29,6 +29,7 @@ class ElasticityForm:
         self.pressures = []      # (marker id, scalar along the outward normal)
         self.body_forces = []    # constant vector | nodal array
         self.thermal = None      # (beta, T: number | nodal array, T_ref)
+        self.stress_tensors = [] # (marker id, dim x dim tensor S): traction S.n per facet
         self.load_sign = -1.0
 
     def assemble(self, space):
@@ -49,6 +50,10 @@ class ElasticityForm:
                 _lib.assemble_source(space.dmesh, b, f, ncomp=dim, scale=self.load_sign)
             else:
                 _lib.assemble_source_nodal(space.dmesh, b, space.vector_from_global(np.asarray(f).reshape(-1)), ncomp=dim, scale=self.load_sign)
+        for marker, S in self.stress_tensors:
+            dofs, vals = facet_traction_entries(s.mesh, space.fs, *s.boundary_facets.facets(marker), S)
+            ld, lv = space.local_dofs(dofs, self.load_sign * vals)
+            b.add_entries(ld, lv)
         if self.thermal is not None:
             beta, T, T_ref = self.thermal
             if isinstance(T, np.ndarray):
@@ -59,6 +64,37 @@ class ElasticityForm:
             else:
                 _lib.assemble_thermal_load(space.dmesh, b, beta, T_const=float(T), T_ref=T_ref)
         return b, True
+
+
+def facet_traction_entries(mesh, fs, fverts, opp, S):
+    """(dofs, values) of  int (S.n).v ds  over the given exterior facets, n the outward unit normal of each facet
+    (LinearElasticitySolver.py:190-196, `dot(g, mesh_normal)`).  Boundary-only work, done on the host and added to the
+    right-hand side with fsb_vec_add_entries.  P1: |F|/d per facet vertex; P2: the facet integrals of the degree-2
+    basis (segment 1/6, 1/6, 2/3; triangle 0 at the vertices, 1/3 at the edge nodes)."""
+    c = mesh.coordinates()
+    fverts = np.asarray(fverts, dtype=np.int64)
+    d = fverts.shape[1]
+    X = c[fverts]
+    if d == 2:
+        t = X[:, 1] - X[:, 0]
+        meas = np.linalg.norm(t, axis=1)
+        n = np.stack([t[:, 1], -t[:, 0]], axis=1)
+    else:
+        n = np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0])
+        meas = 0.5 * np.linalg.norm(n, axis=1)
+    n = n / np.linalg.norm(n, axis=1, keepdims=True)
+    flip = np.einsum("ij,ij->i", n, c[np.asarray(opp, dtype=np.int64)] - X[:, 0]) > 0
+    n[flip] *= -1
+    trac = n @ np.asarray(S, dtype=np.float64).T                     # (S.n) per facet
+    degree = getattr(fs, "degree", 1)
+    if degree == 1:
+        nodes, w = fverts, np.full(d, 1.0 / d)
+    else:
+        nodes = fs.facet_nodes(fverts).astype(np.int64)
+        w = np.array([1 / 6, 1 / 6, 2 / 3]) if d == 2 else np.array([0.0, 0.0, 0.0, 1 / 3, 1 / 3, 1 / 3])
+    vals = meas[:, None, None] * w[None, :, None] * trac[:, None, :]  # [nf, nodes per facet, dim]
+    dofs = nodes[:, :, None] * d + np.arange(d)[None, None, :]
+    return dofs.ravel(), vals.ravel()
 
 
 class LinearElasticitySolver(SolverBase):
@@ -181,8 +217,11 @@ class LinearElasticitySolver(SolverBase):
                 g = self.translate_value(bc['value'])
                 if isinstance(g, np.ndarray) and g.shape == (self.dimension,):
                     F.tractions.append((i, g))                      # Constant vector: used as is (:192-193)
+                elif isinstance(g, np.ndarray) and g.size == self.dimension ** 2:
+                    # a stress tensor: g = dot(g, mesh_normal) (:194-195), one traction per facet
+                    F.stress_tensors.append((i, g.reshape(self.dimension, self.dimension)))
                 else:
-                    raise SolverError('stress tensors (sigma.n) are not implemented on the device path')
+                    raise SolverError('stress must be a constant vector or a constant dim x dim tensor')
             elif btype == 'Neumann':
                 raise SolverError('Neumann boundary type`{}` is not supported'.format(btype))
             elif btype == 'symmetry':

@@ -681,3 +681,34 @@ def test_rotating_flow_expression_velocity_matches_oracle():
     To = fo.solve_direct(Ab, bb)
     assert fo.relative_l2(T.values, To) < TOL
     assert np.abs(To - (300 + 60 * c[:, 1])).max() > 1.0         # the swirl does bend the isotherms
+
+
+def test_elasticity_stress_tensor_boundary():
+    """bcs['tensile'] = {'type': 'stress', 'value': Constant(((..),(..),(..)))}: the traction is S.n per facet
+    (LinearElasticitySolver.py:190-196), with the reference's load sign; degree 1 and the example's degree 2."""
+    S = np.array([[1e8, 2e7, 0.0], [2e7, 0.0, 0.0], [0.0, 0.0, 5e6]])
+    for fe_degree, n in ((1, (8, 3, 3)), (2, (4, 2, 2))):
+        s, mesh = elasticity_settings(fe_degree, n, False, False, False)
+        s['boundary_conditions']["fixed"]['value'] = Constant((0, 0, 0))
+        s['boundary_conditions']["displ"] = {'boundary': Right(), 'boundary_id': 2, 'type': 'stress', 'value': Constant(S)}
+        solver = LinearElasticitySolver.LinearElasticitySolver(s)
+        u = solver.solve()
+        assert solver.solve_info['converged'] == 1
+        c, t = fo.box_mesh((0, 0, 0), (xmax, 1, 1), *n)
+        mu, lam = fo.lame(2e11, 0.27)
+        fv, opp, _ = fo.exterior_facets(t)
+        rsel = c[fv].mean(axis=1)[:, 0] == xmax
+        meas, nrm = fo.facet_measure(c, fv[rsel], opp[rsel])
+        if fe_degree == 1:
+            nn, xn = c.shape[0], c
+            A = fo.assemble_matrix(t, fo.local_elasticity(c, t, mu, lam), nn, 3)
+            b = -fo.assemble_facet_load(c, fv[rsel], nrm @ S.T, nn, 3)
+        else:
+            cn, xn, edges = fp.p2_dofmap(c, t)
+            nn = xn.shape[0]
+            A = fp.assemble_matrix(cn, fp.local_elasticity(c, t, mu, lam), nn, 3)
+            b = -fp.assemble_facet_load(c, fv[rsel], fp.facet_nodes(fv[rsel], edges, c.shape[0]), nrm @ S.T, nn, 3)
+        lv = np.nonzero(xn[:, 0] == 0)[0]
+        dofs = (lv[:, None] * 3 + np.arange(3)).ravel()
+        Ab, bb = fo.apply_dirichlet(A, b, dofs, np.zeros(dofs.size), symmetric=True)
+        assert fo.relative_l2(u.vector().get_local(), fo.solve_direct(Ab, bb)) < 1e-9

@@ -329,3 +329,35 @@ def test_box_meshes_are_nested_and_rediscretisation_is_galerkin(dim):
     Ac = fo.assemble_matrix(tc, fo.local_elasticity(cc, tc, mu, lam), cc.shape[0], dim)
     G = (Pv.T @ Af @ Pv).toarray()
     assert np.abs(G - Ac.toarray()).max() < 1e-11 * np.abs(Ac.toarray()).max()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_stress_tensor_boundary_tractions(dim):
+    """'stress' boundary with a tensor value, g = dot(g, mesh_normal) (LinearElasticitySolver.py:190-196): the host routine
+    that turns it into right-hand-side entries, against the oracle's facet loads with the per-facet traction S.n; a
+    hydrostatic tensor p I on the whole surface of a box is a closed surface integral of the normal: total force zero,
+    and equals the pressure load."""
+    from fenicssolver_b200.LinearElasticitySolver import facet_traction_entries
+    from fenicssolver_b200.dolfin_compat import FunctionSpace, Mesh
+    n = 3
+    c, t = fo.unit_square_mesh(n, n + 1) if dim == 2 else fo.unit_cube_mesh(n, n + 1, n)
+    c = jitter(c, n + 1, 5)
+    mesh = Mesh(c, t)
+    fv, opp, _ = fo.exterior_facets(t)
+    S = np.arange(1.0, dim * dim + 1).reshape(dim, dim) * 1e5
+    meas, nrm = fo.facet_measure(c, fv, opp)
+    for degree in (1, 2):
+        V = FunctionSpace(mesh, "CG", degree, ncomp=dim)
+        dofs, vals = facet_traction_entries(mesh, V, fv, opp, S)
+        b = np.zeros(V.num_nodes() * dim)
+        np.add.at(b, dofs, vals)
+        if degree == 1:
+            ref = fo.assemble_facet_load(c, fv, nrm @ S.T, c.shape[0], dim)
+        else:
+            cn, xn, edges = fp.p2_dofmap(c, t)
+            ref = fp.assemble_facet_load(c, fv, fp.facet_nodes(fv, edges, c.shape[0]), nrm @ S.T, xn.shape[0], dim)
+        assert np.abs(b - ref).max() < 1e-12 * np.abs(ref).max()
+        dofs, vals = facet_traction_entries(mesh, V, fv, opp, 2.5e5 * np.eye(dim))
+        tot = np.zeros(dim)
+        np.add.at(tot, dofs % dim, vals)
+        assert np.abs(tot).max() < 1e-9 * 2.5e5
