@@ -367,3 +367,25 @@ def test_node_partition_lists_are_consistent(nranks, degree):
             assert np.array_equal(sent, got)
             assert np.all(part[sent] == a)
         assert pa.recv_cnt.sum() == pa.ghosts.size
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) on a small cube: exactly one JSON line on
+    stdout with the contract's keys, timed on every core this process may use even when the launcher exported
+    OMP_NUM_THREADS=1 (torchrun does, for every rank)."""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "16", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "Mdof/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mdof/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == ncores
