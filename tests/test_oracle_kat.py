@@ -191,3 +191,41 @@ def test_c_oracle_matches_numpy_oracle():
     assert abs(r["iterations"] - it) <= 1
     assert fo.relative_l2(h.x, fo.solve_direct(A, b)) < 1e-10
     assert co.num_threads() >= 1
+
+
+def test_fenics_tutorial_poisson_is_nodally_exact():
+    """The first program of the FEniCS tutorial (Langtangen & Logg, "Solving PDEs in Python", ft01_poisson.py): -Laplace u = -6
+    on UnitSquareMesh(8, 8) with u_D = 1 + x^2 + 2 y^2 on the whole boundary, P1.  dolfin's published output is
+    error_max = O(1e-15): on this structured triangulation the P1 Galerkin solution interpolates the quadratic exactly.  The same
+    must hold for the oracle on the dolfin-layout mesh (a wrong diagonal direction or vertex order would still be exact here, a
+    wrong load or stiffness scaling would not)."""
+    for n in (8, 16):
+        c, t = fo.unit_square_mesh(n, n)
+        nv = c.shape[0]
+        uD = 1 + c[:, 0] ** 2 + 2 * c[:, 1] ** 2
+        bnd = np.nonzero((c[:, 0] == 0) | (c[:, 0] == 1) | (c[:, 1] == 0) | (c[:, 1] == 1))[0]
+        A, b = fo.heat_system(c, t, 1.0, [(bnd, uD[bnd])], source=-6.0)
+        u = fo.solve_direct(A, b)
+        assert np.abs(u - uD).max() < 5e-14
+    # the program also prints errornorm(u_D, u, 'L2'); the tutorial's published output is  error_L2 = 0.00823509807335  (and
+    # error_max = 1.33226762955e-15).  With u nodally exact that number is the L2 norm of the P1 interpolation error of u_D on
+    # UnitSquareMesh(8, 8): a golden value from dolfin's own documentation that the mesh layout + element geometry reproduce.
+    from oracle import fem_oracle_p2 as fp
+    c, t = fo.unit_square_mesh(8, 8)
+    uD = lambda x: 1 + x[..., 0] ** 2 + 2 * x[..., 1] ** 2       # noqa: E731
+    nv = c.shape[0]
+    bnd = np.nonzero((c[:, 0] == 0) | (c[:, 0] == 1) | (c[:, 1] == 0) | (c[:, 1] == 1))[0]
+    A, b = fo.heat_system(c, t, 1.0, [(bnd, uD(c)[bnd])], source=-6.0)
+    uh = fo.solve_direct(A, b)
+    pts, w = fp._collapsed_rule(2, 6)
+    vol, _ = fo.p1_geometry(c, t)
+    xq = np.einsum('pa,cai->cpi', pts, c[t])
+    e = uD(xq) - np.einsum('pa,ca->cp', pts, uh[t])
+    error_L2 = float(np.sqrt(np.sum(vol[:, None] * w[None, :] * e ** 2)))
+    assert abs(error_L2 - 0.00823509807335) < 5e-15
+    # and in 3D on the dolfin-layout cube: u = 1 + x^2 + 2 y^2 + 3 z^2, f = -12
+    c, t = fo.unit_cube_mesh(4, 4, 4)
+    uD = 1 + c[:, 0] ** 2 + 2 * c[:, 1] ** 2 + 3 * c[:, 2] ** 2
+    bnd = np.nonzero(np.any((c == 0) | (c == 1), axis=1))[0]
+    A, b = fo.heat_system(c, t, 1.0, [(bnd, uD[bnd])], source=-12.0)
+    assert np.abs(fo.solve_direct(A, b) - uD).max() < 5e-14
