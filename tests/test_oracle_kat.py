@@ -229,3 +229,25 @@ def test_fenics_tutorial_poisson_is_nodally_exact():
     bnd = np.nonzero(np.any((c == 0) | (c == 1), axis=1))[0]
     A, b = fo.heat_system(c, t, 1.0, [(bnd, uD[bnd])], source=-12.0)
     assert np.abs(fo.solve_direct(A, b) - uD).max() < 5e-14
+
+
+def test_fenics_tutorial_heat_equation_crank_nicolson_is_nodally_exact():
+    """The tutorial's heat-equation test problem (ft03_heat.py): u = 1 + x^2 + alpha y^2 + beta t, f = beta - 2 - 2 alpha, which dolfin
+    reproduces to 1e-15 at every step because the quadratic is interpolated exactly and the time dependence is linear.  The reference's
+    time scheme (ScalarTransportSolver.py:287-293) is Crank-Nicolson with the load not theta-weighted; it is exact for this solution
+    too: (c/dt) M (T - T_prev) + K (T + T_prev)/2 = int S q, with c = 1, k = 1, S = beta - 2 - 2 alpha."""
+    alpha, beta, dt, nsteps = 3.0, 1.2, 0.3, 5
+    c, t = fo.unit_square_mesh(8, 8)
+    nv = c.shape[0]
+    K = fo.assemble_matrix(t, fo.local_laplace(c, t, 1.0), nv)
+    M = fo.assemble_matrix(t, fo.local_mass(c, t, 1.0), nv)
+    load = fo.assemble_source(c, t, beta - 2 - 2 * alpha)
+    bnd = np.nonzero((c[:, 0] == 0) | (c[:, 0] == 1) | (c[:, 1] == 0) | (c[:, 1] == 1))[0]
+    exact = lambda tt: 1 + c[:, 0] ** 2 + alpha * c[:, 1] ** 2 + beta * tt      # noqa: E731
+    T = exact(0.0)
+    for n in range(1, nsteps + 1):
+        A = M / dt + 0.5 * K
+        b = (M / dt) @ T - 0.5 * (K @ T) + load
+        Ab, bb = fo.apply_dirichlet(A, b, bnd, exact(n * dt)[bnd], symmetric=False)
+        T = fo.solve_direct(Ab, bb)
+        assert np.abs(T - exact(n * dt)).max() < 2e-13
