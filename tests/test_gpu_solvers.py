@@ -345,3 +345,30 @@ def test_unsupported_features_raise_solver_error():
     settings['material']['capacity'] = lambda T: 4.2e6 * (1 + 1e-3 * T)            # nonlinear capacity: unsupported in the reference too
     with pytest.raises(SolverBase.SolverError):
         ScalarTransportSolver.ScalarTransportSolver(settings).solve()
+
+
+def test_fenics_tutorial_poisson_published_output():
+    """ft01_poisson.py of the FEniCS tutorial through the solver API on the GPU: -Laplace u = -6 on UnitSquareMesh(8, 8), u_D = 1 + x^2 +
+    2 y^2 on the whole boundary.  dolfin's published output: error_L2 = 0.00823509807335, error_max = 1.33226762955e-15."""
+    from oracle import fem_oracle_p2 as fp
+    mesh = UnitSquareMesh(8, 8)
+    Q = FunctionSpace(mesh, "P", 1)
+    from fenicssolver_b200.dolfin_compat import Expression
+    u_D = Expression('1 + x[0]*x[0] + 2*x[1]*x[1]', degree=2)
+    boundary = AutoSubDomain(lambda x, on_boundary: on_boundary)
+    settings = {'solver_name': 'ScalarTransportSolver', 'scalar_name': 'temperature', 'mesh': None, 'function_space': Q,
+                'boundary_conditions': {'all': {'boundary': boundary, 'boundary_id': 1, 'type': 'Dirichlet', 'value': u_D}},
+                'body_source': Constant(-6.0), 'initial_values': {'temperature': 0.0},
+                'material': {'conductivity': 1.0, 'capacity': 1.0},
+                'solver_settings': {'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.1, 'ending_time': 1},
+                                    'reference_values': {'temperature': 0.0}, 'solver_parameters': {}},
+                'report_settings': {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0}}
+    u = ScalarTransportSolver.ScalarTransportSolver(settings).solve()
+    c, t = fo.unit_square_mesh(8, 8)
+    exact = lambda x: 1 + x[..., 0] ** 2 + 2 * x[..., 1] ** 2       # noqa: E731
+    assert np.abs(u.compute_vertex_values(mesh) - exact(c)).max() < 1e-11          # error_max (Krylov tolerance instead of LU)
+    pts, w = fp._collapsed_rule(2, 6)
+    vol, _ = fo.p1_geometry(c, t)
+    e = exact(np.einsum('pa,cai->cpi', pts, c[t])) - np.einsum('pa,ca->cp', pts, u.values[t])
+    error_L2 = float(np.sqrt(np.sum(vol[:, None] * w[None, :] * e ** 2)))
+    assert abs(error_L2 - 0.00823509807335) < 1e-13
