@@ -61,7 +61,110 @@ class Constant:
 
 
 _EXPR_NAMES = {k: getattr(np, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt", "fabs", "floor", "ceil", "arctan2")}
-_EXPR_NAMES.update({"pow": np.power, "abs": np.abs, "pi": math.pi, "atan2": np.arctan2, "DOLFIN_PI": math.pi})
+_EXPR_NAMES.update({"pow": np.power, "abs": np.abs, "pi": math.pi, "atan2": np.arctan2, "DOLFIN_PI": math.pi, "where": np.where, "logical_and": np.logical_and, "logical_or": np.logical_or,
+                    "fmin": np.minimum, "fmax": np.maximum, "min": np.minimum, "max": np.maximum, "sinh": np.sinh, "cosh": np.cosh,
+                    "tanh": np.tanh, "asin": np.arcsin, "acos": np.arccos, "atan": np.arctan, "erf": None})
+_EXPR_NAMES.pop("erf")
+
+
+def _cpp_to_python(src):
+    """C++ expression syntax that Python lacks: `cond ? a : b` (right-associative, any nesting) becomes where(cond, a, b);
+    `a && b`, `a || b` become logical_and / logical_or calls (C++ precedence: weaker than the comparisons), `!x` becomes ~x."""
+    def split_ternary(e):
+        depth = 0
+        q = -1
+        for i, ch in enumerate(e):
+            if ch in "([":
+                depth += 1
+            elif ch in ")]":
+                depth -= 1
+            elif ch == "?" and depth == 0:
+                q = i
+                break
+        if q < 0:
+            return None
+        depth, nest = 0, 0
+        for j in range(q + 1, len(e)):
+            ch = e[j]
+            if ch in "([":
+                depth += 1
+            elif ch in ")]":
+                depth -= 1
+            elif depth == 0 and ch == "?":
+                nest += 1
+            elif depth == 0 and ch == ":":
+                if nest == 0:
+                    return e[:q], e[q + 1:j], e[j + 1:]
+                nest -= 1
+        raise SolverError("unbalanced ?: in Expression %r" % e)
+
+    def conv(e):
+        # innermost parenthesised groups first, so a ternary inside f(...) is handled on its own
+        out, i = "", 0
+        while i < len(e):
+            if e[i] == "(":
+                depth, j = 1, i + 1
+                while j < len(e) and depth:
+                    depth += e[j] == "("
+                    depth -= e[j] == ")"
+                    j += 1
+                out += "(" + ", ".join(conv(a) for a in _split_args(e[i + 1:j - 1])) + ")"
+                i = j
+            else:
+                out += e[i]
+                i += 1
+        parts = split_ternary(out)
+        if parts is not None:
+            c, a, b = parts
+            return "where(%s, %s, %s)" % (conv(c).strip(), conv(a).strip(), conv(b).strip())
+        # || binds weaker than &&, both weaker than the comparisons: functions instead of Python's tightly binding | and &
+        for op, fn in (("||", "logical_or"), ("&&", "logical_and")):
+            pieces = _split_top(out, op)
+            if len(pieces) > 1:
+                acc = conv(pieces[0]).strip()
+                for nxt in pieces[1:]:
+                    acc = "%s(%s, %s)" % (fn, acc, conv(nxt).strip())
+                return acc
+        return out
+
+    return conv(re.sub(r"!(?!=)", " ~", src))
+
+
+def _split_top(e, op):
+    """Split at top-level occurrences of the two-character operator `op`."""
+    out, depth, cur, i = [], 0, "", 0
+    while i < len(e):
+        ch = e[i]
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if depth == 0 and e.startswith(op, i):
+            out.append(cur)
+            cur = ""
+            i += len(op)
+            continue
+        cur += ch
+        i += 1
+    out.append(cur)
+    return out
+
+
+def _split_args(e):
+    """Split at top-level commas."""
+    args, depth, cur = [], 0, ""
+    for ch in e:
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            args.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    args.append(cur)
+    return args
 
 
 class Expression:
@@ -79,7 +182,7 @@ class Expression:
         env["x"] = x
         if not re.fullmatch(r"[\w\s\.\+\-\*/\(\)\[\],<>=!&|?:]*", src):
             raise SolverError("unsupported characters in Expression %r" % src)
-        val = eval(src.replace("&&", " and ").replace("||", " or "), {"__builtins__": {}}, env)  # noqa: S307
+        val = eval(_cpp_to_python(src), {"__builtins__": {}}, env)  # noqa: S307
         return np.broadcast_to(np.asarray(val, dtype=np.float64), x[0].shape).copy()
 
     def __call__(self, coords):

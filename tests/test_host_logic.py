@@ -219,6 +219,13 @@ def test_expression_evaluation():
     assert Expression(("10*rho", "0", "0.0"), rho=7800, degree=2)(np.zeros((3, 3))).shape == (3, 3)
     with pytest.raises(SolverBase.SolverError):
         Expression("__import__('os')")(c)
+    # C++ conditionals and logic, as dolfin's JIT-compiled Expression strings allow
+    p = np.array([[0.1, 0.2], [0.6, 0.9], [0.5, 0.5]])
+    assert np.array_equal(Expression("x[0] < 0.5 ? 1.0 : (x[1] > 0.8 ? 3.0 : 2.0)", degree=0)(p), [1.0, 3.0, 2.0])
+    assert np.array_equal(Expression("x[0] < 0.5 ? 1.0 : x[1] > 0.8 ? 3.0 : 2.0", degree=0)(p), [1.0, 3.0, 2.0])
+    assert np.array_equal(Expression("(x[0] > 0.3 && x[1] < 0.95) ? T1 : T0", T0=300, T1=360, degree=1)(p), [300.0, 360.0, 360.0])
+    assert np.array_equal(Expression("x[0] > 0.55 || !(x[1] > 0.3) ? 1 : 0", degree=1)(p), [1.0, 1.0, 0.0])
+    assert np.allclose(Expression("pow(x[0] < 0.5 ? x[0] : 0.5, 2) + fmax(x[1], 0.5)", degree=1)(p), [0.01 + 0.5, 0.25 + 0.9, 0.25 + 0.5])
 
 
 @pytest.mark.parametrize("mesh", [UnitSquareMesh(3, 2), UnitCubeMesh(2, 2, 3)], ids=["2d", "3d"])
