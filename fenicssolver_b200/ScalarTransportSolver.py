@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib
 from .SolverBase import SolverBase, SolverError
-from .dolfin_compat import Constant, DirichletBC, Function, Point, PointSource
+from .dolfin_compat import Constant, DirichletBC, Expression, Function, Point, PointSource
 
 supported_scalars = {'temperature', 'electric_potential', 'species_concentration'}
 electric_permittivity_in_vacumm = 8.854187817e-12
@@ -47,6 +47,7 @@ class ScalarForm:
         self.radiation = None            # (m = emissivity * Stefan-Boltzmann, T_ambient)
         self.point_sources = []          # PointSource objects
         self.conductivity_fn = None      # k(T) callable: the stiffness term moves into add_newton_terms
+        self.conductivity_nodal = None   # k(x) at the vertices (Expression / array): P1 interpolant, own kernel
         self.supg_pe = None              # Peclet number of the SUPG test function q + tau v.grad q (None: Galerkin)
 
     def _k(self):
@@ -91,6 +92,14 @@ class ScalarForm:
                 _lib.assemble_scalar_supg(space.dmesh, A, vel, supg, adv=adv)
         if vel_field is not None:
             _lib.assemble_advection_nodal(space.dmesh, A, vel_field, scale=c)      # fully implicit, like the constant case (:311)
+        if self.conductivity_nodal is not None:
+            # k(x): int k_h grad u . grad v with k_h the P1 interpolant of the nodal values; the Newton kernel with k' = 0 is
+            # exactly that bilinear form (and its action on T_prev for the explicit half of Crank-Nicolson)
+            kd = space.vector_from_global(self.conductivity_nodal)
+            zero = space.scratch_vector('zero')
+            _lib.assemble_scalar_nonlinear_k(space.dmesh, A, None, zero, kd, zero, scale=self.theta if self.transient else 1.0)
+            if self.transient:
+                _lib.assemble_scalar_nonlinear_k(space.dmesh, None, b, tp, kd, zero, scale=1.0 - self.theta, rscale=-1.0)
         for marker, g in self.neumann:
             fv, op = space.local_facets(*s.boundary_facets.facets(marker))
             _lib.assemble_facet_load(space.dmesh, b, fv, g)
@@ -169,8 +178,8 @@ class ScalarTransportSolver(SolverBase):
         self.nonlinear = False
         self.nonlinear_material = False
         for v in self.material.values():
-            if callable(v) and not isinstance(v, Constant):
-                self.nonlinear = True            # as the reference does at construction (:60-66)
+            if callable(v) and not isinstance(v, (Constant, Expression, Function)):
+                self.nonlinear = True            # as the reference does at construction (:60-66); fields k(x) are linear
 
     def _material_number(self, c, T):
         from inspect import isfunction
@@ -288,7 +297,16 @@ class ScalarTransportSolver(SolverBase):
         capacity = self.capacity(T)
         if callable(capacity):
             raise SolverError('nonlinear capacity is not supported (the reference says so too, :291)')
-        if callable(conductivity) and not isinstance(conductivity, Constant):
+        if isinstance(conductivity, (Function, Expression)) or (isinstance(conductivity, np.ndarray) and conductivity.ndim == 1):
+            # k(x): a scalar field given by an Expression, a Function or one value per vertex
+            if self.function_space.degree != 1:
+                raise SolverError('a conductivity field is implemented for degree-1 spaces')
+            kn = self.translate_value(conductivity) if not isinstance(conductivity, np.ndarray) else conductivity
+            kn = np.asarray(kn, dtype=np.float64)
+            if kn.shape != (self.mesh.num_vertices(),):
+                raise SolverError('a conductivity field must be scalar, one value per vertex (tensor fields are not implemented)')
+            F.conductivity_nodal, conductivity = kn, 0.0
+        elif callable(conductivity) and not isinstance(conductivity, Constant):
             # k(T): Newton on the device with k_h the P1 interpolant of the nodal values k(T_a)
             if self.function_space.degree != 1:
                 raise SolverError('temperature-dependent conductivity is implemented for degree-1 spaces')
@@ -296,8 +314,6 @@ class ScalarTransportSolver(SolverBase):
                 raise SolverError('temperature-dependent conductivity is implemented for steady problems')
             self.nonlinear = True
             F.conductivity_fn, conductivity = conductivity, 0.0
-        elif isinstance(conductivity, (Function,)):
-            raise SolverError('conductivity must be a number, a constant tensor or a function of T on the device path')
         F.conductivity, F.capacity = conductivity, capacity
 
         if not hasattr(self, 'convective_velocity'):

@@ -712,3 +712,40 @@ def test_elasticity_stress_tensor_boundary():
         dofs = (lv[:, None] * 3 + np.arange(3)).ravel()
         Ab, bb = fo.apply_dirichlet(A, b, dofs, np.zeros(dofs.size), symmetric=True)
         assert fo.relative_l2(u.vector().get_local(), fo.solve_direct(Ab, bb)) < 1e-9
+
+
+def test_conductivity_field_expression():
+    """material['conductivity'] = Expression(...) : a scalar field k(x), P1-interpolated (the reference's tensor-weighted example
+    passes an Expression too, examples/test_heat_transfer.py:91); steady and Crank-Nicolson."""
+    n = 12
+    kexpr = "0.6 * (1 + x[0] + 2*x[1]*x[1])"
+    c, t = fo.unit_square_mesh(n, n)
+    nv = c.shape[0]
+    kn = 0.6 * (1 + c[:, 0] + 2 * c[:, 1] ** 2)
+    kcell = kn[t].mean(axis=1)
+    tp, bt = np.nonzero(c[:, 1] == 1)[0], np.nonzero(c[:, 1] == 0)[0]
+    dofs = np.concatenate([tp, bt]); vals = np.concatenate([np.full(tp.size, 360.0), np.full(bt.size, 300.0)])
+    K = fo.conform(fo.assemble_matrix(t, fo.local_laplace(c, t, kcell), nv), *fo.csr_pattern(t, nv))
+    settings, mesh = radiation_settings(n)
+    del settings['radiation_settings']
+    settings['body_source'] = 250.0
+    solver = ScalarTransportSolver.ScalarTransportSolver(settings)
+    solver.material['conductivity'] = Expression(kexpr, degree=1)
+    T = solver.solve()
+    assert not solver.nonlinear and solver.solve_info['converged'] == 1
+    Ab, bb = fo.apply_dirichlet(K, fo.assemble_source(c, t, 250.0), dofs, vals, symmetric=True)
+    assert fo.relative_l2(T.values, fo.solve_direct(Ab, bb)) < TOL
+    # transient: theta K(k) on the left, -(1 - theta) K(k) T_prev on the right
+    nsteps, cap = 3, 1000 * 4200.0
+    dt = cap / (n * n) / 0.6
+    settings, mesh = radiation_settings(n, {'transient': True, 'starting_time': 0.0, 'time_step': dt, 'ending_time': dt * (nsteps - 0.5)})
+    del settings['radiation_settings']
+    solver = ScalarTransportSolver.ScalarTransportSolver(settings)
+    solver.material['conductivity'] = Expression(kexpr, degree=1)
+    T = solver.solve()
+    M = fo.assemble_matrix(t, fo.local_mass(c, t, cap), nv)
+    Tn = np.full(nv, 300.0)
+    for _ in range(nsteps):
+        Ab, bb = fo.apply_dirichlet((M / dt + 0.5 * K).tocsr(), (M / dt) @ Tn - 0.5 * (K @ Tn), dofs, vals, symmetric=True)
+        Tn = fo.solve_direct(Ab, bb)
+    assert fo.relative_l2(T.values, Tn) < TOL
