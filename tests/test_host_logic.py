@@ -396,3 +396,28 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "Mdof/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     assert d["cpu_baseline"]["cores"] == ncores
+
+
+def test_multigrid_level_count_rule():
+    """solve_amg picks the multigrid preconditioner only when the box can be coarsened (every cell count even and >= 4) on one GPU
+    with a degree-1 space; otherwise Jacobi (SolverBase._multigrid_levels, no device call)."""
+    import copy
+    from fenicssolver_b200 import LinearElasticitySolver
+    from fenicssolver_b200.dolfin_compat import BoxMesh, Constant, Mesh, Point, VectorFunctionSpace
+
+    def solver(mesh, degree=1):
+        s = copy.deepcopy(SolverBase.default_case_settings)
+        s.update({'function_space': VectorFunctionSpace(mesh, "CG", degree),
+                  'material': {'elastic_modulus': 2e11, 'poisson_ratio': 0.27, 'density': 7800},
+                  'boundary_conditions': {'clamp': {'boundary': AutoSubDomain(lambda x: near(x[0], 0.0)), 'boundary_id': 1, 'type': 'Dirichlet',
+                                                    'value': Constant((0, 0, 0))}},
+                  'report_settings': {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0}})
+        return LinearElasticitySolver.LinearElasticitySolver(s)
+    box = lambda *n: BoxMesh(Point(0, 0, 0), Point(4, 1, 1), *n)       # noqa: E731
+    assert solver(box(128, 128, 128))._multigrid_levels() == 7        # 128 -> 64 -> ... -> 2
+    assert solver(box(32, 8, 8))._multigrid_levels() == 3             # 8 -> 4 -> 2 limits it
+    assert solver(box(16, 4, 4))._multigrid_levels() == 2
+    assert solver(box(12, 3, 3))._multigrid_levels() == 1             # odd count: no coarser level -> Jacobi
+    assert solver(box(16, 4, 4), degree=2)._multigrid_levels() == 0   # degree 2: not covered
+    m = box(4, 4, 4)
+    assert solver(Mesh(m.coordinates().copy(), m.cells().copy()))._multigrid_levels() == 0      # not a generated box
