@@ -124,13 +124,13 @@ def ncu_traffic_bytes():
     return None
 
 
-def cpu_heat(N, iters_full, sample_iters, steps=1, warmup=0):
+def cpu_heat(N, iters_full, sample_iters, steps=1, warmup=0, cube=None):
     """CPU restatement (oracle/fem_oracle_c.c, OpenMP on every host core) of the same step on a bounded
     sample: the whole assembly + Dirichlet, then `sample_iters` CG iterations; the solve time is scaled to
     the `iters_full` iterations the full solve needs (same recurrence => same count)."""
     from oracle import c_oracle as co
     cores = co.use_all_cores()          # not OMP_NUM_THREADS: torchrun exports 1 into every rank
-    h = co.HeatCube(N)
+    h = cube if cube is not None else co.HeatCube(N)
     times = []
     for s in range(warmup + steps):
         r = h.step(rtol=RTOL, maxit=sample_iters)
@@ -145,6 +145,20 @@ def cpu_heat(N, iters_full, sample_iters, steps=1, warmup=0):
                       "solve time scaled to %d iterations; OpenMP C restatement, not dolfin/PETSc"
                       % (N, r["t_assemble"], r["iterations"], iters_full, r["t_solve"] / max(r["iterations"], 1), iters_full),
             "ms_per_step": t_step * 1e3, "setup_s": h.t_setup}
+
+
+def cpu_heat_gmg(mgc):
+    """CPU figure for the `gmg` block: the same multigrid-preconditioned CG (oracle/fem_oracle_c.c fo_mg_pcg, OpenMP on every host
+    core) on the full problem; one warm-up step makes the eigenvalue estimates, the second one is timed, as on the GPU."""
+    from oracle import c_oracle as co
+    cores = co.use_all_cores()
+    mgc.step(rtol=RTOL)
+    r = mgc.step(rtol=RTOL)
+    t = r["t_assemble"] + r["t_solve"]
+    ndof = mgc.cubes[0].nv
+    return {"value": ndof / t / 1e6, "unit": "Mdof/s", "cores": cores, "kind": "port", "iterations": r["iterations"],
+            "sample": "N=%d: whole step, assembly + Dirichlet on %d levels (%.2f s) + %d multigrid-PCG iterations (%.2f s); OpenMP C "
+                      "restatement of the same algorithm" % (mgc.cubes[0].N, r["levels"], r["t_assemble"], r["iterations"], r["t_solve"])}
 
 
 _REAL_STDOUT = None
@@ -422,8 +436,16 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_heat(N, iters, args.cpu_sample_iters)
+            from oracle import c_oracle as co
+            want_mg = gmg is not None and gmg.get("value")
+            mgc = co.HeatCubeMG(N) if want_mg else None          # its finest level doubles as the Jacobi baseline's problem
+            cpu = cpu_heat(N, iters, args.cpu_sample_iters, cube=mgc.cubes[0] if mgc else None)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if mgc is not None:
+                try:
+                    gmg["cpu_baseline"] = cpu_heat_gmg(mgc)
+                except Exception as ex:
+                    gmg["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (ex,)}
         except Exception as ex:          # the baseline is a reported extra, never a reason to lose the bench line
             cpu = {"value": None, "unit": "Mdof/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
 

@@ -46,6 +46,11 @@ def load():
         lib.fo_spmv.argtypes = [i64, vp, vp, vp, vp, vp]
         lib.fo_pcg_jacobi.restype = C.c_int
         lib.fo_pcg_jacobi.argtypes = [i64, vp, vp, vp, vp, vp, dbl, dbl, C.c_int, C.POINTER(dbl)]
+        lib.fo_mg_lambda_max.restype = dbl
+        lib.fo_mg_lambda_max.argtypes = [i64, vp, vp, vp]
+        lib.fo_mg_apply.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        lib.fo_mg_pcg.restype = C.c_int
+        lib.fo_mg_pcg.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, C.c_int, C.c_int, C.c_int, C.POINTER(dbl)]
         _lib = lib
     return _lib
 
@@ -126,3 +131,66 @@ class HeatCube:
         it = lib.fo_pcg_jacobi(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.x), rtol, 0.0, maxit, C.byref(rel))
         t2 = time.perf_counter()
         return {"t_assemble": t1 - t0, "t_solve": t2 - t1, "iterations": it, "relres": rel.value}
+
+
+class MultigridLevels:
+    """ctypes argument pack for fo_mg_apply / fo_mg_pcg: per-level CSR arrays, constrained-dof flags, vertices per axis and
+    eigenvalue estimates (computed with fo_mg_lambda_max unless given)."""
+
+    def __init__(self, levels, lmax=None):
+        """levels: list of dicts with rp (int64), ci (int32), va (float64), bc (uint8 flags), dims (vertices per axis, 3 ints)."""
+        lib = load()
+        self.keep = levels
+        nl = len(levels)
+        self.nlevels = nl
+        self.n = np.array([L["rp"].size - 1 for L in levels], dtype=np.int64)
+        self.dims = np.array([list(L["dims"]) + [1] * (3 - len(L["dims"])) for L in levels], dtype=np.int32)
+        ptrs = lambda key: (C.c_void_p * nl)(*[L[key].ctypes.data for L in levels])      # noqa: E731
+        self.rp, self.ci, self.va, self.bc = ptrs("rp"), ptrs("ci"), ptrs("va"), ptrs("bc")
+        if lmax is None:
+            lmax = [lib.fo_mg_lambda_max(int(self.n[l]), _p(L["rp"]), _p(L["ci"]), _p(L["va"])) for l, L in enumerate(levels)]
+        self.lmax = np.array(lmax, dtype=np.float64)
+
+    def apply(self, r, nu=2, coarse_sweeps=24):
+        z = np.empty_like(r)
+        load().fo_mg_apply(self.nlevels, _p(self.n), _p(self.dims), self.rp, self.ci, self.va, self.bc, _p(self.lmax), _p(r), _p(z), nu, coarse_sweeps)
+        return z
+
+    def pcg(self, b, x, rtol=1e-12, maxit=1000, nu=2, coarse_sweeps=24):
+        rel = C.c_double()
+        it = load().fo_mg_pcg(self.nlevels, _p(self.n), _p(self.dims), self.rp, self.ci, self.va, self.bc, _p(self.lmax), _p(b), _p(x),
+                              rtol, maxit, nu, coarse_sweeps, C.byref(rel))
+        return it, rel.value
+
+
+class HeatCubeMG:
+    """Config C2 on the CPU with CG preconditioned by the geometric multigrid of csrc/fsb_mg.cu: one HeatCube per level (N, N/2, ...
+    while even and >= 4); step() = assemble + Dirichlet on every level, then the multigrid PCG.  The eigenvalue estimates are made
+    once (first step) and reused, as the GPU path does."""
+
+    def __init__(self, N, **kw):
+        sizes = [N]
+        while sizes[-1] % 2 == 0 and sizes[-1] >= 4:
+            sizes.append(sizes[-1] // 2)
+        t = time.perf_counter()
+        self.cubes = [HeatCube(n, **kw) for n in sizes]
+        self.t_setup = time.perf_counter() - t
+        self.lmax = None
+
+    def step(self, rtol=1e-12, maxit=1000):
+        lib = load()
+        t0 = time.perf_counter()
+        for h in self.cubes:
+            h.vals[:] = 0.0
+            h.b[:] = 0.0
+            lib.fo_assemble_heat(h.cells.shape[0], _p(h.cells), _p(h.coords), h.k, h.S, _p(h.rp), _p(h.ci), _p(h.vals), _p(h.b))
+            lib.fo_apply_dirichlet_sym(h.nv, _p(h.rp), _p(h.ci), _p(h.vals), _p(h.b), _p(h.flag), _p(h.g))
+        levels = [{"rp": h.rp, "ci": h.ci, "va": h.vals, "bc": h.flag, "dims": (h.N + 1,) * 3} for h in self.cubes]
+        mg = MultigridLevels(levels, self.lmax)
+        self.lmax = mg.lmax
+        t1 = time.perf_counter()
+        f = self.cubes[0]
+        f.x[:] = np.where(f.flag, f.g, f.T_init)
+        it, rel = mg.pcg(f.b, f.x, rtol=rtol, maxit=maxit)
+        t2 = time.perf_counter()
+        return {"iterations": it, "relres": rel, "t_assemble": t1 - t0, "t_solve": t2 - t1, "x": f.x, "levels": len(levels)}

@@ -239,3 +239,234 @@ int fo_pcg_jacobi(int64_t n, const int64_t* rp, const int32_t* ci, const double*
   free(r); free(p); free(q); free(dinv);
   return it;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * CPU restatement of the multigrid-preconditioned CG of csrc/fsb_mg.cu (scalar problems on nested box meshes), so that the
+ * `gmg` block of the bench line has its own CPU figure: same transfers (fine vertex 2C + d = coarse vertex C or midpoint of the
+ * coarse edge (C, C + d)), Chebyshev smoothing of degree nu on D^-1 A over [lmax/10, lmax], damped Jacobi on the coarsest level,
+ * V(nu,nu) cycle, convergence on ||D^-1 r||.  Checked against oracle/mg_oracle.py (tests/test_oracle_forms.py). */
+typedef struct {
+  int64_t n;
+  int dims[3];
+  const int64_t* rp;
+  const int32_t* ci;
+  const double* va;
+  const uint8_t* bc;
+  double lmax;
+  double *dinv, *x, *b, *r, *y;
+} mg_level;
+
+static void mg_dinv(mg_level* L) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < L->n; ++i) {
+    double d = 1.0;
+    for (int64_t k = L->rp[i]; k < L->rp[i + 1]; ++k)
+      if (L->ci[k] == i) d = L->va[k];
+    L->dinv[i] = d != 0.0 ? 1.0 / d : 1.0;
+  }
+}
+
+/* min(1.1 * power-iteration estimate from a pseudo-random +-1 vector, Gershgorin bound) of lambda_max(D^-1 A) */
+double fo_mg_lambda_max(int64_t n, const int64_t* rp, const int32_t* ci, const double* va) {
+  double* dinv = (double*)malloc(sizeof(double) * n);
+  double* x = (double*)malloc(sizeof(double) * n);
+  double* y = (double*)malloc(sizeof(double) * n);
+  double bound = 0.0;
+#pragma omp parallel for schedule(static) reduction(max : bound)
+  for (int64_t i = 0; i < n; ++i) {
+    double d = 1.0, s = 0.0;
+    for (int64_t k = rp[i]; k < rp[i + 1]; ++k) {
+      if (ci[k] == i) d = va[k];
+      s += fabs(va[k]);
+    }
+    dinv[i] = d != 0.0 ? 1.0 / d : 1.0;
+    bound = fmax(bound, s * fabs(dinv[i]));
+    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    x[i] = (h & 1) ? 1.0 : -1.0;
+  }
+  double lam = 0.0;
+  for (int it = 0; it < 30; ++it) {
+    spmv(n, rp, ci, va, x, y);
+    double xx = 0.0, rr = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : xx, rr)
+    for (int64_t i = 0; i < n; ++i) { y[i] *= dinv[i]; xx += x[i] * x[i]; rr += y[i] * y[i]; }
+    if (!(xx > 0.0) || !(rr > 0.0)) break;
+    lam = sqrt(rr / xx);
+    const double s = 1.0 / sqrt(rr);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) x[i] = s * y[i];
+  }
+  free(dinv); free(x); free(y);
+  double est = 1.1 * lam;
+  if (bound > 0.0 && (est <= 0.0 || est > bound)) est = bound;
+  return est > 0.0 ? est : 2.0;
+}
+
+static void mg_jacobi(mg_level* L, int sweeps) {      /* zero start, damping 4 / (3 lmax) */
+  const double w = 4.0 / (3.0 * L->lmax);
+  for (int s = 0; s < sweeps; ++s) {
+    if (s == 0) {
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < L->n; ++i) L->x[i] = w * L->dinv[i] * L->b[i];
+    } else {
+      spmv(L->n, L->rp, L->ci, L->va, L->x, L->y);
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < L->n; ++i) L->x[i] += w * L->dinv[i] * (L->b[i] - L->y[i]);
+    }
+  }
+}
+
+static void mg_chebyshev(mg_level* L, int deg, int zero_start) {      /* L->r is the direction vector */
+  const double lmax = L->lmax, lmin = lmax / 10.0;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double rho0 = 1.0 / sigma;
+  for (int k = 0; k < deg; ++k) {
+    double c1 = 0.0, c2 = 1.0 / theta;
+    if (k > 0) {
+      const double rho1 = 1.0 / (2.0 * sigma - rho0);
+      c1 = rho1 * rho0; c2 = 2.0 * rho1 / delta;
+      rho0 = rho1;
+    }
+    if (k == 0 && zero_start) {
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < L->n; ++i) { L->r[i] = c2 * L->dinv[i] * L->b[i]; L->x[i] = L->r[i]; }
+    } else {
+      spmv(L->n, L->rp, L->ci, L->va, L->x, L->y);
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < L->n; ++i) {
+        const double d = (c1 != 0.0 ? c1 * L->r[i] : 0.0) + c2 * L->dinv[i] * (L->b[i] - L->y[i]);
+        L->r[i] = d;
+        L->x[i] += d;
+      }
+    }
+  }
+}
+
+static void mg_vcycle(mg_level* lv, int nlevels, int l, int nu, int coarse_sweeps) {
+  mg_level* L = &lv[l];
+  if (l + 1 == nlevels) { mg_jacobi(L, coarse_sweeps); return; }
+  mg_chebyshev(L, nu, 1);
+  spmv(L->n, L->rp, L->ci, L->va, L->x, L->y);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < L->n; ++i) L->r[i] = L->b[i] - L->y[i];
+  mg_level* C = &lv[l + 1];
+  const int f0 = L->dims[0], f1 = L->dims[1], f2 = L->dims[2], c0 = C->dims[0], c1 = C->dims[1];
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < C->n; ++t) {                     /* restriction, gathered per coarse vertex */
+    if (C->bc && C->bc[t]) { C->b[t] = 0.0; continue; }
+    const int I = (int)(t % c0), J = (int)((t / c0) % c1), K = (int)(t / ((int64_t)c0 * c1));
+    const int fi = 2 * I, fj = 2 * J, fk = 2 * K;
+    double s = L->r[fi + (int64_t)f0 * (fj + (int64_t)f1 * fk)];
+    for (int d = 1; d < 8; ++d) {
+      const int di = d & 1, dj = (d >> 1) & 1, dk = (d >> 2) & 1;
+      if ((dj && f1 == 1) || (dk && f2 == 1)) continue;
+      for (int sg = -1; sg <= 1; sg += 2) {
+        const int i = fi + sg * di, j = fj + sg * dj, k = fk + sg * dk;
+        if (i < 0 || j < 0 || k < 0 || i >= f0 || j >= f1 || k >= f2) continue;
+        s += 0.5 * L->r[i + (int64_t)f0 * (j + (int64_t)f1 * k)];
+      }
+    }
+    C->b[t] = s;
+  }
+  mg_vcycle(lv, nlevels, l + 1, nu, coarse_sweeps);
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < L->n; ++t) {                     /* prolongation */
+    if (L->bc && L->bc[t]) continue;
+    const int i = (int)(t % f0), j = (int)((t / f0) % f1), k = (int)(t / ((int64_t)f0 * f1));
+    const int di = i & 1, dj = j & 1, dk = k & 1, I = i >> 1, J = j >> 1, K = k >> 1;
+    const int64_t a = I + (int64_t)c0 * (J + (int64_t)c1 * K);
+    const int64_t bb = (I + di) + (int64_t)c0 * ((J + dj) + (int64_t)c1 * (K + dk));
+    L->x[t] += (di | dj | dk) ? 0.5 * (C->x[a] + C->x[bb]) : C->x[a];
+  }
+  mg_chebyshev(L, nu, 0);
+}
+
+/* z = V(r) on level 0 (for the parity test against the numpy restatement) and the PCG driver.  dims[l][3] = vertices per axis,
+ * lmax[l] = eigenvalue estimates (fo_mg_lambda_max), bc[l] = constrained-dof flags.  x holds the start vector.
+ * Returns the iteration count (fo_mg_pcg) ; *relres = ||D^-1 r|| / ||D^-1 b||. */
+static mg_level* mg_setup(int nlevels, const int64_t* n, const int32_t* dims, const int64_t** rp, const int32_t** ci, const double** va,
+                          const uint8_t** bc, const double* lmax) {
+  mg_level* lv = (mg_level*)calloc(nlevels, sizeof(mg_level));
+  for (int l = 0; l < nlevels; ++l) {
+    mg_level* L = &lv[l];
+    L->n = n[l]; L->rp = rp[l]; L->ci = ci[l]; L->va = va[l]; L->bc = bc ? bc[l] : NULL; L->lmax = lmax[l];
+    for (int a = 0; a < 3; ++a) L->dims[a] = dims[3 * l + a];
+    L->dinv = (double*)malloc(sizeof(double) * L->n);
+    L->x = (double*)calloc(L->n, sizeof(double));
+    L->b = (double*)calloc(L->n, sizeof(double));
+    L->r = (double*)calloc(L->n, sizeof(double));
+    L->y = (double*)calloc(L->n, sizeof(double));
+    mg_dinv(L);
+  }
+  return lv;
+}
+static void mg_free(mg_level* lv, int nlevels) {
+  for (int l = 0; l < nlevels; ++l) { free(lv[l].dinv); free(lv[l].x); free(lv[l].b); free(lv[l].r); free(lv[l].y); }
+  free(lv);
+}
+
+void fo_mg_apply(int nlevels, const int64_t* n, const int32_t* dims, const int64_t** rp, const int32_t** ci, const double** va,
+                 const uint8_t** bc, const double* lmax, const double* r, double* z, int nu, int coarse_sweeps) {
+  mg_level* lv = mg_setup(nlevels, n, dims, rp, ci, va, bc, lmax);
+  memcpy(lv[0].b, r, sizeof(double) * n[0]);
+  mg_vcycle(lv, nlevels, 0, nu, coarse_sweeps);
+  memcpy(z, lv[0].x, sizeof(double) * n[0]);
+  mg_free(lv, nlevels);
+}
+
+int fo_mg_pcg(int nlevels, const int64_t* n, const int32_t* dims, const int64_t** rp, const int32_t** ci, const double** va,
+              const uint8_t** bc, const double* lmax, const double* b, double* x, double rtol, int maxit, int nu, int coarse_sweeps,
+              double* relres) {
+  mg_level* lv = mg_setup(nlevels, n, dims, rp, ci, va, bc, lmax);
+  mg_level* L = &lv[0];
+  const int64_t n0 = L->n;
+  double* r = (double*)malloc(sizeof(double) * n0);
+  double* p = (double*)malloc(sizeof(double) * n0);
+  double* q = (double*)malloc(sizeof(double) * n0);
+  double bbn = 0.0, rr = 0.0, rz = 0.0;
+  spmv(n0, L->rp, L->ci, L->va, x, q);
+#pragma omp parallel for schedule(static) reduction(+ : bbn, rr)
+  for (int64_t i = 0; i < n0; ++i) {
+    r[i] = b[i] - q[i];
+    bbn += (L->dinv[i] * b[i]) * (L->dinv[i] * b[i]);
+    rr += (L->dinv[i] * r[i]) * (L->dinv[i] * r[i]);
+  }
+  const double tol2 = rtol * rtol * bbn;
+  int it = 0;
+  if (rr > tol2) {
+    memcpy(L->b, r, sizeof(double) * n0);
+    mg_vcycle(lv, nlevels, 0, nu, coarse_sweeps);
+#pragma omp parallel for schedule(static) reduction(+ : rz)
+    for (int64_t i = 0; i < n0; ++i) { p[i] = L->x[i]; rz += r[i] * L->x[i]; }
+    while (it < maxit) {
+      spmv(n0, L->rp, L->ci, L->va, p, q);
+      double pq = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : pq)
+      for (int64_t i = 0; i < n0; ++i) pq += p[i] * q[i];
+      const double alpha = rz / pq;
+      rr = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : rr)
+      for (int64_t i = 0; i < n0; ++i) {
+        x[i] += alpha * p[i];
+        r[i] -= alpha * q[i];
+        rr += (L->dinv[i] * r[i]) * (L->dinv[i] * r[i]);
+      }
+      ++it;
+      if (!(rr > tol2)) break;
+      memcpy(L->b, r, sizeof(double) * n0);
+      mg_vcycle(lv, nlevels, 0, nu, coarse_sweeps);
+      double rzn = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : rzn)
+      for (int64_t i = 0; i < n0; ++i) rzn += r[i] * L->x[i];
+      const double beta = rzn / rz;
+      rz = rzn;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < n0; ++i) p[i] = L->x[i] + beta * p[i];
+    }
+  }
+  if (relres) *relres = bbn > 0.0 ? sqrt(rr / bbn) : 0.0;
+  free(r); free(p); free(q);
+  mg_free(lv, nlevels);
+  return it;
+}

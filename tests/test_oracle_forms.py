@@ -361,3 +361,36 @@ def test_stress_tensor_boundary_tractions(dim):
         tot = np.zeros(dim)
         np.add.at(tot, dofs % dim, vals)
         assert np.abs(tot).max() < 1e-9 * 2.5e5
+
+
+def test_c_multigrid_restatement_matches_numpy_and_the_exact_profile():
+    """oracle/fem_oracle_c.c fo_mg_pcg / fo_mg_apply (the CPU figure of the bench's `gmg` block) against oracle/mg_oracle.py on the same
+    level matrices, and config C2's exact 1-D profile; bench.py's helper functions around it."""
+    import scipy.sparse as sp
+    from oracle import c_oracle as co
+    from oracle import mg_oracle as mo
+    N = 16
+    h = co.HeatCubeMG(N)
+    r = h.step()
+    assert r["levels"] == 4 and r["iterations"] <= 14 and r["relres"] < 1e-12
+    z = (np.arange((N + 1) ** 3) // ((N + 1) ** 2)) / N
+    assert fo.relative_l2(r["x"], 350 - 50 * z + 1000 * z * (1 - z) / 40) < 1e-11
+    levels, transfers, nl = [], [], [N] * 3
+    for l, cu in enumerate(h.cubes):
+        M = sp.csr_matrix((cu.vals, cu.ci.astype(np.int64), cu.rp), shape=(cu.nv, cu.nv))
+        levels.append({"A": M, "dinv": 1.0 / M.diagonal(), "bc": cu.flag.astype(bool), "omega": 4.0 / (3.0 * h.lmax[l])})
+        if l + 1 < len(h.cubes):
+            transfers.append(mo.prolongation(nl))
+            nl = [k // 2 for k in nl]
+    assert all(1.5 < lm <= 2.2 for lm in h.lmax)
+    rng = np.random.default_rng(0)
+    res = rng.standard_normal(h.cubes[0].nv)
+    res[levels[0]["bc"]] = 0.0
+    mg = co.MultigridLevels([{"rp": cu.rp, "ci": cu.ci, "va": cu.vals, "bc": cu.flag, "dims": (cu.N + 1,) * 3} for cu in h.cubes], h.lmax)
+    zo = mo.vcycle(levels, transfers, res)
+    assert np.abs(mg.apply(res) - zo).max() < 1e-13 * np.abs(zo).max()
+    import bench
+    g = bench.cpu_heat_gmg(h)
+    assert g["value"] > 0 and g["iterations"] == r["iterations"] and g["kind"] == "port"
+    j = bench.cpu_heat(N, 60, 10, cube=h.cubes[0])
+    assert j["value"] > 0 and "first 10 of 60" in j["sample"]
