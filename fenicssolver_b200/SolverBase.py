@@ -168,8 +168,14 @@ class SolverBase():
             raise SolverError('mesh file: {} , does not exist'. format(filename))
         if filename[-4:] == ".xml":
             self._read_xml_mesh(filename)
-        elif filename[-5:] == ".xdmf" or filename[-3:] == ".h5" or filename[-5:] == ".hdf5":
-            raise SolverError('XDMF/HDF5 meshes are not implemented; convert to dolfin-XML')
+        elif filename[-5:] == ".xdmf":
+            # mesh only, boundaries from the predicates (SolverBase.py:246-252); ASCII-encoded XDMF (no HDF5 library here)
+            from .dolfin_compat import read_xdmf_mesh
+            self.mesh = Mesh(*read_xdmf_mesh(filename))
+            self.generate_boundary_facets()
+            self.subdomains = None
+        elif filename[-3:] == ".h5" or filename[-5:] == ".hdf5":
+            raise SolverError('HDF5 meshes cannot be read here (no HDF5 library in this image); convert to dolfin-XML or ASCII XDMF')
         else:
             raise SolverError('mesh or function space must specified to construct solver object')
 

@@ -413,6 +413,44 @@ def read_dolfin_xml_mesh(path):
     return coords, np.sort(cells, axis=1)
 
 
+def read_xdmf_mesh(path):
+    """XDMF mesh as dolfin's XDMFFile writes it (SolverBase.py:246-252 `XDMFFile(...).read(mesh, True)`), for files whose heavy data is
+    inline (`Format="XML"`, dolfin's `XDMFFile.Encoding.ASCII`).  Files that point into an HDF5 container cannot be read here: the
+    image has no HDF5 library."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+    grid = root.find(".//Grid")
+    if grid is None:
+        raise SolverError("%s holds no XDMF Grid" % path)
+    topo, geom = grid.find("Topology"), grid.find("Geometry")
+    if topo is None or geom is None:
+        raise SolverError("%s: Grid without Topology/Geometry" % path)
+    kind = (topo.get("TopologyType") or topo.get("Type") or "").lower()
+    nl = {"tetrahedron": 4, "triangle": 3}.get(kind)
+    if nl is None:
+        raise SolverError("XDMF topology %r is not supported (Triangle / Tetrahedron)" % kind)
+
+    def data(node, dtype):
+        item = node.find("DataItem")
+        if item is None:
+            raise SolverError("%s: missing DataItem" % path)
+        if (item.get("Format") or "XML").upper() != "XML":
+            raise SolverError("%s stores its arrays in HDF5 (Format=%r); no HDF5 library is available here: re-save with "
+                              "XDMFFile.Encoding.ASCII or convert to dolfin-XML" % (path, item.get("Format")))
+        dims = [int(k) for k in (item.get("Dimensions") or "").split()]
+        a = np.array((item.text or "").split(), dtype=dtype)
+        return a.reshape(dims) if dims and int(np.prod(dims)) == a.size else a
+    cells = data(topo, np.int64).reshape(-1, nl)
+    coords = data(geom, np.float64)
+    gdim = 3 if (geom.get("GeometryType") or "XYZ").upper() == "XYZ" else 2
+    coords = coords.reshape(-1, gdim)
+    if nl == 3 and gdim == 3 and np.all(coords[:, 2] == coords[0, 2]):
+        coords = coords[:, :2]                     # planar triangles written with a z column
+    if cells.min() < 0 or cells.max() >= coords.shape[0]:
+        raise SolverError("%s: connectivity out of range" % path)
+    return coords, np.sort(cells.astype(np.int32), axis=1)
+
+
 def read_mesh_function_xml(path):
     """dolfin-XML MeshFunction (SolverBase.py:229,236) -> (dim, int values[size])."""
     txt = open(path, "r").read()

@@ -421,3 +421,37 @@ def test_multigrid_level_count_rule():
     assert solver(box(16, 4, 4), degree=2)._multigrid_levels() == 0   # degree 2: not covered
     m = box(4, 4, 4)
     assert solver(Mesh(m.coordinates().copy(), m.cells().copy()))._multigrid_levels() == 0      # not a generated box
+
+
+def test_xdmf_ascii_mesh_reader(tmp_path):
+    """read_mesh('*.xdmf') (SolverBase.py:246-252): inline-XML XDMF as dolfin's ASCII encoding writes it; HDF5-backed files raise."""
+    from fenicssolver_b200.dolfin_compat import read_xdmf_mesh
+    c, t = fo.unit_cube_mesh(2, 2, 1)
+    p = os.path.join(str(tmp_path), "mesh.xdmf")
+    with open(p, "w") as f:
+        f.write('<?xml version="1.0"?>\n<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>\n<Xdmf Version="3.0"><Domain><Grid Name="mesh" GridType="Uniform">\n')
+        f.write('<Topology NumberOfElements="%d" TopologyType="Tetrahedron" NodesPerElement="4"><DataItem Dimensions="%d 4" NumberType="UInt" Format="XML">\n' % (t.shape[0], t.shape[0]))
+        f.write("\n".join(" ".join(str(v) for v in row[::-1]) for row in t))          # unsorted on purpose
+        f.write('\n</DataItem></Topology>\n<Geometry GeometryType="XYZ"><DataItem Dimensions="%d 3" Format="XML">\n' % c.shape[0])
+        f.write("\n".join(" ".join(repr(float(x)) for x in row) for row in c))
+        f.write('\n</DataItem></Geometry></Grid></Domain></Xdmf>\n')
+    c2, t2 = read_xdmf_mesh(p)
+    assert np.array_equal(c2, c) and np.array_equal(t2, t)
+    from fenicssolver_b200 import ScalarTransportSolver
+    s = {'solver_name': 'ScalarTransportSolver', 'scalar_name': 'temperature', 'mesh': p,
+         'material': {'density': 1000, 'specific_heat_capacity': 500, 'thermal_conductivity': 20},
+         'boundary_conditions': {'inlet': {'boundary': lambda x: near(x[2], 0.0), 'boundary_id': 1, 'type': 'Dirichlet', 'value': 350}},
+         'body_source': None, 'initial_values': {'temperature': 293},
+         'solver_settings': {'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.01, 'ending_time': 0.03},
+                             'reference_values': {'temperature': 293}, 'solver_parameters': {}},
+         'report_settings': {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0}}
+    solver = ScalarTransportSolver.ScalarTransportSolver(s)
+    assert solver.mesh.num_vertices() == c.shape[0] and (solver.boundary_facets.values == 1).sum() == 8
+    h5 = os.path.join(str(tmp_path), "mesh_h5.xdmf")
+    open(h5, "w").write(open(p).read().replace('Format="XML"', 'Format="HDF"'))
+    with pytest.raises(SolverBase.SolverError):
+        read_xdmf_mesh(h5)
+    with pytest.raises(SolverBase.SolverError):
+        s2 = dict(s, mesh=os.path.join(str(tmp_path), "mesh.h5"))
+        open(s2['mesh'], "w").write("x")
+        ScalarTransportSolver.ScalarTransportSolver(s2)
