@@ -806,7 +806,15 @@ class Function:
         self._name = name
 
     def __call__(self, *x):
-        raise SolverError("point evaluation is not implemented; use .values (vertex order)")
+        """u(x, y[, z]) or u(Point) / u((x, y, z)): the value at a point (a number, or one per component), from the basis functions
+        of the cell that contains it; SolverError outside the mesh."""
+        p = x[0] if len(x) == 1 else x
+        nodes, w = self.function_space.point_weights(p)
+        nc = self.function_space.ncomp
+        a = self.array()
+        if nc == 1:
+            return float(np.dot(w, a[nodes]))
+        return np.dot(w, a.reshape(-1, nc)[nodes])
 
 
 class PointSource:

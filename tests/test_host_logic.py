@@ -455,3 +455,23 @@ def test_xdmf_ascii_mesh_reader(tmp_path):
         s2 = dict(s, mesh=os.path.join(str(tmp_path), "mesh.h5"))
         open(s2['mesh'], "w").write("x")
         ScalarTransportSolver.ScalarTransportSolver(s2)
+
+
+def test_function_point_evaluation():
+    """u(x, y) / u(Point(...)): P1 reproduces linear fields, P2 quadratic ones, vector spaces return one value per component."""
+    from fenicssolver_b200.dolfin_compat import Function, Point
+    mesh = UnitSquareMesh(5, 4)
+    for degree in (1, 2):
+        V = FunctionSpace(mesh, "CG", degree)
+        xn = V.node_coordinates()
+        f = (lambda x: 1 + 2 * x[:, 0] - 3 * x[:, 1]) if degree == 1 else (lambda x: 1 + x[:, 0] ** 2 - 2 * x[:, 0] * x[:, 1])
+        u = Function(V, f(xn))
+        for p in ((0.33, 0.71), (0.0, 1.0), (0.6, 0.25)):
+            assert abs(u(*p) - f(np.array([p]))[0]) < 1e-13
+            assert abs(u(Point(*p)) - u(p)) == 0.0
+    W = VectorFunctionSpace(UnitCubeMesh(2, 2, 2), "CG", 1)
+    xn = W.node_coordinates()
+    u = Function(W, np.stack([xn[:, 0], 2 * xn[:, 1], xn[:, 0] + xn[:, 2]], axis=1).ravel())
+    assert np.allclose(u(0.3, 0.4, 0.9), [0.3, 0.8, 1.2])
+    with pytest.raises(SolverBase.SolverError):
+        u(1.5, 0.2, 0.2)
