@@ -21,7 +21,27 @@ from ._lib import SolverError
 DOLFIN_EPS = 3.0e-16
 __all__ = ["DOLFIN_EPS", "near", "Point", "Constant", "Expression", "Mesh", "UnitSquareMesh", "RectangleMesh",
            "UnitCubeMesh", "BoxMesh", "SubDomain", "AutoSubDomain", "MeshFunction", "FacetMarkers", "FunctionSpace",
-           "VectorFunctionSpace", "Function", "DirichletBC", "PointSource", "SolverError"]
+           "VectorFunctionSpace", "Function", "DirichletBC", "PointSource", "SolverError", "plot", "interactive", "set_log_level",
+           "File", "boundary_flux", "CRITICAL", "ERROR", "WARNING", "INFO", "PROGRESS", "DEBUG", "parameters"]
+
+# log levels and no-op stand-ins for the dolfin calls the reference's example scripts make around the solver
+# (set_log_level(ERROR), plot(...), interactive(): examples/test_linear_elasticity.py:31,141; test_heat_transfer.py:172-192)
+CRITICAL, ERROR, WARNING, INFO, PROGRESS, DEBUG = 50, 40, 30, 20, 16, 10
+parameters = {"linear_algebra_backend": "libfsb", "mesh_partitioner": "rcb", "form_compiler": {"optimize": True}}
+
+
+def set_log_level(level):
+    import logging
+    logging.getLogger("fenicssolver_b200").setLevel(int(level))
+
+
+def plot(*args, **kwargs):
+    """Batch-safe no-op (dolfin.plot); SolverBase.plot() draws 2-D scalar results when plotting is interactive."""
+    return None
+
+
+def interactive():
+    return None
 
 
 def near(a, b, eps=DOLFIN_EPS):
@@ -815,6 +835,63 @@ class Function:
         if nc == 1:
             return float(np.dot(w, a[nodes]))
         return np.dot(w, a.reshape(-1, nc)[nodes])
+
+
+class File:
+    """File("name.pvd") << u  /  << (u, t): ParaView output as dolfin's File writes it (SolverBase.py:570-577): one `.vtu` piece per
+    write, the `.pvd` collection lists them.  Also `.vtu` alone."""
+
+    def __init__(self, filename, encoding=None):
+        self.filename, self.series = filename, []
+
+    def __lshift__(self, what):
+        from .SolverBase import write_pvd, write_vtu
+        u, t = what if isinstance(what, tuple) else (what, float(len(self.series)))
+        mesh = u.function_space.mesh()
+        if self.filename.endswith(".pvd"):
+            import os.path
+            piece = "%s%06d.vtu" % (self.filename[:-4], len(self.series))
+            write_vtu(piece, mesh, u.values, getattr(u, "_name", "f"))
+            self.series.append((float(t), os.path.basename(piece)))
+            write_pvd(self.filename, self.series)
+        elif self.filename.endswith(".vtu"):
+            write_vtu(self.filename, mesh, u.values, getattr(u, "_name", "f"))
+        else:
+            raise SolverError("File supports .pvd and .vtu")
+        return self
+
+
+def boundary_flux(u, markers, marker_id, coefficient=1.0):
+    """assemble(coefficient * dot(grad(u), n) * ds(marker_id)) for a scalar degree-1 Function: what the reference's examples print after
+    the solve (examples/test_heat_transfer.py:181-190 post_process, test_electrostatics.py:126-135).  Boundary-only host work: the
+    gradient of the cell behind each marked facet, its outward unit normal and the facet measure."""
+    V = u.function_space
+    if V.ncomp != 1 or V.degree != 1:
+        raise SolverError("boundary_flux is implemented for scalar degree-1 functions")
+    mesh = V.mesh()
+    c = mesh.coordinates()
+    fverts, opp = markers.facets(marker_id)
+    if len(fverts) == 0:
+        return 0.0
+    fverts, opp = np.asarray(fverts, dtype=np.int64), np.asarray(opp, dtype=np.int64)
+    d = fverts.shape[1]
+    cells = np.hstack([fverts, opp[:, None]])
+    X = c[cells]
+    J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))
+    Jinv = np.linalg.inv(J)
+    G = np.concatenate([-Jinv.sum(axis=1, keepdims=True), Jinv], axis=1)          # gradients of the barycentric coordinates
+    grad = np.einsum("fa,fai->fi", u.array()[cells], G)
+    Xf = c[fverts]
+    if d == 2:
+        tvec = Xf[:, 1] - Xf[:, 0]
+        n = np.stack([tvec[:, 1], -tvec[:, 0]], axis=1)
+        meas = np.linalg.norm(tvec, axis=1)
+    else:
+        n = np.cross(Xf[:, 1] - Xf[:, 0], Xf[:, 2] - Xf[:, 0])
+        meas = 0.5 * np.linalg.norm(n, axis=1)
+    n = n / np.linalg.norm(n, axis=1, keepdims=True)
+    n[np.einsum("ij,ij->i", n, c[opp] - Xf[:, 0]) > 0] *= -1
+    return float(coefficient * np.sum(meas * np.einsum("fi,fi->f", grad, n)))
 
 
 class PointSource:

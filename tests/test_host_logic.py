@@ -475,3 +475,33 @@ def test_function_point_evaluation():
     assert np.allclose(u(0.3, 0.4, 0.9), [0.3, 0.8, 1.2])
     with pytest.raises(SolverBase.SolverError):
         u(1.5, 0.2, 0.2)
+
+
+def test_dolfin_script_stand_ins(tmp_path):
+    """The calls the reference's example scripts make around the solver: set_log_level(ERROR), plot(...), File(...) << u, and the flux
+    integral their post_process() prints (examples/test_heat_transfer.py:181-190)."""
+    from fenicssolver_b200 import dolfin_compat as dc
+    from fenicssolver_b200.dolfin_compat import ERROR, File, Function, boundary_flux, interactive, plot, set_log_level
+    set_log_level(ERROR)
+    assert plot(None, title="x") is None and interactive() is None and dc.parameters["form_compiler"]["optimize"]
+    mesh = UnitSquareMesh(6, 5)
+    V = FunctionSpace(mesh, "CG", 1)
+    c = mesh.coordinates()
+    T = Function(V, 360 + 60 * (1 - c[:, 1]) + 5 * c[:, 0])          # linear: gradient (5, -60)
+    markers = FacetMarkers(mesh)
+    markers.set_all(0)
+    AutoSubDomain(lambda x: near(x[1], 0.0)).mark(markers, 1)
+    AutoSubDomain(lambda x: near(x[0], 1.0)).mark(markers, 2)
+    assert abs(boundary_flux(T, markers, 1, 0.6) - 0.6 * 60.0) < 1e-12       # n = (0, -1) on y = 0, length 1
+    assert abs(boundary_flux(T, markers, 2) - 5.0) < 1e-12                   # n = (1, 0) on x = 1
+    assert boundary_flux(T, markers, 7) == 0.0
+    f = File(os.path.join(str(tmp_path), "T.pvd"))
+    f << (T, 0.0)
+    f << (T, 0.5)
+    import xml.etree.ElementTree as ET
+    ds = ET.parse(os.path.join(str(tmp_path), "T.pvd")).getroot().findall("./Collection/DataSet")
+    assert [d.attrib["file"] for d in ds] == ["T000000.vtu", "T000001.vtu"]
+    assert os.path.exists(os.path.join(str(tmp_path), "T000001.vtu"))
+    W = VectorFunctionSpace(UnitCubeMesh(2, 2, 2), "CG", 1)
+    with pytest.raises(SolverBase.SolverError):
+        boundary_flux(Function(W), markers, 1)
