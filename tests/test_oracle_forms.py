@@ -394,3 +394,20 @@ def test_c_multigrid_restatement_matches_numpy_and_the_exact_profile():
     assert g["value"] > 0 and g["iterations"] == r["iterations"] and g["kind"] == "port"
     j = bench.cpu_heat(N, 60, 10, cube=h.cubes[0])
     assert j["value"] > 0 and "first 10 of 60" in j["sample"]
+
+
+def test_oracle_regression_pins(golden_dir):
+    """tests/golden/forms_expected.npz (made by tests/golden/make_forms_golden.py): the oracle's outputs for fixed small inputs, so an
+    accidental change of the checker itself shows up."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_forms_golden", os.path.join(golden_dir, "make_forms_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.compute()
+    g = np.load(os.path.join(golden_dir, "forms_expected.npz"))
+    assert set(g.files) == set(now)
+    for key in g.files:
+        a, b = np.asarray(now[key], dtype=np.float64), np.asarray(g[key], dtype=np.float64)
+        assert a.shape == b.shape, key
+        scale = max(float(np.abs(b).max()), 1e-300)
+        assert np.abs(a - b).max() <= 1e-12 * scale, key
