@@ -514,7 +514,7 @@ class AutoSubDomain(SubDomain):
         return self.fn(x) if self.nargs == 1 else self.fn(x, on_boundary)
 
 
-def _evaluate_predicate(sub, pts):
+def _evaluate_predicate(sub, pts, on_boundary=True):
     """inside() over points [n, gdim]: vectorised call with x[i] = coordinate arrays, falling back to a
     per-point loop when the predicate is not array-friendly."""
     if not isinstance(sub, SubDomain):
@@ -524,7 +524,7 @@ def _evaluate_predicate(sub, pts):
             raise SolverError("a boundary must be a SubDomain or a predicate, got %r" % type(sub))
     n = pts.shape[0]
     try:
-        r = sub._call([pts[:, i] for i in range(pts.shape[1])], True)
+        r = sub._call([pts[:, i] for i in range(pts.shape[1])], on_boundary)
         r = np.asarray(r)
         if r.shape == (n,):
             return r.astype(bool)
@@ -532,7 +532,7 @@ def _evaluate_predicate(sub, pts):
             return np.full(n, bool(r))
     except (ValueError, TypeError):
         pass
-    return np.array([bool(sub._call(pts[i], True)) for i in range(n)], dtype=bool)
+    return np.array([bool(sub._call(pts[i], on_boundary)) for i in range(n)], dtype=bool)
 
 
 class FacetMarkers:
@@ -612,6 +612,19 @@ class MeshFunction:
 
     def set_all(self, v):
         self.values[:] = v
+
+    def mark_subdomain(self, sub, value):
+        """SubDomain.mark on a cell (or vertex) function: an entity is marked iff all its vertices and its midpoint are inside
+        (dolfin's default check_midpoint=True); on_boundary is False for cells."""
+        c = self.mesh.coordinates()
+        if self.dim == 0:
+            self.values[_evaluate_predicate(sub, c, on_boundary=False)] = value
+            return
+        t = self.mesh.cells()
+        inside_v = _evaluate_predicate(sub, c, on_boundary=False)
+        mid = c[t].mean(axis=1)
+        ok = inside_v[t].all(axis=1) & _evaluate_predicate(sub, mid, on_boundary=False)
+        self.values[ok] = value
 
     def array(self):
         return self.values

@@ -505,3 +505,24 @@ def test_dolfin_script_stand_ins(tmp_path):
     W = VectorFunctionSpace(UnitCubeMesh(2, 2, 2), "CG", 1)
     with pytest.raises(SolverBase.SolverError):
         boundary_flux(Function(W), markers, 1)
+
+
+def test_cell_function_marking_for_subdomain_sources():
+    """SubDomain.mark on a cell MeshFunction (what a script does to give `body_source` per subdomain, ScalarTransportSolver.py:213-221,
+    without a _physical_region.xml): all vertices and the midpoint inside."""
+    from fenicssolver_b200.dolfin_compat import MeshFunction
+    mesh = UnitSquareMesh(4, 4)
+    sub = MeshFunction("size_t", mesh, mesh.topology().dim())
+    sub.set_all(0)
+    AutoSubDomain(lambda x: x[0] <= 0.5 + 1e-12).mark(sub, 3)
+    c, t = mesh.coordinates(), mesh.cells()
+    expect = (c[t][:, :, 0] <= 0.5 + 1e-12).all(axis=1)
+    assert np.array_equal(sub.array() == 3, expect) and expect.sum() == 16
+    class Right(SubDomain):
+        def inside(self, x, on_boundary):
+            return x[0] >= 0.75 - 1e-12 and not on_boundary        # cells are never "on_boundary"
+    Right().mark(sub, 5)
+    assert (sub.array() == 5).sum() == 8
+    vf = MeshFunction("size_t", mesh, 0)
+    AutoSubDomain(lambda x: near(x[1], 1.0)).mark(vf, 1)
+    assert (vf.array() == 1).sum() == 5
