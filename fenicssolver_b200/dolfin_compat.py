@@ -755,7 +755,33 @@ class _Vector:
         return self._fn.function_space.dim()
 
     def norm(self, kind="l2"):
-        return float(np.linalg.norm(self._fn.array()))
+        a = self._fn.array()
+        kind = kind.lower()
+        if kind == "l2":
+            return float(np.linalg.norm(a))
+        if kind == "l1":
+            return float(np.abs(a).sum())
+        if kind == "linf":
+            return float(np.abs(a).max()) if a.size else 0.0
+        raise SolverError("unknown vector norm %r (l1, l2, linf)" % kind)
+
+    def set_local(self, values):
+        self._fn.assign_array(np.asarray(values, dtype=np.float64))
+
+    def apply(self, mode="insert"):
+        return None                       # dolfin finalises assembly / ghost updates here; nothing to do
+
+    def max(self):
+        return float(self._fn.array().max())
+
+    def min(self):
+        return float(self._fn.array().min())
+
+    def sum(self):
+        return float(self._fn.array().sum())
+
+    def __len__(self):
+        return self.size()
 
 
 class Function:

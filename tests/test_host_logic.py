@@ -526,3 +526,22 @@ def test_cell_function_marking_for_subdomain_sources():
     vf = MeshFunction("size_t", mesh, 0)
     AutoSubDomain(lambda x: near(x[1], 1.0)).mark(vf, 1)
     assert (vf.array() == 1).sum() == 5
+
+
+def test_generic_vector_surface():
+    """u.vector(): the GenericVector calls FEniCS scripts use on a result (get_local/set_local/apply, norms, min/max/sum, indexing)."""
+    from fenicssolver_b200.dolfin_compat import Function
+    V = FunctionSpace(UnitSquareMesh(2, 2), "CG", 1)
+    u = Function(V, np.arange(9.0) - 4.0)
+    v = u.vector()
+    assert len(v) == v.size() == 9 and v.max() == 4.0 and v.min() == -4.0 and v.sum() == 0.0
+    assert abs(v.norm("l2") - np.sqrt(60.0)) < 1e-14 and v.norm("l1") == 20.0 and v.norm("linf") == 4.0
+    v.set_local(np.ones(9))
+    v.apply("insert")
+    v[0] = 5.0
+    assert u.values[0] == 5.0 and np.array_equal(v.get_local()[1:], np.ones(8))
+    g = v.get_local()
+    g[:] = 0.0
+    assert u.values[1] == 1.0                     # get_local returns a copy
+    with pytest.raises(SolverBase.SolverError):
+        v.norm("frobenius")
