@@ -46,6 +46,7 @@ def load():
         lib.fo_spmv.argtypes = [i64, vp, vp, vp, vp, vp]
         lib.fo_pcg_jacobi.restype = C.c_int
         lib.fo_pcg_jacobi.argtypes = [i64, vp, vp, vp, vp, vp, dbl, dbl, C.c_int, C.POINTER(dbl)]
+        lib.fo_zero.argtypes = [vp, i64]
         lib.fo_mg_lambda_max.restype = dbl
         lib.fo_mg_lambda_max.argtypes = [i64, vp, vp, vp]
         lib.fo_mg_apply.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
@@ -114,15 +115,17 @@ class HeatCube:
         self.g[:p * p] = T0
         self.flag[-p * p:] = 1
         self.g[-p * p:] = T1
-        self.vals = np.zeros(self.ci.size)
-        self.b = np.zeros(self.nv)
-        self.x = np.zeros(self.nv)
+        self.vals = np.empty(self.ci.size)          # first touched (and zeroed every step) by fo_zero, in parallel
+        self.b = np.empty(self.nv)
+        self.x = np.empty(self.nv)
+        for a in (self.vals, self.b, self.x):
+            self.lib.fo_zero(_p(a), a.size)
 
     def step(self, rtol=1e-12, maxit=100000):
         lib = self.lib
         t0 = time.perf_counter()
-        self.vals[:] = 0.0
-        self.b[:] = 0.0
+        lib.fo_zero(_p(self.vals), self.vals.size)
+        lib.fo_zero(_p(self.b), self.b.size)
         lib.fo_assemble_heat(self.cells.shape[0], _p(self.cells), _p(self.coords), self.k, self.S, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b))
         lib.fo_apply_dirichlet_sym(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.flag), _p(self.g))
         t1 = time.perf_counter()
@@ -181,8 +184,8 @@ class HeatCubeMG:
         lib = load()
         t0 = time.perf_counter()
         for h in self.cubes:
-            h.vals[:] = 0.0
-            h.b[:] = 0.0
+            lib.fo_zero(_p(h.vals), h.vals.size)
+            lib.fo_zero(_p(h.b), h.b.size)
             lib.fo_assemble_heat(h.cells.shape[0], _p(h.cells), _p(h.coords), h.k, h.S, _p(h.rp), _p(h.ci), _p(h.vals), _p(h.b))
             lib.fo_apply_dirichlet_sym(h.nv, _p(h.rp), _p(h.ci), _p(h.vals), _p(h.b), _p(h.flag), _p(h.g))
         levels = [{"rp": h.rp, "ci": h.ci, "va": h.vals, "bc": h.flag, "dims": (h.N + 1,) * 3} for h in self.cubes]

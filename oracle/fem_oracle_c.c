@@ -40,6 +40,13 @@ void fo_set_num_threads(int n) {
 #endif
 }
 
+/* parallel zero fill with the static schedule the other loops use: first touch places the pages next to the threads that
+ * will stream them (numpy's own fill would put a whole array on one NUMA node and run on one core) */
+void fo_zero(double* a, int64_t n) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) a[i] = 0.0;
+}
+
 static const int HEX_TETS[6][4] = {{0, 1, 3, 7}, {0, 1, 5, 7}, {0, 4, 5, 7}, {0, 2, 3, 7}, {0, 4, 6, 7}, {0, 2, 6, 7}};
 
 /* coords[nverts][3], cells[ncells][4] (sorted per cell) in the dolfin BoxMesh layout */
