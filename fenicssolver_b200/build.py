@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libfsb.so")
-SOURCES = ["fsb_core.cu", "fsb_pattern.cu", "fsb_assemble.cu", "fsb_assemble_p2.cu", "fsb_supg.cu", "fsb_spmv.cu", "fsb_squeeze.cu", "fsb_solve.cu", "fsb_mg.cu", "fsb_dist.cu"]
+SOURCES = ["fsb_core.cu", "fsb_pattern.cu", "fsb_assemble.cu", "fsb_assemble_p2.cu", "fsb_supg.cu", "fsb_spmv.cu", "fsb_squeeze.cu", "fsb_solve.cu", "fsb_cgp.cu", "fsb_mg.cu", "fsb_dist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
@@ -37,7 +37,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     """Compile every CUDA translation unit for sm_100a and link libfsb.so.  Returns its path."""
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "fsb_internal.cuh"), os.path.join(CSRC, "fsb_device.cuh"), os.path.join(CSRC, "fsb_p1.cuh"), os.path.join(ROOT, "include", "fsb.h")]
+    headers = [os.path.join(CSRC, "fsb_internal.cuh"), os.path.join(CSRC, "fsb_device.cuh"), os.path.join(CSRC, "fsb_p1.cuh"), os.path.join(CSRC, "fsb_spmv_core.cuh"), os.path.join(CSRC, "fsb_cgp.cuh"), os.path.join(ROOT, "include", "fsb.h")]
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

@@ -57,6 +57,7 @@ extern "C" void fsb_destroy(fsb_ctx* ctx) {
   cudaFree(ctx->d_scalars);
   cudaFree(ctx->d_counters);
   cudaFree(ctx->d_state);
+  cudaFree(ctx->cg_comm);
   cudaFreeHost(ctx->h_state);
   for (int k = 0; k < 2; ++k) {
     if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
@@ -91,6 +92,8 @@ extern "C" int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value) {
   if (s == "asm_mode") ctx->asm_mode = (int)value;
   else if (s == "drop_zeros") ctx->drop_zeros = (int)value;
   else if (s == "cg_variant") ctx->cg_variant = (int)value;
+  else if (s == "cg_umode") ctx->cg_umode = (int)value;
+  else if (s == "cg_timeout_s") ctx->cg_timeout_s = value < 1 ? 1 : (int)value;
   else if (s == "spmv_hint") ctx->spmv_hint = (int)value;
   else if (s == "spmv_mode") ctx->spmv_mode = (int)value;
   else if (s == "dist_p2p") ctx->dist_p2p = (int)value;

@@ -32,7 +32,10 @@ struct fsb_ctx {
   int use_graph = 1;
   int check_every = 32;
   int spmv_hint = 1;     // L2 evict-first on the matrix stream + streaming stores of y (0: plain)
-  int cg_variant = 0;    // 0 auto (classic on one GPU, single-reduction when distributed), 1 classic, 2 single-reduction
+  int cg_variant = 0;    // 0 auto (persistent kernel where it applies, else classic on one GPU / single-reduction when distributed),
+                         // 1 classic 3-kernel chain, 2 single-reduction 2-kernel chain, 3 persistent kernel (fsb_cgp.cu)
+  int cg_umode = 1;      // persistent kernel, update phase: 0 contiguous row slice per CTA, 1 grid-stride (measured faster)
+  int cg_timeout_s = 30; // watchdog of the persistent kernel's spin loops (a lost peer traps instead of hanging the GPU)
   int drop_zeros = 0;    // Krylov SpMVs run on a copy without the exactly-zero blocks (fsb_squeeze.cu)
   // scratch for reductions: per-CTA partials + a few scalars, and a pinned host mirror
   double* d_partials = nullptr;   // [kMaxPartials * 4]
@@ -44,6 +47,8 @@ struct fsb_ctx {
   void* h_stage[2] = {nullptr, nullptr};   // pinned staging chunks for large downloads into pageable memory
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
   fsb_dist* dist = nullptr;
+  void* cg_comm = nullptr;            // single-GPU mailbox of the persistent CG kernel (a CommBuf)
+  unsigned long long cg_seq = 1;      // its next unused sequence number
   // exact-size block cache in front of the stream-ordered pool (see fsb_dmalloc)
   std::unordered_multimap<size_t, void*> free_blocks;
   std::unordered_map<void*, size_t> live_blocks;

@@ -12,6 +12,7 @@
 #include <cmath>
 
 #include "fsb_device.cuh"
+#include "fsb_cgp.cuh"
 
 // ------------------------------------------------------------------------------------ vector kernels
 static constexpr int kVecThreads = 256;
@@ -323,7 +324,7 @@ enum { C1_G0 = 20, C1_Z0 = 21, C1_D0 = 22, C1_G1 = 24, C1_Z1 = 25, C1_D1 = 26, C
 // start values -> parity-0 slots (and, peer path, the local mailboxes as rank 0's contribution)
 __global__ void k_cg1_seed(double* __restrict__ scal, PeerComm pc, unsigned long long seq) {
   if (threadIdx.x == 0) { scal[C1_G0] = scal[S_RZ0]; scal[C1_Z0] = scal[S_RR0]; }
-  if (pc.nranks > 1 && (int)threadIdx.x < pc.nranks) {
+  if (pc.buf[pc.rank] != nullptr && (int)threadIdx.x < pc.nranks) {
     MailEntry* e = &pc.buf[pc.rank]->mail[MAIL_RZ][threadIdx.x];
     e->v[0] = threadIdx.x == 0 ? scal[S_RZ0] : 0.0;
     e->v[1] = threadIdx.x == 0 ? scal[S_RR0] : 0.0;
@@ -446,6 +447,18 @@ k_cg1_update(int64_t n0, int64_t n1, double* __restrict__ scal, int par, int it,
   else finish_partials<2>(mine, partials, kMaxPartials, scal + (par ? C1_G0 : C1_G1), counter, red);
 }
 
+// can this solve run as one persistent kernel?  One GPU, or z-slabs with the peer mailboxes mapped (the same answer on every rank)
+// Default (cg_variant 0): when distributed — there an iteration is latency-bound (98 us of HBM work per rank at 256^3 on
+// 8 GPUs) and the kernel boundaries of the chains are what it costs.  On one GPU the classic chain moves 8 bytes per row
+// less and is as fast or faster (profiles/cg_ab_r2.txt: 0.843 vs 0.898 ms at 256^3, 0.118 vs 0.117 ms on one slab of it);
+// cg_variant 3 forces the persistent kernel there.
+static bool cg_persist_applies(fsb_ctx* ctx, fsb_mat* S) {
+  if (ctx->cg_variant != 0 && ctx->cg_variant != 3) return false;
+  if (!fsb_cgp_supported(S)) return false;
+  if (!fsb_dist_active(ctx)) return ctx->cg_variant == 3;
+  return fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(S);
+}
+
 static int solve_cg1(fsb_mat* A, fsb_mat* S, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit, int32_t precond,
                      fsb_solve_info* info, cudaEvent_t e0, cudaEvent_t e1) {
   fsb_ctx* ctx = A->ctx;
@@ -453,6 +466,7 @@ static int solve_cg1(fsb_mat* A, fsb_mat* S, fsb_vec* b, fsb_vec* x, double rtol
   const int64_t n0 = A->own0 * A->bs, n1 = A->own1 * A->bs;
   const bool dist = fsb_dist_active(ctx);
   const bool p2p = dist && fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(S);
+  const bool persist = cg_persist_applies(ctx, S);
   Workspace ws{A};
   double *r, *u, *w, *p, *s, *dinv;
   int rc;
@@ -469,6 +483,15 @@ static int solve_cg1(fsb_mat* A, fsb_mat* S, fsb_vec* b, fsb_vec* x, double rtol
     seq_base = fsb_dist_seq_reserve(ctx, 0);
   } else if ((rc = ws.alloc(&u, n))) {
     return rc;
+  }
+  if (persist && !dist) {        // single GPU: the kernel's mailbox is a local CommBuf
+    if (!ctx->cg_comm) {
+      FSB_CHECK_CUDA(ctx, cudaMalloc(&ctx->cg_comm, sizeof(CommBuf)));
+      FSB_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->cg_comm, 0, sizeof(CommBuf), ctx->stream));
+    }
+    cp.pc.rank = 0; cp.pc.nranks = 1;
+    cp.pc.buf[0] = (CommBuf*)ctx->cg_comm;
+    seq_base = ctx->cg_seq;
   }
   double* scal = ctx->d_scalars;
   int* state = ctx->d_state;
@@ -493,6 +516,25 @@ static int solve_cg1(fsb_mat* A, fsb_mat* S, fsb_vec* b, fsb_vec* x, double rtol
   if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + C1_D0, 1))) return rc;
   k_cg1_seed<<<1, 32, 0, ctx->stream>>>(scal, cp.pc, seq_base);
   FSB_LAUNCH_CHECK(ctx);
+
+  if (persist) {
+    // the whole iteration loop in one cooperative launch (fsb_cgp.cu); k_check0 has already decided a zero-iteration solve
+    CgpVectors cv{dinv, u, w, p, s, x->d, r};
+    double phase_ms[4] = {0, 0, 0, 0};
+    if ((rc = fsb_cgp_run(A, S, cv, rtol, atol, maxit, S_BB, S_FINAL_RR, cp.pc, seq_base, phase_ms))) return rc;
+    FSB_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    rc = read_outcome(ctx, S_FINAL_RR, S_BB, info);
+    if (rc) return rc;
+    A->last_iters = info->iterations;
+    if (p2p) fsb_dist_seq_reserve(ctx, (unsigned long long)info->iterations + 2);   // identical on every rank
+    else ctx->cg_seq += (unsigned long long)info->iterations + 2;
+    info->spmv_ms = phase_ms[2];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    info->solve_ms = ms;
+    if (info->converged < 0) FSB_FAIL(ctx, FSB_ERR_BREAKDOWN, "CG breakdown (non-finite or zero recurrence scalar)");
+    return FSB_OK;
+  }
 
   int batch_first, batch_rest;
   batch_plan(ctx, A->last_iters, &batch_first, &batch_rest);
@@ -571,7 +613,8 @@ extern "C" int fsb_solve_cg(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, dou
   if (ctx->drop_zeros && (rc = fsb_mat_squeeze(A, &S))) return rc;
   info->operand_nnzb = S->nnzb;
   // cg_variant: 0 = classic on one GPU, single-reduction when distributed; 1 = classic; 2 = single-reduction
-  if (ctx->cg_variant == 2 || (ctx->cg_variant == 0 && dist)) return solve_cg1(A, S, b, x, rtol, atol, maxit, precond, info, e0, e1);
+  if (ctx->cg_variant == 2 || ctx->cg_variant == 3 || (ctx->cg_variant == 0 && (dist || cg_persist_applies(ctx, S))))
+    return solve_cg1(A, S, b, x, rtol, atol, maxit, precond, info, e0, e1);
   // peer-memory path: mailboxes mapped on every rank, staged SpMV kernel; the decision is the same on every rank
   const bool p2p = dist && fsb_dist_p2p_ready(ctx) && fsb_spmv_supports_p2p(S);
   Workspace ws{A};

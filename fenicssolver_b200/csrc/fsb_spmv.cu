@@ -14,35 +14,9 @@
 //   * fused reductions (y.w, y.y) leave per-CTA partials that the last CTA combines in a fixed order.
 // Modes kept for A/B measurements: 2 = first version (one thread per row, no specialisation),
 // 1 = plain row-per-thread kernel without staging (also the fallback for untileable matrices).
-#include "fsb_device.cuh"
+#include "fsb_spmv_core.cuh"
 #include <algorithm>
 #include <cmath>
-
-struct SpmvArgs {
-  const int64_t* row_ptr;
-  const int32_t* col_idx;
-  const double* vals;
-  const int64_t* tile_row;  // [ntiles+1] first block row per tile
-  const int64_t* tile_k;    // [ntiles+1] row_ptr[tile_row[t]]
-  int64_t ntiles;
-  int64_t own0, own1;       // owned block rows
-  int cap;                  // stage capacity in blocks
-  const double* x;
-  double* y;
-  const double* w;          // optional: d0 = sum y.w
-  int want_yy;              // d1 = sum y.y
-  const double* w2;         // optional: d2 = sum y.w2 (then out has 3 entries)
-  int l2_hint;              // 1: matrix stream marked evict-first in L2, y written with streaming stores
-  double* partials;
-  double* out;              // out[0]=d0, out[1]=d1
-  unsigned* counter;
-  const int* done;          // optional early-exit flag
-  // distributed CG over peer memory (pc.nranks <= 1: off)
-  PeerComm pc;
-  unsigned long long halo_seq;   // != 0: wait until the neighbours have delivered their planes of x (flag >= halo_seq)
-  int mail_slot;                 // >= 0: post (d0, d1) to every rank's mailbox with mail_seq instead of `out`
-  unsigned long long mail_seq;
-};
 
 // ------------------------------------------------------------------------------------ mode 2: first version
 template <int BS, int THREADS>
@@ -120,29 +94,16 @@ __global__ void __launch_bounds__(THREADS) k_spmv_tma(SpmvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------ mode 0: producer/consumer
-template <int BS, int ROWS, int LPR>
-struct SpmvCfg {
-  static constexpr int CONSUMERS = ROWS * LPR;         // ROWS scalar rows per pass
-  static constexpr int THREADS = CONSUMERS + 32;       // + one producer warp
-  static constexpr int RCAP = 2 * (ROWS / BS) + 8;     // block rows whose row_ptr slice fits the stage
-  static constexpr int UNR = BS == 1 ? 8 : 4;          // blocks in flight per lane (x BS gathers each)
-};
-
 template <int BS, int ROWS, int LPR, int NST>
 __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(SpmvArgs a) {
   using Cfg = SpmvCfg<BS, ROWS, LPR>;
-  constexpr int CONSUMERS = Cfg::CONSUMERS, RCAP = Cfg::RCAP, UNR = Cfg::UNR;
+  constexpr int CONSUMERS = Cfg::CONSUMERS;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[NST], empty[NST];
   __shared__ int64_t s_info[NST][4];    // per stage: r0, r1, aligned first nnz, aligned first row (or -1: row_ptr not staged)
   __shared__ double red[32];
   if (a.done && *a.done) return;
-  constexpr int VB = 8 * BS * BS;
-  const size_t rp_bytes = (size_t)(RCAP + 4) * 8;
-  const size_t stage_bytes = (size_t)a.cap * (VB + 4) + rp_bytes;
-  auto vals_s = [&](int s) { return reinterpret_cast<const double*>(smem + s * stage_bytes); };
-  auto cols_s = [&](int s) { return reinterpret_cast<const int32_t*>(smem + s * stage_bytes + (size_t)a.cap * VB); };
-  auto rptr_s = [&](int s) { return reinterpret_cast<const int64_t*>(smem + s * stage_bytes + (size_t)a.cap * (VB + 4)); };
+  const SpmvStage<BS, ROWS, LPR> st(smem, a.cap);
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -168,87 +129,17 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
       const int s = it % NST;
       if (threadIdx.x == CONSUMERS) {
         if (it >= NST) mbar_wait(&empty[s], ((it / NST) - 1) & 1);      // consumers have drained this stage
-        const int64_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
-        const int64_t k0 = a.tile_k[tile], k1 = a.tile_k[tile + 1];
-        s_info[s][0] = r0; s_info[s][1] = r1;
-        if (r1 <= r0) {
-          mbar_arrive(&full[s]);
-        } else {
-          const int64_t al0 = k0 & ~3ll;
-          const uint32_t cnt = (uint32_t)(((k1 - al0) + 3) & ~3ll);
-          const int64_t ra0 = r0 & ~1ll;
-          const bool stage_rp = (r1 - ra0 + 1) <= RCAP;
-          const uint32_t nrp = stage_rp ? (uint32_t)(((r1 - ra0 + 1) + 1) & ~1ll) : 0u;
-          s_info[s][2] = al0; s_info[s][3] = stage_rp ? ra0 : -1;
-          mbar_expect_tx(&full[s], cnt * (VB + 4) + nrp * 8);
-          if (a.l2_hint) {
-            bulk_g2s_hint((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &full[s], policy);
-            bulk_g2s_hint((void*)cols_s(s), a.col_idx + al0, cnt * 4, &full[s], policy);
-            if (stage_rp) bulk_g2s_hint((void*)rptr_s(s), a.row_ptr + ra0, nrp * 8, &full[s], policy);
-          } else {
-            bulk_g2s((void*)vals_s(s), a.vals + al0 * BS * BS, cnt * VB, &full[s]);
-            bulk_g2s((void*)cols_s(s), a.col_idx + al0, cnt * 4, &full[s]);
-            if (stage_rp) bulk_g2s((void*)rptr_s(s), a.row_ptr + ra0, nrp * 8, &full[s]);
-          }
-        }
+        spmv_issue_tile<BS, ROWS, LPR>(a, st, tile, s, s_info[s], &full[s], policy);
       }
       __syncwarp();
     }
   } else {
     // ===== consumer warps =====
-    const int sub = threadIdx.x % LPR;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const int s = it % NST;
       mbar_wait(&full[s], (it / NST) & 1);
-      const int64_t r0 = s_info[s][0], r1 = s_info[s][1];
-      if (r1 > r0) {
-        const int64_t al0 = s_info[s][2], ra0 = s_info[s][3];
-        const double* __restrict__ vs = vals_s(s);
-        const int32_t* __restrict__ cs = cols_s(s);
-        const int64_t* __restrict__ rp = rptr_s(s);
-        const int nscalar = (int)(r1 - r0) * BS;
-        for (int base = 0; base < nscalar; base += ROWS) {       // warp-uniform trip count
-          const int lr = base + threadIdx.x / LPR;
-          const bool live = lr < nscalar;
-          const int64_t R = r0 + (live ? lr / BS : 0);
-          const int i = live ? lr % BS : 0;
-          const int64_t row = R * BS + i;
-          int ks, ke;
-          if (ra0 >= 0) { ks = (int)(rp[R - ra0] - al0); ke = (int)(rp[R + 1 - ra0] - al0); }
-          else { ks = (int)(a.row_ptr[R] - al0); ke = (int)(a.row_ptr[R + 1] - al0); }
-          if (!live) ke = ks;
-          const double wv = (a.w && live && sub == 0) ? __ldg(a.w + row) : 0.0;   // issued with the gathers
-          const double wv2 = (a.w2 && live && sub == 0) ? __ldg(a.w2 + row) : 0.0;
-          double acc = 0.0;
-          for (int k = ks + sub; k < ke; k += LPR * UNR) {
-            double v[UNR][BS], xg[UNR][BS];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-              const int kk = k + u * LPR;
-              const bool ok = kk < ke;
-              const int64_t c = ok ? cs[kk] : 0;
-#pragma unroll
-              for (int j = 0; j < BS; ++j) {
-                v[u][j] = ok ? vs[(kk * BS + i) * BS + j] : 0.0;
-                xg[u][j] = ok ? __ldg(a.x + c * BS + j) : 0.0;
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-              for (int j = 0; j < BS; ++j) acc += v[u][j] * xg[u][j];
-          }
-#pragma unroll
-          for (int o = LPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          if (live && sub == 0) {
-            if (a.l2_hint) __stcs(a.y + row, acc); else a.y[row] = acc;
-            d0 += acc * wv;
-            if (a.want_yy) d1 += acc * acc;
-            d2 += acc * wv2;
-          }
-        }
-      }
+      spmv_consume_tile<BS, ROWS, LPR, false>(a, st, s, s_info[s], d0, d1, d2);
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);      // this warp is done with stage s
     }
@@ -386,6 +277,36 @@ int fsb_mat_setup_tiles(fsb_mat* A) {
 // ------------------------------------------------------------------------------------ launch
 bool fsb_spmv_supports_p2p(fsb_mat* A) { return A->ctx->spmv_mode == 0 && A->ntiles > 0; }
 
+// the staged kernel's configuration for A, and the matrix part of its arguments (shared with the persistent CG kernel)
+int fsb_spmv_plan(fsb_mat* A, SpmvPlan* plan) {
+  fsb_ctx* ctx = A->ctx;
+  if (A->own1 <= A->own0) return FSB_ERR_STATE;
+  if (ctx->spmv_mode != 1 && A->tile_rows != spmv_rows(ctx, A)) {
+    int rc = fsb_mat_setup_tiles(A);      // the tile size option changed since the matrix was set up
+    if (rc) return rc;
+  }
+  if (ctx->spmv_mode != 0 || A->ntiles <= 0) return FSB_ERR_STATE;
+  plan->bs = A->bs;
+  plan->rows = A->tile_rows;
+  plan->lpr = spmv_lpr(ctx, A);
+  plan->nst = std::max(2, std::min(spmv_stages(ctx, A), (int)((224 * 1024) / A->stage_bytes)));
+  plan->smem = (size_t)plan->nst * A->stage_bytes;
+  const int threads = plan->rows * plan->lpr + 32;
+  plan->per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / threads, (227 * 1024) / (plan->smem + 1024)));
+  return FSB_OK;
+}
+
+void fsb_spmv_fill_args(fsb_mat* A, SpmvArgs* a) {
+  fsb_ctx* ctx = A->ctx;
+  a->row_ptr = A->row_ptr; a->col_idx = A->col_idx; a->vals = A->vals;
+  a->tile_row = A->tile_row; a->tile_k = A->tile_row ? A->tile_row + A->ntiles + 1 : nullptr;
+  a->ntiles = A->ntiles; a->own0 = A->own0; a->own1 = A->own1; a->cap = A->tile_cap;
+  a->x = nullptr; a->y = nullptr; a->w = nullptr; a->want_yy = 0; a->w2 = nullptr; a->l2_hint = ctx->spmv_hint;
+  a->partials = ctx->d_partials; a->out = nullptr; a->counter = ctx->d_counters + 0; a->done = nullptr;
+  memset(&a->pc, 0, sizeof(a->pc));
+  a->halo_seq = 0; a->mail_slot = -1; a->mail_seq = 0;
+}
+
 int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int want_yy, double* out, const int* done,
                     const fsb_spmv_dist* dd, const double* w2) {
   fsb_ctx* ctx = A->ctx;
@@ -395,13 +316,8 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
     if (rc) return rc;
   }
   SpmvArgs a;
-  a.row_ptr = A->row_ptr; a.col_idx = A->col_idx; a.vals = A->vals;
-  a.tile_row = A->tile_row; a.tile_k = A->tile_row ? A->tile_row + A->ntiles + 1 : nullptr;
-  a.ntiles = A->ntiles; a.own0 = A->own0; a.own1 = A->own1; a.cap = A->tile_cap;
-  a.x = x; a.y = y; a.w = w; a.want_yy = want_yy; a.w2 = w2; a.l2_hint = ctx->spmv_hint;
-  a.partials = ctx->d_partials; a.out = out; a.counter = ctx->d_counters + 0; a.done = done;
-  memset(&a.pc, 0, sizeof(a.pc));
-  a.halo_seq = 0; a.mail_slot = -1; a.mail_seq = 0;
+  fsb_spmv_fill_args(A, &a);
+  a.x = x; a.y = y; a.w = w; a.want_yy = want_yy; a.w2 = w2; a.out = out; a.done = done;
   if (dd) {
     if (!fsb_spmv_supports_p2p(A)) FSB_FAIL(ctx, FSB_ERR_STATE, "peer-memory SpMV needs the staged kernel (spmv_mode 0)");
     a.pc = dd->pc; a.halo_seq = dd->halo_seq; a.mail_slot = dd->mail_slot; a.mail_seq = dd->mail_seq;

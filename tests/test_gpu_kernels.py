@@ -628,3 +628,95 @@ def test_single_reduction_cg_matches_classic(ctx, drop_zeros):
     finally:
         ctx.set_option("cg_variant", 0)
         ctx.set_option("drop_zeros", 0)
+
+
+def _heat_system_on_device(ctx, N, dim=3, jit=False):
+    if dim == 3:
+        c, t, z0, z1 = heat_problem(N, jit=jit)
+    else:
+        c, t = fo.unit_square_mesh(N, N)
+        z0 = np.nonzero(c[:, 1] == 0)[0]
+        z1 = np.nonzero(c[:, 1] == 1)[0]
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    dofs = np.concatenate([z0, z1])
+    vals = np.concatenate([np.full(z0.size, 350.0), np.full(z1.size, 300.0)])
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=20.0)
+    b = _lib.DeviceVector(ctx, nv)
+    _lib.assemble_source(m, b, 1000.0)
+    x = _lib.DeviceVector(ctx, nv)
+    A.apply_dirichlet(b, dofs, vals, symmetric=True, x=x)
+    return m, A, b, x.numpy()
+
+
+@pytest.mark.parametrize("case", ["cube6", "cube20_jitter", "cube48", "square40"])
+def test_persistent_cg_kernel_matches_kernel_chains(ctx, case):
+    """cg_variant 3 — the whole iteration loop in one cooperative launch (fsb_cgp.cu: worker CTAs + a service CTA, grid
+    barrier on an arrival counter, reductions through the mailbox) — against the classic chain (1) and the two-kernel
+    single-reduction chain (2) it shares its recurrences with: same solution, same iteration count as (2), maxit honoured,
+    converged start untouched, bitwise reproducible.  cube6 has fewer tiles than SMs (few workers); cube48 fills the grid;
+    square40 has short rows (one lane per row)."""
+    dim = 2 if case.startswith("square") else 3
+    N = int("".join(ch for ch in case.split("_")[0] if ch.isdigit()))
+    m, A, b, x0 = _heat_system_on_device(ctx, N, dim=dim, jit=case.endswith("jitter"))
+    res = {}
+    try:
+        for variant in (1, 2, 3, 3):
+            ctx.set_option("cg_variant", variant)
+            xv = _lib.DeviceVector.from_numpy(ctx, x0)
+            info = A.solve(b, xv, "cg", rtol=1e-12)
+            assert info["converged"] == 1 and info["rnorm"] <= 1e-12 * info["bnorm"]
+            res.setdefault(variant, []).append((xv.numpy(), info["iterations"]))
+        assert fo.relative_l2(res[3][0][0], res[1][0][0]) < 1e-11
+        assert fo.relative_l2(res[3][0][0], res[2][0][0]) < 1e-11
+        assert abs(res[3][0][1] - res[2][0][1]) <= 1 and abs(res[3][0][1] - res[1][0][1]) <= 2
+        assert res[3][0][1] == res[3][1][1] and np.array_equal(res[3][0][0], res[3][1][0])       # reproducible
+        ctx.set_option("cg_variant", 3)
+        for maxit in (1, 5, 33):
+            xv = _lib.DeviceVector.from_numpy(ctx, x0)
+            info = A.solve(b, xv, "cg", rtol=1e-30, maxit=maxit)
+            assert info["converged"] == 0 and info["iterations"] == maxit
+            ctx.set_option("cg_variant", 2)
+            xc = _lib.DeviceVector.from_numpy(ctx, x0)
+            A.solve(b, xc, "cg", rtol=1e-30, maxit=maxit)
+            ctx.set_option("cg_variant", 3)
+            assert fo.relative_l2(xv.numpy(), xc.numpy()) < 1e-7      # rounding differences grow with the iteration count
+        xs = _lib.DeviceVector.from_numpy(ctx, res[1][0][0])
+        info = A.solve(b, xs, "cg", rtol=1e-9)
+        assert info["converged"] == 1 and info["iterations"] == 0
+        assert np.array_equal(xs.numpy(), res[1][0][0])
+        z = _lib.DeviceVector(ctx, x0.size)
+        info = A.solve(z, _lib.DeviceVector(ctx, x0.size), "cg", rtol=1e-12)       # b = 0
+        assert info["converged"] == 1 and info["iterations"] == 0
+    finally:
+        ctx.set_option("cg_variant", 0)
+
+
+def test_persistent_cg_kernel_block3(ctx):
+    """The 3x3-block instantiation of the persistent kernel on the elasticity cantilever, against the classic chain."""
+    N = 10
+    c, t = fo.box_mesh((0, 0, 0), (4, 1, 1), 2 * N, N, N)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    A = _lib.DeviceMatrix.create(m, 3)
+    E, nu = 2e11, 0.27
+    A.assemble_elasticity(E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu)))
+    nv = c.shape[0]
+    b = _lib.DeviceVector(ctx, 3 * nv)
+    _lib.assemble_source(m, b, [0.0, 0.0, -7800 * 9.81], ncomp=3)
+    fixed = np.nonzero(c[:, 0] == 0)[0]
+    dofs = (3 * fixed[:, None] + np.arange(3)).ravel()
+    x = _lib.DeviceVector(ctx, 3 * nv)
+    A.apply_dirichlet(b, dofs, np.zeros(dofs.size), symmetric=True, x=x)
+    res = {}
+    try:
+        for variant in (1, 3):
+            ctx.set_option("cg_variant", variant)
+            xv = _lib.DeviceVector(ctx, 3 * nv)
+            info = A.solve(b, xv, "cg", rtol=1e-12, maxit=20000)
+            assert info["converged"] == 1
+            res[variant] = (xv.numpy(), info["iterations"])
+        assert fo.relative_l2(res[3][0], res[1][0]) < 1e-9
+        assert abs(res[3][1] - res[1][1]) <= max(3, res[1][1] // 50)
+    finally:
+        ctx.set_option("cg_variant", 0)

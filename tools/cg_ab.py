@@ -10,10 +10,14 @@ from fenicssolver_b200 import _lib, backend  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 ITERS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+NZ = int(sys.argv[3]) if len(sys.argv) > 3 else N          # N x N x NZ cells: NZ = N/8 is one rank's slab of an 8-GPU run
+VARIANTS = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1, 2, 3]
 ctx = backend.get_context()
 ctx.set_option("profile", 1)
-m = _lib.DeviceMesh.box(ctx, (N, N, N), (0, 0, 0), (1, 1, 1))
-nv = (N + 1) ** 3
+if os.environ.get("FSB_CG_UMODE"):
+    ctx.set_option("cg_umode", int(os.environ["FSB_CG_UMODE"]))
+m = _lib.DeviceMesh.box(ctx, (N, N, NZ), (0, 0, 0), (1, 1, NZ / N))
+nv = (N + 1) ** 2 * (NZ + 1)
 A = _lib.DeviceMatrix.create(m, 1)
 A.assemble_scalar(kscale=20.0)
 b = _lib.DeviceVector(ctx, nv)
@@ -24,8 +28,8 @@ vals = np.concatenate([np.full(plane, 350.0), np.full(plane, 300.0)])
 x = _lib.DeviceVector(ctx, nv)
 A.apply_dirichlet(b, dofs, vals, symmetric=True, x=x)
 nnz = A.sizes()["nnz"]
-for variant in (1, 2):
-    for hint in (0, 1):
+for variant in VARIANTS:
+    for hint in (1,):
         for dz in (0, 1):
             ctx.set_option("cg_variant", variant)
             ctx.set_option("spmv_hint", hint)
@@ -39,5 +43,5 @@ for variant in (1, 2):
                 cur = (info["solve_ms"] / it, info["spmv_ms"] / it)
                 best = cur if best is None or cur[0] < best[0] else best
             gb = (12 * info["operand_nnzb"] + 24 * nv) / 1e9
-            print("N=%d variant=%d hint=%d drop_zeros=%d : iteration %.4f ms  spmv %.4f ms (%.0f GB/s)  vector part %.4f ms"
-                  % (N, variant, hint, dz, best[0], best[1], gb / best[1] * 1e3, best[0] - best[1]), flush=True)
+            print("N=%d NZ=%d variant=%d hint=%d drop_zeros=%d : iteration %.4f ms  spmv %.4f ms (%.0f GB/s)  vector part %.4f ms"
+                  % (N, NZ, variant, hint, dz, best[0], best[1], gb / best[1] * 1e3, best[0] - best[1]), flush=True)
