@@ -485,8 +485,11 @@ class SolverBase():
         self._last_x = x
         if self.parallel and self.solver_settings.get('gather_result', True):
             u.assign_array(space.gather_global(x))      # every rank gets the global vertex-ordered vector
-        elif not self.parallel:
-            u.set_device(x)
+        else:
+            # one GPU: the solution stays on the device until someone asks for the array.  Distributed without gather_result:
+            # the Function keeps this rank's part (owned + ghosts), which is what the next time step's T_prev term and the
+            # Krylov start vector consume; the global array is only available through gather_result / local_result()
+            u.set_device(x, local=self.parallel)
         return u
 
     def multigrid_hierarchy(self, space):
@@ -613,8 +616,8 @@ class SolverBase():
         self._last_x = x
         if dist and self.solver_settings.get('gather_result', True):
             u_current.assign_array(space.gather_global(x))
-        elif not dist:
-            u_current.set_device(x)
+        else:
+            u_current.set_device(x, local=dist)
         return u_current
 
 

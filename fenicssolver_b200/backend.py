@@ -267,6 +267,11 @@ class DeviceSpace:
         u = fn.uniform_value()
         if u is not None:
             return self.vector(fill=u)
+        dev = fn.device_vector()
+        if dev is not None and getattr(fn, "_local", False) and dev.n == self.ndof_local:
+            self.activate()
+            dev.halo()                                  # a solve leaves the ghosts of its solution vector stale
+            return dev
         return self.vector_from_global(fn.array())
 
     def owned_values(self, dvec):

@@ -45,6 +45,7 @@ struct CgpArgs {
   PeerComm pc;                 // nranks == 1: buf[0] is a local CommBuf
   unsigned long long seq_base;
   unsigned long long timeout_ns;
+  int debug;                   // timing experiments only (results are wrong): 1 skip the peer stores, 2 skip their system fence
   int umode;                   // update-phase row partition: 0 one contiguous slice per CTA, 1 grid-stride
   unsigned long long* phase_ns;  // [4] accumulated by worker 0: U, B1 wait, S, top wait (profile mode) or null
 };
@@ -57,6 +58,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// streaming 16-byte load that does not allocate a line in L1: the kernel runs with ~200 KB of the SM's 256 KB configured as
+// shared memory and the update phase's seven streams compete for what is left of L1 (measured: 178.5 -> 169.1 us per update
+// phase on the 2-GPU slab of 256^3 against ld.global.cs, profiles/cg_offset_ab_r2.txt)
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void bar_consumers(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
@@ -118,7 +127,6 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
   __shared__ int64_t s_info[NST][4];
   __shared__ double red[32];
   __shared__ double s_mail[2][2][kMaxRanks][2];     // [iteration parity][slot: RZ, PQ][rank][value]
-  __shared__ double s_tot[3];
   const SpmvStage<BS, ROWS, LPR> st(smem, a.sp.cap);
   const int tid = threadIdx.x;
   const int W = (int)gridDim.x - 1;                 // worker CTAs; the last CTA is the service CTA
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
   const bool timing = a.phase_ns != nullptr && c == 0 && tid == 0;
   if (timing) t_mark = globaltimer_ns();
 
+  if (service && tid >= 32) return;     // the service CTA works with one warp (its block-wide barriers below are warp barriers)
   for (int it = 0;; ++it) {
     const int par = it & 1;
     const unsigned long long seq = a.seq_base + (unsigned long long)it;
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
         s_mail[par][which][rk][1] = *reinterpret_cast<const volatile double*>(&e->v[1]);
       }
     }
-    __syncthreads();
+    if (service) __syncwarp(); else __syncthreads();
     if (timing) { const unsigned long long t = globaltimer_ns(); a.phase_ns[3] += t - t_mark; t_mark = t; }
     double g = 0.0, zz = 0.0, d = 0.0;
     for (int rk = 0; rk < a.pc.nranks; ++rk) { g += s_mail[par][0][rk][0]; zz += s_mail[par][0][rk][1]; d += s_mail[par][1][rk][0]; }
@@ -203,38 +212,30 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
     g_prev = g; a_prev = alpha;
 
     if (service) {
-      // ---------------- service CTA: B1 -> halo flags + (r.u, u.u); B2 -> w.u
+      // ---------------- service CTA (its first warp; the others have left): B1 -> halo flags + (r.u, u.u); B2 -> w.u.
+      // One warp, shuffles only: nothing on this path waits for a block-wide barrier
       if (tid == 0) spin_until<false>(a.arrive, (unsigned long long)(2 * it + 1) * (unsigned long long)W, a.timeout_ns);
-      __syncthreads();
+      __syncwarp();
       if (peer && tid == 0) {         // every worker's peer stores happen-before its arrival: the new planes are in place
         if (a.pc.rank > 0) st_release_sys(&a.pc.buf[a.pc.rank - 1]->halo_flag[1], seq + 1);
         if (a.pc.rank < a.pc.nranks - 1) st_release_sys(&a.pc.buf[a.pc.rank + 1]->halo_flag[0], seq + 1);
       }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        double v = 0.0;
-        for (int i = tid; i < W; i += blockDim.x) v += __ldcg(a.part_u + k * kMaxPartials + i);
-        v = block_sum(v, red);
-        if (tid == 0) s_tot[k] = v;
-      }
-      __syncthreads();
+      double t0 = 0.0, t1 = 0.0;
+      for (int i = tid; i < W; i += 32) { t0 += __ldcg(a.part_u + i); t1 += __ldcg(a.part_u + kMaxPartials + i); }
+      t0 = warp_sum(t0); t1 = warp_sum(t1);
       if (tid < a.pc.nranks) {
         MailEntry* e = &a.pc.buf[tid]->mail[MAIL_RZ + (par ^ 1)][a.pc.rank];
-        e->v[0] = s_tot[0]; e->v[1] = s_tot[1];
+        e->v[0] = t0; e->v[1] = t1;
         st_release_sys(&e->seq, seq + 1);
       }
       if (tid == 0) spin_until<false>(a.arrive, (unsigned long long)(2 * it + 2) * (unsigned long long)W, a.timeout_ns);
-      __syncthreads();
-      {
-        double v = 0.0;
-        for (int i = tid; i < W; i += blockDim.x) v += __ldcg(a.part_s + i);
-        v = block_sum(v, red);
-        if (tid == 0) s_tot[2] = v;
-      }
-      __syncthreads();
+      __syncwarp();
+      double t2 = 0.0;
+      for (int i = tid; i < W; i += 32) t2 += __ldcg(a.part_s + i);
+      t2 = warp_sum(t2);
       if (tid < a.pc.nranks) {
         MailEntry* e = &a.pc.buf[tid]->mail[MAIL_PQ + (par ^ 1)][a.pc.rank];
-        e->v[0] = s_tot[2]; e->v[1] = 0.0;
+        e->v[0] = t2; e->v[1] = 0.0;
         st_release_sys(&e->seq, seq + 1);
       }
       continue;
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
       double s0 = 0.0, s1 = 0.0;
       bool pushed = false;
       auto push = [&](int64_t i, double v) {       // owned boundary planes -> neighbours' ghost planes
+        if (a.debug & 1) return;
         if (a.pc.lo_dst && i < n0 + plane) { a.pc.lo_dst[i - n0] = v; pushed = true; }
         if (a.pc.hi_dst && i >= n1 - plane) { a.pc.hi_dst[i - (n1 - plane)] = v; pushed = true; }
       };
@@ -286,10 +288,14 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
         s0 += ri * ui; s1 += ui * ui;
         if (peer) push(i, ui);
       };
-      const int64_t a_up = (n0 + 1) & ~(int64_t)1;
+      // the body starts on a 512-byte boundary = one warp request of 16-byte accesses.  A rank with a lower ghost plane owns rows
+      // from an odd offset on; measured on the 2-GPU slab of 256^3 (profiles/cg_offset_ab_r2.txt): 16-byte aligned body 218 us,
+      // 128-byte 194-199 us, 512-byte 179 us = the time of the rank whose range starts at 0
+      const int64_t amask = 63;
+      const int64_t a_up = (n0 + amask) & ~amask;
       const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
-      if (c == 0 && tid == 0 && a0 > n0) one(n0);
-      if (c == 0 && tid == 1 && a0 + 2 * npair < n1) one(n1 - 1);
+      if (c == 0) for (int64_t i = n0 + tid; i < a0; i += CONSUMERS) one(i);
+      if (c == 1 % W && tid == 32 && a0 + 2 * npair < n1) one(n1 - 1);
       const int64_t jq = npair / W, jr = npair % W;
       const int64_t j0 = a.umode ? (int64_t)c * CONSUMERS : jq * c + (c < jr ? c : jr);
       const int64_t j1 = a.umode ? npair : j0 + jq + (c < jr ? 1 : 0);
@@ -297,10 +303,8 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
       for (int64_t j = j0 + tid; j < j1; j += jstep) {
         const int64_t i = a0 + 2 * j;
         const double2 uv = *reinterpret_cast<const double2*>(a.u + i);
-        const double2 wv = __ldcs(reinterpret_cast<const double2*>(a.w + i));
-        double2 pv = __ldcs(reinterpret_cast<const double2*>(a.p + i)), sv = __ldcs(reinterpret_cast<const double2*>(a.s + i));
-        double2 xv = __ldcs(reinterpret_cast<const double2*>(a.x + i)), rv = __ldcs(reinterpret_cast<const double2*>(a.r + i));
-        const double2 dv = __ldcs(reinterpret_cast<const double2*>(a.dinv + i));
+        const double2 wv = ld_stream2(a.w + i), dv = ld_stream2(a.dinv + i);
+        double2 pv = ld_stream2(a.p + i), sv = ld_stream2(a.s + i), xv = ld_stream2(a.x + i), rv = ld_stream2(a.r + i);
         pv.x = uv.x + beta * pv.x; pv.y = uv.y + beta * pv.y;
         sv.x = wv.x + beta * sv.x; sv.y = wv.y + beta * sv.y;
         xv.x += alpha * pv.x; xv.y += alpha * pv.y;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS, MINB) k_cg_pe
         s1 += un.x * un.x + un.y * un.y;
         if (peer) { push(i, un.x); push(i + 1, un.y); }
       }
-      if (pushed) __threadfence_system();
+      if (pushed && !(a.debug & 2)) __threadfence_system();
       s0 = consumer_sum(s0, red, CONSUMERS);
       s1 = consumer_sum(s1, red, CONSUMERS);
       // ---------------- B1: u is complete on this rank once every worker has arrived
@@ -378,6 +382,7 @@ int fsb_cgp_run(fsb_mat* A, fsb_mat* S, const CgpVectors& v, double rtol, double
   a.timeout_ns = (unsigned long long)std::max(1, ctx->cg_timeout_s) * 1000000000ull;
   a.phase_ns = nullptr;
   a.umode = ctx->cg_umode;
+  a.debug = ctx->cg_debug;
   if (ctx->profile) {
     a.phase_ns = reinterpret_cast<unsigned long long*>(ctx->d_scalars + 48);
     FSB_CHECK_CUDA(ctx, cudaMemsetAsync(a.phase_ns, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -413,8 +418,8 @@ int fsb_cgp_run(fsb_mat* A, fsb_mat* S, const CgpVectors& v, double rtol, double
     for (int k = 0; k < 4; ++k) phase_ms[k] = (double)ns[k] * 1e-6;
     static const bool trace = getenv("FSB_SOLVE_TRACE") != nullptr;
     if (trace)
-      fprintf(stderr, "libfsb: persistent CG, %d workers x %d threads: update %.3f ms, barrier wait %.3f ms, SpMV %.3f ms, scalar wait %.3f ms (worker 0)\n",
-              workers, threads, phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3]);
+      fprintf(stderr, "libfsb: rank %d persistent CG, %d workers x %d threads: update %.3f ms, barrier wait %.3f ms, SpMV %.3f ms, scalar wait %.3f ms (worker 0)\n",
+              pc.rank, workers, threads, phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3]);
   }
   return FSB_OK;
 }

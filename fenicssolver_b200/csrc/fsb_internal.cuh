@@ -35,6 +35,8 @@ struct fsb_ctx {
   int cg_variant = 0;    // 0 auto (persistent kernel where it applies, else classic on one GPU / single-reduction when distributed),
                          // 1 classic 3-kernel chain, 2 single-reduction 2-kernel chain, 3 persistent kernel (fsb_cgp.cu)
   int cg_umode = 1;      // persistent kernel, update phase: 0 contiguous row slice per CTA, 1 grid-stride (measured faster)
+  int vec_skew = 0;      // bytes between the start offsets of consecutive Krylov work vectors inside their blocks (multiple of 256, <= 8192)
+  int cg_debug = 0;      // persistent kernel timing experiments (wrong results): 1 no peer stores, 2 no system fence after them
   int cg_timeout_s = 30; // watchdog of the persistent kernel's spin loops (a lost peer traps instead of hanging the GPU)
   int drop_zeros = 0;    // Krylov SpMVs run on a copy without the exactly-zero blocks (fsb_squeeze.cu)
   // scratch for reductions: per-CTA partials + a few scalars, and a pinned host mirror

@@ -131,12 +131,14 @@ k_cg_update(int64_t n0, int64_t n1, const double* __restrict__ scal, int rz_slot
     s0 += ri * zi;
     s1 += zi * zi;
   };
-  // 16-byte accesses over the even-aligned body (two rows per thread and trip: twice the bytes in flight)
+  // 16-byte accesses over a body that starts on a 512-byte boundary (one warp request): a distributed rank's owned range starts
+  // one vertex plane (an odd number of doubles) into its vectors, and a body that is only 16-byte aligned makes every
+  // quarter-warp request straddle two lines (measured: the update phase 25 % slower on such a rank, profiles/cg_offset_ab_r2.txt)
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  const int64_t a_up = (n0 + 1) & ~(int64_t)1;
+  const int64_t a_up = (n0 + 63) & ~(int64_t)63;      // 512-byte aligned body
   const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
-  if (tid == 0 && a0 > n0) one(n0);
-  if (tid == 1 && a0 + 2 * npair < n1) one(n1 - 1);
+  if (tid < a0 - n0) one(n0 + tid);
+  if (tid == 64 && a0 + 2 * npair < n1) one(n1 - 1);
   // two 16-byte pairs per thread and trip, all ten loads issued before the first use (bytes in flight, not occupancy,
   // is what a 7-stream kernel needs to reach the HBM rate)
   for (int64_t j = tid; j < npair; j += 2 * nth) {
@@ -199,10 +201,10 @@ k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int 
     if (cp.pc.hi_dst && i >= n1 - plane) cp.pc.hi_dst[i - (n1 - plane)] = v;
   };
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  const int64_t a_up = (n0 + 1) & ~(int64_t)1;
+  const int64_t a_up = (n0 + 63) & ~(int64_t)63;
   const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
-  if (tid == 0 && a0 > n0) { const double v = dinv[n0] * r[n0] + beta * p[n0]; p[n0] = v; if (peer) push(n0, v); }
-  if (tid == 1 && a0 + 2 * npair < n1) { const double v = dinv[n1 - 1] * r[n1 - 1] + beta * p[n1 - 1]; p[n1 - 1] = v; if (peer) push(n1 - 1, v); }
+  if (tid < a0 - n0) { const int64_t i = n0 + tid; const double v = dinv[i] * r[i] + beta * p[i]; p[i] = v; if (peer) push(i, v); }
+  if (tid == 64 && a0 + 2 * npair < n1) { const double v = dinv[n1 - 1] * r[n1 - 1] + beta * p[n1 - 1]; p[n1 - 1] = v; if (peer) push(n1 - 1, v); }
   for (int64_t j = tid; j < npair; j += 2 * nth) {
     const int64_t i = a0 + 2 * j, k = i + 2 * nth;
     const bool two = j + nth < npair;
@@ -251,18 +253,22 @@ k_cg_pupdate(int64_t n0, int64_t n1, double* __restrict__ scal, int rz_old, int 
 // Work vectors live on the matrix and are reused by later solves (cudaMalloc/cudaFree synchronise the
 // device; a transient run solves every step).  Every vector is zeroed at hand-out: ghost entries of a
 // distributed solve are read by the SpMV gathers before the first halo exchange touches them.
+static constexpr int kMaxSkew = 64 * 1024;     // bytes; 8 work vectors x the largest accepted vec_skew
 struct Workspace {
   fsb_mat* A;
   int next = 0;
   int alloc(double** p, int64_t n) {
     fsb_ctx* ctx = A->ctx;
     if (next >= 8) FSB_FAIL(ctx, FSB_ERR_STATE, "Krylov workspace exhausted");
+    // vec_skew: work vector k starts k * skew bytes into its block, so that the streams of a fused vector kernel (which all
+    // advance at the same index) do not sit at the same offset of equally sized, equally aligned allocations
+    const size_t skew = (size_t)ctx->vec_skew * (size_t)next;
     if (next >= A->work_count) {
-      int rc = fsb_dmalloc(ctx, &A->work[next], (size_t)n);
+      int rc = fsb_dmalloc(ctx, &A->work[next], (size_t)n, 512 + 8 * (size_t)kMaxSkew);
       if (rc) return rc;
       A->work_count = next + 1;
     }
-    *p = A->work[next++];
+    *p = A->work[next++] + skew / sizeof(double);
     FSB_CHECK_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(double) * n, ctx->stream));
     return FSB_OK;
   }
@@ -403,10 +409,10 @@ k_cg1_update(int64_t n0, int64_t n1, double* __restrict__ scal, int par, int it,
     if (peer) push(i, ui);
   };
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  const int64_t a_up = (n0 + 1) & ~(int64_t)1;
+  const int64_t a_up = (n0 + 63) & ~(int64_t)63;      // 512-byte aligned body
   const int64_t a0 = a_up < n1 ? a_up : n1, npair = (n1 - a0) >> 1;
-  if (tid == 0 && a0 > n0) one(n0);
-  if (tid == 1 && a0 + 2 * npair < n1) one(n1 - 1);
+  if (tid < a0 - n0) one(n0 + tid);
+  if (tid == 64 && a0 + 2 * npair < n1) one(n1 - 1);
   for (int64_t j = tid; j < npair; j += nth) {
     const int64_t i = a0 + 2 * j;
     const double2 uv = *reinterpret_cast<const double2*>(u + i);

@@ -805,6 +805,9 @@ class Function:
 
     def array(self):
         if not self._host_valid:
+            if getattr(self, "_local", False):
+                raise SolverError("this Function holds one rank's part of a distributed solution (solver_settings['gather_result'] = False): "
+                                  "the global nodal array was never assembled; use solver.local_result() or gather_result=True")
             self._host = self._dev.numpy()       # the one D2H copy of a solve result, on demand
             self._host_valid = True
         elif self._host is None:
@@ -815,12 +818,15 @@ class Function:
         self._host = np.ascontiguousarray(a, dtype=np.float64).ravel().copy()
         self._host_valid = True
         self._dev = None
+        self._local = False
 
-    def set_device(self, dev):
-        """Adopt a device vector as the current value (host copy becomes stale)."""
+    def set_device(self, dev, local=False):
+        """Adopt a device vector as the current value (host copy becomes stale).  `local`: the vector is one rank's part
+        (owned + ghost nodes) of a distributed field, not the global nodal array."""
         self._dev = dev
         self._host_valid = False
         self._host = None
+        self._local = bool(local)
 
     def device_vector(self):
         return self._dev
@@ -829,6 +835,7 @@ class Function:
         if isinstance(other, Function):
             if other.uniform_value() is not None:
                 self._host, self._dev, self._host_valid, self._fill = None, None, True, other._fill
+                self._local = False
             elif other._dev is not None and not other._host_valid:
                 # device-resident value: copy on the device, no PCIe round trip per time step
                 from ._lib import DeviceVector
@@ -836,6 +843,8 @@ class Function:
                     self._dev = DeviceVector(other._dev.ctx, other._dev.n)
                 self._dev.copy_from(other._dev)
                 self._host_valid = False
+                self._host = None
+                self._local = getattr(other, "_local", False)
             else:
                 self.assign_array(other.array())
         else:

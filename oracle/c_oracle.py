@@ -47,6 +47,12 @@ def load():
         lib.fo_pcg_jacobi.restype = C.c_int
         lib.fo_pcg_jacobi.argtypes = [i64, vp, vp, vp, vp, vp, dbl, dbl, C.c_int, C.POINTER(dbl)]
         lib.fo_zero.argtypes = [vp, i64]
+        lib.fo_assemble_scalar.argtypes = [i64, vp, vp, dbl, dbl, dbl, vp, vp, vp, vp]
+        lib.fo_apply_scalar.argtypes = [i64, vp, vp, dbl, dbl, vp, vp]
+        lib.fo_apply_dirichlet_nonsym.argtypes = [i64, vp, vp, vp, vp, vp, vp]
+        lib.fo_bicgstab_jacobi.restype = C.c_int
+        lib.fo_bicgstab_jacobi.argtypes = [i64, vp, vp, vp, vp, vp, dbl, dbl, C.c_int, C.POINTER(dbl)]
+        lib.fo_assemble_elasticity.argtypes = [i64, vp, vp, dbl, dbl, vp, vp, vp, vp, vp]
         lib.fo_mg_lambda_max.restype = dbl
         lib.fo_mg_lambda_max.argtypes = [i64, vp, vp, vp]
         lib.fo_mg_apply.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
@@ -197,3 +203,122 @@ class HeatCubeMG:
         it, rel = mg.pcg(f.b, f.x, rtol=rtol, maxit=maxit)
         t2 = time.perf_counter()
         return {"iterations": it, "relres": rel, "t_assemble": t1 - t0, "t_solve": t2 - t1, "x": f.x, "levels": len(levels)}
+
+
+def expand_pattern(rp, ci, ncomp):
+    """Scalar CSR pattern of a vector space with dof = ncomp * node + component from the node pattern (columns stay sorted)."""
+    lens = np.diff(rp)
+    rp3 = np.zeros(ncomp * lens.size + 1, dtype=np.int64)
+    np.cumsum(np.repeat(lens * ncomp, ncomp), out=rp3[1:])
+    ci3 = np.empty(int(rp3[-1]), dtype=np.int32)
+    cols = (ci.astype(np.int64)[:, None] * ncomp + np.arange(ncomp)).astype(np.int32)          # [nnz, ncomp]
+    for r in range(lens.size):                      # small meshes only; the sized path below builds it block-wise
+        blk = cols[rp[r]:rp[r + 1]].ravel()
+        for i in range(ncomp):
+            ci3[rp3[ncomp * r + i]:rp3[ncomp * r + i + 1]] = blk
+    return rp3, ci3
+
+
+def expand_pattern_fast(rp, ci, ncomp):
+    """The same without a Python loop over rows (vectorised; used at bench sizes)."""
+    lens = np.diff(rp)
+    n = lens.size
+    rp3 = np.zeros(ncomp * n + 1, dtype=np.int64)
+    np.cumsum(np.repeat(lens * ncomp, ncomp), out=rp3[1:])
+    cols = (ci.astype(np.int64)[:, None] * ncomp + np.arange(ncomp)).astype(np.int32).reshape(-1)     # row-major: entry k -> ncomp columns
+    # every node row r contributes its block of ncomp*len columns ncomp times in a row
+    starts = rp[:-1] * ncomp
+    out = np.empty(int(rp3[-1]), dtype=np.int32)
+    row_of = np.repeat(np.arange(n), lens * ncomp)                    # node row of each expanded column entry
+    offs = np.arange(cols.size) - np.repeat(starts, lens * ncomp)     # position inside the node row's expanded block
+    for i in range(ncomp):
+        out[rp3[ncomp * row_of + i] + offs] = cols
+    return rp3, out
+
+
+class ElasticityCube:
+    """Config C3 on the CPU: unit cube N^3 P1, 3 dofs per node, clamp on x = 0, body force (0, 0, -rho g) with the reference's
+    load sign (a(u, v) = -L(v)); step() = assemble + symmetric Dirichlet + Jacobi-PCG on the scalar CSR."""
+
+    def __init__(self, N, E=2e11, nu=0.27, rho=7800.0):
+        self.lib = load()
+        self.N = N
+        self.mu, self.lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+        self.f = np.array([0.0, 0.0, -rho * 9.81]) * -1.0          # reference sign flip (LinearElasticitySolver.py:242-243)
+        t = time.perf_counter()
+        self.coords, self.cells = box_mesh((N, N, N))
+        self.nv = self.coords.shape[0]
+        rp, ci = csr_pattern(self.cells, self.nv)
+        self.rp, self.ci = expand_pattern_fast(rp, ci, 3)
+        self.n = 3 * self.nv
+        self.t_setup = time.perf_counter() - t
+        clamp = np.nonzero(self.coords[:, 0] == 0.0)[0]
+        self.flag = np.zeros(self.n, dtype=np.uint8)
+        self.flag[(3 * clamp[:, None] + np.arange(3)).ravel()] = 1
+        self.g = np.zeros(self.n)
+        self.vals = np.empty(self.ci.size)
+        self.b = np.empty(self.n)
+        self.x = np.empty(self.n)
+        for a in (self.vals, self.b, self.x):
+            self.lib.fo_zero(_p(a), a.size)
+
+    def step(self, rtol=1e-12, maxit=100000):
+        lib = self.lib
+        t0 = time.perf_counter()
+        lib.fo_zero(_p(self.vals), self.vals.size)
+        lib.fo_zero(_p(self.b), self.b.size)
+        lib.fo_assemble_elasticity(self.cells.shape[0], _p(self.cells), _p(self.coords), self.mu, self.lam, _p(self.f), _p(self.rp), _p(self.ci),
+                                   _p(self.vals), _p(self.b))
+        lib.fo_apply_dirichlet_sym(self.n, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.flag), _p(self.g))
+        t1 = time.perf_counter()
+        lib.fo_zero(_p(self.x), self.x.size)
+        rel = C.c_double()
+        it = lib.fo_pcg_jacobi(self.n, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.x), rtol, 0.0, maxit, C.byref(rel))
+        t2 = time.perf_counter()
+        return {"t_assemble": t1 - t0, "t_solve": t2 - t1, "iterations": it, "relres": rel.value}
+
+
+class TransientCube:
+    """Config C4 on the CPU: 3D transient advection-diffusion on the unit cube N^3 P1, Crank-Nicolson (theta = 0.5) with the
+    convection term fully implicit as the reference has it (ScalarTransportSolver.py:292-293, 311), matrix re-assembled every step,
+    plain bc.apply + Jacobi-BiCGStab.  step() advances one time step; T holds the current field."""
+
+    def __init__(self, N, k=0.6, rho=1000.0, cp=4200.0, T_hot=360.0, T_cold=300.0, T_init=300.0):
+        self.lib = load()
+        self.N, self.k = N, k
+        self.c = rho * cp
+        h = 1.0 / N
+        self.dt = self.c * h * h / k
+        self.vel = np.array([0.0, 0.0, 2 * k / (self.c * h) * 0.5])          # cell Peclet number 0.5
+        self.coords, self.cells = box_mesh((N, N, N))
+        self.nv = self.coords.shape[0]
+        self.rp, self.ci = csr_pattern(self.cells, self.nv)
+        p = (N + 1) ** 2
+        self.flag = np.zeros(self.nv, dtype=np.uint8)
+        self.g = np.zeros(self.nv)
+        self.flag[:p] = 1; self.g[:p] = T_hot
+        self.flag[-p:] = 1; self.g[-p:] = T_cold
+        self.vals = np.empty(self.ci.size)
+        self.b = np.empty(self.nv)
+        self.T = np.empty(self.nv)
+        for a in (self.vals, self.b, self.T):
+            self.lib.fo_zero(_p(a), a.size)
+        self.T[:] = T_init
+        self.iterations = []
+
+    def step(self, rtol=1e-12, maxit=100000, theta=0.5):
+        lib = self.lib
+        nc = self.cells.shape[0]
+        t0 = time.perf_counter()
+        lib.fo_zero(_p(self.vals), self.vals.size)
+        lib.fo_zero(_p(self.b), self.b.size)
+        lib.fo_assemble_scalar(nc, _p(self.cells), _p(self.coords), theta * self.k, self.c / self.dt, self.c, _p(self.vel), _p(self.rp), _p(self.ci), _p(self.vals))
+        lib.fo_apply_scalar(nc, _p(self.cells), _p(self.coords), -(1.0 - theta) * self.k, self.c / self.dt, _p(self.T), _p(self.b))
+        lib.fo_apply_dirichlet_nonsym(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.flag), _p(self.g))
+        t1 = time.perf_counter()
+        self.T[self.flag.astype(bool)] = self.g[self.flag.astype(bool)]      # start vector: previous field with the Dirichlet values imposed
+        rel = C.c_double()
+        it = lib.fo_bicgstab_jacobi(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.T), rtol, 0.0, maxit, C.byref(rel))
+        t2 = time.perf_counter()
+        self.iterations.append(it)
+        return {"t_assemble": t1 - t0, "t_solve": t2 - t1, "iterations": it, "relres": rel.value}

@@ -248,6 +248,181 @@ int fo_pcg_jacobi(int64_t n, const int64_t* rp, const int32_t* ci, const double*
 }
 
 /* ------------------------------------------------------------------------------------------------------------------------
+ * BASELINE configs C3 (elasticity) and C4 (transient advection-diffusion): the cell loops and BiCGStab, so that the bench's
+ * `c3` / `c4` blocks have a CPU figure and a full-size oracle to be compared with.  Same closed-form P1 element matrices as
+ * oracle/fem_oracle.py (local_laplace / local_mass / local_advection / local_elasticity), checked against it in
+ * tests/test_oracle_kat.py. */
+static inline double tet_geometry(const int32_t* v, const double* coords, double G[4][3]) {
+  const double* x0 = coords + 3 * (int64_t)v[0];
+  double a[3], bb[3], cc[3];
+  for (int i = 0; i < 3; ++i) {
+    a[i] = coords[3 * (int64_t)v[1] + i] - x0[i];
+    bb[i] = coords[3 * (int64_t)v[2] + i] - x0[i];
+    cc[i] = coords[3 * (int64_t)v[3] + i] - x0[i];
+  }
+  double bc[3] = {bb[1] * cc[2] - bb[2] * cc[1], bb[2] * cc[0] - bb[0] * cc[2], bb[0] * cc[1] - bb[1] * cc[0]};
+  double ca[3] = {cc[1] * a[2] - cc[2] * a[1], cc[2] * a[0] - cc[0] * a[2], cc[0] * a[1] - cc[1] * a[0]};
+  double ab[3] = {a[1] * bb[2] - a[2] * bb[1], a[2] * bb[0] - a[0] * bb[2], a[0] * bb[1] - a[1] * bb[0]};
+  double det = a[0] * bc[0] + a[1] * bc[1] + a[2] * bc[2], inv = 1.0 / det;
+  for (int i = 0; i < 3; ++i) {
+    G[1][i] = bc[i] * inv; G[2][i] = ca[i] * inv; G[3][i] = ab[i] * inv;
+    G[0][i] = -(G[1][i] + G[2][i] + G[3][i]);
+  }
+  return fabs(det) / 6.0;
+}
+
+/* vals += kscale K + mass M + adv C(vel)   (ScalarTransportSolver.py:284-285, 292, 311; vel may be NULL when adv == 0) */
+void fo_assemble_scalar(int64_t ncells, const int32_t* cells, const double* coords, double kscale, double mass, double adv,
+                        const double* vel, const int64_t* row_ptr, const int32_t* col_idx, double* vals) {
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < ncells; ++c) {
+    const int32_t* v = cells + 4 * c;
+    double G[4][3];
+    const double vol = tet_geometry(v, coords, G);
+    double vg[4] = {0, 0, 0, 0};
+    if (adv != 0.0 && vel)
+      for (int q = 0; q < 4; ++q) vg[q] = vel[0] * G[q][0] + vel[1] * G[q][1] + vel[2] * G[q][2];
+    for (int p = 0; p < 4; ++p) {
+      const int64_t end = row_ptr[v[p] + 1];
+      int64_t lo = row_ptr[v[p]];
+      for (int q = 0; q < 4; ++q) {
+        lo = find_col(col_idx, lo, end, v[q]);
+        const double e = vol * (kscale * (G[p][0] * G[q][0] + G[p][1] * G[q][1] + G[p][2] * G[q][2]) + mass * (p == q ? 0.1 : 0.05) +
+                                adv * 0.25 * vg[q]);
+#pragma omp atomic
+        vals[lo] += e;
+        ++lo;
+      }
+    }
+  }
+}
+
+/* y += (kscale K + mass M) x, cell by cell: the explicit half of Crank-Nicolson (ScalarTransportSolver.py:292-293) */
+void fo_apply_scalar(int64_t ncells, const int32_t* cells, const double* coords, double kscale, double mass, const double* x, double* y) {
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < ncells; ++c) {
+    const int32_t* v = cells + 4 * c;
+    double G[4][3];
+    const double vol = tet_geometry(v, coords, G);
+    double xe[4], gx[3] = {0, 0, 0}, sx = 0.0;
+    for (int q = 0; q < 4; ++q) {
+      xe[q] = x[v[q]];
+      sx += xe[q];
+      for (int i = 0; i < 3; ++i) gx[i] += G[q][i] * xe[q];
+    }
+    for (int p = 0; p < 4; ++p) {
+      const double e = vol * (kscale * (G[p][0] * gx[0] + G[p][1] * gx[1] + G[p][2] * gx[2]) + mass * 0.05 * (sx + xe[p]));
+#pragma omp atomic
+      y[v[p]] += e;
+    }
+  }
+}
+
+/* bc.apply(A, b): zero row, unit diagonal, b = g */
+void fo_apply_dirichlet_nonsym(int64_t n, const int64_t* row_ptr, const int32_t* col_idx, double* vals, double* b, const uint8_t* flag,
+                               const double* g) {
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < n; ++r)
+    if (flag[r]) {
+      for (int64_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) vals[k] = (col_idx[k] == r) ? 1.0 : 0.0;
+      b[r] = g[r];
+    }
+}
+
+/* right-Jacobi BiCGStab, r0_hat = r0, convergence on ||M^-1 r|| (oracle/fem_oracle.py bicgstab_jacobi) */
+int fo_bicgstab_jacobi(int64_t n, const int64_t* rp, const int32_t* ci, const double* va, const double* b, double* x, double rtol,
+                       double atol, int maxit, double* relres) {
+  double* buf = (double*)malloc(sizeof(double) * n * 8);
+  double *r = buf, *rhat = buf + n, *p = buf + 2 * n, *ph = buf + 3 * n, *v = buf + 4 * n, *sh = buf + 5 * n, *t = buf + 6 * n, *dinv = buf + 7 * n;
+  spmv(n, rp, ci, va, x, v);
+  double bn = 0.0, rn = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : bn, rn)
+  for (int64_t i = 0; i < n; ++i) {
+    double d = 1.0;
+    for (int64_t k = rp[i]; k < rp[i + 1]; ++k)
+      if (ci[k] == i) d = va[k];
+    dinv[i] = 1.0 / d;
+    r[i] = b[i] - v[i];
+    rhat[i] = r[i];
+    p[i] = 0.0; v[i] = 0.0;
+    bn += (dinv[i] * b[i]) * (dinv[i] * b[i]);
+    rn += (dinv[i] * r[i]) * (dinv[i] * r[i]);
+  }
+  const double tol2 = fmax(rtol * rtol * bn, atol * atol);
+  double rho = 1.0, alpha = 1.0, omega = 1.0;
+  int it = 0;
+  while (rn > tol2 && it < maxit) {
+    double rho_new = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : rho_new)
+    for (int64_t i = 0; i < n; ++i) rho_new += rhat[i] * r[i];
+    const double beta = (rho_new / rho) * (alpha / omega);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      p[i] = r[i] + beta * (p[i] - omega * v[i]);
+      ph[i] = dinv[i] * p[i];
+    }
+    spmv(n, rp, ci, va, ph, v);
+    double rv = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : rv)
+    for (int64_t i = 0; i < n; ++i) rv += rhat[i] * v[i];
+    alpha = rho_new / rv;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      r[i] -= alpha * v[i];           /* s */
+      sh[i] = dinv[i] * r[i];
+    }
+    spmv(n, rp, ci, va, sh, t);
+    double ts = 0.0, tt = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : ts, tt)
+    for (int64_t i = 0; i < n; ++i) { ts += t[i] * r[i]; tt += t[i] * t[i]; }
+    omega = ts / tt;
+    rn = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : rn)
+    for (int64_t i = 0; i < n; ++i) {
+      x[i] += alpha * ph[i] + omega * sh[i];
+      r[i] -= omega * t[i];
+      rn += (dinv[i] * r[i]) * (dinv[i] * r[i]);
+    }
+    rho = rho_new;
+    ++it;
+  }
+  if (relres) *relres = bn > 0 ? sqrt(rn / bn) : sqrt(rn);
+  free(buf);
+  return it;
+}
+
+/* vals += int sigma(u):grad(v), sigma = 2 mu sym(grad u) + lambda div(u) I, on the scalar CSR of the 3-component space
+ * (dof = 3 v + i; LinearElasticitySolver.py:62-69, 215); b += vol/4 * f per vertex (body force, may be NULL) */
+void fo_assemble_elasticity(int64_t ncells, const int32_t* cells, const double* coords, double mu, double lambda, const double* f,
+                            const int64_t* row_ptr, const int32_t* col_idx, double* vals, double* b) {
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < ncells; ++c) {
+    const int32_t* v = cells + 4 * c;
+    double G[4][3];
+    const double vol = tet_geometry(v, coords, G);
+    for (int p = 0; p < 4; ++p)
+      for (int i = 0; i < 3; ++i) {
+        const int64_t row = 3 * (int64_t)v[p] + i, end = row_ptr[row + 1];
+        int64_t lo = row_ptr[row];
+        for (int q = 0; q < 4; ++q) {
+          const double gg = G[p][0] * G[q][0] + G[p][1] * G[q][1] + G[p][2] * G[q][2];
+          for (int j = 0; j < 3; ++j) {
+            lo = find_col(col_idx, lo, end, 3 * v[q] + j);
+            const double e = vol * (mu * ((i == j ? gg : 0.0) + G[p][j] * G[q][i]) + lambda * G[p][i] * G[q][j]);
+#pragma omp atomic
+            vals[lo] += e;
+            ++lo;
+          }
+        }
+        if (b && f) {
+#pragma omp atomic
+          b[row] += 0.25 * vol * f[i];
+        }
+      }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------------
  * CPU restatement of the multigrid-preconditioned CG of csrc/fsb_mg.cu (scalar problems on nested box meshes), so that the
  * `gmg` block of the bench line has its own CPU figure: same transfers (fine vertex 2C + d = coarse vertex C or midpoint of the
  * coarse edge (C, C + d)), Chebyshev smoothing of degree nu on D^-1 A over [lmax/10, lmax], damped Jacobi on the coarsest level,

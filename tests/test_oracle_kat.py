@@ -251,3 +251,38 @@ def test_fenics_tutorial_heat_equation_crank_nicolson_is_nodally_exact():
         Ab, bb = fo.apply_dirichlet(A, b, bnd, exact(n * dt)[bnd], symmetric=False)
         T = fo.solve_direct(Ab, bb)
         assert np.abs(T - exact(n * dt)).max() < 2e-13
+
+
+def test_c_oracle_elasticity_and_transient_match_numpy_oracle():
+    """The C/OpenMP restatements behind the bench's c3 / c4 CPU figures (oracle/fem_oracle_c.c fo_assemble_elasticity,
+    fo_assemble_scalar, fo_apply_scalar, fo_bicgstab_jacobi) against the numpy oracle on a 6^3 cube: expanded CSR pattern
+    bit-exact, matrix 1e-14, cantilever solution and three Crank-Nicolson steps against direct solves."""
+    import scipy.sparse as sp
+    from oracle import c_oracle as co
+    N = 6
+    c, t = fo.unit_cube_mesh(N, N, N)
+    ec = co.ElasticityCube(N)
+    ec.step()
+    rp0, ci0 = fo.csr_pattern(t, c.shape[0], ncomp=3)
+    assert np.array_equal(rp0, ec.rp) and np.array_equal(ci0, ec.ci)
+    rp1, ci1 = co.expand_pattern(*co.csr_pattern(t, c.shape[0]), 3)
+    assert np.array_equal(rp1, ec.rp) and np.array_equal(ci1, ec.ci)
+    A = fo.conform(fo.assemble_matrix(t, fo.local_elasticity(c, t, ec.mu, ec.lam), c.shape[0], ncomp=3), rp0, ci0)
+    b = fo.assemble_source(c, t, ec.f, ncomp=3)
+    dofs = np.nonzero(ec.flag)[0]
+    A2, b2 = fo.apply_dirichlet(A, b, dofs, np.zeros(dofs.size), True)
+    Ac = sp.csr_matrix((ec.vals, ec.ci, ec.rp), shape=(ec.n, ec.n))
+    assert abs(Ac - A2).max() <= 1e-14 * abs(A2).max()
+    assert fo.relative_l2(ec.x, fo.solve_direct(A2, b2)) < 1e-10
+    tc = co.TransientCube(N)
+    T = np.full(tc.nv, 300.0)
+    K = fo.assemble_matrix(t, fo.local_laplace(c, t, tc.k), c.shape[0])
+    M = fo.assemble_matrix(t, fo.local_mass(c, t, tc.c), c.shape[0])
+    Cm = fo.assemble_matrix(t, fo.local_advection(c, t, tc.vel, tc.c), c.shape[0])
+    rp, ci = fo.csr_pattern(t, c.shape[0])
+    d = np.nonzero(tc.flag)[0]
+    for _ in range(3):
+        tc.step()
+        A2, b2 = fo.apply_dirichlet(fo.conform(M / tc.dt + 0.5 * K + Cm, rp, ci), (M / tc.dt - 0.5 * K) @ T, d, tc.g[d], False)
+        T = fo.solve_direct(A2, b2)
+        assert fo.relative_l2(tc.T, T) < 1e-10

@@ -55,6 +55,27 @@ def main():
               % (N, world, info["iterations"], solver1.solve_info["iterations"], err, d, dt), flush=True)
         ok = ok and err < 1e-10 and d < 1e-10 and info["converged"] == 1
         # the concatenated owned row blocks reproduce the global CSR pattern exactly
+    # transient run with gather_result=False: every rank keeps only its part of the solution on the device between the steps
+    # (the T_prev term and the Krylov start vector of the next step read it there); compared with the gathered run
+    def transient_settings(gather):
+        st = bench.case_settings(N, distributed=True)
+        st['solver_settings']['gather_result'] = gather
+        st['solver_settings']['transient_settings'] = {'transient': True, 'starting_time': 0.0, 'time_step': 50.0, 'ending_time': 175.0}
+        return st
+    tr_local = ScalarTransportSolver.ScalarTransportSolver(transient_settings(False))
+    tr_local.solve()
+    mine_local = tr_local.local_result().copy()
+    tr_gath = ScalarTransportSolver.ScalarTransportSolver(transient_settings(True))
+    xg = tr_gath.solve().vector().get_local()
+    spc = tr_local.device_space()
+    ref_slice = xg[spc.v_off + spc.own_v0:spc.v_off + spc.own_v1]
+    dtr = float(np.linalg.norm(mine_local - ref_slice) / np.linalg.norm(ref_slice))
+    moved = float(np.abs(ref_slice - 293.0).max())
+    t = torch.tensor([dtr, -moved], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("transient, %d steps, gather_result=False vs True: rel diff %.2e (field moved by up to %.1f)" % (tr_local.current_step, t[0].item(), -t[1].item()), flush=True)
+    ok = ok and t[0].item() < 1e-12 and tr_local.current_step >= 3
     rp, ci, va = solver.device_space().A.download_csr()
     sp_ = solver.device_space()
     lo, hi = sp_.own_v0, sp_.own_v1
