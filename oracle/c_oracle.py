@@ -47,6 +47,8 @@ def load():
         lib.fo_pcg_jacobi.restype = C.c_int
         lib.fo_pcg_jacobi.argtypes = [i64, vp, vp, vp, vp, vp, dbl, dbl, C.c_int, C.POINTER(dbl)]
         lib.fo_zero.argtypes = [vp, i64]
+        lib.fo_pcg_jacobi_segment.restype = C.c_int
+        lib.fo_pcg_jacobi_segment.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, C.c_int]
         lib.fo_assemble_scalar.argtypes = [i64, vp, vp, dbl, dbl, dbl, vp, vp, vp, vp]
         lib.fo_apply_scalar.argtypes = [i64, vp, vp, dbl, dbl, vp, vp]
         lib.fo_apply_dirichlet_nonsym.argtypes = [i64, vp, vp, vp, vp, vp, vp]
@@ -140,6 +142,35 @@ class HeatCube:
         it = lib.fo_pcg_jacobi(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.x), rtol, 0.0, maxit, C.byref(rel))
         t2 = time.perf_counter()
         return {"t_assemble": t1 - t0, "t_solve": t2 - t1, "iterations": it, "relres": rel.value}
+
+    # ---- the same step cut into consecutive segments (bench.py --impl reference: the driver's K steps are K segments of ONE
+    # complete step, every second of it measured, none extrapolated)
+    def begin_step(self):
+        """Segment 0's first part: zero, assemble, Dirichlet, start vector.  Returns the seconds it took."""
+        lib = self.lib
+        t0 = time.perf_counter()
+        if getattr(self, "_work", None) is None:
+            self._work = np.empty(4 * self.nv)
+            lib.fo_zero(_p(self._work), self._work.size)        # parallel first touch
+        lib.fo_zero(_p(self.vals), self.vals.size)
+        lib.fo_zero(_p(self.b), self.b.size)
+        lib.fo_assemble_heat(self.cells.shape[0], _p(self.cells), _p(self.coords), self.k, self.S, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b))
+        lib.fo_apply_dirichlet_sym(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.flag), _p(self.g))
+        self.x[:] = np.where(self.flag, self.g, self.T_init)
+        self._state = np.zeros(8)
+        return time.perf_counter() - t0
+
+    def solve_segment(self, iters, rtol=1e-12):
+        """Up to `iters` more CG iterations of the step begun by begin_step().  Returns (seconds, converged, iterations so far)."""
+        t0 = time.perf_counter()
+        done = self.lib.fo_pcg_jacobi_segment(self.nv, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.x), _p(self._work),
+                                              _p(self._state), rtol, 0.0, int(iters))
+        return time.perf_counter() - t0, bool(done), int(self._state[4])
+
+    def exact_profile(self):
+        """Nodally exact solution of this problem (SURVEY 8c KAT 4): T(z) = T0 + (T1 - T0) z + S z (1 - z) / (2 k)."""
+        z = self.coords[:, 2]
+        return self.g[0] + (self.g[-1] - self.g[0]) * z + self.S * z * (1 - z) / (2 * self.k)
 
 
 class MultigridLevels:

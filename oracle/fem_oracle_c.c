@@ -247,6 +247,59 @@ int fo_pcg_jacobi(int64_t n, const int64_t* rp, const int32_t* ci, const double*
   return it;
 }
 
+/* The same Jacobi-PCG in resumable form, for bench.py --impl reference: ONE complete solve is run as K consecutive segments (the
+ * driver's "steps"), the recurrence state carried in `work` (4n doubles: r, p, q, dinv) and `state` (8 doubles: [0] initialised,
+ * [1] r.z, [2] z.z, [3] ||M^-1 b||^2, [4] iterations so far).  Runs at most `seg_iters` iterations; returns 1 once converged.
+ * The arithmetic (and therefore the iteration count) is fo_pcg_jacobi's. */
+int fo_pcg_jacobi_segment(int64_t n, const int64_t* rp, const int32_t* ci, const double* va, const double* b, double* x, double* work,
+                          double* state, double rtol, double atol, int seg_iters) {
+  double *r = work, *p = work + n, *q = work + 2 * n, *dinv = work + 3 * n;
+  double rz = state[1], rr = state[2], bbn = state[3];
+  if (state[0] == 0.0) {
+    rz = rr = bbn = 0.0;
+    spmv(n, rp, ci, va, x, q);
+#pragma omp parallel for schedule(static) reduction(+ : rz, rr, bbn)
+    for (int64_t i = 0; i < n; ++i) {
+      double d = 1.0;
+      for (int64_t k = rp[i]; k < rp[i + 1]; ++k)
+        if (ci[k] == i) d = va[k];
+      dinv[i] = 1.0 / d;
+      r[i] = b[i] - q[i];
+      const double z = dinv[i] * r[i];
+      p[i] = z;
+      rz += r[i] * z; rr += z * z; bbn += (dinv[i] * b[i]) * (dinv[i] * b[i]);
+    }
+    state[0] = 1.0; state[4] = 0.0;
+  }
+  const double tol2 = fmax(rtol * rtol * bbn, atol * atol);
+  int it = 0;
+  while (rr > tol2 && it < seg_iters) {
+    spmv(n, rp, ci, va, p, q);
+    double pq = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : pq)
+    for (int64_t i = 0; i < n; ++i) pq += p[i] * q[i];
+    const double alpha = rz / pq;
+    double rzn = 0.0;
+    rr = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : rzn, rr)
+    for (int64_t i = 0; i < n; ++i) {
+      x[i] += alpha * p[i];
+      const double ri = r[i] - alpha * q[i];
+      r[i] = ri;
+      const double zi = dinv[i] * ri;
+      rzn += ri * zi;
+      rr += zi * zi;
+    }
+    const double beta = rzn / rz;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) p[i] = dinv[i] * r[i] + beta * p[i];
+    rz = rzn;
+    ++it;
+  }
+  state[1] = rz; state[2] = rr; state[3] = bbn; state[4] += it;
+  return rr <= tol2;
+}
+
 /* ------------------------------------------------------------------------------------------------------------------------
  * BASELINE configs C3 (elasticity) and C4 (transient advection-diffusion): the cell loops and BiCGStab, so that the bench's
  * `c3` / `c4` blocks have a CPU figure and a full-size oracle to be compared with.  Same closed-form P1 element matrices as

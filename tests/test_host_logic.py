@@ -382,7 +382,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     OMP_NUM_THREADS=1 (torchrun does, for every rank)."""
     import json
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "16", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "16", "--steps", "4", "--warmup", "1"],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -392,6 +392,11 @@ def test_bench_reference_arm_prints_one_contract_line():
                 "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "Mdof/s" and d["value"] > 0 and d["vs_baseline"] is None
+    import bench
+    assert d["config"] == {"workload": bench.workload(16)}                  # the very string the GPU arm prints
+    assert d["converged"] == 1 and d["rel_l2_vs_exact"] < 1e-10 and d["steps"] == 4
+    # the K steps are K segments of one complete step: value * (ms_per_step * steps) = DoF
+    assert abs(d["value"] * 1e6 * d["ms_per_step"] * 1e-3 * d["steps"] - 17 ** 3) < 1e-6 * 17 ** 3
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mdof/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()

@@ -392,8 +392,10 @@ def test_c_multigrid_restatement_matches_numpy_and_the_exact_profile():
     import bench
     g = bench.cpu_heat_gmg(h)
     assert g["value"] > 0 and g["iterations"] == r["iterations"] and g["kind"] == "port"
-    j = bench.cpu_heat(N, 60, 10, cube=h.cubes[0])
-    assert j["value"] > 0 and "first 10 of 60" in j["sample"]
+    j = bench.cpu_heat_full(N, nseg=4, warmup=1, cube=h.cubes[0])
+    one = h.cubes[0].step(rtol=bench.RTOL)
+    assert j["value"] > 0 and j["converged"] == 1 and j["iterations"] == one["iterations"] and len(j["segments_s"]) == 4
+    assert j["rel_l2_vs_exact"] < 1e-10 and abs(sum(j["segments_s"]) - j["total_s"]) < 1e-9
 
 
 def test_oracle_regression_pins(golden_dir):
