@@ -153,6 +153,7 @@ class SolverBase():
         mesh = Mesh(filename)
         bmeshfile = filename[:-4] + "_facet_region.xml"
         self.mesh = mesh
+        self._mark_distribution()
         if os.path.exists(bmeshfile):
             self.boundary_facets = MeshFunction("size_t", mesh, bmeshfile)
         else:
@@ -190,7 +191,20 @@ class SolverBase():
         else:
             raise SolverError('only scalar or vector solver has a base method of generate_function_space()')
 
+    def _mark_distribution(self):
+        """Tell the mesh whether this solver runs slab/RCB-distributed (settings['solver_settings']['distributed'] with an
+        initialised torch.distributed group of more than one rank): no rank then holds the whole mesh on its device."""
+        on = False
+        if (self.settings.get('solver_settings') or {}).get('distributed'):
+            try:
+                import torch.distributed as dist
+                on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            except ImportError:
+                on = False
+        self.mesh.distributed = on
+
     def generate_boundary_facets(self):
+        self._mark_distribution()
         boundary_facets = FacetMarkers(self.mesh)
         boundary_facets.set_all(0)
         for name, bc in self.boundary_conditions.items():
@@ -445,7 +459,7 @@ class SolverBase():
             rtol, maxit = min(rtol, PARITY_RTOL), max(maxit, PARITY_MAXIT)
         return {'rtol': rtol, 'atol': float(sp.get('absolute_tolerance', 0.0)), 'maxit': maxit,
                 'method': sp.get('linear_solver'), 'precond': sp.get('preconditioner', 'jacobi'),
-                'drop_zeros': bool(sp.get('drop_zeros', False)), 'mg_sweeps': sp.get('mg_sweeps', 2)}
+                'drop_zeros': {True: 1, False: 0, 'auto': 2}.get(sp.get('drop_zeros', 'auto'), 2), 'mg_sweeps': sp.get('mg_sweeps', 2)}
 
     def solve_linear_problem(self, F, u, Dirichlet_bcs):
         """assemble A and b, apply the Dirichlet conditions, solve (SolverBase.py:592-613).  F is the
@@ -464,8 +478,9 @@ class SolverBase():
         space.ctx.sync()
         self.timings['assemble'] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        # 'drop_zeros': the Krylov SpMVs skip the entries that are exactly zero after assembly (same solution;
-        # the assembled pattern, which is the parity object, keeps them as dolfin/PETSc do)
+        # 'drop_zeros' (True / False / 'auto', default 'auto' = when >= 20 % of the stored entries are exactly zero): the Krylov
+        # SpMVs skip the entries that are exactly zero after assembly (same products, same iterates; the assembled pattern,
+        # which is the parity object, keeps them as dolfin/PETSc do)
         space.ctx.set_option("drop_zeros", int(kp['drop_zeros']))
         if kp['precond'] in ('gmg', 'amg', 'petsc_amg') and method == 'cg':
             # CG preconditioned by geometric multigrid on the nested box meshes: what solve_amg's CG + GAMG is for the

@@ -42,6 +42,8 @@ SIGNATURES = {
     "fsb_mesh_upload_p2": (C.c_int, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp, c_i64, P(c_vp)]),
     "fsb_mesh_sizes": (C.c_int, [c_vp, P(c_i32), P(c_i32), P(c_i64), P(c_i64)]),
     "fsb_mesh_download": (C.c_int, [c_vp, c_vp, c_vp]),
+    "fsb_mesh_exterior_facets": (C.c_int, [c_vp, P(c_i64), P(c_i64)]),
+    "fsb_mesh_exterior_facets_get": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "fsb_mesh_destroy": (None, [c_vp]),
     "fsb_vec_create": (C.c_int, [c_vp, c_i64, P(c_vp)]),
     "fsb_vec_fill": (C.c_int, [c_vp, c_dbl]),
@@ -254,6 +256,20 @@ class DeviceMesh(_Handle):
         g, t, nv, nc = c_i32(), c_i32(), c_i64(), c_i64()
         self.ctx.check(self.ctx.lib.fsb_mesh_sizes(self.h, C.byref(g), C.byref(t), C.byref(nv), C.byref(nc)))
         return g.value, t.value, nv.value, nc.value
+
+    def exterior_facets(self):
+        """K1 on the device: (fverts[nbf, tdim], opp[nbf], cell[nbf], facet_id[nbf]) of the facets held by exactly one cell, in
+        lexicographic order of the vertex tuples; facet_id is dolfin's global facet index."""
+        nbf, nf = c_i64(), c_i64()
+        self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets(self.h, C.byref(nbf), C.byref(nf)))
+        _, t, _, _ = self.sizes()
+        fv = np.empty((nbf.value, t), dtype=np.int32)
+        opp = np.empty(nbf.value, dtype=np.int32)
+        cell = np.empty(nbf.value, dtype=np.int32)
+        fid = np.empty(nbf.value, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets_get(self.h, _ptr(fv), _ptr(opp), _ptr(cell), _ptr(fid)))
+        self.num_facets = nf.value
+        return fv, opp, cell, fid
 
     def download(self):
         g, t, nv, nc = self.sizes()

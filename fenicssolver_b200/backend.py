@@ -129,10 +129,8 @@ class DeviceSpace:
                 uid = self.comm.bootstrap(uid)
                 self.ctx.dist_init(self.comm.rank, self.comm.nranks, uid)
             self.activate(force=True)
-        elif mesh.box and not getattr(mesh, "force_upload", False):
-            self.dmesh = _lib.DeviceMesh.box(self.ctx, mesh.box["n"], mesh.box["p0"], mesh.box["p1"])
         else:
-            self.dmesh = _lib.DeviceMesh.upload(self.ctx, mesh.coordinates(), mesh.cells())
+            self.dmesh = mesh.device_mesh(self.ctx)         # generated (box) or uploaded once; shared with the boundary search (K1)
         _, _, self.nv_local, self.nc_local = self.dmesh.sizes()
         if self.degree == 2:
             self.nv_local = space.num_nodes()           # rows are P2 nodes (vertices + edges)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libfsb.so")
-SOURCES = ["fsb_core.cu", "fsb_pattern.cu", "fsb_assemble.cu", "fsb_assemble_p2.cu", "fsb_supg.cu", "fsb_spmv.cu", "fsb_squeeze.cu", "fsb_solve.cu", "fsb_cgp.cu", "fsb_mg.cu", "fsb_dist.cu"]
+SOURCES = ["fsb_core.cu", "fsb_pattern.cu", "fsb_facets.cu", "fsb_assemble.cu", "fsb_assemble_p2.cu", "fsb_supg.cu", "fsb_spmv.cu", "fsb_squeeze.cu", "fsb_solve.cu", "fsb_cgp.cu", "fsb_mg.cu", "fsb_dist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 

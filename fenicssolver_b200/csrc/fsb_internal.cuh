@@ -38,7 +38,8 @@ struct fsb_ctx {
   int vec_skew = 0;      // bytes between the start offsets of consecutive Krylov work vectors inside their blocks (multiple of 256, <= 8192)
   int cg_debug = 0;      // persistent kernel timing experiments (wrong results): 1 no peer stores, 2 no system fence after them
   int cg_timeout_s = 30; // watchdog of the persistent kernel's spin loops (a lost peer traps instead of hanging the GPU)
-  int drop_zeros = 0;    // Krylov SpMVs run on a copy without the exactly-zero blocks (fsb_squeeze.cu)
+  int drop_zeros = 2;    // Krylov SpMVs run on a copy without the exactly-zero blocks (fsb_squeeze.cu): 0 never, 1 always,
+                         // 2 (default) when at least 20 % of the stored blocks are exactly zero
   // scratch for reductions: per-CTA partials + a few scalars, and a pinned host mirror
   double* d_partials = nullptr;   // [kMaxPartials * 4]
   double* d_scalars = nullptr;    // [64]
@@ -73,6 +74,12 @@ struct fsb_mesh {
   int64_t nnodes = 0;
   int32_t* cell_nodes = nullptr;   // [ncells][nl]; owned only when degree == 2
   double* p2_tables = nullptr;     // device copy of the P2 reference tensors for this dimension (degree 2)
+  // K1 (fsb_facets.cu): exterior facets in lexicographic order, made on first request
+  int64_t nbf = -1, nfacets = 0;   // exterior facets / distinct facets of the mesh
+  int32_t* bf_verts = nullptr;     // [nbf][tdim] sorted vertex tuples
+  int32_t* bf_opp = nullptr;       // [nbf] vertex of the cell opposite the facet
+  int32_t* bf_cell = nullptr;      // [nbf] the one cell holding the facet
+  int64_t* bf_id = nullptr;        // [nbf] dolfin facet index = rank among all distinct facets
 };
 
 struct fsb_vec {

@@ -221,13 +221,18 @@ class Mesh:
     """A simplex mesh.  Either host arrays (file / user supplied) or a dolfin-layout box description
     that is generated directly on the device (UnitCubeMesh(256,256,256) never crosses PCIe)."""
 
-    def __init__(self, coordinates=None, cells=None, box=None):
+    def __init__(self, coordinates=None, cells=None, box=None, cells_sorted=False):
+        """`cells_sorted`: the caller guarantees int32, C-contiguous cells with ascending vertex ids per cell (what mesh.order()
+        gives); the arrays are then adopted as they are (e.g. pinned host memory) instead of sorted into a copy."""
         if isinstance(coordinates, str):
             c, t = read_dolfin_xml_mesh(coordinates)
             coordinates, cells = c, t
         self.box = box                      # dict(n=(..), p0=(..), p1=(..)) or None
         self._coords = None if coordinates is None else np.ascontiguousarray(coordinates, dtype=np.float64)
-        self._cells = None if cells is None else np.sort(np.ascontiguousarray(cells, dtype=np.int32), axis=1)
+        if cells is not None and cells_sorted and isinstance(cells, np.ndarray) and cells.dtype == np.int32 and cells.flags.c_contiguous:
+            self._cells = cells
+        else:
+            self._cells = None if cells is None else np.sort(np.ascontiguousarray(cells, dtype=np.int32), axis=1)
         if box is None and (self._coords is None or self._cells is None):
             raise SolverError("Mesh needs coordinates and cells, or a box description")
         self._exterior = None
@@ -279,17 +284,41 @@ class Mesh:
         return self._cells
 
     # ---- facets -------------------------------------------------------------------------------
-    def exterior_facets(self):
-        """(fverts[nbf, tdim], opposite_vertex[nbf]) of the exterior facets."""
-        if self._exterior is None:
-            if self.box:
-                self._exterior = box_exterior_facets(self.box["n"])
+    def device_mesh(self, ctx=None):
+        """The whole mesh on this process's GPU — generated there from a box description, uploaded from the host arrays
+        otherwise — created once and shared by the boundary search (K1) and the single-GPU DeviceSpace."""
+        from . import _lib, backend
+        ctx = ctx or backend.get_context()
+        dm = self.__dict__.get("_dmesh")
+        if dm is None or dm.h is None or dm.ctx is not ctx:
+            if self.box and not getattr(self, "force_upload", False):
+                dm = _lib.DeviceMesh.box(ctx, self.box["n"], self.box["p0"], self.box["p1"])
             else:
+                dm = _lib.DeviceMesh.upload(ctx, self.coordinates(), self.cells())
+            self._dmesh = dm
+        return dm
+
+    def exterior_facets(self):
+        """(fverts[nbf, tdim], opposite_vertex[nbf]) of the exterior facets, in lexicographic order of the vertex tuples.
+        Found on the device (libfsb K1, csrc/fsb_facets.cu).  Two host routes remain, both index arithmetic on a known
+        layout rather than a search: a generated box in a slab-distributed run (no rank holds the whole mesh; the surface
+        facets of the dolfin box layout are enumerated directly, O(surface)) and the same enumeration when this process has
+        no GPU at all (mesh inspection in host-only tools).  An array / file mesh always needs the device."""
+        if self._exterior is None:
+            if self.box and (getattr(self, "distributed", False) or not _device_present()):
+                self._exterior = box_exterior_facets(self.box["n"])
+            elif getattr(self, "distributed", False):
+                # general (RCB) partition of a replicated host mesh: every rank needs the global list and holds only its part
+                # on the device; host table (small meshes only)
                 facets, cf, count = self.facet_table()
                 ci, li = np.nonzero(count[cf] == 1)
                 fid = cf[ci, li]
                 order = np.argsort(fid, kind="stable")
                 self._exterior = (facets[fid[order]].astype(np.int32), self._cells[ci[order], li[order]].astype(np.int32), fid[order])
+            else:
+                fv, opp, cell, fid = self.device_mesh().exterior_facets()
+                self._exterior = (fv, opp, fid)
+                self._exterior_cells = cell
         return self._exterior[0], self._exterior[1]
 
     def locate_point(self, p, tol=1e-12):
@@ -314,10 +343,10 @@ class Mesh:
         return best
 
     def exterior_facet_ids(self):
-        """dolfin facet indices of the exterior facets (file meshes only)."""
+        """dolfin facet indices of the exterior facets (rank of the sorted vertex tuple among all distinct facets)."""
         self.exterior_facets()
         if len(self._exterior) < 3:
-            raise SolverError("global facet numbering is not materialised for generated box meshes")
+            raise SolverError("global facet numbering is not materialised on this route (slab-distributed box / no GPU)")
         return self._exterior[2]
 
     def facet_table(self):
@@ -331,6 +360,22 @@ class Mesh:
             facets, inv, count = np.unique(allf, axis=0, return_inverse=True, return_counts=True)
             self._facet_table = (facets, inv.reshape(nc, nl), count)
         return self._facet_table
+
+
+_DEVICE_PRESENT = None
+
+
+def _device_present():
+    """True when this process can create a libfsb context (a CUDA device is visible); probed once."""
+    global _DEVICE_PRESENT
+    if _DEVICE_PRESENT is None:
+        try:
+            from . import backend
+            backend.get_context()
+            _DEVICE_PRESENT = True
+        except Exception:
+            _DEVICE_PRESENT = False
+    return _DEVICE_PRESENT
 
 
 def box_cells(n):

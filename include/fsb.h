@@ -67,8 +67,9 @@ int fsb_sync(fsb_ctx* ctx);
 int fsb_device_info(fsb_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes);
 /* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 position-map+atomics),
  * "spmv_mode" (0 TMA-staged tiles, 1 plain row-per-thread), "profile" (0/1), "graph" (0/1),
- * "check_every" (iterations between host convergence polls), "drop_zeros" (0/1: the Krylov SpMVs run on a
- * compacted copy without the blocks that are exactly zero after assembly; the assembled CSR is untouched),
+ * "check_every" (iterations between host convergence polls), "drop_zeros" (the Krylov SpMVs run on a
+ * compacted copy without the blocks that are exactly zero after assembly; the assembled CSR, the parity object, is untouched:
+ * 0 never, 1 always, 2 = default: when at least 20 % of the stored blocks are exactly zero),
  * "alloc_cache_mb" (bound on released device blocks kept for exact-size reuse; 0 releases them and disables it). */
 int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value);
 int64_t fsb_launch_count(fsb_ctx* ctx);   /* kernels launched by this library on ctx so far */
@@ -99,6 +100,14 @@ int fsb_mesh_upload_p2(fsb_ctx* ctx, int32_t gdim, int32_t tdim, int64_t nverts,
                        int64_t ncells, const int32_t* cell_nodes, int64_t nnodes, fsb_mesh** mesh);
 int fsb_mesh_sizes(fsb_mesh* mesh, int32_t* gdim, int32_t* tdim, int64_t* nverts, int64_t* ncells);
 int fsb_mesh_download(fsb_mesh* mesh, double* xyz, int32_t* cells);
+/* Boundary detection and facet numbering (K1): what mesh.init(tdim-1), `facet.exterior()` and dolfin's global facet
+ * numbering give FacetFunction / SubDomain.mark / MeshFunction(mesh, "..._facet_region.xml") in SolverBase.py:229,236,277-283.
+ * The first call computes, on the device, the facets held by exactly one cell; *nbf = their number, *nfacets = the number
+ * of distinct facets of the mesh (either may be NULL).  _get copies them to host arrays (any may be NULL), in lexicographic
+ * order of the sorted vertex tuples: fverts[nbf][tdim], opp[nbf] = the cell's vertex opposite the facet, cell[nbf], and
+ * facet_id[nbf] = the facet's index in dolfin's numbering (rank of its vertex tuple among all distinct facets). */
+int fsb_mesh_exterior_facets(fsb_mesh* mesh, int64_t* nbf, int64_t* nfacets);
+int fsb_mesh_exterior_facets_get(fsb_mesh* mesh, int32_t* fverts, int32_t* opp, int32_t* cell, int64_t* facet_id);
 void fsb_mesh_destroy(fsb_mesh* mesh);
 
 /* ---- vectors: dolfin GenericVector ----------------------------------------------------------- */

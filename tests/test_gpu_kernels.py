@@ -52,6 +52,68 @@ def test_box_mesh_bit_exact(ctx, n):
     assert np.array_equal(xyz, c)          # bit-exact coordinates
 
 
+# ----------------------------------------------------------------------------------- K1: boundary search + facet numbering
+def _shuffled(c, t, seed):
+    """The same mesh with its cells in a random order and its vertices renumbered at random (cells re-sorted per cell)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(c.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    t2 = np.sort(inv[t], axis=1).astype(np.int32)
+    return c[perm], t2[rng.permutation(t2.shape[0])]
+
+
+@pytest.mark.parametrize("case", ["fixture", "cube", "cube_shuffled", "square", "square_shuffled", "two_cells", "non_manifold"])
+def test_exterior_facets_and_facet_ids_bit_exact(ctx, golden_dir, case):
+    """fsb_mesh_exterior_facets (csrc/fsb_facets.cu) against oracle.fem_oracle.facet_table / exterior_facets: the same facets in
+    the same (lexicographic) order, opposite vertices, owning cells and dolfin facet ids — integer work, bit-exact.  The shipped
+    fixture mesh is the one whose facet numbering was verified against data/mesh_facet_region.xml."""
+    if case == "fixture":
+        g = np.load(os.path.join(golden_dir, "fixture_mesh.npz"))
+        c, t = g["coords"], g["cells"]
+    elif case.startswith("cube"):
+        c, t = fo.unit_cube_mesh(5, 4, 6)
+        if case.endswith("shuffled"):
+            c, t = _shuffled(c, t, 3)
+    elif case.startswith("square"):
+        c, t = fo.unit_square_mesh(9, 7)
+        if case.endswith("shuffled"):
+            c, t = _shuffled(c, t, 4)
+    elif case == "two_cells":
+        c = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]])
+        t = np.array([[0, 1, 2, 3], [1, 2, 3, 4]], dtype=np.int32)
+    else:
+        # three tetrahedra around one triangle (not a manifold): that facet has three holders, is interior, and is counted once
+        c = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 0, -1], [1, 1, 0.3]])
+        t = np.array([[0, 1, 2, 3], [0, 1, 2, 4], [0, 1, 2, 5]], dtype=np.int32)
+    t = np.ascontiguousarray(t, dtype=np.int32)
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    fv, opp, cell, fid = m.exterior_facets()
+    facets, cf, count = fo.facet_table(t)
+    f0, o0, id0 = fo.exterior_facets(t)
+    assert m.num_facets == facets.shape[0]
+    assert np.array_equal(fv, f0) and np.array_equal(opp, o0) and np.array_equal(fid, id0)
+    # the owning cell really holds the facet opposite `opp`
+    assert np.all(np.sort(np.hstack([fv, opp[:, None]]), axis=1) == t[cell])
+    # second request: served from the mesh, same arrays
+    fv2, opp2, cell2, fid2 = m.exterior_facets()
+    assert np.array_equal(fv, fv2) and np.array_equal(fid, fid2)
+
+
+def test_exterior_facets_through_mesh_api(ctx):
+    """Mesh.exterior_facets()/exterior_facet_ids() of an array mesh and of a generated box both come from the device search and agree
+    with the direct enumeration of the dolfin box layout."""
+    from fenicssolver_b200.dolfin_compat import Mesh, UnitCubeMesh, box_exterior_facets
+    box = UnitCubeMesh(6, 5, 4)
+    fv, opp = box.exterior_facets()
+    f1, o1 = box_exterior_facets((6, 5, 4))
+    assert np.array_equal(fv, f1) and np.array_equal(opp, o1)
+    arr = Mesh(box.coordinates().copy(), box.cells().copy())
+    fv2, opp2 = arr.exterior_facets()
+    assert np.array_equal(fv2, f1) and np.array_equal(opp2, o1)
+    assert np.array_equal(arr.exterior_facet_ids(), fo.exterior_facets(box.cells())[2])
+
+
 def test_box_mesh_slab_matches_global(ctx):
     n = (4, 3, 6)
     c, t = fo.unit_cube_mesh(*n)

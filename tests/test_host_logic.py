@@ -113,6 +113,19 @@ def test_xml_readers_and_marker_files(tmp_path, golden_dir):
     path = write_dolfin_xml(str(tmp_path), g)
     mesh = Mesh(path)
     assert np.array_equal(mesh.coordinates(), g["coords"]) and np.array_equal(mesh.cells(), g["cells"])
+    cm = MeshFunction("size_t", mesh, path[:-4] + "_physical_region.xml")
+    assert np.all(cm.array() == 3) and cm.array().size == 4355
+    with pytest.raises(SolverBase.SolverError):             # the boundary search of a file mesh is device work: loud without a GPU
+        MeshFunction("size_t", mesh, path[:-4] + "_facet_region.xml")
+
+
+@pytest.mark.gpu
+def test_marker_files_and_solver_from_xml(tmp_path, golden_dir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_solvers import write_dolfin_xml
+    g = np.load(os.path.join(golden_dir, "fixture_mesh.npz"))
+    path = write_dolfin_xml(str(tmp_path), g)
+    mesh = Mesh(path)
     fm = MeshFunction("size_t", mesh, path[:-4] + "_facet_region.xml")
     assert (fm.values == 1).sum() == 100 and (fm.values == 2).sum() == 100 and fm.values.size == 1400
     assert np.all(mesh.coordinates()[fm.vertices(1), 2] == 0.0) and np.all(mesh.coordinates()[fm.vertices(2), 2] == 20.0)
@@ -425,7 +438,9 @@ def test_multigrid_level_count_rule():
     assert solver(box(12, 3, 3))._multigrid_levels() == 1             # odd count: no coarser level -> Jacobi
     assert solver(box(16, 4, 4), degree=2)._multigrid_levels() == 0   # degree 2: not covered
     m = box(4, 4, 4)
-    assert solver(Mesh(m.coordinates().copy(), m.cells().copy()))._multigrid_levels() == 0      # not a generated box
+    sv = solver(m)
+    sv.mesh = Mesh(m.coordinates().copy(), m.cells().copy())          # not a generated box (constructing a solver on it needs the device)
+    assert sv._multigrid_levels() == 0
 
 
 def test_xdmf_ascii_mesh_reader(tmp_path):
@@ -450,8 +465,13 @@ def test_xdmf_ascii_mesh_reader(tmp_path):
          'solver_settings': {'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.01, 'ending_time': 0.03},
                              'reference_values': {'temperature': 293}, 'solver_parameters': {}},
          'report_settings': {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_freq': 0}}
-    solver = ScalarTransportSolver.ScalarTransportSolver(s)
-    assert solver.mesh.num_vertices() == c.shape[0] and (solver.boundary_facets.values == 1).sum() == 8
+    from fenicssolver_b200.dolfin_compat import _device_present
+    if _device_present():              # the boundary search of a file mesh is device work (K1)
+        solver = ScalarTransportSolver.ScalarTransportSolver(s)
+        assert solver.mesh.num_vertices() == c.shape[0] and (solver.boundary_facets.values == 1).sum() == 8
+    else:
+        with pytest.raises(SolverBase.SolverError):
+            ScalarTransportSolver.ScalarTransportSolver(s)
     h5 = os.path.join(str(tmp_path), "mesh_h5.xdmf")
     open(h5, "w").write(open(p).read().replace('Format="XML"', 'Format="HDF"'))
     with pytest.raises(SolverBase.SolverError):
