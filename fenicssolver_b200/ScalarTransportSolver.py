@@ -60,7 +60,6 @@ class ScalarForm:
         """-> (rhs DeviceVector, matrix_is_symmetric).  A is assembled into space.A."""
         s = self.solver
         A = space.A
-        A.zero()
         kscale, ktensor = self._k()
         c = float(self.capacity)
         vel = None if self.velocity is None else np.asarray(self.velocity, dtype=np.float64)
@@ -76,7 +75,7 @@ class ScalarForm:
         b = space.scratch_vector('rhs')
         supg = self.supg_pe if vel is not None else None
         if self.transient:
-            A.assemble_scalar(kscale=self.theta * kscale, ktensor=ktensor, mass=c / self.dt, adv=adv, vel=vel)
+            A.assemble_scalar(kscale=self.theta * kscale, ktensor=ktensor, mass=c / self.dt, adv=adv, vel=vel, overwrite=True)
             tp = self.T_prev.device_vector()
             if tp is None or tp.n != space.ndof_local:
                 tp = space.vector_from_function(self.T_prev)
@@ -87,7 +86,7 @@ class ScalarForm:
                 _lib.assemble_scalar_supg(space.dmesh, A, vel, supg, mass=c / self.dt, adv=adv)
                 _lib.assemble_scalar_supg(space.dmesh, None, vel, supg, mass=c / self.dt, x=tp, y=b)
         else:
-            A.assemble_scalar(kscale=kscale, ktensor=ktensor, adv=adv, vel=vel)
+            A.assemble_scalar(kscale=kscale, ktensor=ktensor, adv=adv, vel=vel, overwrite=True)      # A = form: first term after what was A.zero()
             if supg:
                 _lib.assemble_scalar_supg(space.dmesh, A, vel, supg, adv=adv)
         if vel_field is not None:

@@ -63,6 +63,7 @@ SIGNATURES = {
     "fsb_mat_set_owned_rows": (C.c_int, [c_vp, c_i64, c_i64]),
     "fsb_mat_destroy": (None, [c_vp]),
     "fsb_assemble_scalar": (C.c_int, [c_vp, c_vp, c_dbl, c_vp, c_dbl, c_dbl, c_vp]),
+    "fsb_assemble_scalar_set": (C.c_int, [c_vp, c_vp, c_dbl, c_vp, c_dbl, c_dbl, c_vp]),
     "fsb_apply_scalar": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_vp, c_dbl, c_dbl, c_vp]),
     "fsb_assemble_elasticity": (C.c_int, [c_vp, c_vp, c_dbl, c_dbl]),
     "fsb_assemble_source": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_dbl, c_vp, c_i32]),
@@ -370,10 +371,12 @@ class DeviceMatrix(_Handle):
         self.ctx.check(self.ctx.lib.fsb_mat_set_owned_rows(self.h, int(r0), int(r1)))
 
     # assembly ------------------------------------------------------------------------------------
-    def assemble_scalar(self, kscale=1.0, ktensor=None, mass=0.0, adv=0.0, vel=None):
+    def assemble_scalar(self, kscale=1.0, ktensor=None, mass=0.0, adv=0.0, vel=None, overwrite=False):
+        """A += the scalar form; `overwrite`: A = the form (zero() + assemble in one call; the row-gather kernel skips the zero-fill)."""
         kt = None if ktensor is None else _np(ktensor, np.float64)
         ve = None if vel is None else _np(vel, np.float64)
-        self.ctx.check(self.ctx.lib.fsb_assemble_scalar(self.mesh.h, self.h, float(kscale), _ptr(kt), float(mass), float(adv), _ptr(ve)))
+        fn = self.ctx.lib.fsb_assemble_scalar_set if overwrite else self.ctx.lib.fsb_assemble_scalar
+        self.ctx.check(fn(self.mesh.h, self.h, float(kscale), _ptr(kt), float(mass), float(adv), _ptr(ve)))
 
     def assemble_elasticity(self, mu, lmbda):
         self.ctx.check(self.ctx.lib.fsb_assemble_elasticity(self.mesh.h, self.h, float(mu), float(lmbda)))

@@ -75,6 +75,98 @@ k_scalar_form(int64_t ncells, const int32_t* __restrict__ cells, const double* _
   }
 }
 
+// ------------------------------------------------------------------------------------ row-gather form of the same kernel
+// asm_mode 2 (default).  ncu on the scatter kernel above (profiles/assembly_r1.txt): 0.17 of the HBM roofline, bound by the RATE of
+// scalar fp64 REDs (9.2 per tet, SM-side issue ~1.3 cycles per lane), DRAM traffic 1.9x the algorithmic bytes because every RED that
+// misses L2 fetches its sector and A has to be zero-filled first.  Here the OWNER of a row computes it: one thread per row walks the
+// cells around its vertex (the sorted vertex->cell adjacency the symbolic phase keeps), recomputes their affine geometry (4x
+// redundant fp64 work — cheap next to the REDs it replaces), accumulates row `a` of every local matrix in thread-private shared
+// memory slots addressed by the position map, and writes the finished row once: no atomics, no zero-fill, no read-modify-write of
+// A, and the sum order is fixed (ascending cell index), so the assembled matrix is bitwise reproducible run to run.
+// MODE 0: vals += row, 1: vals = row (caller would otherwise zero A first), 2: y[row] += (row of K_e) . x (matrix-free action).
+constexpr int kRowSlots = 32;       // longest row the shared-memory slots hold (host falls back to the scatter kernel beyond)
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(128)
+k_scalar_rows(int64_t nrows, const int32_t* __restrict__ cells, const double* __restrict__ xyz, ScalarForm f,
+              const int64_t* __restrict__ vptr, const int32_t* __restrict__ v2c, const int64_t* __restrict__ row_ptr,
+              double* __restrict__ vals, const uint8_t* __restrict__ posmap, const double* __restrict__ x, double* __restrict__ y) {
+  constexpr int NL = D + 1;
+  __shared__ double acc[MODE == 2 ? 1 : kRowSlots][128];
+  const int tid = threadIdx.x;
+  for (int64_t base = blockIdx.x * (int64_t)128; base < nrows; base += (int64_t)gridDim.x * 128) {
+    const int64_t row = base + tid;
+    if (row >= nrows) continue;
+    int64_t k0 = 0;
+    int len = 0;
+    if (MODE != 2) {
+      k0 = __ldg(row_ptr + row);
+      len = (int)(__ldg(row_ptr + row + 1) - k0);
+      for (int s = 0; s < len; ++s) acc[s][tid] = 0.0;
+    }
+    double sum = 0.0;
+    const int64_t p0 = __ldg(vptr + row), p1 = __ldg(vptr + row + 1);
+    for (int64_t p = p0; p < p1; ++p) {
+      const int64_t c = __ldg(v2c + p);
+      int v[NL];
+      load_cell<D>(cells, c, v);
+      Geo<D> g;
+      p1_geometry<D>(xyz, v, g);
+      int la = 0;
+#pragma unroll
+      for (int a = 1; a < NL; ++a) la = (v[a] == (int)row) ? a : la;
+      double Ga[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double t = g.G[0][i];
+#pragma unroll
+        for (int a = 1; a < NL; ++a) t = (la == a) ? g.G[a][i] : t;
+        Ga[i] = t;
+      }
+      const double kw = f.kscale * g.vol, mw = f.mass * g.vol / (double)(NL * (NL + 1)), aw = f.adv * g.vol / (double)NL;
+      double ke[NL];
+#pragma unroll
+      for (int b = 0; b < NL; ++b) {
+        double s = 0.0, vg = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          double kg = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) kg += f.K[i * D + j] * g.G[b][j];
+          s += Ga[i] * kg;
+          vg += f.vel[i] * g.G[b][i];
+        }
+        ke[b] = kw * s + mw * (la == b ? 2.0 : 1.0) + aw * vg;
+      }
+      if (MODE == 2) {
+#pragma unroll
+        for (int b = 0; b < NL; ++b) sum += ke[b] * __ldg(x + v[b]);
+      } else if (D == 3) {
+        const unsigned w = __ldg(reinterpret_cast<const unsigned*>(posmap) + c * NL + la);
+#pragma unroll
+        for (int b = 0; b < NL; ++b) acc[(w >> (8 * b)) & 0xff][tid] += ke[b];
+      } else {
+#pragma unroll
+        for (int b = 0; b < NL; ++b) acc[__ldg(posmap + c * NL * NL + la * NL + b)][tid] += ke[b];
+      }
+    }
+    if (MODE == 2) {
+      y[row] += sum;
+    } else if (MODE == 1) {
+      for (int s = 0; s < len; ++s) vals[k0 + s] = acc[s][tid];
+    } else {
+      for (int s = 0; s < len; ++s) vals[k0 + s] += acc[s][tid];
+    }
+  }
+}
+
+// the row-gather kernels apply to a degree-1 mesh whose adjacency was kept, a position map and rows that fit the slots
+static bool rows_path(fsb_ctx* ctx, fsb_mesh* mesh, fsb_mat* A) {
+  if (ctx->asm_mode < 2 || mesh->degree != 1 || !mesh->v2c) return false;
+  if (A && (A->mesh != mesh || !A->posmap || A->max_row_len > kRowSlots)) return false;
+  return true;
+}
+
 // K_e[(a,i),(b,j)] = |T| ( mu (G_a.G_b d_ij + G_a[j] G_b[i]) + lambda G_a[i] G_b[j] ), DxD blocks
 template <int D>
 __global__ void __launch_bounds__(128)
@@ -452,16 +544,31 @@ static void fill_form(ScalarForm& f, int D, double kscale, const double* ktensor
   if (vel) for (int i = 0; i < D; ++i) f.vel[i] = vel[i];
 }
 
-extern "C" int fsb_assemble_scalar(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor, double mass,
-                                   double adv, const double* vel) {
+static int assemble_scalar_impl(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor, double mass, double adv, const double* vel,
+                                int overwrite) {
   if (!mesh || !A) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;
   if (A->bs != 1 || A->nbrows != mesh->nnodes) FSB_FAIL(ctx, FSB_ERR_ARG, "matrix does not belong to a scalar P1 space on this mesh");
   if (adv != 0.0 && !vel) FSB_FAIL(ctx, FSB_ERR_ARG, "advection needs a velocity");
-  if (mesh->degree == 2) return fsb_p2_scalar(mesh, A, nullptr, nullptr, kscale, ktensor, mass, adv, vel);
   ScalarForm f;
+  if (mesh->degree == 1 && rows_path(ctx, mesh, A)) {
+    fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
+    const unsigned grid = fsb_grid(mesh->nnodes, 128, (int64_t)ctx->sm_count * 64);
+#define ROWS_LAUNCH(D, MODE) k_scalar_rows<D, MODE><<<grid, 128, 0, ctx->stream>>>(mesh->nnodes, mesh->cells, mesh->xyz, f, mesh->v2c_ptr, mesh->v2c, \
+                                                                                  A->row_ptr, A->vals, A->posmap, nullptr, nullptr)
+    if (mesh->tdim == 3) { if (overwrite) ROWS_LAUNCH(3, 1); else ROWS_LAUNCH(3, 0); }
+    else { if (overwrite) ROWS_LAUNCH(2, 1); else ROWS_LAUNCH(2, 0); }
+#undef ROWS_LAUNCH
+    FSB_LAUNCH_CHECK(ctx);
+    return FSB_OK;
+  }
+  if (overwrite) {
+    int rc = fsb_mat_zero(A);
+    if (rc) return rc;
+  }
+  if (mesh->degree == 2) return fsb_p2_scalar(mesh, A, nullptr, nullptr, kscale, ktensor, mass, adv, vel);
   fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
-  const uint8_t* pm = (ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const uint8_t* pm = (ctx->asm_mode >= 1 && A->mesh == mesh) ? A->posmap : nullptr;
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3)
     k_scalar_form<3, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, f, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);
@@ -469,6 +576,16 @@ extern "C" int fsb_assemble_scalar(fsb_mesh* mesh, fsb_mat* A, double kscale, co
     k_scalar_form<2, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, f, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);
   FSB_LAUNCH_CHECK(ctx);
   return FSB_OK;
+}
+
+extern "C" int fsb_assemble_scalar(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor, double mass,
+                                   double adv, const double* vel) {
+  return assemble_scalar_impl(mesh, A, kscale, ktensor, mass, adv, vel, 0);
+}
+
+extern "C" int fsb_assemble_scalar_set(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor, double mass,
+                                       double adv, const double* vel) {
+  return assemble_scalar_impl(mesh, A, kscale, ktensor, mass, adv, vel, 1);
 }
 
 extern "C" int fsb_apply_scalar(fsb_mesh* mesh, fsb_vec* x, fsb_vec* y, double kscale, const double* ktensor, double mass,
@@ -479,6 +596,15 @@ extern "C" int fsb_apply_scalar(fsb_mesh* mesh, fsb_vec* x, fsb_vec* y, double k
   if (mesh->degree == 2) return fsb_p2_scalar(mesh, nullptr, x, y, kscale, ktensor, mass, adv, vel);
   ScalarForm f;
   fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
+  if (rows_path(ctx, mesh, nullptr)) {
+    const unsigned g2 = fsb_grid(mesh->nnodes, 128, (int64_t)ctx->sm_count * 64);
+    if (mesh->tdim == 3)
+      k_scalar_rows<3, 2><<<g2, 128, 0, ctx->stream>>>(mesh->nnodes, mesh->cells, mesh->xyz, f, mesh->v2c_ptr, mesh->v2c, nullptr, nullptr, nullptr, x->d, y->d);
+    else
+      k_scalar_rows<2, 2><<<g2, 128, 0, ctx->stream>>>(mesh->nnodes, mesh->cells, mesh->xyz, f, mesh->v2c_ptr, mesh->v2c, nullptr, nullptr, nullptr, x->d, y->d);
+    FSB_LAUNCH_CHECK(ctx);
+    return FSB_OK;
+  }
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3)
     k_scalar_form<3, true><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, f, nullptr, nullptr, nullptr, nullptr, x->d, y->d);
@@ -493,7 +619,7 @@ extern "C" int fsb_assemble_elasticity(fsb_mesh* mesh, fsb_mat* A, double mu, do
   fsb_ctx* ctx = mesh->ctx;
   if (A->bs != mesh->tdim || A->nbrows != mesh->nnodes) FSB_FAIL(ctx, FSB_ERR_ARG, "elasticity needs a matrix with ncomp == dim on this mesh");
   if (mesh->degree == 2) return fsb_p2_elasticity(mesh, A, mu, lambda);
-  const uint8_t* pm = (ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const uint8_t* pm = (ctx->asm_mode >= 1 && A->mesh == mesh) ? A->posmap : nullptr;
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3)
     k_elasticity<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, mu, lambda, A->row_ptr, A->col_idx, A->vals, pm);
@@ -710,7 +836,7 @@ extern "C" int fsb_assemble_scalar_nonlinear_k(fsb_mesh* mesh, fsb_mat* A, fsb_v
   const int64_t n = mesh->nnodes;
   if (T->n != n || k->n != n || dk->n != n || (r && r->n != n) || (A && (A->bs != 1 || A->nbrows != n)))
     FSB_FAIL(ctx, FSB_ERR_ARG, "nonlinear conductivity needs the scalar matrix / nodal vectors of this mesh");
-  const uint8_t* pm = (A && ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const uint8_t* pm = (A && ctx->asm_mode >= 1 && A->mesh == mesh) ? A->posmap : nullptr;
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3)
     k_scalar_nonlinear_k<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, T->d, k->d, dk->d, scale, rscale,
@@ -730,7 +856,7 @@ extern "C" int fsb_assemble_advection_nodal(fsb_mesh* mesh, fsb_mat* A, fsb_vec*
   if (vel->n != n * mesh->tdim) FSB_FAIL(ctx, FSB_ERR_ARG, "the velocity field needs dim values per vertex");
   if (A && (A->bs != 1 || A->nbrows != n)) FSB_FAIL(ctx, FSB_ERR_ARG, "matrix does not belong to a scalar P1 space on this mesh");
   if (!A && (x->n != n || y->n != n || x == y)) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the mesh");
-  const uint8_t* pm = (A && ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const uint8_t* pm = (A && ctx->asm_mode >= 1 && A->mesh == mesh) ? A->posmap : nullptr;
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3) {
     if (A) k_advection_nodal<3, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, vel->d, scale, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);

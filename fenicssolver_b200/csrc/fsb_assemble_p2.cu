@@ -512,7 +512,7 @@ int fsb_p2_scalar(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, fsb_vec* y, double ksc
   fill_form(f, mesh->tdim, kscale, ktensor, mass, adv, vel);
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   const bool action = A == nullptr;
-  const uint8_t* pm = (!action && ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const uint8_t* pm = (!action && ctx->asm_mode >= 1 && A->mesh == mesh) ? A->posmap : nullptr;
   if (mesh->tdim == 3) {
     if (action) k_p2_scalar<3, true><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, f, mesh->p2_tables, nullptr, nullptr, nullptr, nullptr, x->d, y->d);
     else k_p2_scalar<3, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, f, mesh->p2_tables, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);
@@ -529,7 +529,7 @@ int fsb_p2_elasticity(fsb_mesh* mesh, fsb_mat* A, double mu, double lambda) {
   int rc = ensure_tables(mesh);
   if (rc) return rc;
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
-  const uint8_t* pm = (ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const uint8_t* pm = (ctx->asm_mode >= 1 && A->mesh == mesh) ? A->posmap : nullptr;
   if (mesh->tdim == 3) k_p2_elasticity<3><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, mu, lambda, mesh->p2_tables, A->row_ptr, A->col_idx, A->vals, pm);
   else k_p2_elasticity<2><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cell_nodes, mesh->xyz, mu, lambda, mesh->p2_tables, A->row_ptr, A->col_idx, A->vals, pm);
   FSB_LAUNCH_CHECK(ctx);

@@ -22,7 +22,7 @@ struct fsb_ctx {
   std::string err;
   int64_t launches = 0;
   // options
-  int asm_mode = 1;      // 0 search+atomics, 1 position map + atomics
+  int asm_mode = 2;      // 0 search+atomics, 1 position map + atomics, 2 row-gather (owner computes, no atomics) where it applies
   int spmv_mode = 0;     // 0 TMA-staged tiles v2, 1 plain row-per-thread, 2 TMA-staged v1 (one thread per row)
   int spmv_lpr = 0;      // lanes per row in the staged kernel (1, 2 or 4; 0 = best per block size)
   int spmv_rows = 0;     // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks; 0 = best per block size)
@@ -74,6 +74,10 @@ struct fsb_mesh {
   int64_t nnodes = 0;
   int32_t* cell_nodes = nullptr;   // [ncells][nl]; owned only when degree == 2
   double* p2_tables = nullptr;     // device copy of the P2 reference tensors for this dimension (degree 2)
+  // vertex -> cell adjacency of a degree-1 mesh (built with the first matrix, cell ids ascending per vertex): the row-gather
+  // assembly kernels walk it
+  int64_t* v2c_ptr = nullptr;      // [nverts+1]
+  int32_t* v2c = nullptr;          // [ncells*(tdim+1)]
   // K1 (fsb_facets.cu): exterior facets in lexicographic order, made on first request
   int64_t nbf = -1, nfacets = 0;   // exterior facets / distinct facets of the mesh
   int32_t* bf_verts = nullptr;     // [nbf][tdim] sorted vertex tuples

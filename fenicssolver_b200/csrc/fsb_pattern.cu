@@ -138,6 +138,20 @@ __global__ void k_v2c_fill(const int32_t* __restrict__ cells, int64_t ncells, in
     }
 }
 
+// ascending cell order inside every vertex's list: the atomic cursor of k_v2c_fill leaves them in arrival order, and the row-gather
+// assembly (fsb_assemble_rows.cu) sums a row's contributions in list order — sorted lists make it bitwise reproducible
+__global__ void k_v2c_sort(int64_t nverts, const int64_t* __restrict__ vptr, int32_t* __restrict__ v2c) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nverts; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = vptr[v], p1 = vptr[v + 1];
+    for (int64_t i = p0 + 1; i < p1; ++i) {
+      const int32_t c = v2c[i];
+      int64_t j = i;
+      while (j > p0 && v2c[j - 1] > c) { v2c[j] = v2c[j - 1]; --j; }
+      v2c[j] = c;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ rows
 // One warp per row.  Candidates L[i] = cells[v2c[p0 + i/nl]][i%nl], i < m = deg*nl.  They are sorted in
 // shared memory when m <= kRowCap, otherwise scanned from global memory (L1).
@@ -342,20 +356,37 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
   int32_t *deg = nullptr, *v2c = nullptr, *d_max = nullptr, *keep = nullptr;
   int64_t* vptr = nullptr;
   int rc = FSB_OK;
-  auto cleanup = [&]() { fsb_dfree(ctx, deg); fsb_dfree(ctx, v2c); fsb_dfree(ctx, vptr); fsb_dfree(ctx, d_max); fsb_dfree(ctx, keep); };
+  auto cleanup = [&]() {
+    fsb_dfree(ctx, deg); fsb_dfree(ctx, d_max); fsb_dfree(ctx, keep);
+    if (v2c != mesh->v2c) fsb_dfree(ctx, v2c);          // the mesh owns a kept adjacency
+    if (vptr != mesh->v2c_ptr) fsb_dfree(ctx, vptr);
+    v2c = nullptr; vptr = nullptr;
+  };
 #define TRY(x) do { rc = (x); if (rc) { cleanup(); fsb_mat_destroy(A); return rc; } } while (0)
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); fsb_mat_destroy(A); return FSB_ERR_CUDA; } } while (0)
   TRY(fsb_dmalloc(ctx, &deg, (size_t)nv + 1));
-  TRY(fsb_dmalloc(ctx, &vptr, (size_t)nv + 1));
-  TRY(fsb_dmalloc(ctx, &v2c, (size_t)nc * nl));
   TRY(fsb_dmalloc(ctx, &d_max, 1));
-  TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
-  k_v2c_count<<<fsb_grid(nc * nl, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc * nl, deg);
-  ctx->launches++; TRYCUDA(cudaGetLastError());
-  TRY(fsb_exclusive_scan(ctx, deg, vptr, nv));
-  TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
-  k_v2c_fill<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc, nl, vptr, deg, v2c);
-  ctx->launches++; TRYCUDA(cudaGetLastError());
+  // vertex -> cell adjacency.  A degree-1 mesh keeps it (sorted per vertex) for the row-gather assembly kernels; a second
+  // matrix on the same mesh reuses it
+  const bool keep_adj = mesh->degree == 1;
+  if (keep_adj && mesh->v2c) {
+    vptr = mesh->v2c_ptr; v2c = mesh->v2c;
+  } else {
+    TRY(fsb_dmalloc(ctx, &vptr, (size_t)nv + 1));
+    TRY(fsb_dmalloc(ctx, &v2c, (size_t)nc * nl));
+    TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+    k_v2c_count<<<fsb_grid(nc * nl, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc * nl, deg);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+    TRY(fsb_exclusive_scan(ctx, deg, vptr, nv));
+    TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+    k_v2c_fill<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc, nl, vptr, deg, v2c);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+    if (keep_adj) {
+      k_v2c_sort<<<fsb_grid(nv, 256, cap), 256, 0, ctx->stream>>>(nv, vptr, v2c);
+      ctx->launches++; TRYCUDA(cudaGetLastError());
+      mesh->v2c_ptr = vptr; mesh->v2c = v2c;
+    }
+  }
   // row lengths -> row_ptr
   TRY(fsb_dmalloc(ctx, &A->row_ptr, (size_t)nv + 1));
   // scratch for the sorted short rows (128 B per row); without it the fill pass simply sorts every row again
@@ -383,8 +414,9 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
     ctx->launches++; TRYCUDA(cudaGetLastError());
   }
   TRYCUDA(cudaStreamSynchronize(ctx->stream));
-  fsb_dfree(ctx, v2c); v2c = nullptr;
-  fsb_dfree(ctx, vptr); vptr = nullptr;
+  if (v2c != mesh->v2c) fsb_dfree(ctx, v2c);
+  if (vptr != mesh->v2c_ptr) fsb_dfree(ctx, vptr);
+  v2c = nullptr; vptr = nullptr;
   fsb_dfree(ctx, keep); keep = nullptr;
   TRY(fsb_dmalloc(ctx, &A->vals, (size_t)nnzb * ncomp * ncomp));
   TRYCUDA(cudaMemsetAsync(A->vals, 0, sizeof(double) * nnzb * ncomp * ncomp + 512, ctx->stream));

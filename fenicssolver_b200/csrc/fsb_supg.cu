@@ -158,7 +158,7 @@ extern "C" int fsb_assemble_scalar_supg(fsb_mesh* mesh, fsb_mat* A, fsb_vec* x, 
   if (rc) return rc;
   if (A && (A->bs != 1 || A->nbrows != mesh->nnodes)) FSB_FAIL(ctx, FSB_ERR_ARG, "matrix does not belong to a scalar P1 space on this mesh");
   if (!A && (x->n != mesh->nnodes || y->n != mesh->nnodes || x == y)) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the mesh");
-  const uint8_t* pm = (A && ctx->asm_mode == 1 && A->mesh == mesh) ? A->posmap : nullptr;
+  const uint8_t* pm = (A && ctx->asm_mode >= 1 && A->mesh == mesh) ? A->posmap : nullptr;
   const unsigned grid = fsb_grid(mesh->ncells, 128, (int64_t)ctx->sm_count * 64);
   if (mesh->tdim == 3) {
     if (A) k_scalar_supg<3, false><<<grid, 128, 0, ctx->stream>>>(mesh->ncells, mesh->cells, mesh->xyz, p, mass, adv, A->row_ptr, A->col_idx, A->vals, pm, nullptr, nullptr);

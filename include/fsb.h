@@ -65,7 +65,8 @@ void fsb_destroy(fsb_ctx* ctx);
 const char* fsb_last_error(fsb_ctx* ctx);
 int fsb_sync(fsb_ctx* ctx);
 int fsb_device_info(fsb_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes);
-/* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 position-map+atomics),
+/* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 position-map+atomics, 2 = default: row-gather kernels
+ * without atomics for the degree-1 scalar forms, position-map+atomics elsewhere),
  * "spmv_mode" (0 TMA-staged tiles, 1 plain row-per-thread), "profile" (0/1), "graph" (0/1),
  * "check_every" (iterations between host convergence polls), "drop_zeros" (the Krylov SpMVs run on a
  * compacted copy without the blocks that are exactly zero after assembly; the assembled CSR, the parity object, is untouched:
@@ -142,6 +143,10 @@ void fsb_mat_destroy(fsb_mat* A);
  * Restates ScalarTransportSolver.py:284-285 (F_static), :292 (transient mass), :311 (convection). */
 int fsb_assemble_scalar(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor,
                         double mass, double adv, const double* vel);
+/* A = the same form (what `A = assemble(a)` on a fresh tensor is): equal to fsb_mat_zero + fsb_assemble_scalar; the row-gather
+ * kernel writes every row once and skips the zero-fill. */
+int fsb_assemble_scalar_set(fsb_mesh* mesh, fsb_mat* A, double kscale, const double* ktensor,
+                            double mass, double adv, const double* vel);
 /* y += (kscale*K + mass*M + adv*C(vel)) x   cell by cell without forming the matrix: the
  * Crank-Nicolson right-hand side (1/dt) c M T_prev - (1-theta) K T_prev, ScalarTransportSolver.py:292-293 */
 int fsb_apply_scalar(fsb_mesh* mesh, fsb_vec* x, fsb_vec* y, double kscale, const double* ktensor,

@@ -174,7 +174,7 @@ def test_pattern_high_valence_vertex(ctx):
 
 
 # ----------------------------------------------------------------------------------- assembly
-@pytest.mark.parametrize("asm_mode", [0, 1])
+@pytest.mark.parametrize("asm_mode", [0, 1, 2])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_assemble_scalar_terms(ctx, dim, asm_mode):
     n = (7, 5) if dim == 2 else (5, 4, 6)
@@ -207,7 +207,45 @@ def test_assemble_scalar_terms(ctx, dim, asm_mode):
             assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
             assert_vals_close(dev.data, ref.data)
     finally:
-        ctx.set_option("asm_mode", 1)
+        ctx.set_option("asm_mode", 2)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_row_gather_assembly_overwrite_action_and_reproducibility(ctx, dim):
+    """asm_mode 2 (default), k_scalar_rows: `overwrite` equals zero + add on a matrix holding garbage, the matrix-free action equals
+    A x, two assemblies are bitwise identical (fixed summation order — the atomic scatter cannot promise that), and the result equals
+    the scatter kernel's to rounding."""
+    n = (9, 6) if dim == 2 else (6, 5, 4)
+    c, t = (fo.rectangle_mesh(0, 0, 2, 1, *n) if dim == 2 else fo.box_mesh((0, 0, 0), (2, 1, 3), *n))
+    c = jitter(c, max(n), seed=5)
+    nv = c.shape[0]
+    m = _lib.DeviceMesh.upload(ctx, c, t)
+    rng = np.random.default_rng(7)
+    vel = rng.random(dim) - 0.5
+    kw = dict(kscale=0.7, mass=1.25, adv=4.0, vel=vel)
+    A = _lib.DeviceMatrix.create(m, 1)
+    A.assemble_scalar(kscale=123.0, mass=7.0)                    # garbage to be overwritten
+    A.assemble_scalar(overwrite=True, **kw)
+    v1 = A.download_csr()[2].copy()
+    A.zero()
+    A.assemble_scalar(**kw)
+    v2 = A.download_csr()[2].copy()
+    assert np.array_equal(v1, v2)                                # bitwise: same kernel, same order, with and without the zero-fill
+    A.assemble_scalar(overwrite=True, **kw)
+    assert np.array_equal(A.download_csr()[2], v1)
+    ctx.set_option("asm_mode", 1)
+    try:
+        B = _lib.DeviceMatrix.create(m, 1)
+        B.assemble_scalar(**kw)
+        assert_vals_close(B.download_csr()[2], v1)
+    finally:
+        ctx.set_option("asm_mode", 2)
+    xh = rng.standard_normal(nv)
+    x, y = _lib.DeviceVector.from_numpy(ctx, xh), _lib.DeviceVector.from_numpy(ctx, np.ones(nv))
+    _lib.apply_scalar(m, x, y, **kw)
+    Am, _, _ = csr_from_device(A)
+    ref = 1.0 + Am @ xh
+    assert np.abs(y.numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
 def test_assemble_accumulates_and_zero(ctx):
@@ -261,7 +299,7 @@ def test_apply_scalar_matches_matrix_action(ctx, dim):
     assert_vals_close(y.numpy(), ref)
 
 
-@pytest.mark.parametrize("asm_mode", [0, 1])
+@pytest.mark.parametrize("asm_mode", [0, 1, 2])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_assemble_elasticity(ctx, dim, asm_mode):
     n = (5, 4) if dim == 2 else (3, 4, 3)
@@ -275,7 +313,7 @@ def test_assemble_elasticity(ctx, dim, asm_mode):
         A = _lib.DeviceMatrix.create(m, dim)
         A.assemble_elasticity(mu, lam)
     finally:
-        ctx.set_option("asm_mode", 1)
+        ctx.set_option("asm_mode", 2)
     dev, rp, ci = csr_from_device(A)
     rp0, ci0 = fo.csr_pattern(t, nv, dim)
     ref = fo.conform(fo.assemble_matrix(t, fo.local_elasticity(c, t, mu, lam), nv, dim), rp0, ci0)

@@ -35,7 +35,7 @@ def close(dev, ref, tol=1e-13):
     assert np.abs(dev - ref).max() <= tol * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("asm_mode", [0, 1])
+@pytest.mark.parametrize("asm_mode", [0, 1, 2])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_p2_pattern_and_scalar_terms(ctx, dim, asm_mode):
     c, t, cn, xc, edges = mesh_case(dim)
@@ -61,7 +61,7 @@ def test_p2_pattern_and_scalar_terms(ctx, dim, asm_mode):
             ref = fo.conform(p2.assemble_matrix(cn, Ke, nn), rp0, ci0)
             close(dev.data, ref.data)
     finally:
-        ctx.set_option("asm_mode", 1)
+        ctx.set_option("asm_mode", 2)
     # matrix-free action (Crank-Nicolson right-hand side)
     xh = rng.random(nn)
     x, y = _lib.DeviceVector.from_numpy(ctx, xh), _lib.DeviceVector(ctx, nn)
