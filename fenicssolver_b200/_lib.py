@@ -44,6 +44,7 @@ SIGNATURES = {
     "fsb_mesh_download": (C.c_int, [c_vp, c_vp, c_vp]),
     "fsb_mesh_exterior_facets": (C.c_int, [c_vp, P(c_i64), P(c_i64)]),
     "fsb_mesh_exterior_facets_get": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "fsb_mesh_boundary_geometry": (C.c_int, [c_vp, P(c_i64), c_vp, c_vp, c_vp, c_vp]),
     "fsb_mesh_destroy": (None, [c_vp]),
     "fsb_vec_create": (C.c_int, [c_vp, c_i64, P(c_vp)]),
     "fsb_vec_fill": (C.c_int, [c_vp, c_dbl]),
@@ -271,6 +272,20 @@ class DeviceMesh(_Handle):
         self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets_get(self.h, _ptr(fv), _ptr(opp), _ptr(cell), _ptr(fid)))
         self.num_facets = nf.value
         return fv, opp, cell, fid
+
+    def boundary_geometry(self):
+        """(bverts[nbv], finv[nbf, tdim], bxyz[nbv, gdim], mid[nbf, gdim]): distinct boundary vertices, the exterior facets in terms of
+        them, their coordinates and the facet midpoints — what SubDomain.mark evaluates its predicate on."""
+        nbv, nbf = c_i64(), c_i64()
+        self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets(self.h, C.byref(nbf), None))
+        self.ctx.check(self.ctx.lib.fsb_mesh_boundary_geometry(self.h, C.byref(nbv), None, None, None, None))
+        g, t, _, _ = self.sizes()
+        bv = np.empty(nbv.value, dtype=np.int32)
+        finv = np.empty((nbf.value, t), dtype=np.int32)
+        bxyz = np.empty((nbv.value, g), dtype=np.float64)
+        mid = np.empty((nbf.value, g), dtype=np.float64)
+        self.ctx.check(self.ctx.lib.fsb_mesh_boundary_geometry(self.h, None, _ptr(bv), _ptr(finv), _ptr(bxyz), _ptr(mid)))
+        return bv, finv, bxyz, mid
 
     def download(self):
         g, t, nv, nc = self.sizes()

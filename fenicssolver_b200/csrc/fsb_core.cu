@@ -395,6 +395,7 @@ extern "C" void fsb_mesh_destroy(fsb_mesh* m) {
   fsb_dfree(m->ctx, m->cells);
   fsb_dfree(m->ctx, m->p2_tables);
   fsb_dfree(m->ctx, m->v2c_ptr); fsb_dfree(m->ctx, m->v2c);
+  fsb_dfree(m->ctx, m->bg_verts); fsb_dfree(m->ctx, m->bg_finv); fsb_dfree(m->ctx, m->bg_xyz); fsb_dfree(m->ctx, m->bg_mid);
   fsb_dfree(m->ctx, m->bf_verts); fsb_dfree(m->ctx, m->bf_opp); fsb_dfree(m->ctx, m->bf_cell); fsb_dfree(m->ctx, m->bf_id);
   delete m;
 }

@@ -247,6 +247,82 @@ int exterior_facets_impl(fsb_mesh* mesh) {
 
 }  // namespace
 
+// ---- boundary geometry for SubDomain.mark: the distinct boundary vertices (ascending), each facet's vertices as indices into that
+// list, the boundary vertices' coordinates and the facet midpoints ((x_a + x_b [+ x_c]) / tdim, summed in that order)
+namespace {
+
+__global__ void k_bg_flag(const int32_t* __restrict__ fverts, int64_t n, int32_t* __restrict__ flag) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) flag[fverts[i]] = 1;
+}
+__global__ void k_bg_compact(const int32_t* __restrict__ flag, const int64_t* __restrict__ rank, int64_t nverts, const double* __restrict__ xyz, int gdim,
+                             int32_t* __restrict__ bverts, double* __restrict__ bxyz) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nverts; v += (int64_t)gridDim.x * blockDim.x)
+    if (flag[v]) {
+      const int64_t k = rank[v];
+      bverts[k] = (int32_t)v;
+      for (int i = 0; i < gdim; ++i) bxyz[k * gdim + i] = xyz[v * gdim + i];
+    }
+}
+__global__ void k_bg_facets(const int32_t* __restrict__ fverts, int64_t nbf, int d, const int64_t* __restrict__ rank, const double* __restrict__ xyz, int gdim,
+                            int32_t* __restrict__ finv, double* __restrict__ mid) {
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nbf; f += (int64_t)gridDim.x * blockDim.x) {
+    for (int j = 0; j < d; ++j) finv[f * d + j] = (int32_t)rank[fverts[f * d + j]];
+    for (int i = 0; i < gdim; ++i) {
+      double s = xyz[(int64_t)fverts[f * d] * gdim + i];
+      for (int j = 1; j < d; ++j) s = __dadd_rn(s, xyz[(int64_t)fverts[f * d + j] * gdim + i]);
+      mid[f * gdim + i] = __ddiv_rn(s, (double)d);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int fsb_mesh_boundary_geometry(fsb_mesh* mesh, int64_t* nbv_out, int32_t* bverts, int32_t* finv, double* bxyz, double* mid) {
+  if (!mesh) return FSB_ERR_ARG;
+  fsb_ctx* ctx = mesh->ctx;
+  int rc = fsb_mesh_exterior_facets(mesh, nullptr, nullptr);
+  if (rc) return rc;
+  const int64_t nbf = mesh->nbf, nv = mesh->nverts;
+  const int d = mesh->tdim, g = mesh->gdim;
+  const int cap = ctx->sm_count * 16;
+  if (mesh->nbv < 0) {
+    int32_t* flag = nullptr;
+    int64_t* rank = nullptr;
+    if ((rc = fsb_dmalloc(ctx, &flag, (size_t)nv + 1)) || (rc = fsb_dmalloc(ctx, &rank, (size_t)nv + 1))) { fsb_dfree(ctx, flag); return rc; }
+    FSB_CHECK_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+    if (nbf > 0) {
+      k_bg_flag<<<fsb_grid(nbf * d, 256, cap), 256, 0, ctx->stream>>>(mesh->bf_verts, nbf * d, flag);
+      ctx->launches++;
+    }
+    rc = fsb_exclusive_scan(ctx, flag, rank, nv);
+    int64_t nbv = 0;
+    if (!rc) {
+      FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(&nbv, rank + nv, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (!(rc = fsb_dmalloc(ctx, &mesh->bg_verts, (size_t)nbv + 1)) && !(rc = fsb_dmalloc(ctx, &mesh->bg_finv, (size_t)nbf * d + 1)) &&
+          !(rc = fsb_dmalloc(ctx, &mesh->bg_xyz, (size_t)nbv * g + 1)) && !(rc = fsb_dmalloc(ctx, &mesh->bg_mid, (size_t)nbf * g + 1)) && nbf > 0) {
+        k_bg_compact<<<fsb_grid(nv, 256, cap), 256, 0, ctx->stream>>>(flag, rank, nv, mesh->xyz, g, mesh->bg_verts, mesh->bg_xyz);
+        ctx->launches++;
+        k_bg_facets<<<fsb_grid(nbf, 256, cap), 256, 0, ctx->stream>>>(mesh->bf_verts, nbf, d, rank, mesh->xyz, g, mesh->bg_finv, mesh->bg_mid);
+        ctx->launches++;
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    fsb_dfree(ctx, flag); fsb_dfree(ctx, rank);
+    if (rc) return rc;
+    if (e != cudaSuccess) FSB_FAIL(ctx, FSB_ERR_CUDA, cudaGetErrorString(e));
+    mesh->nbv = nbv;
+  }
+  if (nbv_out) *nbv_out = mesh->nbv;
+  const int64_t nbv = mesh->nbv;
+  if (bverts && nbv) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(bverts, mesh->bg_verts, sizeof(int32_t) * nbv, cudaMemcpyDeviceToHost, ctx->stream));
+  if (finv && nbf) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(finv, mesh->bg_finv, sizeof(int32_t) * nbf * d, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bxyz && nbv) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(bxyz, mesh->bg_xyz, sizeof(double) * nbv * g, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mid && nbf) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(mid, mesh->bg_mid, sizeof(double) * nbf * g, cudaMemcpyDeviceToHost, ctx->stream));
+  FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FSB_OK;
+}
+
 extern "C" int fsb_mesh_exterior_facets(fsb_mesh* mesh, int64_t* nbf, int64_t* nfacets) {
   if (!mesh) return FSB_ERR_ARG;
   fsb_ctx* ctx = mesh->ctx;

@@ -84,6 +84,11 @@ struct fsb_mesh {
   int32_t* bf_opp = nullptr;       // [nbf] vertex of the cell opposite the facet
   int32_t* bf_cell = nullptr;      // [nbf] the one cell holding the facet
   int64_t* bf_id = nullptr;        // [nbf] dolfin facet index = rank among all distinct facets
+  int64_t nbv = -1;                // distinct boundary vertices (fsb_mesh_boundary_geometry)
+  int32_t* bg_verts = nullptr;     // [nbv] ascending
+  int32_t* bg_finv = nullptr;      // [nbf][tdim] facet vertices as indices into bg_verts
+  double* bg_xyz = nullptr;        // [nbv][gdim]
+  double* bg_mid = nullptr;        // [nbf][gdim] facet midpoints
 };
 
 struct fsb_vec {

@@ -614,10 +614,15 @@ class FacetMarkers:
         (dolfin's default check_midpoint=True; SolverBase.py:281-282)."""
         geom = getattr(self.mesh, "_boundary_geometry", None)
         if geom is None:      # unique boundary vertices, their coordinates and the facet midpoints: once per mesh
-            uv, inv = np.unique(self.fverts, return_inverse=True)
-            inv = inv.reshape(self.fverts.shape)
-            pts = self.mesh.coordinates()[uv]
-            geom = self.mesh._boundary_geometry = (inv, pts, pts[inv].mean(axis=1))
+            dm = self.mesh.__dict__.get("_dmesh")
+            if dm is not None and dm.h is not None and getattr(self.mesh, "_exterior_cells", None) is not None:
+                _bv, inv, pts, mid = dm.boundary_geometry()          # made on the device next to the facet search (K1)
+                geom = self.mesh._boundary_geometry = (inv, pts, mid)
+            else:                                                    # host-enumerated box surface (slab-distributed / no GPU)
+                uv, inv = np.unique(self.fverts, return_inverse=True)
+                inv = inv.reshape(self.fverts.shape)
+                pts = self.mesh.coordinates()[uv]
+                geom = self.mesh._boundary_geometry = (inv, pts, pts[inv].mean(axis=1))
         inv, pts, mid = geom
         ok = _evaluate_predicate(sub, mid) & _evaluate_predicate(sub, pts)[inv].all(axis=1)
         self._values[ok] = value

@@ -109,6 +109,10 @@ int fsb_mesh_download(fsb_mesh* mesh, double* xyz, int32_t* cells);
  * facet_id[nbf] = the facet's index in dolfin's numbering (rank of its vertex tuple among all distinct facets). */
 int fsb_mesh_exterior_facets(fsb_mesh* mesh, int64_t* nbf, int64_t* nfacets);
 int fsb_mesh_exterior_facets_get(fsb_mesh* mesh, int32_t* fverts, int32_t* opp, int32_t* cell, int64_t* facet_id);
+/* What SubDomain.mark evaluates `inside` on (SolverBase.py:281-282: all vertices of a facet and its midpoint): *nbv = number of
+ * distinct boundary vertices; bverts[nbv] ascending; finv[nbf][tdim] = the facets' vertices as indices into bverts;
+ * bxyz[nbv][gdim] their coordinates; mid[nbf][gdim] the facet midpoints.  Call once with NULL arrays for the size. */
+int fsb_mesh_boundary_geometry(fsb_mesh* mesh, int64_t* nbv, int32_t* bverts, int32_t* finv, double* bxyz, double* mid);
 void fsb_mesh_destroy(fsb_mesh* mesh);
 
 /* ---- vectors: dolfin GenericVector ----------------------------------------------------------- */

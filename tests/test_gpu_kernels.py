@@ -100,6 +100,20 @@ def test_exterior_facets_and_facet_ids_bit_exact(ctx, golden_dir, case):
     assert np.array_equal(fv, fv2) and np.array_equal(fid, fid2)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_boundary_geometry_for_subdomain_marking(ctx, dim):
+    """fsb_mesh_boundary_geometry: distinct boundary vertices, facets in terms of them, coordinates and midpoints — bit-exact against
+    the numpy statement (np.unique / fancy indexing / mean) that FacetMarkers.mark_subdomain used on the host."""
+    c, t = (fo.unit_square_mesh(7, 5) if dim == 2 else fo.unit_cube_mesh(4, 5, 3))
+    c = jitter(c, 7, seed=11)
+    m = _lib.DeviceMesh.upload(ctx, c, np.ascontiguousarray(t, dtype=np.int32))
+    fv, _, _, _ = m.exterior_facets()
+    bv, finv, bxyz, mid = m.boundary_geometry()
+    uv, inv = np.unique(fv, return_inverse=True)
+    assert np.array_equal(bv, uv) and np.array_equal(finv, inv.reshape(fv.shape))
+    assert np.array_equal(bxyz, c[uv]) and np.array_equal(mid, c[uv][inv.reshape(fv.shape)].mean(axis=1))
+
+
 def test_exterior_facets_through_mesh_api(ctx):
     """Mesh.exterior_facets()/exterior_facet_ids() of an array mesh and of a generated box both come from the device search and agree
     with the direct enumeration of the dolfin box layout."""

@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh <timeout_s> '<command>'   — retries while the pod answers busy (exit 3 / transient), up to 12 times
+T=$1; shift
+for i in $(seq 1 12); do
+  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@" > /tmp/gpurun_last.log 2>&1
+  rc=$?
+  if grep -q "status=transient" /tmp/gpurun_last.log || [ $rc -eq 3 ]; then sleep 90; continue; fi
+  break
+done
+tail -60 /tmp/gpurun_last.log
