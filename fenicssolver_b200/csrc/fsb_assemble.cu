@@ -877,7 +877,11 @@ extern "C" int fsb_apply_dirichlet(fsb_mat* A, fsb_vec* b, fsb_vec* x, int64_t n
   if (b->n != n || (x && x->n != n)) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the matrix");
   for (int64_t i = 0; i < nbc; ++i)
     if (dofs[i] < 0 || dofs[i] >= n) FSB_FAIL(ctx, FSB_ERR_ARG, "Dirichlet dof out of range");
-  if (nbc == 0) return FSB_OK;
+  if (nbc == 0) {
+    // no constrained dof this time: flags left by an earlier call must not survive (the multigrid transfers read them)
+    if (A->bc_flag) FSB_CHECK_CUDA(ctx, cudaMemsetAsync(A->bc_flag, 0, (size_t)n, ctx->stream));
+    return FSB_OK;
+  }
   if (!A->bc_flag) {
     int rc = fsb_dmalloc(ctx, &A->bc_flag, (size_t)n);
     if (!rc) rc = fsb_dmalloc(ctx, &A->bc_val, (size_t)n);

@@ -81,7 +81,7 @@ class Constant:
 
 
 _EXPR_NAMES = {k: getattr(np, k) for k in ("sin", "cos", "tan", "exp", "log", "sqrt", "fabs", "floor", "ceil", "arctan2")}
-_EXPR_NAMES.update({"pow": np.power, "abs": np.abs, "pi": math.pi, "atan2": np.arctan2, "DOLFIN_PI": math.pi, "where": np.where, "logical_and": np.logical_and, "logical_or": np.logical_or,
+_EXPR_NAMES.update({"pow": np.power, "abs": np.abs, "pi": math.pi, "atan2": np.arctan2, "DOLFIN_PI": math.pi, "where": np.where, "logical_and": np.logical_and, "logical_or": np.logical_or, "logical_not": np.logical_not,
                     "fmin": np.minimum, "fmax": np.maximum, "min": np.minimum, "max": np.maximum, "sinh": np.sinh, "cosh": np.cosh,
                     "tanh": np.tanh, "asin": np.arcsin, "acos": np.arccos, "atan": np.arctan, "erf": None})
 _EXPR_NAMES.pop("erf")
@@ -147,7 +147,45 @@ def _cpp_to_python(src):
                 return acc
         return out
 
-    return conv(re.sub(r"!(?!=)", " ~", src))
+    return conv(re.sub(r"!(?!=)", " _not_ ", src))
+
+
+def _validate_expression_ast(py_src, names):
+    """Only arithmetic on whitelisted names: no attribute access, no dunder names, no lambdas/comprehensions/strings.  Returns the
+    compiled code.  `_not_ x` (from C++ `!x`) was rewritten to a logical_not call before parsing; integer-literal division follows
+    C++ (both operands integer literals -> truncating division), everything else is floating point as in a compiled Expression."""
+    import ast
+    py_src = re.sub(r"_not_\s*(\w+(\[[^\]]*\])?|\([^()]*\))", r"logical_not(\1)", py_src)
+    if "_not_" in py_src:
+        raise SolverError("unsupported use of ! in Expression")
+    try:
+        tree = ast.parse(py_src.strip(), mode="eval")
+    except SyntaxError as ex:
+        raise SolverError("cannot parse Expression %r: %s" % (py_src, ex))
+    allowed = (ast.Expression, ast.BinOp, ast.UnaryOp, ast.Compare, ast.Call, ast.Name, ast.Load, ast.Constant, ast.Subscript, ast.Tuple,
+               ast.Add, ast.Sub, ast.Mult, ast.Div, ast.Pow, ast.Mod, ast.USub, ast.UAdd, ast.Invert, ast.Lt, ast.LtE, ast.Gt, ast.GtE,
+               ast.Eq, ast.NotEq, ast.BitAnd, ast.BitOr, ast.FloorDiv)
+
+    class IntDiv(ast.NodeTransformer):
+        def visit_BinOp(self, node):
+            self.generic_visit(node)
+            if (isinstance(node.op, ast.Div) and isinstance(node.left, ast.Constant) and isinstance(node.right, ast.Constant)
+                    and type(node.left.value) is int and type(node.right.value) is int and node.right.value != 0):
+                q = abs(node.left.value) // abs(node.right.value)          # C++ truncates toward zero
+                return ast.copy_location(ast.Constant(q if (node.left.value < 0) == (node.right.value < 0) else -q), node)
+            return node
+
+    for node in ast.walk(tree):
+        if not isinstance(node, allowed):
+            raise SolverError("unsupported construct %s in Expression %r" % (type(node).__name__, py_src))
+        if isinstance(node, ast.Name) and (node.id.startswith("_") or node.id not in names):
+            raise SolverError("unknown name %r in Expression %r" % (node.id, py_src))
+        if isinstance(node, ast.Call) and not isinstance(node.func, ast.Name):
+            raise SolverError("only calls of the math functions are allowed in Expression %r" % py_src)
+        if isinstance(node, ast.Constant) and not isinstance(node.value, (int, float)):
+            raise SolverError("only numeric literals are allowed in Expression %r" % py_src)
+    tree = ast.fix_missing_locations(IntDiv().visit(tree))
+    return compile(tree, "<Expression>", "eval")
 
 
 def _split_top(e, op):
@@ -202,7 +240,8 @@ class Expression:
         env["x"] = x
         if not re.fullmatch(r"[\w\s\.\+\-\*/\(\)\[\],<>=!&|?:]*", src):
             raise SolverError("unsupported characters in Expression %r" % src)
-        val = eval(_cpp_to_python(src), {"__builtins__": {}}, env)  # noqa: S307
+        code = _validate_expression_ast(_cpp_to_python(src), env)
+        val = eval(code, {"__builtins__": {}}, env)  # noqa: S307  (validated: arithmetic on whitelisted names only)
         return np.broadcast_to(np.asarray(val, dtype=np.float64), x[0].shape).copy()
 
     def __call__(self, coords):

@@ -570,3 +570,16 @@ def test_generic_vector_surface():
     assert u.values[1] == 1.0                     # get_local returns a copy
     with pytest.raises(SolverBase.SolverError):
         v.norm("frobenius")
+
+
+def test_expression_is_validated_and_follows_cpp_integer_division():
+    """Expression strings (they also arrive in JSON case files) are parsed and restricted to arithmetic on whitelisted names: no
+    attribute access, no dunder names, no strings or lambdas; `!x` is logical not; a quotient of two integer literals truncates as
+    in the reference's compiled C++ Expression."""
+    c = np.array([[0.2, 0.7], [0.8, 0.1]])
+    assert np.allclose(Expression("x[0] < 0.5 && !(x[1] < 0.5) ? 1/2 + 1.0/2 : pow(x[0], 2)")(c), [0.5, 0.64])
+    assert np.allclose(Expression("a*sin(pi*x[0]) + 7/2", a=2.0)(c), 2.0 * np.sin(np.pi * c[:, 0]) + 3)
+    assert np.allclose(Expression("-7/2 + x[1]")(c), -3 + c[:, 1])
+    for bad in ["x.__class__", "__import__('os')", "x[0].real", "(lambda: 1)()", "'a'*3", "x[0] if 1 else 2", "[v for v in x]"]:
+        with pytest.raises(SolverBase.SolverError):
+            Expression(bad)(c)
