@@ -167,6 +167,12 @@ def _validate_expression_ast(py_src, names):
                ast.Eq, ast.NotEq, ast.BitAnd, ast.BitOr, ast.FloorDiv)
 
     class IntDiv(ast.NodeTransformer):
+        def visit_UnaryOp(self, node):
+            self.generic_visit(node)
+            if isinstance(node.op, ast.USub) and isinstance(node.operand, ast.Constant) and type(node.operand.value) is int:
+                return ast.copy_location(ast.Constant(-node.operand.value), node)
+            return node
+
         def visit_BinOp(self, node):
             self.generic_visit(node)
             if (isinstance(node.op, ast.Div) and isinstance(node.left, ast.Constant) and isinstance(node.right, ast.Constant)
