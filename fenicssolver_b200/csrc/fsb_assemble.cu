@@ -76,13 +76,16 @@ k_scalar_form(int64_t ncells, const int32_t* __restrict__ cells, const double* _
 }
 
 // ------------------------------------------------------------------------------------ row-gather form of the same kernel
-// asm_mode 2 (default).  ncu on the scatter kernel above (profiles/assembly_r1.txt): 0.17 of the HBM roofline, bound by the RATE of
+// asm_mode 2 (opt-in; the A/B below decided against it as the default).  ncu on the scatter kernel above (profiles/assembly_r1.txt): 0.17 of the HBM roofline, bound by the RATE of
 // scalar fp64 REDs (9.2 per tet, SM-side issue ~1.3 cycles per lane), DRAM traffic 1.9x the algorithmic bytes because every RED that
 // misses L2 fetches its sector and A has to be zero-filled first.  Here the OWNER of a row computes it: one thread per row walks the
 // cells around its vertex (the sorted vertex->cell adjacency the symbolic phase keeps), recomputes their affine geometry (4x
 // redundant fp64 work — cheap next to the REDs it replaces), accumulates row `a` of every local matrix in thread-private shared
 // memory slots addressed by the position map, and writes the finished row once: no atomics, no zero-fill, no read-modify-write of
 // A, and the sum order is fixed (ascending cell index), so the assembled matrix is bitwise reproducible run to run.
+// MEASURED (tools/asm_ab.py, profiles/asm_ab_r2.txt, 256^3): 10.6 ms against the scatter kernel's 5.4 ms (zero-fill included), the
+// matrix-free action 4.7 ms against 2.2 ms: 403 M cell visits of dependent gathers (cell -> 4 coordinates) cost more than the 926 M
+// REDs they replace.  Kept for runs that need reproducible sums.
 // MODE 0: vals += row, 1: vals = row (caller would otherwise zero A first), 2: y[row] += (row of K_e) . x (matrix-free action).
 constexpr int kRowSlots = 32;       // longest row the shared-memory slots hold (host falls back to the scatter kernel beyond)
 

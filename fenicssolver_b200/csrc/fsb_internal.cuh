@@ -22,7 +22,8 @@ struct fsb_ctx {
   std::string err;
   int64_t launches = 0;
   // options
-  int asm_mode = 2;      // 0 search+atomics, 1 position map + atomics, 2 row-gather (owner computes, no atomics) where it applies
+  int asm_mode = 1;      // 0 search+atomics, 1 position map + atomics (default), 2 row-gather (owner computes, no atomics, bitwise
+                         // reproducible; measured 2x slower than 1 at 256^3, profiles/asm_ab_r2.txt) for the degree-1 scalar forms
   int spmv_mode = 0;     // 0 TMA-staged tiles v2, 1 plain row-per-thread, 2 TMA-staged v1 (one thread per row)
   int spmv_lpr = 0;      // lanes per row in the staged kernel (1, 2 or 4; 0 = best per block size)
   int spmv_rows = 0;     // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks; 0 = best per block size)

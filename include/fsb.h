@@ -65,8 +65,8 @@ void fsb_destroy(fsb_ctx* ctx);
 const char* fsb_last_error(fsb_ctx* ctx);
 int fsb_sync(fsb_ctx* ctx);
 int fsb_device_info(fsb_ctx* ctx, int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes);
-/* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 position-map+atomics, 2 = default: row-gather kernels
- * without atomics for the degree-1 scalar forms, position-map+atomics elsewhere),
+/* tuning/diagnostic switches: "asm_mode" (0 search+atomics, 1 = default: position-map+atomics, 2: row-gather kernels
+ * without atomics for the degree-1 scalar forms — bitwise reproducible sums, about 2x slower — position-map+atomics elsewhere),
  * "spmv_mode" (0 TMA-staged tiles, 1 plain row-per-thread), "profile" (0/1), "graph" (0/1),
  * "check_every" (iterations between host convergence polls), "drop_zeros" (the Krylov SpMVs run on a
  * compacted copy without the blocks that are exactly zero after assembly; the assembled CSR, the parity object, is untouched:

@@ -221,12 +221,12 @@ def test_assemble_scalar_terms(ctx, dim, asm_mode):
             assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
             assert_vals_close(dev.data, ref.data)
     finally:
-        ctx.set_option("asm_mode", 2)
+        ctx.set_option("asm_mode", 1)
 
 
 @pytest.mark.parametrize("dim", [2, 3])
 def test_row_gather_assembly_overwrite_action_and_reproducibility(ctx, dim):
-    """asm_mode 2 (default), k_scalar_rows: `overwrite` equals zero + add on a matrix holding garbage, the matrix-free action equals
+    """asm_mode 2 (opt-in), k_scalar_rows: `overwrite` equals zero + add on a matrix holding garbage, the matrix-free action equals
     A x, two assemblies are bitwise identical (fixed summation order — the atomic scatter cannot promise that), and the result equals
     the scatter kernel's to rounding."""
     n = (9, 6) if dim == 2 else (6, 5, 4)
@@ -238,28 +238,30 @@ def test_row_gather_assembly_overwrite_action_and_reproducibility(ctx, dim):
     vel = rng.random(dim) - 0.5
     kw = dict(kscale=0.7, mass=1.25, adv=4.0, vel=vel)
     A = _lib.DeviceMatrix.create(m, 1)
-    A.assemble_scalar(kscale=123.0, mass=7.0)                    # garbage to be overwritten
-    A.assemble_scalar(overwrite=True, **kw)
-    v1 = A.download_csr()[2].copy()
-    A.zero()
-    A.assemble_scalar(**kw)
-    v2 = A.download_csr()[2].copy()
-    assert np.array_equal(v1, v2)                                # bitwise: same kernel, same order, with and without the zero-fill
-    A.assemble_scalar(overwrite=True, **kw)
-    assert np.array_equal(A.download_csr()[2], v1)
-    ctx.set_option("asm_mode", 1)
     try:
-        B = _lib.DeviceMatrix.create(m, 1)
-        B.assemble_scalar(**kw)
-        assert_vals_close(B.download_csr()[2], v1)
-    finally:
         ctx.set_option("asm_mode", 2)
-    xh = rng.standard_normal(nv)
-    x, y = _lib.DeviceVector.from_numpy(ctx, xh), _lib.DeviceVector.from_numpy(ctx, np.ones(nv))
-    _lib.apply_scalar(m, x, y, **kw)
-    Am, _, _ = csr_from_device(A)
-    ref = 1.0 + Am @ xh
-    assert np.abs(y.numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+        A.assemble_scalar(kscale=123.0, mass=7.0)                    # garbage to be overwritten
+        A.assemble_scalar(overwrite=True, **kw)
+        v1 = A.download_csr()[2].copy()
+        A.zero()
+        A.assemble_scalar(**kw)
+        v2 = A.download_csr()[2].copy()
+        assert np.array_equal(v1, v2)                                # bitwise: same kernel, same order, with and without the zero-fill
+        A.assemble_scalar(overwrite=True, **kw)
+        assert np.array_equal(A.download_csr()[2], v1)
+        ctx.set_option("asm_mode", 1)
+        B = _lib.DeviceMatrix.create(m, 1)
+        B.assemble_scalar(overwrite=True, **kw)
+        assert_vals_close(B.download_csr()[2], v1)
+        ctx.set_option("asm_mode", 2)
+        xh = rng.standard_normal(nv)
+        x, y = _lib.DeviceVector.from_numpy(ctx, xh), _lib.DeviceVector.from_numpy(ctx, np.ones(nv))
+        _lib.apply_scalar(m, x, y, **kw)
+        Am, _, _ = csr_from_device(A)
+        ref = 1.0 + Am @ xh
+        assert np.abs(y.numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    finally:
+        ctx.set_option("asm_mode", 1)
 
 
 def test_assemble_accumulates_and_zero(ctx):
@@ -327,7 +329,7 @@ def test_assemble_elasticity(ctx, dim, asm_mode):
         A = _lib.DeviceMatrix.create(m, dim)
         A.assemble_elasticity(mu, lam)
     finally:
-        ctx.set_option("asm_mode", 2)
+        ctx.set_option("asm_mode", 1)
     dev, rp, ci = csr_from_device(A)
     rp0, ci0 = fo.csr_pattern(t, nv, dim)
     ref = fo.conform(fo.assemble_matrix(t, fo.local_elasticity(c, t, mu, lam), nv, dim), rp0, ci0)

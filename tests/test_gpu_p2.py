@@ -61,7 +61,7 @@ def test_p2_pattern_and_scalar_terms(ctx, dim, asm_mode):
             ref = fo.conform(p2.assemble_matrix(cn, Ke, nn), rp0, ci0)
             close(dev.data, ref.data)
     finally:
-        ctx.set_option("asm_mode", 2)
+        ctx.set_option("asm_mode", 1)
     # matrix-free action (Crank-Nicolson right-hand side)
     xh = rng.random(nn)
     x, y = _lib.DeviceVector.from_numpy(ctx, xh), _lib.DeviceVector(ctx, nn)
