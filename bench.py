@@ -411,6 +411,7 @@ def main():
         def e2e_step():
             hmesh._exterior = None            # the boundary-facet search and the mesh upload are part of every end-to-end step
             hmesh.__dict__.pop("_dmesh", None)
+            hmesh.__dict__.pop("_slab", None)
             hmesh.__dict__.pop("_boundary_geometry", None)
             ta = time.perf_counter()
             sv = ScalarTransportSolver.ScalarTransportSolver(case_settings(N, mesh=hmesh, distributed=world > 1))

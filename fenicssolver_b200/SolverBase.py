@@ -194,14 +194,25 @@ class SolverBase():
     def _mark_distribution(self):
         """Tell the mesh whether this solver runs slab/RCB-distributed (settings['solver_settings']['distributed'] with an
         initialised torch.distributed group of more than one rank): no rank then holds the whole mesh on its device."""
-        on = False
+        on = None
         if (self.settings.get('solver_settings') or {}).get('distributed'):
             try:
                 import torch.distributed as dist
-                on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    on = (dist.get_rank(), dist.get_world_size())
             except ImportError:
-                on = False
+                on = None
+        # the z-slab layout (and with it the slab-local boundary search) is the one of degree-1 spaces on generated boxes; degree 2
+        # and array meshes are RCB-partitioned and keep the global facet list
+        fs = getattr(self, 'function_space', None) if 'function_space' in self.settings and self.settings.get('function_space') else None
+        degree = fs.degree if fs is not None else int(self.settings.get('fe_degree', 1) or 1)
+        slab = degree == 1
+        if getattr(self.mesh, 'distributed', None) != on or getattr(self.mesh, 'slab_partition', True) != slab:
+            for k in ('_exterior', '_boundary_geometry'):            # lists made for another layout do not carry over
+                if k in self.mesh.__dict__:
+                    setattr(self.mesh, k, None)
         self.mesh.distributed = on
+        self.mesh.slab_partition = slab
 
     def generate_boundary_facets(self):
         self._mark_distribution()
@@ -636,12 +647,28 @@ class SolverBase():
         return u_current
 
 
+class _NodeCoordinates:
+    """What DirichletBC.dofs_and_values needs from the node coordinates — their number and rows picked by index — without
+    materialising all of them on the host (a generated 256^3 box would cost 0.4 GB and a second of numpy for two faces)."""
+
+    def __init__(self, space):
+        self.space = space
+        n = space.num_nodes() if hasattr(space, "num_nodes") else space.num_vertices()
+        d = space.mesh().gdim if hasattr(space, "mesh") and callable(getattr(space, "mesh")) else space.gdim
+        self.shape = (n, d)
+
+    def __getitem__(self, idx):
+        if hasattr(self.space, "node_coordinates_at"):
+            return self.space.node_coordinates_at(idx)
+        return self.space.vertex_coordinates(idx)
+
+
 def collect_dirichlet(bcs, space):
     """DirichletBC list -> (global dofs, values); later conditions win on shared dofs, as repeated
     bc.apply calls do.  `space`: the FunctionSpace (a Mesh is accepted for P1)."""
     if not bcs:
         return np.zeros(0, dtype=np.int64), np.zeros(0)
-    coords = space.node_coordinates() if hasattr(space, "node_coordinates") else space.coordinates()
+    coords = _NodeCoordinates(space)
     dofs_all, vals_all = [], []
     for bc in bcs:
         if not isinstance(bc, DirichletBC):

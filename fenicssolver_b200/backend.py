@@ -106,24 +106,15 @@ class DeviceSpace:
             # degree-2 node layout: host integer work (edge numbering), then one upload
             self.dmesh = _lib.DeviceMesh.upload_p2(self.ctx, mesh.coordinates(), space.cell_nodes(), space.num_nodes())
         elif self.comm.nranks > 1:
-            n = mesh.box["n"]
-            nlast = n[-1]
-            if nlast + 1 < self.comm.nranks:
-                raise SolverError("more ranks than vertex planes")
-            self.plane = int(np.prod([k + 1 for k in n[:-1]]))
-            zp0, zp1 = slab_partition(nlast + 1, self.comm.nranks)[self.comm.rank]
-            layer0, layer1 = max(zp0 - 1, 0), min(zp1, nlast)
-            self.ghost_lo, self.ghost_hi = int(zp0 > 0), int(zp1 <= nlast)
-            self.owned_planes = zp1 - zp0
-            self.v_off = layer0 * self.plane
-            if getattr(mesh, "force_upload", False):
-                # host mesh arrays (e.g. pinned): upload this rank's slab, renumbered to local vertex ids
-                per_layer = mesh.num_cells() // nlast
-                nvl = (layer1 - layer0 + 1) * self.plane
-                self.dmesh = _lib.DeviceMesh.upload(self.ctx, mesh.coordinates()[self.v_off:self.v_off + nvl],
-                                                    mesh.cells()[per_layer * layer0:per_layer * layer1], vertex_offset=self.v_off)
-            else:
-                self.dmesh = _lib.DeviceMesh.box(self.ctx, n, mesh.box["p0"], mesh.box["p1"], layer0, layer1)
+            if getattr(mesh, "distributed", None) != (self.comm.rank, self.comm.nranks):
+                mesh.distributed = (self.comm.rank, self.comm.nranks)
+                mesh._exterior = None
+                mesh.__dict__.pop("_boundary_geometry", None)
+            self.dmesh, lay = mesh.slab_device_mesh(self.ctx)          # made once; the boundary search (K1) ran on the same slab
+            self.plane = lay["plane"]
+            self.ghost_lo, self.ghost_hi = lay["ghost_lo"], lay["ghost_hi"]
+            self.owned_planes = lay["owned_planes"]
+            self.v_off = lay["v_off"]
             if self.ctx.nranks == 1:
                 uid = self.ctx.dist_unique_id() if self.comm.rank == 0 else None
                 uid = self.comm.bootstrap(uid)

@@ -328,6 +328,21 @@ class Mesh:
             self._cells = box_cells(self.box["n"])
         return self._cells
 
+    def vertex_coordinates(self, ids):
+        """Coordinates of the vertices `ids` ([k, gdim]); a generated box computes them from the ids (the same expression
+        coordinates() evaluates, bit for bit) instead of materialising every vertex on the host."""
+        ids = np.asarray(ids, dtype=np.int64)
+        if self._coords is not None or not self.box:
+            return self.coordinates()[ids]
+        n, p0, p1 = self.box["n"], self.box["p0"], self.box["p1"]
+        out = np.empty((ids.size, len(n)))
+        rem = ids
+        for i in range(len(n)):
+            idx = rem % (n[i] + 1)
+            rem = rem // (n[i] + 1)
+            out[:, i] = p0[i] + idx * (p1[i] - p0[i]) / n[i]
+        return out
+
     # ---- facets -------------------------------------------------------------------------------
     def device_mesh(self, ctx=None):
         """The whole mesh on this process's GPU — generated there from a box description, uploaded from the host arrays
@@ -343,28 +358,109 @@ class Mesh:
             self._dmesh = dm
         return dm
 
+    def slab_device_mesh(self, ctx=None):
+        """Slab-distributed run on a box layout: this rank's z-slab (its owned vertex planes plus one ghost plane per neighbour)
+        on its GPU — generated there, or uploaded from the host arrays when the mesh came as arrays with a box description
+        (force_upload).  Returns (DeviceMesh, layout dict); made once per mesh and shared by the boundary search and the
+        DeviceSpace.  Vertex ids on the device are local: global id - v_off."""
+        from . import _lib, backend
+        ctx = ctx or backend.get_context()
+        rank, nranks = self.distributed
+        hit = self.__dict__.get("_slab")
+        if hit is not None and hit[0].h is not None and hit[0].ctx is ctx and hit[1]["rank"] == rank and hit[1]["nranks"] == nranks:
+            return hit
+        n = self.box["n"]
+        nlast = n[-1]
+        if nlast + 1 < nranks:
+            raise SolverError("more ranks than vertex planes")
+        plane = int(np.prod([k + 1 for k in n[:-1]]))
+        zp0, zp1 = backend.slab_partition(nlast + 1, nranks)[rank]
+        layer0, layer1 = max(zp0 - 1, 0), min(zp1, nlast)
+        lay = dict(rank=rank, nranks=nranks, plane=plane, layer0=layer0, layer1=layer1, ghost_lo=int(zp0 > 0), ghost_hi=int(zp1 <= nlast),
+                   owned_planes=zp1 - zp0, v_off=layer0 * plane, nlast=nlast)
+        if getattr(self, "force_upload", False):
+            per_layer = self.num_cells() // nlast
+            nvl = (layer1 - layer0 + 1) * plane
+            dm = _lib.DeviceMesh.upload(ctx, self.coordinates()[lay["v_off"]:lay["v_off"] + nvl],
+                                        self.cells()[per_layer * layer0:per_layer * layer1], vertex_offset=lay["v_off"])
+        else:
+            dm = _lib.DeviceMesh.box(ctx, n, self.box["p0"], self.box["p1"], layer0, layer1)
+        self._slab = (dm, lay)
+        return self._slab
+
     def exterior_facets(self):
         """(fverts[nbf, tdim], opposite_vertex[nbf]) of the exterior facets, in lexicographic order of the vertex tuples.
-        Found on the device (libfsb K1, csrc/fsb_facets.cu).  Two host routes remain, both index arithmetic on a known
-        layout rather than a search: a generated box in a slab-distributed run (no rank holds the whole mesh; the surface
-        facets of the dolfin box layout are enumerated directly, O(surface)) and the same enumeration when this process has
-        no GPU at all (mesh inspection in host-only tools).  An array / file mesh always needs the device."""
+        Found on the device (libfsb K1, csrc/fsb_facets.cu).  One GPU: the whole mesh.  Slab-distributed box: the search runs
+        on this rank's slab and the list holds the boundary facets of that slab only (global vertex ids; the facets of the two
+        cut planes, interior to the whole mesh, are dropped) — every consumer restricts facet lists to the rank's vertices
+        anyway (DeviceSpace.local_facets).  Host routes that remain: a generated box when this process has no GPU at all
+        (direct enumeration of the box surface: host-only mesh inspection) and the RCB-distributed array mesh (np.unique table
+        of the replicated host mesh)."""
         if self._exterior is None:
-            if self.box and (getattr(self, "distributed", False) or not _device_present()):
+            dist = getattr(self, "distributed", None)
+            if self.box and not _device_present():
                 self._exterior = box_exterior_facets(self.box["n"])
-            elif getattr(self, "distributed", False):
-                # general (RCB) partition of a replicated host mesh: every rank needs the global list and holds only its part
-                # on the device; host table (small meshes only)
+            elif self.box and dist and getattr(self, "slab_partition", True) and not getattr(self, "force_general_partition", False):
+                dm, lay = self.slab_device_mesh()
+                fv, opp, cell, _fid = dm.exterior_facets()
+                zl = fv // lay["plane"]
+                nplanes = lay["layer1"] - lay["layer0"] + 1
+                cut = np.zeros(fv.shape[0], dtype=bool)
+                if lay["layer0"] > 0:
+                    cut |= np.all(zl == 0, axis=1)
+                if lay["layer1"] < lay["nlast"]:
+                    cut |= np.all(zl == nplanes - 1, axis=1)
+                keep = ~cut
+                self._exterior = ((fv[keep] + lay["v_off"]).astype(np.int32), (opp[keep] + lay["v_off"]).astype(np.int32))
+                self._exterior_keep = keep
+                self._exterior_cells = cell[keep]
+            elif self.box and dist:
+                # RCB-partitioned space on a generated box (degree 2): every rank needs the global list; direct enumeration
+                self._exterior = box_exterior_facets(self.box["n"])
+                self._exterior_cells = None
+            elif dist:
                 facets, cf, count = self.facet_table()
                 ci, li = np.nonzero(count[cf] == 1)
                 fid = cf[ci, li]
                 order = np.argsort(fid, kind="stable")
-                self._exterior = (facets[fid[order]].astype(np.int32), self._cells[ci[order], li[order]].astype(np.int32), fid[order])
+                self._exterior = (facets[fid[order]].astype(np.int32), self.cells()[ci[order], li[order]].astype(np.int32), fid[order])
+                self._exterior_cells = None
             else:
                 fv, opp, cell, fid = self.device_mesh().exterior_facets()
                 self._exterior = (fv, opp, fid)
                 self._exterior_cells = cell
+                self._exterior_keep = None
         return self._exterior[0], self._exterior[1]
+
+    def boundary_geometry(self):
+        """(finv[nbf, tdim], pts[nbv, gdim], mid[nbf, gdim]) for the facets of exterior_facets(): the facets' vertices as indices into
+        the distinct boundary vertices, those vertices' coordinates and the facet midpoints (what SubDomain.mark evaluates on)."""
+        geom = self.__dict__.get("_boundary_geometry")
+        if geom is None:
+            fverts, _ = self.exterior_facets()
+            dm = None
+            if getattr(self, "_exterior_cells", None) is not None:
+                dm = self._slab[0] if getattr(self, "_exterior_keep", None) is not None else self.__dict__.get("_dmesh")
+            if dm is not None and dm.h is not None:
+                _bv, inv, pts, mid = dm.boundary_geometry()          # made on the device next to the facet search (K1)
+                keep = getattr(self, "_exterior_keep", None)
+                if keep is not None:
+                    inv, mid = inv[keep], mid[keep]
+                geom = (inv, pts, mid)
+            else:                                                    # host-enumerated box surface / RCB table
+                flag = np.zeros(self.num_vertices(), dtype=bool)
+                flag[fverts.ravel()] = True
+                uv = np.flatnonzero(flag)                            # distinct boundary vertices, ascending
+                rank = np.empty(flag.size, dtype=np.int32)
+                rank[uv] = np.arange(uv.size, dtype=np.int32)
+                inv = rank[fverts]
+                pts = self.vertex_coordinates(uv)
+                mid = pts[inv[:, 0]].copy()
+                for j in range(1, inv.shape[1]):
+                    mid += pts[inv[:, j]]
+                geom = (inv, pts, mid / inv.shape[1])
+            self._boundary_geometry = geom
+        return geom
 
     def locate_point(self, p, tol=1e-12):
         """(cell index, barycentric coordinates) of a cell containing point p (the first one in cell order, as a
@@ -441,42 +537,51 @@ def box_cells(n):
     return hv[:, _HEX_TETS].reshape(-1, 4).astype(np.int32)
 
 
+def _box_face_templates(d):
+    """For one box of the dolfin layout (local vertex k: bit 0 = x, bit 1 = y, bit 2 = z): the simplex facets lying in each of
+    its 2 d faces, as {(axis, side): [(facet local vertices ascending, opposite local vertex), ...]}."""
+    tets = _HEX_TETS if d == 3 else np.array([(0, 1, 3), (0, 2, 3)])
+    out = {}
+    for tet in tets:
+        for i in range(d + 1):
+            f = tuple(int(v) for k, v in enumerate(tet) if k != i)
+            for axis in range(d):
+                bits = {(v >> axis) & 1 for v in f}
+                if len(bits) == 1:
+                    out.setdefault((axis, bits.pop()), []).append((f, int(tet[i])))
+    return out
+
+
 def box_exterior_facets(n):
-    """Exterior facets of the box layout without touching the interior: O(surface) work.
-    For every boundary plane take the layer of boxes touching it, form their simplices and keep the
-    facets whose vertices all lie in the plane."""
+    """Exterior facets of the box layout by direct enumeration: every boundary face of a boundary box contributes the simplex
+    facets its template (one box) has in that face — index arithmetic on the known layout, O(surface), no search.  Returns
+    (fverts, opposite vertex) in lexicographic order of the vertex tuples."""
     d = len(n)
-    strides = np.cumprod([1] + [k + 1 for k in n[:-1]])
+    strides = np.cumprod([1] + [k + 1 for k in n[:-1]]).astype(np.int64)
+    off = np.array([sum(((k >> a) & 1) * int(strides[a]) for a in range(d)) for k in range(1 << d)], dtype=np.int64)
+    tmpl = _box_face_templates(d)
     fv_all, opp_all = [], []
-
-    def layer_cells(axis, idx):
-        rng = [np.arange(k) for k in n]
-        rng[axis] = np.array([idx])
-        grids = np.meshgrid(*rng[::-1], indexing="ij")
-        c = [g.ravel() for g in grids[::-1]]
-        v0 = sum(ci * s for ci, s in zip(c, strides))
-        if d == 2:
-            px = strides[1]
-            v1, v2, v3 = v0 + 1, v0 + px, v0 + px + 1
-            return np.stack([np.stack([v0, v1, v3], 1), np.stack([v0, v2, v3], 1)], axis=1).reshape(-1, 3)
-        px, py = strides[1], strides[2]
-        hv = np.stack([v0, v0 + 1, v0 + px, v0 + px + 1, v0 + py, v0 + py + 1, v0 + py + px, v0 + py + px + 1], axis=1)
-        return hv[:, _HEX_TETS].reshape(-1, 4)
-
     for axis in range(d):
-        for idx, plane in ((0, 0), (n[axis] - 1, n[axis])):
-            cells = layer_cells(axis, idx)
-            nl = cells.shape[1]
-            for i in range(nl):
-                f = np.delete(cells, i, axis=1)
-                coord = (f // strides[axis]) % (n[axis] + 1)
-                keep = np.all(coord == plane, axis=1)
-                fv_all.append(f[keep])
-                opp_all.append(cells[keep, i])
-    fv = np.concatenate(fv_all).astype(np.int32)
-    opp = np.concatenate(opp_all).astype(np.int32)
-    order = np.lexsort(fv.T[::-1])
-    return fv[order], opp[order]
+        other = [a for a in range(d) if a != axis]
+        grids = np.meshgrid(*[np.arange(n[a], dtype=np.int64) for a in other[::-1]], indexing="ij")
+        base_other = sum(g.ravel() * strides[a] for g, a in zip(grids[::-1], other)) if other else np.zeros(1, dtype=np.int64)
+        for side in (0, 1):
+            v0 = base_other + (0 if side == 0 else (n[axis] - 1)) * strides[axis]
+            for f, o in tmpl[(axis, side)]:
+                fv_all.append(v0[:, None] + off[list(f)][None, :])
+                opp_all.append(v0 + off[o])
+    fv = np.concatenate(fv_all)
+    opp = np.concatenate(opp_all)
+    # lexicographic order through one 64-bit key per facet when the ids fit (3 x 21 bits), else a lexsort
+    nv = int(np.prod([k + 1 for k in n]))
+    if nv < (1 << 21):
+        key = fv[:, 0]
+        for j in range(1, d):
+            key = (key << 21) | fv[:, j]
+        order = np.argsort(key, kind="stable")
+    else:
+        order = np.lexsort(fv.T[::-1])
+    return fv[order].astype(np.int32), opp[order].astype(np.int32)
 
 
 def UnitSquareMesh(nx, ny, diagonal="right"):
@@ -657,17 +762,7 @@ class FacetMarkers:
     def mark_subdomain(self, sub, value):
         """SubDomain.mark: a facet is marked iff all its vertices and its midpoint are inside
         (dolfin's default check_midpoint=True; SolverBase.py:281-282)."""
-        geom = getattr(self.mesh, "_boundary_geometry", None)
-        if geom is None:      # unique boundary vertices, their coordinates and the facet midpoints: once per mesh
-            dm = self.mesh.__dict__.get("_dmesh")
-            if dm is not None and dm.h is not None and getattr(self.mesh, "_exterior_cells", None) is not None:
-                _bv, inv, pts, mid = dm.boundary_geometry()          # made on the device next to the facet search (K1)
-                geom = self.mesh._boundary_geometry = (inv, pts, mid)
-            else:                                                    # host-enumerated box surface (slab-distributed / no GPU)
-                uv, inv = np.unique(self.fverts, return_inverse=True)
-                inv = inv.reshape(self.fverts.shape)
-                pts = self.mesh.coordinates()[uv]
-                geom = self.mesh._boundary_geometry = (inv, pts, pts[inv].mean(axis=1))
+        geom = self.mesh.boundary_geometry()
         inv, pts, mid = geom
         ok = _evaluate_predicate(sub, mid) & _evaluate_predicate(sub, pts)[inv].all(axis=1)
         self._values[ok] = value
@@ -784,6 +879,12 @@ class FunctionSpace:
             return self._mesh.cells()
         self.edges()
         return self._cell_nodes
+
+    def node_coordinates_at(self, nodes):
+        """Coordinates of the given nodes only (degree 1 on a generated box: from the ids, no host copy of the whole mesh)."""
+        if self.degree == 1:
+            return self._mesh.vertex_coordinates(nodes)
+        return self.node_coordinates()[np.asarray(nodes, dtype=np.int64)]
 
     def node_coordinates(self):
         c = self._mesh.coordinates()
@@ -1074,7 +1175,7 @@ class DirichletBC:
             val = val[0] if val.size == 1 else val
         at_nodes = isinstance(val, Expression)
         if at_nodes:
-            val = val(coords[verts])                # evaluated at the constrained nodes only
+            val = val(coords[verts])                # evaluated at the constrained nodes only (coords may be a lazy view)
         elif isinstance(val, Function):
             val = val.values
         val = np.asarray(val, dtype=np.float64)
