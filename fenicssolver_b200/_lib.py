@@ -50,6 +50,8 @@ SIGNATURES = {
     "fsb_vec_fill": (C.c_int, [c_vp, c_dbl]),
     "fsb_vec_upload": (C.c_int, [c_vp, c_vp, c_i64]),
     "fsb_vec_download": (C.c_int, [c_vp, c_vp, c_i64]),
+    "fsb_host_alloc": (C.c_int, [c_vp, c_i64, P(c_vp)]),
+    "fsb_host_free": (C.c_int, [c_vp, c_vp]),
     "fsb_vec_copy": (C.c_int, [c_vp, c_vp]),
     "fsb_vec_axpy": (C.c_int, [c_vp, c_dbl, c_vp]),
     "fsb_vec_add_entries": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
@@ -295,6 +297,31 @@ class DeviceMesh(_Handle):
         return xyz, cells
 
 
+class _PinnedBlock:
+    """One fsb_host_alloc block; released (back to the library's pool) with the last array that views it."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.ptr = ctx, c_vp()
+        ctx.check(ctx.lib.fsb_host_alloc(ctx.h, int(nbytes), C.byref(self.ptr)))
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ctx.h is not None:
+                self.ctx.lib.fsb_host_free(self.ctx.h, self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
+
+
+def pinned_empty(ctx, n, dtype=np.float64):
+    """np.empty(n, dtype) in page-locked memory owned by the context's pool."""
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    blk = _PinnedBlock(ctx, max(nbytes, 8))
+    buf = (C.c_char * max(nbytes, 8)).from_address(blk.ptr.value)
+    buf._fsb_block = blk                       # the ctypes buffer is the numpy array's base: keeps the block alive
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
 class DeviceVector(_Handle):
     _destroy = "fsb_vec_destroy"
 
@@ -317,7 +344,9 @@ class DeviceVector(_Handle):
         self.ctx.check(self.ctx.lib.fsb_vec_upload(self.h, _ptr(a), a.size))
 
     def numpy(self):
-        out = np.empty(self.n, dtype=np.float64)
+        """Host copy.  Large vectors land in a page-locked block of the library's pool (one direct DMA, no page faults on a fresh
+        array); the block returns to the pool when the array is garbage-collected."""
+        out = pinned_empty(self.ctx, self.n) if self.n >= (1 << 20) else np.empty(self.n, dtype=np.float64)
         self.ctx.check(self.ctx.lib.fsb_vec_download(self.h, _ptr(out), self.n))
         return out
 

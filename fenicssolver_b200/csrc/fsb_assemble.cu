@@ -167,7 +167,7 @@ k_scalar_rows(int64_t nrows, const int32_t* __restrict__ cells, const double* __
 static bool rows_path(fsb_ctx* ctx, fsb_mesh* mesh, fsb_mat* A) {
   if (ctx->asm_mode < 2 || mesh->degree != 1 || !mesh->v2c) return false;
   if (A && (A->mesh != mesh || !A->posmap || A->max_row_len > kRowSlots)) return false;
-  return true;
+  return fsb_mesh_sort_adjacency(mesh) == FSB_OK;       // fixed (ascending cell) summation order
 }
 
 // K_e[(a,i),(b,j)] = |T| ( mu (G_a.G_b d_ij + G_a[j] G_b[i]) + lambda G_a[i] G_b[j] ), DxD blocks

@@ -64,6 +64,8 @@ extern "C" void fsb_destroy(fsb_ctx* ctx) {
     if (ctx->stage_done[k]) cudaEventDestroy(ctx->stage_done[k]);
   }
   cudaFreeHost(ctx->h_pinned);
+  for (auto& kv : ctx->host_free) cudaFreeHost(kv.second);
+  // blocks still handed out stay mapped: arrays that view them may outlive the context
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -167,12 +169,57 @@ extern "C" int fsb_vec_upload(fsb_vec* v, const double* host, int64_t n) {
   FSB_CHECK_CUDA(v->ctx, cudaStreamSynchronize(v->ctx->stream));
   return FSB_OK;
 }
+// Page-locked host blocks for results (fsb_host_alloc / fsb_host_free): a released block goes to an exact-size free list
+// and is handed to the next request of that size, so the solve of every time step downloads into memory that is already
+// pinned and already touched (a fresh pageable array costs a page fault per 4 KB: 26 ms for the 136 MB of a 256^3 field
+// against 2.5 ms of DMA).
+extern "C" int fsb_host_alloc(fsb_ctx* ctx, int64_t bytes, void** out) {
+  if (!ctx || !out || bytes <= 0) return FSB_ERR_ARG;
+  auto hit = ctx->host_free.find((size_t)bytes);
+  if (hit != ctx->host_free.end()) {
+    *out = hit->second;
+    ctx->host_free.erase(hit);
+    ctx->host_cached -= (size_t)bytes;
+  } else {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, (size_t)bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (auto& kv : ctx->host_free) cudaFreeHost(kv.second);       // give the cached blocks back and try once more
+      ctx->host_free.clear(); ctx->host_cached = 0;
+      e = cudaMallocHost(&p, (size_t)bytes);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); FSB_FAIL(ctx, FSB_ERR_NOMEM, "cudaMallocHost failed"); }
+    *out = p;
+  }
+  ctx->host_live[*out] = (size_t)bytes;
+  return FSB_OK;
+}
+
+extern "C" int fsb_host_free(fsb_ctx* ctx, void* p) {
+  if (!ctx || !p) return FSB_ERR_ARG;
+  auto it = ctx->host_live.find(p);
+  if (it == ctx->host_live.end()) FSB_FAIL(ctx, FSB_ERR_ARG, "fsb_host_free: not a block of fsb_host_alloc");
+  const size_t bytes = it->second;
+  ctx->host_live.erase(it);
+  if (ctx->host_cached + bytes <= ((size_t)2 << 30)) {      // at most 2 GB of released host blocks wait for reuse
+    ctx->host_free.emplace(bytes, p);
+    ctx->host_cached += bytes;
+  } else {
+    cudaFreeHost(p);
+  }
+  return FSB_OK;
+}
+
 extern "C" int fsb_vec_download(fsb_vec* v, double* host, int64_t n) {
   if (!v || !host || n != v->n) return FSB_ERR_ARG;
   fsb_ctx* ctx = v->ctx;
   const size_t bytes = sizeof(double) * (size_t)n;
   constexpr size_t kChunk = 8u << 20;
-  if (bytes < 4 * kChunk) {
+  bool pinned = false;
+  for (auto& kv : ctx->host_live)       // a handful of blocks at most
+    if ((char*)host >= (char*)kv.first && (char*)host + bytes <= (char*)kv.first + kv.second) { pinned = true; break; }
+  if (pinned || bytes < 4 * kChunk) {
     FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(host, v->d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FSB_OK;

@@ -185,14 +185,24 @@ int exterior_facets_impl(fsb_mesh* mesh) {
   int* d_over = nullptr;
   int rc = FSB_OK;
   auto cleanup = [&]() {
-    fsb_dfree(ctx, deg); fsb_dfree(ctx, v2c); fsb_dfree(ctx, ecnt); fsb_dfree(ctx, ucnt); fsb_dfree(ctx, vptr); fsb_dfree(ctx, eptr);
+    if (v2c != mesh->v2c) fsb_dfree(ctx, v2c);          // an adjacency left on the mesh belongs to the mesh
+    if (vptr != mesh->v2c_ptr) fsb_dfree(ctx, vptr);
+    v2c = nullptr; vptr = nullptr;
+    fsb_dfree(ctx, deg); fsb_dfree(ctx, ecnt); fsb_dfree(ctx, ucnt); fsb_dfree(ctx, eptr);
     fsb_dfree(ctx, ubase); fsb_dfree(ctx, mask); fsb_dfree(ctx, rec); fsb_dfree(ctx, d_over);
   };
 #define TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
 #define TRYCUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); return FSB_ERR_CUDA; } } while (0)
   TRY(fsb_dmalloc(ctx, &deg, (size_t)nv + 1));
-  TRY(fsb_dmalloc(ctx, &vptr, (size_t)nv + 1));
-  TRY(fsb_dmalloc(ctx, &v2c, (size_t)nc * NL));
+  // the vertex -> cell adjacency is shared with the symbolic phase of a degree-1 mesh (fsb_mat_create): whoever runs first
+  // builds it and leaves it on the mesh
+  const bool share_adj = mesh->degree == 1;
+  const bool have_adj = share_adj && mesh->v2c != nullptr;
+  if (have_adj) { vptr = mesh->v2c_ptr; v2c = mesh->v2c; }
+  else {
+    TRY(fsb_dmalloc(ctx, &vptr, (size_t)nv + 1));
+    TRY(fsb_dmalloc(ctx, &v2c, (size_t)nc * NL));
+  }
   TRY(fsb_dmalloc(ctx, &ecnt, (size_t)nv + 1));
   TRY(fsb_dmalloc(ctx, &ucnt, (size_t)nv + 1));
   TRY(fsb_dmalloc(ctx, &eptr, (size_t)nv + 1));
@@ -203,12 +213,15 @@ int exterior_facets_impl(fsb_mesh* mesh) {
   TRYCUDA(cudaMemsetAsync(ecnt, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
   TRYCUDA(cudaMemsetAsync(ucnt, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
   TRYCUDA(cudaMemsetAsync(d_over, 0, sizeof(int), ctx->stream));
-  k_f_v2c_count<<<fsb_grid(nc * NL, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc * NL, deg);
-  ctx->launches++; TRYCUDA(cudaGetLastError());
-  TRY(fsb_exclusive_scan(ctx, deg, vptr, nv));
-  TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
-  k_f_v2c_fill<NL><<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, vptr, deg, v2c);
-  ctx->launches++; TRYCUDA(cudaGetLastError());
+  if (!have_adj) {
+    k_f_v2c_count<<<fsb_grid(nc * NL, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc * NL, deg);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+    TRY(fsb_exclusive_scan(ctx, deg, vptr, nv));
+    TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+    k_f_v2c_fill<NL><<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, vptr, deg, v2c);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+    if (share_adj) { mesh->v2c_ptr = vptr; mesh->v2c = v2c; mesh->v2c_sorted = false; }
+  }
   k_f_classify<NL><<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, vptr, v2c, mask, ecnt, ucnt);
   ctx->launches++; TRYCUDA(cudaGetLastError());
   TRY(fsb_exclusive_scan(ctx, ecnt, eptr, nv));

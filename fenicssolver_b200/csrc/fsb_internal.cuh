@@ -58,6 +58,10 @@ struct fsb_ctx {
   std::unordered_map<void*, size_t> live_blocks;
   size_t cached_bytes = 0;
   size_t cache_limit = (size_t)96 << 30;
+  // page-locked host blocks handed out by fsb_host_alloc, and the released ones kept for exact-size reuse
+  std::unordered_map<void*, size_t> host_live;
+  std::unordered_multimap<size_t, void*> host_free;
+  size_t host_cached = 0;
 };
 
 static constexpr int kMaxPartials = 4096;
@@ -79,6 +83,7 @@ struct fsb_mesh {
   // assembly kernels walk it
   int64_t* v2c_ptr = nullptr;      // [nverts+1]
   int32_t* v2c = nullptr;          // [ncells*(tdim+1)]
+  bool v2c_sorted = false;         // cell ids ascending inside every vertex's list (fsb_mesh_sort_adjacency)
   // K1 (fsb_facets.cu): exterior facets in lexicographic order, made on first request
   int64_t nbf = -1, nfacets = 0;   // exterior facets / distinct facets of the mesh
   int32_t* bf_verts = nullptr;     // [nbf][tdim] sorted vertex tuples
@@ -237,6 +242,7 @@ static inline unsigned fsb_grid(int64_t n, int block, int64_t cap = (1ll << 31) 
 
 // device-wide exclusive scan int32 -> int64 (out has n+1 entries, out[n] = total)   [fsb_pattern.cu]
 int fsb_exclusive_scan(fsb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
+int fsb_mesh_sort_adjacency(fsb_mesh* mesh);      // ascending cell ids per vertex in mesh->v2c (once; no-op afterwards)
 // SpMV tiling setup after row_ptr / owned range are known, and y = A x (+ fused dots d0 = y.w, d1 = y.y
 // written to out[0..2)) on the ctx stream; `done` is an optional device early-exit flag   [fsb_spmv.cu]
 int fsb_mat_setup_tiles(fsb_mat* A);

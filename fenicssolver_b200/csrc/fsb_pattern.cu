@@ -152,6 +152,15 @@ __global__ void k_v2c_sort(int64_t nverts, const int64_t* __restrict__ vptr, int
   }
 }
 
+int fsb_mesh_sort_adjacency(fsb_mesh* mesh) {
+  fsb_ctx* ctx = mesh->ctx;
+  if (!mesh->v2c || mesh->v2c_sorted) return FSB_OK;
+  k_v2c_sort<<<fsb_grid(mesh->nverts, 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(mesh->nverts, mesh->v2c_ptr, mesh->v2c);
+  FSB_LAUNCH_CHECK(ctx);
+  mesh->v2c_sorted = true;
+  return FSB_OK;
+}
+
 // ------------------------------------------------------------------------------------ rows
 // One warp per row.  Candidates L[i] = cells[v2c[p0 + i/nl]][i%nl], i < m = deg*nl.  They are sorted in
 // shared memory when m <= kRowCap, otherwise scanned from global memory (L1).
@@ -381,11 +390,7 @@ extern "C" int fsb_mat_create(fsb_mesh* mesh, int32_t ncomp, fsb_mat** out) {
     TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
     k_v2c_fill<<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cell_nodes, nc, nl, vptr, deg, v2c);
     ctx->launches++; TRYCUDA(cudaGetLastError());
-    if (keep_adj) {
-      k_v2c_sort<<<fsb_grid(nv, 256, cap), 256, 0, ctx->stream>>>(nv, vptr, v2c);
-      ctx->launches++; TRYCUDA(cudaGetLastError());
-      mesh->v2c_ptr = vptr; mesh->v2c = v2c;
-    }
+    if (keep_adj) { mesh->v2c_ptr = vptr; mesh->v2c = v2c; mesh->v2c_sorted = false; }
   }
   // row lengths -> row_ptr
   TRY(fsb_dmalloc(ctx, &A->row_ptr, (size_t)nv + 1));

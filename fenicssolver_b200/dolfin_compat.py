@@ -764,7 +764,10 @@ class FacetMarkers:
         (dolfin's default check_midpoint=True; SolverBase.py:281-282)."""
         geom = self.mesh.boundary_geometry()
         inv, pts, mid = geom
-        ok = _evaluate_predicate(sub, mid) & _evaluate_predicate(sub, pts)[inv].all(axis=1)
+        ok = _evaluate_predicate(sub, mid)
+        pv = _evaluate_predicate(sub, pts)
+        for j in range(inv.shape[1]):                     # all vertices inside: one 1-D gather per facet vertex
+            ok &= pv[inv[:, j]]
         self._values[ok] = value
         self.touch()
 

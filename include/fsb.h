@@ -120,6 +120,10 @@ int fsb_vec_create(fsb_ctx* ctx, int64_t n, fsb_vec** v);
 int fsb_vec_fill(fsb_vec* v, double value);
 int fsb_vec_upload(fsb_vec* v, const double* host, int64_t n);
 int fsb_vec_download(fsb_vec* v, double* host, int64_t n);
+/* Page-locked host memory for results (what vector().get_local() hands to the caller): a block released with fsb_host_free is
+ * kept and reused by the next request of the same size; fsb_vec_download into such a block is one direct DMA. */
+int fsb_host_alloc(fsb_ctx* ctx, int64_t bytes, void** ptr);
+int fsb_host_free(fsb_ctx* ctx, void* ptr);
 int fsb_vec_copy(fsb_vec* dst, fsb_vec* src);
 int fsb_vec_axpy(fsb_vec* y, double a, fsb_vec* x);            /* y += a x */
 /* v[idx[i]] += vals[i] (host lists; repeated indices accumulate): PointSource.apply(b), SolverBase.py:598-602 */
