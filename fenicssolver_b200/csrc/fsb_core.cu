@@ -104,6 +104,7 @@ extern "C" int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value) {
   else if (s == "spmv_lpr") ctx->spmv_lpr = (int)value;
   else if (s == "spmv_rows") ctx->spmv_rows = (int)value;
   else if (s == "spmv_stages") ctx->spmv_stages = (int)value;
+  else if (s == "spmv_flat") ctx->spmv_flat = (int)value;
   else if (s == "profile") ctx->profile = (int)value;
   else if (s == "alloc_cache_mb") { ctx->cache_limit = (size_t)(value < 0 ? 0 : value) << 20; if (!value) fsb_cache_flush(ctx); }
   else if (s == "graph") ctx->use_graph = (int)value;

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const int s = it % NST;
       mbar_wait(&full[s], (it / NST) & 1);
-      spmv_consume_tile<BS, ROWS, LPR, false>(a, st, s, s_info[s], d0, d1, d2);
+      if (a.flat) spmv_consume_tile_flat<BS, ROWS, LPR>(a, st, s, s_info[s], d0, d1, d2);
+      else spmv_consume_tile<BS, ROWS, LPR, false>(a, st, s, s_info[s], d0, d1, d2);
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);      // this warp is done with stage s
     }
@@ -302,6 +303,7 @@ void fsb_spmv_fill_args(fsb_mat* A, SpmvArgs* a) {
   a->tile_row = A->tile_row; a->tile_k = A->tile_row ? A->tile_row + A->ntiles + 1 : nullptr;
   a->ntiles = A->ntiles; a->own0 = A->own0; a->own1 = A->own1; a->cap = A->tile_cap;
   a->x = nullptr; a->y = nullptr; a->w = nullptr; a->want_yy = 0; a->w2 = nullptr; a->l2_hint = ctx->spmv_hint;
+  a->flat = ctx->spmv_flat == 1 || (ctx->spmv_flat == 0 && spmv_long_rows(A));
   a->partials = ctx->d_partials; a->out = nullptr; a->counter = ctx->d_counters + 0; a->done = nullptr;
   memset(&a->pc, 0, sizeof(a->pc));
   a->halo_seq = 0; a->mail_slot = -1; a->mail_seq = 0;

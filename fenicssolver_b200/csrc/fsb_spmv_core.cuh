@@ -23,6 +23,7 @@ struct SpmvArgs {
   int want_yy;              // d1 = sum y.y
   const double* w2;         // optional: d2 = sum y.w2 (then out has 3 entries)
   int l2_hint;              // 1: matrix stream marked evict-first in L2, y written with streaming stores
+  int flat;                 // 1: two-phase tiles (products over the tile's non-zeros, then row sums): long, uneven rows
   double* partials;
   double* out;              // out[0]=d0, out[1]=d1
   unsigned* counter;
@@ -152,6 +153,87 @@ __device__ __forceinline__ void spmv_consume_tile(const SpmvArgs& a, const SpmvS
       d2 += acc * wv2;
     }
   }
+}
+
+// Two-phase form of the same tile for long, uneven rows (degree-2 spaces: 28 blocks per row on average, 10 to 90 per row).
+// With LPR lanes per row the gathers of a tile are as unbalanced as its rows: a warp waits for its longest row while the lanes
+// of short rows idle.  Here phase A walks the tile's NON-ZEROS, not its rows: every consumer thread takes blocks k, k + CONSUMERS,
+// ... of the staged tile, gathers x, and overwrites the block's first BS values in shared memory with its BS products-sums —
+// perfectly balanced, UNR gathers in flight per thread.  After a consumer barrier phase B adds up each row's entries from shared
+// memory (LPR lanes per row, shuffle-combined) and writes y and the fused dots.
+template <int BS, int ROWS, int LPR>
+__device__ __forceinline__ void spmv_consume_tile_flat(const SpmvArgs& a, const SpmvStage<BS, ROWS, LPR>& st, int s, const int64_t* info,
+                                                       double& d0, double& d1, double& d2) {
+  using Cfg = SpmvCfg<BS, ROWS, LPR>;
+  constexpr int UNR = BS == 1 ? 8 : 2, CONSUMERS = Cfg::CONSUMERS;      // blocks in flight per thread in phase A
+  const int64_t r0 = info[0], r1 = info[1];
+  if (r1 <= r0) return;                                  // uniform over the consumers: nobody reaches the barrier below
+  const int64_t al0 = info[2], ra0 = info[3];
+  double* __restrict__ vs = const_cast<double*>(st.vals(s));
+  const int32_t* __restrict__ cs = st.cols(s);
+  const int64_t* __restrict__ rp = st.rptr(s);
+  int kt0, kt1;
+  if (ra0 >= 0) { kt0 = (int)(rp[r0 - ra0] - al0); kt1 = (int)(rp[r1 - ra0] - al0); }
+  else { kt0 = (int)(a.row_ptr[r0] - al0); kt1 = (int)(a.row_ptr[r1] - al0); }
+  // ---- phase A: one product (BS == 1) or one block-times-vector (BS products-sums) per non-zero block, in place
+  for (int k = kt0 + (int)threadIdx.x; k < kt1; k += CONSUMERS * UNR) {
+    double v[UNR][BS * BS], xg[UNR][BS];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int kk = k + u * CONSUMERS;
+      const bool ok = kk < kt1;
+      const int64_t c = ok ? cs[kk] : 0;
+#pragma unroll
+      for (int j = 0; j < BS; ++j) xg[u][j] = ok ? __ldg(a.x + c * BS + j) : 0.0;
+#pragma unroll
+      for (int e = 0; e < BS * BS; ++e) v[u][e] = ok ? vs[kk * BS * BS + e] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int kk = k + u * CONSUMERS;
+      if (kk < kt1) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < BS; ++j) t += v[u][i * BS + j] * xg[u][j];
+          vs[kk * BS * BS + i] = t;
+        }
+      }
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(CONSUMERS) : "memory");
+  // ---- phase B: row sums from shared memory
+  const int sub = threadIdx.x % LPR;
+  const int nscalar = (int)(r1 - r0) * BS;
+  for (int base = 0; base < nscalar; base += ROWS) {
+    const int lr = base + threadIdx.x / LPR;
+    const bool live = lr < nscalar;
+    const int64_t R = r0 + (live ? lr / BS : 0);
+    const int i = live ? lr % BS : 0;
+    const int64_t row = R * BS + i;
+    int ks, ke;
+    if (ra0 >= 0) { ks = (int)(rp[R - ra0] - al0); ke = (int)(rp[R + 1 - ra0] - al0); }
+    else { ks = (int)(a.row_ptr[R] - al0); ke = (int)(a.row_ptr[R + 1] - al0); }
+    if (!live) ke = ks;
+    const double wv = (a.w && live && sub == 0) ? __ldg(a.w + row) : 0.0;
+    const double wv2 = (a.w2 && live && sub == 0) ? __ldg(a.w2 + row) : 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = ks + sub;
+    for (; k + LPR < ke; k += 2 * LPR) { acc0 += vs[k * BS * BS + i]; acc1 += vs[(k + LPR) * BS * BS + i]; }
+    if (k < ke) acc0 += vs[k * BS * BS + i];
+    double acc = acc0 + acc1;
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && sub == 0) {
+      if (a.l2_hint) __stcs(a.y + row, acc); else a.y[row] = acc;
+      d0 += acc * wv;
+      if (a.want_yy) d1 += acc * acc;
+      d2 += acc * wv2;
+    }
+  }
+  // the stage's values were rewritten through the generic proxy; the next bulk copy into it goes through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // SpMV configuration chosen for a matrix (fsb_spmv.cu)
