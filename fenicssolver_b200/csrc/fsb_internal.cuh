@@ -28,7 +28,7 @@ struct fsb_ctx {
   int spmv_lpr = 0;      // lanes per row in the staged kernel (1, 2 or 4; 0 = best per block size)
   int spmv_rows = 0;     // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks; 0 = best per block size)
   int spmv_stages = 0;   // TMA pipeline depth (2..4; 0 = 2)
-  int spmv_flat = 0;     // two-phase tiles (products over non-zeros, then row sums): 0 = for long rows (avg > 20), 1 always, 2 never
+  int spmv_flat = 0;     // two-phase tiles (products over non-zeros, then row sums): 0 = long rows of 3x3 blocks, 1 always, 2 never
   int dist_p2p = 1;      // distributed CG through peer-memory mailboxes/halo (1) or NCCL collectives (0)
   int profile = 0;
   int use_graph = 1;

@@ -222,18 +222,22 @@ __global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, i
 // with 2 lanes x 8 slots per row: they get one lane per row (tools/spmv_short_rows.py on the squeezed C2
 // operand: 256 rows x 1 lane x 2 stages 6 265 GB/s, x 2 lanes 3 062 GB/s; deeper pipelines lose the second CTA).
 static bool spmv_short_rows(const fsb_mat* A) { return A->bs == 1 && A->avg_row > 0.0 && A->avg_row <= 8.5; }
-// Long rows (degree-2 spaces: ~28 blocks per row on average, up to ~90): a tile of 256 / 192 scalar rows no longer fits a
-// stage (3x3 blocks fell back to the plain kernel) and 2 lanes per row leave most of a row's gathers serial.  Half the rows
-// per tile and 4 lanes per row (tools/spmv_long_rows.py, P2 on 48^3: CSR 2 564 -> 3 348 GB/s, 3x3 BSR 3 481 -> 4 186 GB/s).
+// Long rows (degree-2 spaces: ~28 blocks per row on average, 10 to ~90 per row).  Measured on P2 operands at 48^3 and 64^3
+// (tools/spmv_long_rows.py, profiles/spmv_long_rows_r2.txt):
+//   * 3x3 blocks: a tile of 192 scalar rows does not fit a stage (the plain kernel ran: 3 350 GB/s).  Half the rows, 4 lanes per
+//     row, 3 stages and the two-phase ("flat") tile consumer — products over the tile's non-zeros, then row sums, so the gathers
+//     are balanced whatever the row lengths: 4 600 GB/s (rows-per-lane form of the same tiling: 3 740);
+//   * scalar CSR: 256 rows x 2 lanes x 2 stages, rows-per-lane form: 4 180 GB/s (128 x 4: 3 190; flat 128 x 2: 4 185, a tie).
 static bool spmv_long_rows(const fsb_mat* A) { return A->avg_row > 20.0; }
 static int spmv_rows(fsb_ctx* ctx, const fsb_mat* A) {
   const int big = A->bs == 3 ? 192 : 256;
-  const int opt = ctx->spmv_rows ? ctx->spmv_rows : (spmv_long_rows(A) ? 128 : 256);
+  const int opt = ctx->spmv_rows ? ctx->spmv_rows : (spmv_long_rows(A) && A->bs != 1 ? 128 : 256);
   return opt == 128 ? big / 2 : (opt == 512 && A->bs == 1 ? 512 : big);
 }
 static int spmv_lpr(fsb_ctx* ctx, const fsb_mat* A) {
-  return ctx->spmv_lpr ? ctx->spmv_lpr : (spmv_short_rows(A) ? 1 : (spmv_long_rows(A) && A->bs != 2 ? 4 : 2));      // 2x2 blocks: 2 lanes only
+  return ctx->spmv_lpr ? ctx->spmv_lpr : (spmv_short_rows(A) ? 1 : (spmv_long_rows(A) && A->bs == 3 ? 4 : 2));
 }
+static bool spmv_flat(fsb_ctx* ctx, const fsb_mat* A) { return ctx->spmv_flat == 1 || (ctx->spmv_flat == 0 && spmv_long_rows(A) && A->bs == 3); }
 static int spmv_stages(fsb_ctx* ctx, const fsb_mat* A) { return ctx->spmv_stages ? ctx->spmv_stages : (A->bs == 3 ? 3 : 2); }
 static constexpr size_t kSmemBudget = 200 * 1024;
 
@@ -303,7 +307,7 @@ void fsb_spmv_fill_args(fsb_mat* A, SpmvArgs* a) {
   a->tile_row = A->tile_row; a->tile_k = A->tile_row ? A->tile_row + A->ntiles + 1 : nullptr;
   a->ntiles = A->ntiles; a->own0 = A->own0; a->own1 = A->own1; a->cap = A->tile_cap;
   a->x = nullptr; a->y = nullptr; a->w = nullptr; a->want_yy = 0; a->w2 = nullptr; a->l2_hint = ctx->spmv_hint;
-  a->flat = ctx->spmv_flat == 1 || (ctx->spmv_flat == 0 && spmv_long_rows(A));
+  a->flat = spmv_flat(ctx, A);
   a->partials = ctx->d_partials; a->out = nullptr; a->counter = ctx->d_counters + 0; a->done = nullptr;
   memset(&a->pc, 0, sizeof(a->pc));
   a->halo_seq = 0; a->mail_slot = -1; a->mail_seq = 0;
