@@ -23,7 +23,8 @@ struct fsb_ctx {
   int64_t launches = 0;
   // options
   int asm_mode = 1;      // 0 search+atomics, 1 position map + atomics (default), 2 row-gather (owner computes, no atomics, bitwise
-                         // reproducible; measured 2x slower than 1 at 256^3, profiles/asm_ab_r2.txt) for the degree-1 scalar forms
+                         // reproducible; measured 2x slower than 1 at 256^3, profiles/asm_ab_r2.txt) for the degree-1 scalar forms,
+                         // 3 per-warp combine plan (sorted contributions, one RED per distinct slot of a warp) for P1 tetrahedra
   int spmv_mode = 0;     // 0 TMA-staged tiles v2, 1 plain row-per-thread, 2 TMA-staged v1 (one thread per row)
   int spmv_lpr = 0;      // lanes per row in the staged kernel (1, 2 or 4; 0 = best per block size)
   int spmv_rows = 0;     // scalar rows per tile: 256 or 128 (x 3/4 for 3x3 blocks; 0 = best per block size)
@@ -114,6 +115,12 @@ struct fsb_mat {
   int32_t* col_idx = nullptr;  // [nnzb] (+pad)
   double* vals = nullptr;      // [nnzb][bs][bs] (+pad)
   uint8_t* posmap = nullptr;   // [ncells][(tdim+1)^2] in-row offsets, or null
+  // per-warp combine plan of the degree-1 tetrahedron scatter (asm_mode 3, fsb_assemble.cu), built on first use
+  uint16_t* plan_rank = nullptr;   // [nchunk][16][32]
+  uint16_t* plan_head = nullptr;   // [nchunk][32]
+  int64_t* plan_run_ptr = nullptr; // [nchunk+1]
+  uint32_t* plan_dest = nullptr;   // [plan_runs]
+  int64_t plan_runs = 0;
   int max_row_len = 0;
   int64_t own0 = 0, own1 = 0;  // owned block rows
   // SpMV tiling (TMA-staged): tiles of ~tile_nnz blocks snapped to row boundaries

@@ -342,6 +342,7 @@ extern "C" void fsb_mat_destroy(fsb_mat* A) {
   fsb_dfree(A->ctx, A->col_idx);
   fsb_dfree(A->ctx, A->vals);
   fsb_dfree(A->ctx, A->posmap);
+  fsb_dfree(A->ctx, A->plan_rank); fsb_dfree(A->ctx, A->plan_head); fsb_dfree(A->ctx, A->plan_run_ptr); fsb_dfree(A->ctx, A->plan_dest);
   fsb_dfree(A->ctx, A->tile_row);
   fsb_dfree(A->ctx, A->bc_flag);
   fsb_dfree(A->ctx, A->bc_val);

@@ -188,7 +188,7 @@ def test_pattern_high_valence_vertex(ctx):
 
 
 # ----------------------------------------------------------------------------------- assembly
-@pytest.mark.parametrize("asm_mode", [0, 1, 2])
+@pytest.mark.parametrize("asm_mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_assemble_scalar_terms(ctx, dim, asm_mode):
     n = (7, 5) if dim == 2 else (5, 4, 6)
@@ -260,6 +260,32 @@ def test_row_gather_assembly_overwrite_action_and_reproducibility(ctx, dim):
         Am, _, _ = csr_from_device(A)
         ref = 1.0 + Am @ xh
         assert np.abs(y.numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    finally:
+        ctx.set_option("asm_mode", 1)
+
+
+def test_combine_plan_assembly_on_fixture_and_ragged_meshes(ctx, golden_dir):
+    """asm_mode 3 (per-warp combine plan) on meshes whose cell count is not a multiple of 32 and whose numbering is unstructured
+    (the reference's shipped fixture mesh, a shuffled cube): same matrix as the oracle, accumulation across calls, reuse of the plan."""
+    g = np.load(os.path.join(golden_dir, "fixture_mesh.npz"))
+    cases = [(g["coords"], np.ascontiguousarray(g["cells"], dtype=np.int32)), _shuffled(*fo.unit_cube_mesh(5, 3, 4), seed=9),
+             (np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]), np.array([[0, 1, 2, 3]], dtype=np.int32))]
+    ctx.set_option("asm_mode", 3)
+    try:
+        for c, t in cases:
+            nv = c.shape[0]
+            m = _lib.DeviceMesh.upload(ctx, c, t)
+            A = _lib.DeviceMatrix.create(m, 1)
+            A.assemble_scalar(kscale=2.0, mass=0.5)
+            A.assemble_scalar(kscale=1.0)                        # second call: the plan is reused and the values accumulate
+            dev, rp, ci = csr_from_device(A)
+            rp0, ci0 = fo.csr_pattern(t, nv)
+            ref = fo.conform(fo.assemble_matrix(t, 3.0 * fo.local_laplace(c, t, 1.0) + fo.local_mass(c, t, 0.5), nv), rp0, ci0)
+            assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+            assert_vals_close(dev.data, ref.data)
+            A.assemble_scalar(kscale=1.0, overwrite=True)
+            ref1 = fo.conform(fo.assemble_matrix(t, fo.local_laplace(c, t, 1.0), nv), rp0, ci0)
+            assert_vals_close(A.download_csr()[2], ref1.data)
     finally:
         ctx.set_option("asm_mode", 1)
 

@@ -1,5 +1,6 @@
 """A/B of the degree-1 scalar matrix assembly on one GPU: atomic scatter (asm_mode 1: one thread per cell, fp64 REDs at the position
-map) against row gather (asm_mode 2: one thread per row, no atomics), CUDA-event timed, at config C2's mesh size.
+map) against row gather (asm_mode 2: one thread per row, no atomics) and the per-warp combine plan (asm_mode 3: sorted contributions,
+one RED per distinct slot of a warp), CUDA-event timed, at config C2's mesh size.
     python tools/asm_ab.py [N] [reps]
 Prints ms per call for: zero-fill, Laplace, Laplace + mass + advection (config C4's form), and the matrix-free action."""
 import os
@@ -39,9 +40,15 @@ def timed(fn):
 print("N=%d: %d vertices, %d cells, nnz %d" % (N, nv, nc, A.sizes()["nnz"]), flush=True)
 print("zero-fill of A: %.3f ms" % timed(A.zero), flush=True)
 ref = {}
-for mode in (1, 2):
+for mode in (1, 2, 3):
     ctx.set_option("asm_mode", mode)
-    name = {1: "scatter (REDs)", 2: "row gather"}[mode]
+    name = {1: "scatter (REDs)", 2: "row gather", 3: "warp combine plan"}[mode]
+    if mode == 3:
+        import time
+        t0 = time.perf_counter()
+        A.assemble_scalar(kscale=1.0)          # first call in this mode builds the plan (two sort passes over the mesh)
+        ctx.sync()
+        print("%-16s plan build + first assembly %.1f ms (once per matrix)" % (name, (time.perf_counter() - t0) * 1e3), flush=True)
     for label, kw in (("Laplace", dict(kscale=20.0)), ("Laplace+mass+advection", dict(kscale=0.3, mass=2.5e6, adv=4.2e6, vel=vel))):
         t_add = timed(lambda: A.assemble_scalar(**kw))
         t_set = timed(lambda: A.assemble_scalar(overwrite=True, **kw))
