@@ -370,7 +370,7 @@ static int plan_build(fsb_mesh* mesh, fsb_mat* A) {
 
 // the row-gather kernels apply to a degree-1 mesh whose adjacency was kept, a position map and rows that fit the slots
 static bool rows_path(fsb_ctx* ctx, fsb_mesh* mesh, fsb_mat* A) {
-  if (ctx->asm_mode < 2 || mesh->degree != 1 || !mesh->v2c) return false;
+  if (ctx->asm_mode != 2 || mesh->degree != 1 || !mesh->v2c) return false;
   if (A && (A->mesh != mesh || !A->posmap || A->max_row_len > kRowSlots)) return false;
   return fsb_mesh_sort_adjacency(mesh) == FSB_OK;       // fixed (ascending cell) summation order
 }
