@@ -57,9 +57,7 @@ class ElasticityForm:
         if self.thermal is not None:
             beta, T, T_ref = self.thermal
             if isinstance(T, np.ndarray):
-                if space.comm.nranks > 1:
-                    raise SolverError('a nodal temperature distribution is not implemented for distributed runs')
-                Td = _lib.DeviceVector.from_numpy(space.ctx, T)
+                Td = space.local_nodal(T, 1) if space.comm.nranks > 1 else _lib.DeviceVector.from_numpy(space.ctx, T)
                 _lib.assemble_thermal_load(space.dmesh, b, beta, T=Td, T_ref=T_ref)
             else:
                 _lib.assemble_thermal_load(space.dmesh, b, beta, T_const=float(T), T_ref=T_ref)
@@ -128,34 +126,45 @@ class LinearElasticitySolver(SolverBase):
         from .backend import DeviceSpace
         from .dolfin_compat import Function, FunctionSpace
         space = self.device_space()
-        if space.comm.nranks > 1:
-            raise SolverError('von_Mises projection is not implemented for distributed runs')
+        dist = space.comm.nranks > 1
         mu, lmbda = self.lame_parameters()
         V1 = FunctionSpace(self.mesh, 'P', 1)
         proj = getattr(self, '_vm_space', None)
         if proj is None:
-            # the scalar P1 pattern: on the displacement's own device mesh when that is degree 1
-            if space.degree == 1:
+            # the scalar P1 space of the projection: on the displacement's own device mesh when that is degree 1 on one GPU;
+            # distributed, a scalar DeviceSpace over the same partition (same slab / same RCB cut of the same nodes)
+            if space.degree == 1 and not dist:
                 proj = (space.dmesh, _lib.DeviceMatrix.create(space.dmesh, 1), None)
             else:
-                s1 = DeviceSpace(self.mesh, 1, ctx=space.ctx)
+                s1 = DeviceSpace(self.mesh, 1, ctx=space.ctx, comm=space.comm)
                 proj = (s1.dmesh, s1.A, s1)
             self._vm_space = proj
-        dmesh1, M, _keep = proj
+        dmesh1, M, s1 = proj
+        if dist and space.degree != 1:
+            raise SolverError('von_Mises projection of a distributed degree-2 displacement is not implemented')
         ud = u.device_vector() if isinstance(u, Function) else None
         if ud is None or ud.n != space.ndof_local:
             ud = space.vector_from_global(u.array() if isinstance(u, Function) else np.asarray(u).reshape(-1))
-        nv = self.mesh.num_vertices()
+        elif dist:
+            space.activate()
+            ud.halo()                                       # the cell loop reads the displacement at the ghost nodes
+        nv = s1.nv_local if s1 is not None else self.mesh.num_vertices()
         b = _lib.DeviceVector(space.ctx, nv)
         _lib.assemble_von_mises_load(space.dmesh, ud, mu, lmbda, b)
         M.zero()
         M.assemble_scalar(kscale=0.0, mass=1.0)
         x = _lib.DeviceVector(space.ctx, nv)
-        info = M.solve(b, x, method='cg', rtol=1e-12, maxit=100000)
+        if s1 is not None:
+            info = s1.solve(b, x, method='cg', rtol=1e-12, maxit=100000)
+        else:
+            info = M.solve(b, x, method='cg', rtol=1e-12, maxit=100000)
         if info['converged'] != 1:
             self.logger.warning('von Mises projection did not converge: %s', info)
         out = Function(V1)
-        out.set_device(x)
+        if dist:
+            out.assign_array(s1.gather_global(x))           # every rank gets the global vertex-ordered field
+        else:
+            out.set_device(x)
         return out
 
     def _vector_constant(self, value, what):

@@ -68,9 +68,7 @@ class ScalarForm:
             # a velocity FIELD: the convection matrix comes from its own kernel, nothing else sees the velocity
             if self.supg_pe:
                 raise SolverError('SUPG with a velocity field is not implemented (constant velocity only)')
-            if space.comm.nranks > 1:
-                raise SolverError('a velocity field is implemented for single-GPU runs')
-            vel_field, vel = _lib.DeviceVector.from_numpy(space.ctx, vel.ravel()), None
+            vel_field, vel = space.local_nodal(vel, vel.shape[1]), None       # this rank's nodes (owned + ghosts) of the global field
         adv = c if vel is not None else 0.0
         b = space.scratch_vector('rhs')
         supg = self.supg_pe if vel is not None else None
@@ -129,7 +127,7 @@ class ScalarForm:
         for ps in self.point_sources:
             nodes, w = ps.entries()
             if space.comm.nranks > 1:
-                raise SolverError('point sources are not implemented for distributed runs')
+                nodes, w = space.local_dofs(nodes, w)       # every rank adds the entries of its own rows (owner computes)
             b.add_entries(nodes, w)
         symmetric = vel is None and vel_field is None and (ktensor is None or np.allclose(ktensor, ktensor.T, rtol=0, atol=0))
         return b, symmetric and self.conductivity_fn is None       # the k'(T) Jacobian term is not symmetric

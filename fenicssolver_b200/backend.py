@@ -240,6 +240,18 @@ class DeviceSpace:
         lo = self.v_off * self.ncomp
         return _lib.DeviceVector.from_numpy(self.ctx, a[lo:lo + self.ndof_local])
 
+    def local_nodal(self, values, ncomp=1):
+        """Device vector with this rank's part (owned + ghost nodes) of a GLOBAL nodal field with `ncomp` values per node — a
+        field on another space over the same nodes, e.g. a velocity or temperature field entering a form."""
+        a = np.asarray(values, dtype=np.float64).reshape(-1, ncomp)
+        if a.shape[0] != self.nv_global:
+            raise SolverError("a nodal field needs one value per node: got %d rows for %d nodes" % (a.shape[0], self.nv_global))
+        if self.part is not None:
+            a = a[self.part.l2g]
+        elif self.comm.nranks > 1:
+            a = a[self.v_off:self.v_off + self.nv_local]
+        return _lib.DeviceVector.from_numpy(self.ctx, a.ravel())
+
     def scratch_vector(self, key):
         """A zeroed device vector owned by the space and reused between calls (the right-hand side of every
         time step): cudaMalloc/cudaFree synchronise the device and are kept out of the step."""
