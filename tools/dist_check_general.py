@@ -54,12 +54,12 @@ def field_case(mesh, coords, distributed):
 
 def thermoelastic_case(mesh, coords, distributed):
     """F: clamp on x = 0, gravity, and a nodal temperature field T(x) = 293 + 60 x z."""
-    from fenicssolver_b200.dolfin_compat import near
+    from fenicssolver_b200.dolfin_compat import Expression, near
     return {'solver_name': 'LinearElasticitySolver', 'mesh': mesh, 'fe_degree': 1, 'fe_family': 'CG', 'vector_name': 'displacement',
             'material': {'elastic_modulus': 2e11, 'poisson_ratio': 0.27, 'density': 7800, 'thermal_expansion_coefficient': 2e-6},
             'boundary_conditions': {'clamp': {'boundary': lambda x: near(x[0], 0.0), 'boundary_id': 1, 'type': 'Dirichlet', 'value': (0, 0, 0)}},
             'body_source': (0.0, 0.0, -7800 * 9.81), 'initial_values': {},
-            'temperature_distribution': 293.0 + 60.0 * coords[:, 0] * coords[:, 2],
+            'temperature_distribution': Expression("293 + 60*x[0]*x[2]", degree=1),       # interpolated: one value per node
             'solver_settings': {'transient_settings': {'transient': False, 'starting_time': 0, 'time_step': 0.01, 'ending_time': 0.03},
                                 'reference_values': {'temperature': 293}, 'solver_parameters': {'preconditioner': 'jacobi'},
                                 'distributed': distributed, 'gather_result': True},
