@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(THREADS) k_spmv_tma(SpmvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------ mode 0: producer/consumer
-template <int BS, int ROWS, int LPR, int NST>
+// FLAT: the two-phase tile consumer (spmv_consume_tile_flat) — a template parameter, not a run-time branch: carrying both consumers
+// in one kernel cost the 256 x 2 configuration 16 registers and with them its second CTA per SM (measured: 0.88 -> 0.66 of peak)
+template <int BS, int ROWS, int LPR, int NST, bool FLAT = false>
 __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(SpmvArgs a) {
   using Cfg = SpmvCfg<BS, ROWS, LPR>;
   constexpr int CONSUMERS = Cfg::CONSUMERS;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(SpmvCfg<BS, ROWS, LPR>::THREADS) k_spmv_ws(Spm
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const int s = it % NST;
       mbar_wait(&full[s], (it / NST) & 1);
-      if (a.flat) spmv_consume_tile_flat<BS, ROWS, LPR>(a, st, s, s_info[s], d0, d1, d2);
+      if (FLAT) spmv_consume_tile_flat<BS, ROWS, LPR>(a, st, s, s_info[s], d0, d1, d2);
       else spmv_consume_tile<BS, ROWS, LPR, false>(a, st, s, s_info[s], d0, d1, d2);
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);      // this warp is done with stage s
@@ -335,23 +337,30 @@ int fsb_launch_spmv(fsb_mat* A, const double* x, double* y, const double* w, int
     const int nst = std::max(2, std::min(spmv_stages(ctx, A), (int)((224 * 1024) / A->stage_bytes)));
     const size_t smem = (size_t)nst * A->stage_bytes;
     bool launched = false;
-#define FSB_SPMV_CASE(BS, ROWS, LPR, NST)                                                                              \
-  if (!launched && A->bs == BS && rows == ROWS && lpr == LPR && nst == NST) {                                          \
+#define FSB_SPMV_CASE(BS, ROWS, LPR, NST, FLAT)                                                                        \
+  if (!launched && A->bs == BS && rows == ROWS && lpr == LPR && nst == NST && (a.flat != 0) == FLAT) {                 \
     using Cfg = SpmvCfg<BS, ROWS, LPR>;                                                                                \
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / Cfg::THREADS, (227 * 1024) / (smem + 1024)));  \
     const unsigned grid = (unsigned)std::min<int64_t>(A->ntiles, (int64_t)ctx->sm_count * per_sm);                     \
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
-      FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_spmv_ws<BS, ROWS, LPR, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
+      FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_spmv_ws<BS, ROWS, LPR, NST, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
-    k_spmv_ws<BS, ROWS, LPR, NST><<<grid, Cfg::THREADS, smem, ctx->stream>>>(a);                                       \
+    k_spmv_ws<BS, ROWS, LPR, NST, FLAT><<<grid, Cfg::THREADS, smem, ctx->stream>>>(a);                                 \
     launched = true;                                                                                                   \
   }
-#define FSB_SPMV_NST(BS, ROWS, LPR) FSB_SPMV_CASE(BS, ROWS, LPR, 2) FSB_SPMV_CASE(BS, ROWS, LPR, 3) FSB_SPMV_CASE(BS, ROWS, LPR, 4)
+#define FSB_SPMV_NST(BS, ROWS, LPR) FSB_SPMV_CASE(BS, ROWS, LPR, 2, false) FSB_SPMV_CASE(BS, ROWS, LPR, 3, false) FSB_SPMV_CASE(BS, ROWS, LPR, 4, false)
+#define FSB_SPMV_NST_FLAT(BS, ROWS, LPR) FSB_SPMV_CASE(BS, ROWS, LPR, 2, true) FSB_SPMV_CASE(BS, ROWS, LPR, 3, true)
+    // the flat (two-phase) consumer exists for the long-row configurations only; asked for elsewhere, the rows form runs
+    if (a.flat && !((A->bs == 3 && rows == 96 && (lpr == 2 || lpr == 4)) || (A->bs == 1 && rows == 128 && (lpr == 2 || lpr == 4)) || (A->bs == 1 && rows == 256 && lpr == 2)) )
+      a.flat = 0;
+    if (a.flat && nst > 3) a.flat = 0;
     FSB_SPMV_NST(1, 512, 1) FSB_SPMV_NST(1, 256, 1) FSB_SPMV_NST(1, 256, 2) FSB_SPMV_NST(1, 128, 1) FSB_SPMV_NST(1, 128, 2) FSB_SPMV_NST(1, 128, 4)
     FSB_SPMV_NST(2, 256, 2) FSB_SPMV_NST(2, 128, 2)
     FSB_SPMV_NST(3, 192, 2) FSB_SPMV_NST(3, 192, 4) FSB_SPMV_NST(3, 96, 2) FSB_SPMV_NST(3, 96, 4) FSB_SPMV_NST(3, 96, 8)
+    FSB_SPMV_NST_FLAT(3, 96, 2) FSB_SPMV_NST_FLAT(3, 96, 4) FSB_SPMV_NST_FLAT(1, 128, 2) FSB_SPMV_NST_FLAT(1, 128, 4) FSB_SPMV_NST_FLAT(1, 256, 2)
+#undef FSB_SPMV_NST_FLAT
 #undef FSB_SPMV_NST
 #undef FSB_SPMV_CASE
     if (!launched) FSB_FAIL(ctx, FSB_ERR_ARG, "unsupported spmv_rows/spmv_lpr/spmv_stages combination");
