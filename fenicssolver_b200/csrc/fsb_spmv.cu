@@ -225,15 +225,17 @@ __global__ void k_tile_rows(const int64_t* __restrict__ row_ptr, int64_t own0, i
 // operand: 256 rows x 1 lane x 2 stages 6 265 GB/s, x 2 lanes 3 062 GB/s; deeper pipelines lose the second CTA).
 static bool spmv_short_rows(const fsb_mat* A) { return A->bs == 1 && A->avg_row > 0.0 && A->avg_row <= 8.5; }
 // Long rows (degree-2 spaces: ~28 blocks per row on average, 10 to ~90 per row).  Measured on P2 operands at 48^3 and 64^3
-// (tools/spmv_long_rows.py, profiles/spmv_long_rows_r2.txt):
-//   * 3x3 blocks: a tile of 192 scalar rows does not fit a stage (the plain kernel ran: 3 350 GB/s).  Half the rows, 4 lanes per
+// (tools/spmv_long_rows.py, profiles/spmv_long_rows_r2.txt, last table = after the flat consumer became a template parameter):
+//   * 3x3 blocks: a tile of 192 scalar rows does not fit a stage (the plain kernel ran: 3 340 GB/s).  Half the rows, 4 lanes per
 //     row, 3 stages and the two-phase ("flat") tile consumer — products over the tile's non-zeros, then row sums, so the gathers
-//     are balanced whatever the row lengths: 4 600 GB/s (rows-per-lane form of the same tiling: 3 740);
-//   * scalar CSR: 256 rows x 2 lanes x 2 stages, rows-per-lane form: 4 180 GB/s (128 x 4: 3 190; flat 128 x 2: 4 185, a tie).
+//     are balanced whatever the row lengths: 4 680 GB/s (rows-per-lane form of the same tiling: 4 150);
+//   * scalar CSR: 128 rows x 2 lanes x 2 stages, rows form: 4 250 GB/s (flat: 4 195, a tie; 256 rows x 2 lanes: 2 670 with two CTAs
+//     per SM).  These operands gather 28 x-entries per row from two distant index ranges (vertex nodes, edge nodes): at 32 B per
+//     gathered sector that is 0.9 KB of L2 -> SM traffic per row against 0.36 KB from HBM, so the L2 rate, not HBM, bounds them.
 static bool spmv_long_rows(const fsb_mat* A) { return A->avg_row > 20.0; }
 static int spmv_rows(fsb_ctx* ctx, const fsb_mat* A) {
   const int big = A->bs == 3 ? 192 : 256;
-  const int opt = ctx->spmv_rows ? ctx->spmv_rows : (spmv_long_rows(A) && A->bs != 1 ? 128 : 256);
+  const int opt = ctx->spmv_rows ? ctx->spmv_rows : (spmv_long_rows(A) ? 128 : 256);
   return opt == 128 ? big / 2 : (opt == 512 && A->bs == 1 ? 512 : big);
 }
 static int spmv_lpr(fsb_ctx* ctx, const fsb_mat* A) {
