@@ -22,6 +22,7 @@ namespace {
 
 struct Level {
   fsb_mat* A = nullptr;
+  fsb_mat* S = nullptr;         // SpMV operand: A, or its compacted copy without the exactly-zero blocks (drop_zeros)
   int dims[3] = {1, 1, 1};      // vertices per axis
   int64_t nnode = 0, n = 0;     // nodes, scalar dofs
   double omega = 0.6;
@@ -207,7 +208,21 @@ static int mg_dot(fsb_mg* mg, int64_t n, const double* x, const double* y, const
   return FSB_OK;
 }
 
-static int mg_spmv(Level& L, const double* x, double* y) { return fsb_launch_spmv(L.A, x, y, nullptr, 0, nullptr, nullptr); }
+static int mg_spmv(Level& L, const double* x, double* y) { return fsb_launch_spmv(L.S ? L.S : L.A, x, y, nullptr, 0, nullptr, nullptr); }
+
+// The level matrices were (re)assembled since the last cycle: refresh the operands the smoothers and residuals multiply by.
+// With drop_zeros (default 'auto') a level whose stored blocks are >= 20 % exact zeros (every level of a right-angled box
+// hierarchy) gets the compacted copy: a V(2,2) cycle runs five SpMVs per level, the count + compact passes cost two.
+static int mg_prepare_operands(fsb_mg* mg) {
+  for (Level& L : mg->lv) {
+    L.S = L.A;
+    if (mg->ctx->drop_zeros) {
+      int rc = fsb_mat_squeeze(L.A, &L.S);
+      if (rc) return rc;
+    }
+  }
+  return FSB_OK;
+}
 
 static int mg_smooth(fsb_mg* mg, Level& L, int sweeps, bool zero_start) {
   fsb_ctx* ctx = mg->ctx;
@@ -377,6 +392,8 @@ extern "C" int fsb_mg_apply(fsb_mg* mg, fsb_vec* r, fsb_vec* z, int32_t nu) {
   if (!mg || !r || !z) return FSB_ERR_ARG;
   if (r->n != mg->lv[0].n || z->n != r->n || r == z) FSB_FAIL(mg->ctx, FSB_ERR_ARG, "vector sizes do not match the fine level");
   mg->nu = nu > 0 ? nu : 2;
+  int rc = mg_prepare_operands(mg);
+  if (rc) return rc;
   return mg_apply(mg, r->d, z->d);
 }
 
@@ -389,7 +406,7 @@ extern "C" int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, 
   if (b->n != n || x->n != n) FSB_FAIL(ctx, FSB_ERR_ARG, "vector sizes do not match the fine level");
   memset(info, 0, sizeof(*info));
   mg->nu = nu > 0 ? nu : 2;
-  info->operand_nnzb = L.A->nnzb;
+
   cudaEvent_t e0, e1;
   FSB_CHECK_CUDA(ctx, cudaEventCreate(&e0));
   FSB_CHECK_CUDA(ctx, cudaEventCreate(&e1));
@@ -398,6 +415,8 @@ extern "C" int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, 
   const unsigned g = mg_grid(ctx, n);
   double *p = mg->p, *q = mg->q, *z = mg->z, *r = mg->r;
   int rc;
+  if ((rc = mg_prepare_operands(mg))) return rc;        // inside the timed solve
+  info->operand_nnzb = L.S->nnzb;
   // convergence on the Jacobi-scaled residual ||D^-1 r|| <= max(rtol ||D^-1 b||, atol): the same norm as fsb_solve_cg
   double bb, rr, rz, pq;
   if ((rc = mg_dot(mg, n, b->d, b->d, L.dinv, &bb))) return rc;
@@ -415,7 +434,7 @@ extern "C" int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, 
     if ((rc = mg_dot(mg, n, r, z, nullptr, &rz))) return rc;
     while (it < maxit) {
       // q = A p with p.q fused into the SpMV (no separate pass over p and q)
-      if ((rc = fsb_launch_spmv(L.A, p, q, p, 0, ctx->d_scalars + 50, nullptr))) return rc;
+      if ((rc = fsb_launch_spmv(L.S, p, q, p, 0, ctx->d_scalars + 50, nullptr))) return rc;
       FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(&pq, ctx->d_scalars + 50, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       if (!(pq == pq) || pq == 0.0 || !(rz == rz)) { outcome = -1; break; }
