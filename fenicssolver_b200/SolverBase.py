@@ -247,6 +247,10 @@ class SolverBase():
 
         nv = self.function_space.num_nodes()
         if 'vector_name' in self.settings and isinstance(v0, (tuple, list)) and isinstance(v0[0], (str, numbers.Number)):
+            if all(isinstance(v, numbers.Number) for v in v0) and len(set(float(v) for v in v0)) == 1:
+                # the same constant in every component (the usual zero start): stays symbolic, filled on the device — no host
+                # arrays, no H2D copy (51 MB each for w_current / w_prev / w_pp of a 128^3 elasticity run)
+                return Function(self.function_space, fill=float(v0[0]))
             if all(isinstance(v, numbers.Number) for v in v0):
                 vals = np.tile(np.asarray(v0, dtype=np.float64), nv)
             else:
