@@ -261,19 +261,27 @@ class DeviceMesh(_Handle):
         self.ctx.check(self.ctx.lib.fsb_mesh_sizes(self.h, C.byref(g), C.byref(t), C.byref(nv), C.byref(nc)))
         return g.value, t.value, nv.value, nc.value
 
-    def exterior_facets(self):
+    def exterior_facets(self, ids=True):
         """K1 on the device: (fverts[nbf, tdim], opp[nbf], cell[nbf], facet_id[nbf]) of the facets held by exactly one cell, in
-        lexicographic order of the vertex tuples; facet_id is dolfin's global facet index."""
+        lexicographic order of the vertex tuples; facet_id is dolfin's global facet index (`ids=False`: None — the ranking pass
+        is only run when the ids are asked for)."""
         nbf, nf = c_i64(), c_i64()
         self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets(self.h, C.byref(nbf), C.byref(nf)))
         _, t, _, _ = self.sizes()
         fv = np.empty((nbf.value, t), dtype=np.int32)
         opp = np.empty(nbf.value, dtype=np.int32)
         cell = np.empty(nbf.value, dtype=np.int32)
-        fid = np.empty(nbf.value, dtype=np.int64)
+        fid = np.empty(nbf.value, dtype=np.int64) if ids else None
         self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets_get(self.h, _ptr(fv), _ptr(opp), _ptr(cell), _ptr(fid)))
         self.num_facets = nf.value
         return fv, opp, cell, fid
+
+    def exterior_facet_ids(self):
+        nbf = c_i64()
+        self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets(self.h, C.byref(nbf), None))
+        fid = np.empty(nbf.value, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.fsb_mesh_exterior_facets_get(self.h, None, None, None, _ptr(fid)))
+        return fid
 
     def boundary_geometry(self):
         """(bverts[nbv], finv[nbf, tdim], bxyz[nbv, gdim], mid[nbf, gdim]): distinct boundary vertices, the exterior facets in terms of

@@ -116,11 +116,12 @@ k_f_fill(const int32_t* __restrict__ cells, int64_t ncells, const uint8_t* __res
 
 __device__ __forceinline__ unsigned long long key_of(int b, int c) { return ((unsigned long long)(unsigned)b << 32) | (unsigned)(c < 0 ? 0 : c); }
 
+// step 5a: one thread per boundary vertex sorts its bucket by (b, c) and writes the final arrays; fid[] receives the number of
+// distinct facets filed under smaller vertices (the rank inside the star of a is added on demand by k_f_rank)
 template <int NL>
 __global__ void __launch_bounds__(128)
-k_f_sort_rank(const int32_t* __restrict__ cells, int64_t nverts, const int64_t* __restrict__ vptr, const int32_t* __restrict__ v2c,
-              const int64_t* __restrict__ eptr, const int64_t* __restrict__ ubase, FacetRec* __restrict__ rec, int32_t* __restrict__ fverts,
-              int32_t* __restrict__ opp, int32_t* __restrict__ cell, int64_t* __restrict__ fid, int* __restrict__ overflow) {
+k_f_sort(int64_t nverts, const int64_t* __restrict__ eptr, const int64_t* __restrict__ ubase, FacetRec* __restrict__ rec,
+         int32_t* __restrict__ fverts, int32_t* __restrict__ opp, int32_t* __restrict__ cell, int64_t* __restrict__ fid) {
   for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nverts; a += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = eptr[a], e1 = eptr[a + 1];
     if (e1 == e0) continue;
@@ -131,8 +132,29 @@ k_f_sort_rank(const int32_t* __restrict__ cells, int64_t nverts, const int64_t* 
       while (j > e0 && key_of(rec[j - 1].b, rec[j - 1].c) > k) { rec[j] = rec[j - 1]; --j; }
       rec[j] = r;
     }
-    // distinct facets of the star of a whose smallest vertex is a, as sorted keys
-    unsigned long long cand[kStarCap];
+    for (int64_t i = e0; i < e1; ++i) {
+      const FacetRec r = rec[i];
+      fverts[i * (NL - 1) + 0] = (int32_t)a;
+      fverts[i * (NL - 1) + 1] = r.b;
+      if (NL == 4) fverts[i * (NL - 1) + (NL - 2)] = r.c;
+      opp[i] = r.opp;
+      cell[i] = r.cell;
+      fid[i] = ubase[a];
+    }
+  }
+}
+
+// step 5b, only when the facet ids are asked for (marker files): one thread per exterior facet (a, b, c) ranks it among the
+// distinct facets of the star of a that have a as smallest vertex and adds the rank to fid.  The candidate list lives in local
+// memory (3 KB per thread), which is why this is not part of the always-run path.
+template <int NL>
+__global__ void __launch_bounds__(128)
+k_f_rank(const int32_t* __restrict__ cells, int64_t nbf, const int64_t* __restrict__ vptr, const int32_t* __restrict__ v2c,
+         const int32_t* __restrict__ fverts, int64_t* __restrict__ fid, int* __restrict__ overflow) {
+  for (int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; f < nbf; f += (int64_t)gridDim.x * blockDim.x) {
+    const int a = fverts[f * (NL - 1)];
+    const unsigned long long mine = key_of(fverts[f * (NL - 1) + 1], NL == 4 ? fverts[f * (NL - 1) + (NL - 2)] : -1);
+    unsigned long long cand[kStarCap];               // distinct keys smaller than mine, sorted
     int n = 0;
     bool over = false;
     for (int64_t p = vptr[a]; p < vptr[a + 1]; ++p) {
@@ -140,14 +162,15 @@ k_f_sort_rank(const int32_t* __restrict__ cells, int64_t nverts, const int64_t* 
       load_cell<NL>(cells, v2c[p], w);
       int pa = 0;
 #pragma unroll
-      for (int q = 0; q < NL; ++q) pa = (w[q] == (int)a) ? q : pa;
+      for (int q = 0; q < NL; ++q) pa = (w[q] == a) ? q : pa;
       if (pa > 1) continue;                             // a facet of this cell cannot start with a
 #pragma unroll
       for (int i = 0; i < NL; ++i) {
         if ((pa == 0) != (i != 0)) continue;            // pa == 0: every facet but facet 0; pa == 1: facet 0 only
-        int f[NL - 1];
-        facet_of<NL>(w, i, f);
-        const unsigned long long k = key_of(f[1], NL == 4 ? f[NL - 2] : -1);
+        int fc[NL - 1];
+        facet_of<NL>(w, i, fc);
+        const unsigned long long k = key_of(fc[1], NL == 4 ? fc[NL - 2] : -1);
+        if (k >= mine) continue;
         int lo = 0, hi = n;                             // sorted insert, duplicates dropped
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (cand[mid] < k) lo = mid + 1; else hi = mid; }
         if (lo < n && cand[lo] == k) continue;
@@ -158,18 +181,7 @@ k_f_sort_rank(const int32_t* __restrict__ cells, int64_t nverts, const int64_t* 
       }
     }
     if (over) atomicExch(overflow, 1);
-    for (int64_t i = e0; i < e1; ++i) {
-      const FacetRec r = rec[i];
-      const unsigned long long k = key_of(r.b, r.c);
-      int lo = 0, hi = n;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cand[mid] < k) lo = mid + 1; else hi = mid; }
-      fverts[i * (NL - 1) + 0] = (int32_t)a;
-      fverts[i * (NL - 1) + 1] = r.b;
-      if (NL == 4) fverts[i * (NL - 1) + (NL - 2)] = r.c;
-      opp[i] = r.opp;
-      cell[i] = r.cell;
-      fid[i] = ubase[a] + lo;
-    }
+    fid[f] += n;
   }
 }
 
@@ -242,10 +254,51 @@ int exterior_facets_impl(fsb_mesh* mesh) {
     TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
     k_f_fill<NL><<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, mask, eptr, deg, rec);
     ctx->launches++; TRYCUDA(cudaGetLastError());
-    k_f_sort_rank<NL><<<fsb_grid(nv, 128, cap), 128, 0, ctx->stream>>>(mesh->cells, nv, vptr, v2c, eptr, ubase, rec, mesh->bf_verts, mesh->bf_opp,
-                                                                        mesh->bf_cell, mesh->bf_id, d_over);
+    k_f_sort<NL><<<fsb_grid(nv, 128, cap), 128, 0, ctx->stream>>>(nv, eptr, ubase, rec, mesh->bf_verts, mesh->bf_opp, mesh->bf_cell, mesh->bf_id);
     ctx->launches++; TRYCUDA(cudaGetLastError());
   }
+  TRYCUDA(cudaStreamSynchronize(ctx->stream));
+  cleanup();
+  mesh->nbf = nbf;
+  mesh->nfacets = nfacets;
+  mesh->bf_id_ranked = false;
+  return FSB_OK;
+}
+
+// dolfin facet ids of the exterior facets: bf_id holds ubase[a]; add each facet's rank inside the star of its smallest vertex
+template <int NL>
+int facet_ids_impl(fsb_mesh* mesh) {
+  fsb_ctx* ctx = mesh->ctx;
+  if (mesh->bf_id_ranked || mesh->nbf <= 0) { mesh->bf_id_ranked = true; return FSB_OK; }
+  const int64_t nv = mesh->nverts, nc = mesh->ncells;
+  const int cap = ctx->sm_count * 16;
+  int32_t *deg = nullptr, *v2c = nullptr;
+  int64_t* vptr = nullptr;
+  int* d_over = nullptr;
+  int rc = FSB_OK;
+  auto cleanup = [&]() {
+    if (v2c != mesh->v2c) fsb_dfree(ctx, v2c);
+    if (vptr != mesh->v2c_ptr) fsb_dfree(ctx, vptr);
+    v2c = nullptr; vptr = nullptr;
+    fsb_dfree(ctx, deg); fsb_dfree(ctx, d_over);
+  };
+  TRY(fsb_dmalloc(ctx, &d_over, 1));
+  TRYCUDA(cudaMemsetAsync(d_over, 0, sizeof(int), ctx->stream));
+  if (mesh->degree == 1 && mesh->v2c) { vptr = mesh->v2c_ptr; v2c = mesh->v2c; }
+  else {                                    // a degree-2 mesh keeps no vertex adjacency: rebuild it for this one pass
+    TRY(fsb_dmalloc(ctx, &deg, (size_t)nv + 1));
+    TRY(fsb_dmalloc(ctx, &vptr, (size_t)nv + 1));
+    TRY(fsb_dmalloc(ctx, &v2c, (size_t)nc * NL));
+    TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+    k_f_v2c_count<<<fsb_grid(nc * NL, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc * NL, deg);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+    TRY(fsb_exclusive_scan(ctx, deg, vptr, nv));
+    TRYCUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nv + 1), ctx->stream));
+    k_f_v2c_fill<NL><<<fsb_grid(nc, 256, cap), 256, 0, ctx->stream>>>(mesh->cells, nc, vptr, deg, v2c);
+    ctx->launches++; TRYCUDA(cudaGetLastError());
+  }
+  k_f_rank<NL><<<fsb_grid(mesh->nbf, 128, (int64_t)ctx->sm_count * 4), 128, 0, ctx->stream>>>(mesh->cells, mesh->nbf, vptr, v2c, mesh->bf_verts, mesh->bf_id, d_over);
+  ctx->launches++; TRYCUDA(cudaGetLastError());
   int over = 0;
   TRYCUDA(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   TRYCUDA(cudaStreamSynchronize(ctx->stream));
@@ -253,8 +306,7 @@ int exterior_facets_impl(fsb_mesh* mesh) {
 #undef TRY
 #undef TRYCUDA
   if (over) FSB_FAIL(ctx, FSB_ERR_STATE, "facet numbering: a vertex star holds more than 384 distinct facets");
-  mesh->nbf = nbf;
-  mesh->nfacets = nfacets;
+  mesh->bf_id_ranked = true;
   return FSB_OK;
 }
 
@@ -356,6 +408,10 @@ extern "C" int fsb_mesh_exterior_facets_get(fsb_mesh* mesh, int32_t* fverts, int
   fsb_ctx* ctx = mesh->ctx;
   if (mesh->nbf < 0) FSB_FAIL(ctx, FSB_ERR_STATE, "call fsb_mesh_exterior_facets first");
   const int64_t n = mesh->nbf;
+  if (facet_id && !mesh->bf_id_ranked) {
+    const int rc = mesh->tdim == 3 ? facet_ids_impl<4>(mesh) : facet_ids_impl<3>(mesh);
+    if (rc) return rc;
+  }
   if (n > 0) {
     if (fverts) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(fverts, mesh->bf_verts, sizeof(int32_t) * n * mesh->tdim, cudaMemcpyDeviceToHost, ctx->stream));
     if (opp) FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(opp, mesh->bf_opp, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));

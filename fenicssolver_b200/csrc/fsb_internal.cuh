@@ -91,7 +91,8 @@ struct fsb_mesh {
   int32_t* bf_verts = nullptr;     // [nbf][tdim] sorted vertex tuples
   int32_t* bf_opp = nullptr;       // [nbf] vertex of the cell opposite the facet
   int32_t* bf_cell = nullptr;      // [nbf] the one cell holding the facet
-  int64_t* bf_id = nullptr;        // [nbf] dolfin facet index = rank among all distinct facets
+  int64_t* bf_id = nullptr;        // [nbf] dolfin facet index = rank among all distinct facets (complete once bf_id_ranked)
+  bool bf_id_ranked = false;
   int64_t nbv = -1;                // distinct boundary vertices (fsb_mesh_boundary_geometry)
   int32_t* bg_verts = nullptr;     // [nbv] ascending
   int32_t* bg_finv = nullptr;      // [nbf][tdim] facet vertices as indices into bg_verts

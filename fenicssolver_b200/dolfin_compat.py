@@ -402,7 +402,7 @@ class Mesh:
                 self._exterior = box_exterior_facets(self.box["n"])
             elif self.box and dist and getattr(self, "slab_partition", True) and not getattr(self, "force_general_partition", False):
                 dm, lay = self.slab_device_mesh()
-                fv, opp, cell, _fid = dm.exterior_facets()
+                fv, opp, cell, _fid = dm.exterior_facets(ids=False)
                 zl = fv // lay["plane"]
                 nplanes = lay["layer1"] - lay["layer0"] + 1
                 cut = np.zeros(fv.shape[0], dtype=bool)
@@ -426,8 +426,8 @@ class Mesh:
                 self._exterior = (facets[fid[order]].astype(np.int32), self.cells()[ci[order], li[order]].astype(np.int32), fid[order])
                 self._exterior_cells = None
             else:
-                fv, opp, cell, fid = self.device_mesh().exterior_facets()
-                self._exterior = (fv, opp, fid)
+                fv, opp, cell, _fid = self.device_mesh().exterior_facets(ids=False)
+                self._exterior = (fv, opp, "device")          # the ids are ranked on the device when first asked for
                 self._exterior_cells = cell
                 self._exterior_keep = None
         return self._exterior[0], self._exterior[1]
@@ -488,6 +488,8 @@ class Mesh:
         self.exterior_facets()
         if len(self._exterior) < 3:
             raise SolverError("global facet numbering is not materialised on this route (slab-distributed box / no GPU)")
+        if isinstance(self._exterior[2], str):
+            self._exterior = (self._exterior[0], self._exterior[1], self.device_mesh().exterior_facet_ids())
         return self._exterior[2]
 
     def facet_table(self):
