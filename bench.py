@@ -46,6 +46,10 @@ QUIET = {'logging_level': 40, 'logging_file': None, 'plotting_freq': 0, 'saving_
 KNOWN_ITERS = {256: 993, 512: 1835}
 
 
+PEAK_NOTE = ("peak = MEASURED_PEAKS.json hbm_gbs, a device copy (1 byte written per byte read); an SpMV stream is almost all reads, "
+             "which HBM serves somewhat faster than a 1:1 mix, so a fraction slightly above 1 is possible")
+
+
 def workload(N):
     """The one workload string both arms print (config.workload)."""
     return ("3D steady heat (ScalarTransportSolver), UnitCubeMesh %d^3 P1 tets, %d DoF, k=20, S=1000, Dirichlet 350/300 on z faces, "
@@ -160,13 +164,14 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic_bytes():
-    """dram bytes per SpMV launch from the committed ncu capture (profiles/spmv_traffic.json), else None."""
+def ncu_traffic_bytes(squeezed):
+    """dram bytes per SpMV launch from the committed ncu capture (profiles/spmv_traffic.json: one entry for the squeezed operand
+    the default path multiplies by, one for the full assembled pattern), else None.  256^3 only."""
     p = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
-        except ValueError:
+            return json.load(open(p)).get("squeezed" if squeezed else "full", {}).get("dram_bytes_per_launch")
+        except (ValueError, AttributeError):
             return None
     return None
 
@@ -506,7 +511,7 @@ def main():
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     solve_ms = float(np.mean([i["solve_ms"] for i in infos]))
     roofline = {"bound": "hbm", "kernel": "k_spmv_ws<1,256,2,2> (CSR SpMV + fused dot; inside k_cg_persist when the persistent CG kernel runs the solve)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(nnz_operand != int(nnz_local)), "peak_source": peak_src, "peak_note": PEAK_NOTE,
                 "bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_ms, "launches_per_step": iters,
                 "operand_nnz_this_rank": nnz_operand, "assembled_nnz_this_rank": int(nnz_local),
                 "share_of_step": spmv_ms * iters / ms_per_step,
@@ -587,7 +592,8 @@ def main():
             return None
         m = tot / its
         return {"bound": "hbm", "kernel": kernel, "achieved": by / (m * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": by / (m * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_launch": by, "avg_launch_ms": m, "launches": its}
+                "frac": by / (m * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_launch": by, "avg_launch_ms": m, "launches": its,
+                "peak_note": PEAK_NOTE}
 
     c3 = c4 = p2 = None
     c4_field = None
@@ -725,7 +731,7 @@ def main():
             c5 = {"workload": workload(n5), "value": nd5 / (ms5 * 1e-3) / 1e6, "unit": "Mdof/s", "n_gpus": world, "scaling": "strong", "ms_per_step": ms5, "steps": n5s,
                   "iterations": inf5[-1]["iterations"], "converged": inf5[-1]["converged"], "rel_l2_vs_exact": err5,
                   "roofline": {"bound": "hbm", "kernel": "CSR SpMV + fused dot (this rank's rows)", "achieved": by5 / (sm5 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                               "frac": by5 / (sm5 * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_launch": by5, "avg_launch_ms": sm5,
+                               "frac": by5 / (sm5 * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_launch": by5, "avg_launch_ms": sm5, "peak_note": PEAK_NOTE,
                                "cg_iteration_ms": float(np.mean([i["solve_ms"] for i in inf5])) / max(inf5[-1]["iterations"], 1)},
                   "cpu_baseline": None, "cpu_baseline_note": "not run: a 134 M DoF CPU set-up + solve takes many minutes; the per-DoF CPU cost is the headline's cpu_baseline "
                                                              "times the iteration ratio (%d vs %d)" % (inf5[-1]["iterations"], iters)}

@@ -870,6 +870,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   fsb_mat* S = A;
   if (ctx->drop_zeros && (rc = fsb_mat_squeeze(A, &S))) return rc;
   info->operand_nnzb = S->nnzb;
+  SpmvTimer timer;
   Workspace ws{A};
   double *r, *rhat, *p, *ph, *v, *sh, *t, *dinv;
   if ((rc = ws.alloc(&r, n)) || (rc = ws.alloc(&rhat, n)) || (rc = ws.alloc(&p, n)) || (rc = ws.alloc(&ph, n)) ||
@@ -902,6 +903,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
 
     int first, rest;
     batch_plan(ctx, A->last_iters, &first, &rest);
+    if (ctx->profile) timer.ensure(2 * std::max(first, rest));      // two SpMVs per iteration, collected after every batch's sync
     const int base = launched;
     bool stopped = false;
     while (!stopped) {
@@ -910,12 +912,16 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
         const int par = (launched - base + k) & 1;
         const int rho = par ? S_RHO1 : S_RHO0, rhon = par ? S_RHO0 : S_RHO1, rrn = par ? S_RRB0 : S_RRB1;
         if (dist && (rc = fsb_dist_halo_raw(ctx, ph, n))) return rc;
+        if (ctx->profile) cudaEventRecord(timer.next(0), ctx->stream);
         if ((rc = fsb_launch_spmv(S, ph, v, rhat, 0, scal + S_RV, state))) return rc;
+        if (ctx->profile) cudaEventRecord(timer.next(0), ctx->stream);
         if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_RV, 1))) return rc;
         k_bcg_s<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, v, rhat, dinv, r, sh, ctx->d_partials, scal + S_RS, ctx->d_counters + 5, state);
         FSB_LAUNCH_CHECK(ctx);
         if (dist && (rc = fsb_dist_halo_raw(ctx, sh, n))) return rc;
+        if (ctx->profile) cudaEventRecord(timer.next(0), ctx->stream);
         if ((rc = fsb_launch_spmv(S, sh, t, r, 1, scal + S_TS, state, nullptr, rhat))) return rc;
+        if (ctx->profile) cudaEventRecord(timer.next(0), ctx->stream);
         if (dist && (rc = fsb_dist_allreduce_sum_dev(ctx, scal + S_TS, 4))) return rc;        // t.s, t.t, rhat.t, rhat.s
         k_bcg_xp<<<vg, kVecThreads, 0, ctx->stream>>>(n0, n1, scal, rho, rhon, rrn, sh, t, v, dinv, x->d, r, p, ph, ctx->d_partials,
                                                       ctx->d_counters + 2, rtol, atol, maxit, state, dist ? 0 : 1);
@@ -929,6 +935,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
       launched += batch;
       FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, state, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
       FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (ctx->profile) timer.collect(0);
       if (ctx->h_state[0] || launched >= maxit) stopped = true;
     }
     // outcome -1 with iterations to spare: restart (state[1] keeps counting across restarts)
@@ -948,6 +955,7 @@ extern "C" int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rto
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   info->solve_ms = ms;
+  if (ctx->profile) info->spmv_ms = timer.total_ms;      // includes the launches of a batch's tail that early-exit on `done`
   // restarts exhausted with a valid iterate: the recurrences stall at rounding level; report "not converged" with the
   // last valid residual norm instead of an error (x is the best iterate).  Non-finite data still raises.
   if (info->converged < 0 && restarts >= 4 && std::isfinite(info->rnorm) && info->rnorm > 0.0) info->converged = 0;
