@@ -77,6 +77,15 @@ struct fsb_dist {
   CommBuf* comm_of[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool p2p = false;
   unsigned long long seq = 1;     // next unused sequence number; advances identically on every rank
+  // The halo-carrying Krylov vector of the peer-memory path (p / u), exported by CUDA IPC.  It belongs to the CONTEXT: export,
+  // import and release of IPC memory cost tens of milliseconds and synchronise the device, so a matrix (one per solver object,
+  // one per time-loop restart) borrows this buffer for the length of a solve instead of owning one (measured at 8 GPUs: 60-100 ms
+  // spikes per solver construction / release, 36 % of an end-to-end 256^3 step)
+  double* p_shared = nullptr;
+  long long p_cap = 0;            // doubles
+  double* p_lo_map = nullptr;     // rank-1's buffer mapped here
+  double* p_hi_map = nullptr;     // rank+1's buffer
+  char* d_rec = nullptr;          // device staging of allgather_records
 };
 
 #define FSB_CHECK_NCCL(ctx, call)                                                             \
@@ -128,6 +137,10 @@ void fsb_dist_destroy(fsb_ctx* ctx) {
   for (int r = 0; r < kMaxRanks; ++r)
     if (ctx->dist->comm_of[r] && r != ctx->dist->rank) cudaIpcCloseMemHandle(ctx->dist->comm_of[r]);
   cudaFree(ctx->dist->comm_local);
+  if (ctx->dist->p_lo_map) cudaIpcCloseMemHandle(ctx->dist->p_lo_map);
+  if (ctx->dist->p_hi_map) cudaIpcCloseMemHandle(ctx->dist->p_hi_map);
+  cudaFree(ctx->dist->p_shared);
+  cudaFree(ctx->dist->d_rec);
   cudaFree(ctx->dist->d_send_idx);
   cudaFree(ctx->dist->d_sendbuf);
   if (ctx->dist->comm && nccl().ok) nccl().CommDestroy(ctx->dist->comm);
@@ -142,21 +155,21 @@ bool fsb_dist_active(fsb_ctx* ctx) { return ctx && ctx->dist && ctx->dist->nrank
 struct ShareRec {
   cudaIpcMemHandle_t handle;    // 64 bytes
   long long ghost_lo, owned, n, plane;
-  char pad[128 - 64 - 32];
+  long long cap;                // capacity of the rank's shared buffer (doubles) when the record was made
+  char pad[128 - 64 - 40];
 };
 static_assert(sizeof(ShareRec) == 128, "ShareRec must be 128 bytes");
 
 static int allgather_records(fsb_ctx* ctx, const ShareRec& mine, std::vector<ShareRec>& all) {
   fsb_dist* d = ctx->dist;
-  char* dbuf = nullptr;
-  FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&dbuf, sizeof(ShareRec) * (d->nranks + 1)));
+  if (!d->d_rec) FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&d->d_rec, sizeof(ShareRec) * (kMaxRanks + 1)));      // kept: cudaMalloc/cudaFree synchronise
+  char* dbuf = d->d_rec;
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(dbuf, &mine, sizeof(ShareRec), cudaMemcpyHostToDevice, ctx->stream));
   int r = nccl().AllGather(dbuf, dbuf + sizeof(ShareRec), sizeof(ShareRec), 0 /* ncclInt8 */, d->comm, ctx->stream);
-  if (r != kNcclSuccess) { cudaFree(dbuf); FSB_FAIL(ctx, FSB_ERR_NCCL, std::string("ncclAllGather: ") + nccl().GetErrorString(r)); }
+  if (r != kNcclSuccess) FSB_FAIL(ctx, FSB_ERR_NCCL, std::string("ncclAllGather: ") + nccl().GetErrorString(r));
   all.resize(d->nranks);
   FSB_CHECK_CUDA(ctx, cudaMemcpyAsync(all.data(), dbuf + sizeof(ShareRec), sizeof(ShareRec) * d->nranks, cudaMemcpyDeviceToHost, ctx->stream));
   FSB_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  cudaFree(dbuf);
   return FSB_OK;
 }
 
@@ -189,40 +202,61 @@ unsigned long long fsb_dist_seq_reserve(fsb_ctx* ctx, unsigned long long count) 
 }
 
 // Collective: (re)allocate the IPC-exportable search-direction vector of A and map the neighbours' copies.
+static void release_shared_p(fsb_dist* d) {
+  if (d->p_lo_map) cudaIpcCloseMemHandle(d->p_lo_map);
+  if (d->p_hi_map) cudaIpcCloseMemHandle(d->p_hi_map);
+  if (d->p_shared) cudaFree(d->p_shared);
+  d->p_lo_map = d->p_hi_map = d->p_shared = nullptr;
+  d->p_cap = 0;
+}
+
+// Collective.  Lends the context's exported buffer to A for the coming solve.  Every call all-gathers (n, capacity, slab layout) of
+// all ranks — one small NCCL all-gather — and every rank takes the same decision from the same data: if any rank's buffer is too
+// small (first use, or a larger problem) ALL ranks free, re-allocate, re-export and re-import; otherwise nothing is allocated.  The
+// decision never depends on when a rank's garbage collector released an earlier matrix.
 int fsb_dist_share_p(fsb_mat* A, int64_t n) {
   fsb_ctx* ctx = A->ctx;
   fsb_dist* d = ctx->dist;
-  if (A->p_dist && A->p_dist_n == n) return FSB_OK;
-  fsb_dist_release_mat(A);
-  FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&A->p_dist, sizeof(double) * n + 512));
-  FSB_CHECK_CUDA(ctx, cudaMemset(A->p_dist, 0, sizeof(double) * n + 512));
-  A->p_dist_n = n;
   const long long planes = d->ghost_lo + d->owned_planes + d->ghost_hi;
   ShareRec mine;
   memset(&mine, 0, sizeof(mine));
-  FSB_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&mine.handle, A->p_dist));
-  mine.ghost_lo = d->ghost_lo; mine.owned = d->owned_planes; mine.n = n; mine.plane = n / planes;
+  mine.ghost_lo = d->ghost_lo; mine.owned = d->owned_planes; mine.n = n; mine.plane = n / planes; mine.cap = d->p_cap;
   std::vector<ShareRec> all;
   int rc = allgather_records(ctx, mine, all);
   if (rc) return rc;
-  if (d->ghost_lo) {
-    void* q = nullptr;
-    FSB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&q, all[d->rank - 1].handle, cudaIpcMemLazyEnablePeerAccess));
-    A->p_lo_remote = (double*)q;
-    A->lo_ghost_offset = (all[d->rank - 1].ghost_lo + all[d->rank - 1].owned) * all[d->rank - 1].plane;
+  bool grow = false;
+  for (int r = 0; r < d->nranks; ++r) grow = grow || all[r].cap < all[r].n;
+  if (grow) {
+    release_shared_p(d);
+    const long long cap = n + n / 8 + 64;                      // head room: a slightly larger slab does not re-export
+    FSB_CHECK_CUDA(ctx, cudaMalloc((void**)&d->p_shared, sizeof(double) * cap + 512));
+    d->p_cap = cap;
+    FSB_CHECK_CUDA(ctx, cudaIpcGetMemHandle(&mine.handle, d->p_shared));
+    mine.cap = cap;
+    std::vector<ShareRec> handles;
+    if ((rc = allgather_records(ctx, mine, handles))) return rc;
+    if (d->rank > 0) {
+      void* q = nullptr;
+      FSB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&q, handles[d->rank - 1].handle, cudaIpcMemLazyEnablePeerAccess));
+      d->p_lo_map = (double*)q;
+    }
+    if (d->rank < d->nranks - 1) {
+      void* q = nullptr;
+      FSB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&q, handles[d->rank + 1].handle, cudaIpcMemLazyEnablePeerAccess));
+      d->p_hi_map = (double*)q;
+    }
   }
-  if (d->ghost_hi) {
-    void* q = nullptr;
-    FSB_CHECK_CUDA(ctx, cudaIpcOpenMemHandle(&q, all[d->rank + 1].handle, cudaIpcMemLazyEnablePeerAccess));
-    A->p_hi_remote = (double*)q;
-  }
+  A->p_dist = d->p_shared;
+  A->p_dist_n = n;
+  A->p_lo_remote = d->ghost_lo ? d->p_lo_map : nullptr;
+  A->p_hi_remote = d->ghost_hi ? d->p_hi_map : nullptr;
+  A->lo_ghost_offset = d->ghost_lo ? (all[d->rank - 1].ghost_lo + all[d->rank - 1].owned) * all[d->rank - 1].plane : 0;
+  FSB_CHECK_CUDA(ctx, cudaMemsetAsync(A->p_dist, 0, sizeof(double) * n + 512, ctx->stream));
   return FSB_OK;
 }
 
+// the buffer is the context's: a matrix only forgets it
 void fsb_dist_release_mat(fsb_mat* A) {
-  if (A->p_lo_remote) cudaIpcCloseMemHandle(A->p_lo_remote);
-  if (A->p_hi_remote) cudaIpcCloseMemHandle(A->p_hi_remote);
-  if (A->p_dist) cudaFree(A->p_dist);
   A->p_lo_remote = A->p_hi_remote = A->p_dist = nullptr;
   A->p_dist_n = 0;
 }
