@@ -530,12 +530,15 @@ class SolverBase():
         import copy as _copy
         from . import _lib as L
         mesh = self.mesh
-        if not getattr(mesh, 'box', None) or self.parallel or self.function_space.degree != 1:
-            raise SolverError("preconditioner 'gmg' needs a generated box mesh (UnitCubeMesh/BoxMesh/...), degree 1, one GPU")
+        slab_dist = self.parallel and space.part is None
+        if not getattr(mesh, 'box', None) or (self.parallel and not slab_dist) or self.function_space.degree != 1:
+            raise SolverError("preconditioner 'gmg' needs a generated box mesh (UnitCubeMesh/BoxMesh/...) and degree 1 (one GPU, or z-slabs)")
         n = [int(k) for k in mesh.box['n']]
         sizes = [n]
         while all(k % 2 == 0 and k >= 4 for k in sizes[-1]):
             sizes.append([k // 2 for k in sizes[-1]])
+        if slab_dist and len(sizes) < 2:
+            raise SolverError("the distributed multigrid preconditioner needs at least one coarser level")
         levels = self.__dict__.setdefault('_mg_levels', {})
         mats = [space.A]
         for nl in sizes[1:]:
@@ -543,6 +546,11 @@ class SolverBase():
             c = levels.get(key)
             if c is None:
                 c = _copy.copy(self)
+                # coarse levels live whole on every rank (replicated) even when the fine level is slab-distributed
+                c.settings = dict(self.settings)
+                c.settings['solver_settings'] = dict(self.settings['solver_settings'], distributed=False)
+                c.solver_settings = c.settings['solver_settings']
+                c.comm, c.parallel = Comm(), False
                 c.mesh = Mesh(box={'n': tuple(nl), 'p0': mesh.box['p0'], 'p1': mesh.box['p1']})
                 c.subdomains = None
                 c.generate_boundary_facets()
@@ -563,7 +571,13 @@ class SolverBase():
         prev = self.__dict__.get('_mg_omega')
         reuse = prev if (prev is not None and prev[0] == [tuple(k) for k in sizes]
                          and self.solver_settings.get('solver_parameters', {}).get('mg_reuse_damping', True)) else None
-        mg = L.Multigrid(space.ctx, mats, sizes, mesh.tdim, omega=None if reuse is None else reuse[1])
+        slab = None
+        if slab_dist:
+            space.activate()                                 # the fine space's slab layout carries the halo exchanges of the cycle
+            layer0 = space.v_off // space.plane
+            oz0 = layer0 + space.ghost_lo
+            slab = (layer0, oz0, oz0 + space.owned_planes)
+        mg = L.Multigrid(space.ctx, mats, sizes, mesh.tdim, omega=None if reuse is None else reuse[1], slab=slab)
         self._mg_omega = ([tuple(k) for k in sizes], [mg.omega(l) for l in range(len(mats))])
         self._mg = mg
         return mg
@@ -590,8 +604,10 @@ class SolverBase():
 
     def _multigrid_levels(self):
         mesh = self.mesh
-        if not getattr(mesh, 'box', None) or self.parallel or self.function_space.degree != 1:
+        if not getattr(mesh, 'box', None) or self.function_space.degree != 1:
             return 0
+        if self.parallel and (getattr(mesh, 'force_general_partition', False) or not getattr(mesh, 'slab_partition', True)):
+            return 0                                          # RCB-partitioned: no geometric hierarchy
         n, levels = [int(k) for k in mesh.box['n']], 1
         while all(k % 2 == 0 and k >= 4 for k in n):
             n, levels = [k // 2 for k in n], levels + 1

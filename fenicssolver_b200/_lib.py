@@ -88,6 +88,7 @@ SIGNATURES = {
     "fsb_solve_cg": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
     "fsb_solve_bicgstab": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
     "fsb_mg_create": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, P(c_vp)]),
+    "fsb_mg_create_slab": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, P(c_vp)]),
     "fsb_mg_omega": (C.c_int, [c_vp, c_i32, P(c_dbl)]),
     "fsb_mg_apply": (C.c_int, [c_vp, c_vp, c_vp, c_i32]),
     "fsb_solve_cg_mg": (C.c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i32, c_i32, P(SolveInfo)]),
@@ -459,8 +460,10 @@ class Multigrid(_Handle):
     """Geometric multigrid hierarchy over assembled level matrices (fine first) on nested box meshes."""
     _destroy = "fsb_mg_destroy"
 
-    def __init__(self, ctx, matrices, ncells, tdim, omega=None):
-        """`omega`: per-level dampings from an earlier hierarchy on the same levels (skips the eigenvalue estimates)."""
+    def __init__(self, ctx, matrices, ncells, tdim, omega=None, slab=None):
+        """`omega`: per-level dampings from an earlier hierarchy on the same levels (skips the eigenvalue estimates).
+        `slab`: (layer0, owned_z0, owned_z1) of a slab-distributed fine level — matrices[0] is this rank's slab, the coarser
+        matrices are whole levels replicated on every rank."""
         self.matrices = list(matrices)              # keep the level matrices alive
         arr = (c_vp * len(matrices))(*[m.h for m in matrices])
         nc = np.zeros((len(matrices), 3), dtype=np.int32)
@@ -468,7 +471,10 @@ class Multigrid(_Handle):
             nc[l, :len(n)] = n
         h = c_vp()
         om = None if omega is None else _np(omega, np.float64)
-        ctx.check(ctx.lib.fsb_mg_create(ctx.h, len(matrices), arr, _ptr(nc), int(tdim), _ptr(om), C.byref(h)))
+        if slab is None:
+            ctx.check(ctx.lib.fsb_mg_create(ctx.h, len(matrices), arr, _ptr(nc), int(tdim), _ptr(om), C.byref(h)))
+        else:
+            ctx.check(ctx.lib.fsb_mg_create_slab(ctx.h, len(matrices), arr, _ptr(nc), int(tdim), _ptr(om), int(slab[0]), int(slab[1]), int(slab[2]), C.byref(h)))
         super().__init__(ctx, h)
 
     def apply(self, r, z, nu=2):

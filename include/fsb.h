@@ -246,6 +246,14 @@ int fsb_solve_bicgstab(fsb_mat* A, fsb_vec* b, fsb_vec* x, double rtol, double a
 int fsb_mg_create(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells /*[nlevels][3]*/, int32_t tdim,
                   const double* omega /* per-level values to reuse from an earlier hierarchy (entries <= 0 or NULL: estimate) */,
                   fsb_mg** mg);
+/* The same hierarchy for a slab-distributed fine level (one process per GPU, fsb_dist_set_slab active): A[0] is this rank's slab of
+ * the fine matrix (local plane 0 = global vertex plane layer0, owned planes [owned_z0, owned_z1) of the fine grid), ncells[0..3) the
+ * GLOBAL fine cell counts; A[1..] are whole coarse-level matrices, replicated on every rank.  Fine-level smoothing, residuals and the
+ * outer CG run distributed (ghost-plane halo, all-reduced dot products); the restricted residual is summed over the ranks by one
+ * all-reduce and every rank cycles the coarse levels itself.  What KSPCG + PCGAMG on an MPI communicator are to solve_amg
+ * (SolverBase.py:643-672) when the reference runs under mpirun. */
+int fsb_mg_create_slab(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int32_t* ncells, int32_t tdim, const double* omega,
+                       int32_t layer0, int32_t owned_z0, int32_t owned_z1, fsb_mg** mg);
 int fsb_mg_omega(fsb_mg* mg, int32_t level, double* omega);      /* 4 / (3 lambda_max estimate) of a level */
 int fsb_mg_apply(fsb_mg* mg, fsb_vec* r, fsb_vec* z, int32_t nu);  /* z = one V(nu,nu) cycle applied to r (zero start) */
 int fsb_solve_cg_mg(fsb_mg* mg, fsb_vec* b, fsb_vec* x, double rtol, double atol, int32_t maxit, int32_t nu,

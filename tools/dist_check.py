@@ -76,6 +76,39 @@ def main():
     if rank == 0:
         print("transient, %d steps, gather_result=False vs True: rel diff %.2e (field moved by up to %.1f)" % (tr_local.current_step, t[0].item(), -t[1].item()), flush=True)
     ok = ok and t[0].item() < 1e-12 and tr_local.current_step >= 3
+    # multigrid-preconditioned CG with the fine level on z-slabs and the coarse hierarchy replicated: the same cycle as on one GPU, so
+    # the same iteration count and the same solution (heat, and the elasticity cantilever through its default solve_amg path)
+    from fenicssolver_b200 import LinearElasticitySolver
+    Nm = N if N % 4 == 0 else 4 * (N // 4)
+    sg = bench.case_settings(Nm, distributed=True)
+    sg['solver_settings']['gather_result'] = True
+    sg['solver_settings']['solver_parameters']['preconditioner'] = 'gmg'
+    mgd = ScalarTransportSolver.ScalarTransportSolver(sg)
+    xmg = mgd.solve().vector().get_local()
+    el = bench.c3_settings(Nm, None)
+    el['solver_settings']['distributed'] = True
+    el['solver_settings']['gather_result'] = True
+    eld = LinearElasticitySolver.LinearElasticitySolver(el)
+    xel = eld.solve().vector().get_local()
+    if rank == 0:
+        s1g = bench.case_settings(Nm, distributed=False)
+        s1g['solver_settings']['solver_parameters']['preconditioner'] = 'gmg'
+        mg1 = ScalarTransportSolver.ScalarTransportSolver(s1g)
+        mg1._space = backend.DeviceSpace(mg1.mesh, 1, ctx=ctx1)
+        x1g = mg1.solve().vector().get_local()
+        el1 = LinearElasticitySolver.LinearElasticitySolver(bench.c3_settings(Nm, None))
+        el1._space = backend.DeviceSpace(el1.mesh, 3, ctx=ctx1, space=el1.function_space)
+        x1e = el1.solve().vector().get_local()
+        dg = float(np.linalg.norm(xmg - x1g) / np.linalg.norm(x1g))
+        de = float(np.linalg.norm(xel - x1e) / np.linalg.norm(x1e))
+        zc = (np.arange((Nm + 1) ** 3) // ((Nm + 1) ** 2)) / Nm
+        eg = float(np.linalg.norm(xmg - (350 - 50 * zc + 1000 * zc * (1 - zc) / 40)) / np.linalg.norm(xmg))
+        print("distributed multigrid-CG %d^3: heat %d iterations (%d levels; one GPU %d) rel diff %.2e, vs exact %.2e | elasticity (solve_amg default) %d "
+              "iterations (one GPU %d) rel diff %.2e" % (Nm, mgd.solve_info["iterations"], mgd.solve_info.get("mg_levels", 0), mg1.solve_info["iterations"], dg, eg,
+                                                         eld.solve_info["iterations"], el1.solve_info["iterations"], de), flush=True)
+        ok = ok and dg < 1e-10 and de < 1e-9 and eg < 1e-10 and mgd.solve_info["converged"] == 1 and eld.solve_info["converged"] == 1
+        ok = ok and abs(mgd.solve_info["iterations"] - mg1.solve_info["iterations"]) <= 1 and abs(eld.solve_info["iterations"] - el1.solve_info["iterations"]) <= 1
+        ok = ok and eld.solve_info.get("mg_levels", 0) >= 2
     rp, ci, va = solver.device_space().A.download_csr()
     sp_ = solver.device_space()
     lo, hi = sp_.own_v0, sp_.own_v1
