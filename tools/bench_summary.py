@@ -23,6 +23,10 @@ for f in sys.argv[1:]:
     c = d.get("c3")
     if c and c.get("value"):
         j, a = c["jacobi"], c["default_solve_amg"]
+        j.setdefault("roofline", None)
+        if not j["roofline"]:
+            j["roofline"] = {"frac": float("nan")}
+        print("   norms: %s %s" % (c.get("solution_l2_norm"), c.get("max_abs_deflection_z")))
         print("c3 jacobi %.2f Mdof/s %.0f ms %d its spmv frac %.3f | solve_amg %.1f Mdof/s %.1f ms %d its | cross %.1e | cpu %s" % (j["value"], j["ms_per_step"], j["iterations"], j["roofline"]["frac"], a["value"], a["ms_per_step"], a["iterations"], c["rel_l2_default_vs_jacobi"], (c.get("cpu_baseline") or {}).get("value")))
     c = d.get("c4")
     if c and c.get("value"):
@@ -33,3 +37,5 @@ for f in sys.argv[1:]:
     c = d.get("c5")
     if c and c.get("value"):
         print("c5 %.2f Mdof/s %.1f ms %d its err %.1e spmv frac %.3f iteration %.4f ms" % (c["value"], c["ms_per_step"], c["iterations"], c["rel_l2_vs_exact"], c["roofline"]["frac"], c["roofline"]["cg_iteration_ms"]))
+        if c.get("gmg"):
+            print("   c5.gmg %s" % ({k: v for k, v in c["gmg"].items() if k != "what"},))
