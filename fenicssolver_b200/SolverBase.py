@@ -577,6 +577,7 @@ class SolverBase():
             layer0 = space.v_off // space.plane
             oz0 = layer0 + space.ghost_lo
             slab = (layer0, oz0, oz0 + space.owned_planes)
+        self._mg = None            # release the previous hierarchy's level vectors first: the new one takes exactly those blocks back
         mg = L.Multigrid(space.ctx, mats, sizes, mesh.tdim, omega=None if reuse is None else reuse[1], slab=slab)
         self._mg_omega = ([tuple(k) for k in sizes], [mg.omega(l) for l in range(len(mats))])
         self._mg = mg
