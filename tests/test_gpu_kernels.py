@@ -862,3 +862,38 @@ def test_persistent_cg_kernel_block3(ctx):
         assert abs(res[3][1] - res[1][1]) <= max(3, res[1][1] // 50)
     finally:
         ctx.set_option("cg_variant", 0)
+
+
+def test_pinned_result_pool_and_drop_zeros_auto(ctx):
+    """DeviceVector.numpy() of a large vector lands in a page-locked block of the library's pool (reused once released); drop_zeros
+    'auto' (2) compacts the Krylov operand of a right-angled box (exact zeros) and leaves an unstructured mesh's operand alone."""
+    n = (1 << 20) + 5
+    v = _lib.DeviceVector(ctx, n)
+    v.fill(2.5)
+    a = v.numpy()
+    assert a.shape == (n,) and np.all(a == 2.5) and a.flags.writeable
+    a[0] = 7.0                                                       # caller-owned memory
+    addr = a.ctypes.data
+    del a
+    b = v.numpy()
+    assert b.ctypes.data == addr and b[0] == 2.5                     # the released block served the next request of that size
+    small = _lib.DeviceVector(ctx, 100)
+    small.fill(1.0)
+    assert np.all(small.numpy() == 1.0)
+    c, t = fo.unit_cube_mesh(6, 6, 6)
+    ctx.set_option("drop_zeros", 2)
+    try:
+        for coords, squeezed in ((c, True), (jitter(c, 6, seed=3), False)):
+            m = _lib.DeviceMesh.upload(ctx, coords, t)
+            A = _lib.DeviceMatrix.create(m, 1)
+            A.assemble_scalar(kscale=1.0)
+            nv = coords.shape[0]
+            bvec, x = _lib.DeviceVector(ctx, nv), _lib.DeviceVector(ctx, nv)
+            bvec.fill(1.0)
+            d = np.nonzero(coords[:, 2] == 0)[0]
+            A.apply_dirichlet(bvec, d, np.zeros(d.size), True, x)
+            info = A.solve(bvec, x, "cg", rtol=1e-12, maxit=1000)
+            assert info["converged"] == 1
+            assert (info["operand_nnzb"] < A.sizes()["nnz"]) == squeezed
+    finally:
+        ctx.set_option("drop_zeros", 0)

@@ -583,3 +583,24 @@ def test_expression_is_validated_and_follows_cpp_integer_division():
     for bad in ["x.__class__", "__import__('os')", "x[0].real", "(lambda: 1)()", "'a'*3", "x[0] if 1 else 2", "[v for v in x]"]:
         with pytest.raises(SolverBase.SolverError):
             Expression(bad)(c)
+
+
+def test_box_surface_enumeration_and_lazy_coordinates():
+    """box_exterior_facets enumerates the surface of the dolfin box layout directly (no search): the same facets, opposite vertices AND
+    order as the oracle's facet table; Mesh.vertex_coordinates computes selected vertices of a generated box bit-identically to
+    coordinates() without materialising the mesh; cells_sorted adopts caller arrays as they are."""
+    from fenicssolver_b200.dolfin_compat import box_exterior_facets
+    for n in [(5, 3), (1, 1), (4, 3, 2), (1, 1, 1), (2, 1, 3), (6, 5, 7)]:
+        c, t = (fo.unit_square_mesh(*n) if len(n) == 2 else fo.unit_cube_mesh(*n))
+        fv, opp = box_exterior_facets(n)
+        f0, o0, _ = fo.exterior_facets(t)
+        assert np.array_equal(fv, f0) and np.array_equal(opp, o0), n
+    m = BoxMesh(Point(0, -1, 0.5), Point(10, 1, 1.75), 5, 4, 3)
+    ids = np.array([0, 7, 119, 3, 64])
+    got = m.vertex_coordinates(ids)
+    assert m._coords is None                                         # nothing was materialised
+    assert np.array_equal(got, BoxMesh(Point(0, -1, 0.5), Point(10, 1, 1.75), 5, 4, 3).coordinates()[ids])
+    cells = np.ascontiguousarray(m.cells(), dtype=np.int32)
+    m2 = Mesh(m.coordinates(), cells, cells_sorted=True)
+    assert m2.cells() is cells                                       # adopted, not copied
+    assert Mesh(m.coordinates(), cells[:, ::-1]).cells() is not cells and np.array_equal(Mesh(m.coordinates(), cells[:, ::-1]).cells(), cells)
