@@ -391,14 +391,21 @@ int fsb_cgp_run(fsb_mat* A, fsb_mat* S, const CgpVectors& v, double rtol, double
 
   const void* fn = nullptr;
   int threads = 0;
-#define FSB_CGP_CASE(BS, ROWS, LPR, NST, MINB)                                                       \
-  if (!fn && pl.bs == BS && pl.rows == ROWS && pl.lpr == LPR && pl.nst == NST) {                     \
+#define FSB_CGP_CASE(BS, ROWS, LPR, NST, MINB, COND)                                                 \
+  if (!fn && pl.bs == BS && pl.rows == ROWS && pl.lpr == LPR && pl.nst == NST && (COND)) {           \
     fn = (const void*)k_cg_persist<BS, ROWS, LPR, NST, MINB>;                                        \
     threads = SpmvCfg<BS, ROWS, LPR>::THREADS;                                                       \
   }
-  FSB_CGP_CASE(1, 256, 2, 2, 2)
-  FSB_CGP_CASE(1, 256, 1, 2, 2)
-  FSB_CGP_CASE(3, 192, 2, 3, 1)
+  // The one-lane (short-row, squeezed operand) configuration exists at two register budgets.  4 CTAs per SM (56 registers) bring its
+  // SpMV phase to the stand-alone kernel's rate (6 390 against 4 980 GB/s on the 17 M-row operand) at the price of a slower update
+  // phase and a dearer grid barrier (591 instead of 295 arrivals): measured (tools/cg_ab.py, profiles/cg_ab_r2.txt) 0.627 against
+  // 0.656 ms per iteration at 17 M rows but 90.1 against 80.6 us at 2.1 M rows (one rank of an 8-GPU 256^3 run).  Large slabs take 4.
+  const int64_t nrows = (A->own1 - A->own0) * A->bs;
+  const int want4 = ctx->cg_minb ? ctx->cg_minb == 4 : nrows >= 6000000;
+  FSB_CGP_CASE(1, 256, 2, 2, 2, true)
+  FSB_CGP_CASE(1, 256, 1, 2, 4, want4)
+  FSB_CGP_CASE(1, 256, 1, 2, 2, true)
+  FSB_CGP_CASE(3, 192, 2, 3, 1, true)
 #undef FSB_CGP_CASE
   if (!fn) FSB_FAIL(ctx, FSB_ERR_STATE, "persistent CG: no kernel for this SpMV configuration");
   FSB_CHECK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

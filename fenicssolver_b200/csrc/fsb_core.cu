@@ -95,6 +95,7 @@ extern "C" int fsb_set_option(fsb_ctx* ctx, const char* name, int64_t value) {
   else if (s == "drop_zeros") ctx->drop_zeros = (int)value;
   else if (s == "cg_variant") ctx->cg_variant = (int)value;
   else if (s == "cg_umode") ctx->cg_umode = (int)value;
+  else if (s == "cg_minb") ctx->cg_minb = (int)value;
   else if (s == "vec_skew") ctx->vec_skew = (int)(value < 0 ? 0 : (value > 8192 ? 8192 : (value & ~255ll)));
   else if (s == "cg_debug") ctx->cg_debug = (int)value;
   else if (s == "cg_timeout_s") ctx->cg_timeout_s = value < 1 ? 1 : (int)value;

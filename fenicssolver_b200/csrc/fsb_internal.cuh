@@ -37,6 +37,7 @@ struct fsb_ctx {
   int spmv_hint = 1;     // L2 evict-first on the matrix stream + streaming stores of y (0: plain)
   int cg_variant = 0;    // 0 auto (persistent kernel where it applies, else classic on one GPU / single-reduction when distributed),
                          // 1 classic 3-kernel chain, 2 single-reduction 2-kernel chain, 3 persistent kernel (fsb_cgp.cu)
+  int cg_minb = 0;       // persistent kernel, one-lane configuration: CTAs per SM (2 or 4; 0 = by slab size)
   int cg_umode = 1;      // persistent kernel, update phase: 0 contiguous row slice per CTA, 1 grid-stride (measured faster)
   int vec_skew = 0;      // bytes between the start offsets of consecutive Krylov work vectors inside their blocks (multiple of 256, <= 8192)
   int cg_debug = 0;      // persistent kernel timing experiments (wrong results): 1 no peer stores, 2 no system fence after them
