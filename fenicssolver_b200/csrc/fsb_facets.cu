@@ -81,7 +81,11 @@ k_f_classify(const int32_t* __restrict__ cells, int64_t ncells, const int64_t* _
           for (int q = 0; q < NL; ++q) has |= (w[q] == f[j]);
           all &= has;
         }
-        if (all) { ++holders; smallest &= (c < c2); }
+        if (all) {
+          ++holders;
+          smallest &= (c < c2);
+          if (c2 < c) break;          // neither exterior nor the facet's representative: nothing left to learn from the rest of the star
+        }
       }
       if (holders == 0) { m |= 1u << i; atomicAdd(ecnt + a, 1); }
       if (smallest) atomicAdd(ucnt + a, 1);
