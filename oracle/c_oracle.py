@@ -55,6 +55,7 @@ def load():
         lib.fo_bicgstab_jacobi.restype = C.c_int
         lib.fo_bicgstab_jacobi.argtypes = [i64, vp, vp, vp, vp, vp, dbl, dbl, C.c_int, C.POINTER(dbl)]
         lib.fo_assemble_elasticity.argtypes = [i64, vp, vp, dbl, dbl, vp, vp, vp, vp, vp]
+        lib.fo_assemble_heat_p2.argtypes = [i64, vp, vp, vp, vp, dbl, dbl, vp, vp, vp, vp]
         lib.fo_mg_lambda_max.restype = dbl
         lib.fo_mg_lambda_max.argtypes = [i64, vp, vp, vp]
         lib.fo_mg_apply.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
@@ -353,3 +354,51 @@ class TransientCube:
         t2 = time.perf_counter()
         self.iterations.append(it)
         return {"t_assemble": t1 - t0, "t_solve": t2 - t1, "iterations": it, "relres": rel.value}
+
+
+class HeatCubeP2:
+    """The degree-2 heat problem of the bench's `p2` block on the CPU: unit cube N^3, P2 tetrahedra, Dirichlet 350 / 300 on z = 0 / 1, source S;
+    set-up (edge numbering, node table, pattern: numpy oracle, untimed like the GPU arm's symbolic phase), then step() = C/OpenMP assembly
+    (fo_assemble_heat_p2 with the numpy oracle's exact reference tensors) + symmetric Dirichlet + Jacobi-PCG."""
+
+    def __init__(self, N, k=20.0, S=1000.0, T0=350.0, T1=300.0, T_init=293.0):
+        from . import fem_oracle_p2 as p2
+        self.lib = load()
+        self.N, self.k, self.S, self.T_init = N, k, S, T_init
+        t = time.perf_counter()
+        coords, cells = box_mesh((N, N, N))
+        self.cell_nodes, self.node_coords, _ = p2.p2_dofmap(coords, cells)
+        self.cell_nodes = np.ascontiguousarray(self.cell_nodes, dtype=np.int32)
+        self.coords = coords
+        self.n = self.node_coords.shape[0]
+        rp, ci = p2.csr_pattern(self.cell_nodes, self.n)
+        self.rp, self.ci = np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(ci, dtype=np.int32)
+        R, _, _, F = p2.reference_tensors(3)
+        self.R, self.F = np.ascontiguousarray(R, dtype=np.float64), np.ascontiguousarray(F, dtype=np.float64)
+        self.t_setup = time.perf_counter() - t
+        z = self.node_coords[:, 2]
+        self.flag = ((z == 0.0) | (z == 1.0)).astype(np.uint8)
+        self.g = np.where(z == 0.0, T0, np.where(z == 1.0, T1, 0.0))
+        self.vals = np.empty(self.ci.size)
+        self.b = np.empty(self.n)
+        self.x = np.empty(self.n)
+        for a in (self.vals, self.b, self.x):
+            self.lib.fo_zero(_p(a), a.size)
+
+    def step(self, rtol=1e-12, maxit=100000):
+        lib = self.lib
+        t0 = time.perf_counter()
+        lib.fo_zero(_p(self.vals), self.vals.size)
+        lib.fo_zero(_p(self.b), self.b.size)
+        lib.fo_assemble_heat_p2(self.cell_nodes.shape[0], _p(self.cell_nodes), _p(self.coords), _p(self.R), _p(self.F), self.k, self.S,
+                                _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b))
+        lib.fo_apply_dirichlet_sym(self.n, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.flag), _p(self.g))
+        t1 = time.perf_counter()
+        self.x[:] = np.where(self.flag, self.g, self.T_init)
+        rel = C.c_double()
+        it = lib.fo_pcg_jacobi(self.n, _p(self.rp), _p(self.ci), _p(self.vals), _p(self.b), _p(self.x), rtol, 0.0, maxit, C.byref(rel))
+        t2 = time.perf_counter()
+        z = self.node_coords[:, 2]
+        exact = self.g[np.argmin(z)] + (self.g[np.argmax(z)] - self.g[np.argmin(z)]) * z + self.S * z * (1 - z) / (2 * self.k)
+        err = float(np.linalg.norm(self.x - exact) / np.linalg.norm(exact))
+        return {"t_assemble": t1 - t0, "t_solve": t2 - t1, "iterations": it, "relres": rel.value, "rel_l2_vs_exact": err}

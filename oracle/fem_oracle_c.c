@@ -300,6 +300,42 @@ int fo_pcg_jacobi_segment(int64_t n, const int64_t* rp, const int32_t* ci, const
   return rr <= tol2;
 }
 
+static inline double tet_geometry(const int32_t* v, const double* coords, double G[4][3]);
+static inline double tet_geometry_fwd(const int32_t* v, const double* coords, double G[4][3]) { return tet_geometry(v, coords, G); }
+
+/* Degree-2 (P2) heat on tetrahedra, for the bench's `p2` block: vals += k |T| sum_{c,e} (G_c . G_e) R[i][j][c][e], b += S |T| F[i].
+ * cell_nodes[nc][10] = the cell's 4 vertices (sorted) then its 6 edge nodes in UFC order; R[10][10][4][4] and F[10] are the exact
+ * reference tensors of oracle/fem_oracle_p2.py reference_tensors(3) (this function is checked against that module's assembly in
+ * tests/test_oracle_p2.py).  The affine geometry is fo_assemble_heat's. */
+void fo_assemble_heat_p2(int64_t ncells, const int32_t* cell_nodes, const double* coords, const double* R, const double* F, double k, double S,
+                         const int64_t* row_ptr, const int32_t* col_idx, double* vals, double* b) {
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < ncells; ++c) {
+    const int32_t* nd = cell_nodes + 10 * c;
+    double G[4][3];
+    const double vol = tet_geometry_fwd(nd, coords, G);
+    double gg[4][4];
+    for (int p = 0; p < 4; ++p)
+      for (int q = 0; q < 4; ++q) gg[p][q] = G[p][0] * G[q][0] + G[p][1] * G[q][1] + G[p][2] * G[q][2];
+    for (int i = 0; i < 10; ++i) {
+      const int64_t base = row_ptr[nd[i]], end = row_ptr[nd[i] + 1];
+      for (int j = 0; j < 10; ++j) {
+        const double* r = R + ((i * 10 + j) * 16);
+        double e = 0.0;
+        for (int p = 0; p < 4; ++p)
+          for (int q = 0; q < 4; ++q) e += gg[p][q] * r[p * 4 + q];
+        const int64_t pos = find_col(col_idx, base, end, nd[j]);
+#pragma omp atomic
+        vals[pos] += k * vol * e;
+      }
+      if (b) {
+#pragma omp atomic
+        b[nd[i]] += S * vol * F[i];
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------------------------------
  * BASELINE configs C3 (elasticity) and C4 (transient advection-diffusion): the cell loops and BiCGStab, so that the bench's
  * `c3` / `c4` blocks have a CPU figure and a full-size oracle to be compared with.  Same closed-form P1 element matrices as

@@ -97,3 +97,24 @@ def test_facet_terms_and_dofmap_conventions():
     assert np.abs(load[:nv]).max() < 1e-15                                  # P2 vertex functions integrate to zero on a facet
     Mf = fo._scatter(fn, p2.local_facet_mass(c, fv, 1.0), xc.shape[0])
     assert abs(Mf.sum() - 6.0) < 1e-13
+
+
+def test_c_oracle_degree_2_heat_matches_numpy_oracle():
+    """oracle/fem_oracle_c.c fo_assemble_heat_p2 (the CPU figure of the bench's `p2` block) against the numpy degree-2 oracle on a 5^3 cube:
+    matrix and load vector to rounding, and the solved problem reproduces the exact quadratic profile at every node."""
+    from oracle import c_oracle as co
+    from oracle import fem_oracle as fo
+    N = 5
+    h = co.HeatCubeP2(N)
+    c, t = fo.unit_cube_mesh(N, N, N)
+    cn, xn, _ = p2.p2_dofmap(c, t)
+    assert np.array_equal(cn, h.cell_nodes) and np.array_equal(xn, h.node_coords)
+    A = fo.conform(p2.assemble_matrix(cn, p2.local_laplace(c, t, h.k), xn.shape[0]), h.rp, h.ci)
+    h.lib.fo_zero(co._p(h.vals), h.vals.size)
+    h.lib.fo_zero(co._p(h.b), h.b.size)
+    h.lib.fo_assemble_heat_p2(h.cell_nodes.shape[0], co._p(h.cell_nodes), co._p(h.coords), co._p(h.R), co._p(h.F), h.k, h.S,
+                              co._p(h.rp), co._p(h.ci), co._p(h.vals), co._p(h.b))
+    assert np.abs(h.vals - A.data).max() <= 1e-14 * np.abs(A.data).max()
+    assert np.abs(h.b - p2.assemble_source(c, t, cn, xn.shape[0], h.S)).max() <= 1e-13 * np.abs(h.b).max()
+    r = h.step()
+    assert r["rel_l2_vs_exact"] < 1e-10 and r["iterations"] > 10

@@ -33,7 +33,7 @@ for f in sys.argv[1:]:
         print("c4 %.1f Mdof*steps/s %.3f ms/time step, its %s, oracle diff %s, cpu %s, roofline %s" % (c["value"], c["ms_per_time_step"], c["iterations_per_step"], c.get("rel_l2_vs_cpu_oracle_after_20_steps"), (c.get("cpu_baseline") or {}).get("value"), (c.get("roofline") or {}).get("frac")))
     c = d.get("p2")
     if c and c.get("value"):
-        print("p2 %.2f Mdof/s %.1f ms %d its err %.1e spmv frac %.3f" % (c["value"], c["ms_per_step"], c["iterations"], c["rel_l2_vs_exact"], c["roofline"]["frac"]))
+        print("p2 %.2f Mdof/s %.1f ms %d its err %.1e spmv frac %.3f cpu %s" % (c["value"], c["ms_per_step"], c["iterations"], c["rel_l2_vs_exact"], c["roofline"]["frac"], (c.get("cpu_baseline") or {}).get("value")))
     c = d.get("c5")
     if c and c.get("value"):
         print("c5 %.2f Mdof/s %.1f ms %d its err %.1e spmv frac %.3f iteration %.4f ms" % (c["value"], c["ms_per_step"], c["iterations"], c["rel_l2_vs_exact"], c["roofline"]["frac"], c["roofline"]["cg_iteration_ms"]))
