@@ -15,8 +15,10 @@ copy of the mesh, the boundary-facet search, the symbolic phase, the solve and t
 Inputs are larger than L2 (CSR 3 GB, vectors 136 MB each at 256^3), so no explicit L2 flush is needed.
 
 The same JSON line carries the other BASELINE.json configs as side blocks, each with its own error check,
-roofline and (N = 1) CPU figure: `c3` (elasticity cantilever 128^3), `c4` (200 Crank-Nicolson steps of
-advection-diffusion at 128^3), `p2` (degree-2 heat 64^3) at N = 1 and `c5` (heat 512^3) at every N.
+roofline and (N = 1) CPU figure: `c3` (elasticity cantilever 128^3: Jacobi-CG and the default solve_amg path) and
+`c5` (heat 512^3, Jacobi-CG and multigrid-CG) at every N, `c4` (200 Crank-Nicolson steps of advection-diffusion
+at 128^3) and `p2` (degree-2 heat 64^3) at N = 1; `gmg` (the headline problem with the multigrid preconditioner)
+and `keep_zeros` (the headline step without the compacted Krylov operand) at every N.
 
 Parity gate: the process exits with code 3 (after printing the line, with the reasons under `parity_failures`)
 when any measured solve did not converge or misses its analytic / oracle check, at any N.
