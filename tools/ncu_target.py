@@ -9,6 +9,9 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 ctx = _lib.Context(0)
 m = _lib.DeviceMesh.box(ctx, (N, N, N), (0, 0, 0), (1, 1, 1))
+if os.environ.get("FSB_NCU_K1"):
+    fv, opp, cell, fid = m.exterior_facets()          # K1: boundary search + facet ids (set-up launch list)
+    m.boundary_geometry()
 A = _lib.DeviceMatrix.create(m, 1)
 nv = m.sizes()[2]
 A.assemble_scalar(kscale=20.0)
