@@ -539,6 +539,8 @@ class SolverBase():
             sizes.append([k // 2 for k in sizes[-1]])
         if slab_dist and len(sizes) < 2:
             raise SolverError("the distributed multigrid preconditioner needs at least one coarser level")
+        if slab_dist and mesh.tdim != 3:
+            raise SolverError("the distributed multigrid preconditioner is implemented for 3-D boxes (z-slabs); use 'jacobi' for a distributed 2-D run")
         levels = self.__dict__.setdefault('_mg_levels', {})
         mats = [space.A]
         for nl in sizes[1:]:
@@ -607,8 +609,8 @@ class SolverBase():
         mesh = self.mesh
         if not getattr(mesh, 'box', None) or self.function_space.degree != 1:
             return 0
-        if self.parallel and (getattr(mesh, 'force_general_partition', False) or not getattr(mesh, 'slab_partition', True)):
-            return 0                                          # RCB-partitioned: no geometric hierarchy
+        if self.parallel and (getattr(mesh, 'force_general_partition', False) or not getattr(mesh, 'slab_partition', True) or mesh.tdim != 3):
+            return 0                                          # RCB-partitioned or 2-D slabs: no distributed geometric hierarchy
         n, levels = [int(k) for k in mesh.box['n']], 1
         while all(k % 2 == 0 and k >= 4 for k in n):
             n, levels = [k // 2 for k in n], levels + 1

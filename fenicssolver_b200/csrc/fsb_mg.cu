@@ -388,6 +388,7 @@ static int mg_create_impl(fsb_ctx* ctx, int32_t nlevels, fsb_mat** A, const int3
   if (!ctx || !A || !ncells || !out || nlevels < 1 || (tdim != 2 && tdim != 3)) return FSB_ERR_ARG;
   if (fsb_dist_active(ctx) && !dist) FSB_FAIL(ctx, FSB_ERR_STATE, "a distributed context needs fsb_mg_create_slab (slab-distributed fine level)");
   if (dist && (!fsb_dist_active(ctx) || nlevels < 2)) FSB_FAIL(ctx, FSB_ERR_STATE, "fsb_mg_create_slab needs an initialised distributed context and a coarse level");
+  if (dist && tdim != 3) FSB_FAIL(ctx, FSB_ERR_ARG, "the slab-distributed multigrid is implemented for 3-D boxes (slabs along z)");
   fsb_mg* mg = new fsb_mg();
   mg->ctx = ctx; mg->tdim = tdim; mg->bs = A[0]->bs;
   mg->dist = dist; mg->fz0 = layer0; mg->oz0 = oz0; mg->oz1 = oz1;
