@@ -305,6 +305,31 @@ assert np.array_equal(allv, np.arange(mesh.num_vertices()))
 cells = mesh.cells()
 touch = np.isin(cells, owned).any(axis=1)
 assert cells[touch].min() >= v_off and cells[touch].max() < v_off + nv_local
+# ---- slab-local boundary list (the rule Mesh.exterior_facets applies to the device search of a rank's slab): the exterior facets of
+# the slab's own cells, minus those lying in a cut plane, shifted to global ids = the global boundary facets whose vertices are all
+# local (what DeviceSpace.local_facets keeps of the global list)
+from oracle import fem_oracle as fo0
+from fenicssolver_b200.dolfin_compat import box_exterior_facets
+fl, ol, _ = fo0.exterior_facets(np.ascontiguousarray(local_cells, dtype=np.int32))
+zl = fl // plane
+nplanes = layer1 - layer0 + 1
+cut = np.zeros(fl.shape[0], dtype=bool)
+if layer0 > 0:
+    cut |= np.all(zl == 0, axis=1)
+if layer1 < N:
+    cut |= np.all(zl == nplanes - 1, axis=1)
+mine = np.hstack([fl[~cut] + v_off, (ol[~cut] + v_off)[:, None]])
+fg, og = box_exterior_facets((N, N, N))
+keep = np.all((fg >= v_off) & (fg < v_off + nv_local), axis=1) & (og >= v_off) & (og < v_off + nv_local)
+want = np.hstack([fg[keep], og[keep][:, None]])
+assert np.array_equal(mine, want), (mine.shape, want.shape)
+# a solver built with solver_settings['distributed'] on this 2-rank group marks its mesh as slab-distributed and, without a GPU,
+# falls back to the direct enumeration of the box surface (host-only inspection): same markers on both ranks
+from fenicssolver_b200 import ScalarTransportSolver
+import bench
+sv = ScalarTransportSolver.ScalarTransportSolver(bench.case_settings(N, distributed=True))
+assert sv.mesh.distributed == (comm.rank, 2) and sv.mesh.slab_partition is True and sv.parallel
+assert (sv.boundary_facets.values == 1).sum() == 2 * N * N and (sv.boundary_facets.values == 2).sum() == 2 * N * N
 # ---- general node partition (unstructured meshes / degree 2): the halo lists drive a real exchange over gloo and the
 # owner-computes SpMV of the locally assembled matrices reproduces the global product on the owned rows
 import torch
