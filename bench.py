@@ -850,8 +850,8 @@ def main():
                                   "krylov_operand": "drop_zeros 'auto' (default): %d of %d assembled entries on rank 0 are exactly 0.0 on this right-angled mesh; the CG "
                                                     "SpMVs run on a compacted copy (count + compact passes inside the timed step), the assembled CSR keeps its "
                                                     "full pattern; `keep_zeros` is the same step without it" % (int(nnz_local) - nnz_operand, int(nnz_local)),
-                                  "timed": "A.zero + assemble K,b + symmetric Dirichlet + Jacobi-PCG; symbolic phase (%.0f ms, first construction of this "
-                                           "process: cold) reused across steps" % symbolic_ms},
+                                  "timed": "A.zero + assemble K,b + symmetric Dirichlet + Jacobi-PCG; symbolic phase (%.0f ms, %s) reused across steps"
+                                           % (symbolic_ms, "warm: the e2e arm built spaces of this size before" if e2e is not None else "cold: first construction of this process")},
                 "iterations": iters, "converged": info["converged"], "rel_l2_vs_exact": rel_err,
                 "parity_failures": failures, "parity_failures_all_ranks": nfail,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "keep_zeros": drop, "gmg": gmg,
